@@ -1,0 +1,181 @@
+/*
+ * zsb.h -- C ABI of the B200-native Zstandard decode path ("zsb" = zstd on Blackwell).
+ *
+ * This header is the drop-in boundary for the decode path of the Rust crate
+ * AchilleBailly/zstd-decompressor.  The crate has no FFI of its own; the boundary is its public
+ * Rust API, and every entry point below names the reference interface it replaces
+ * (paths relative to /root/reference/zstd-decompressor/src).  A Rust `-sys` crate binds this
+ * header unchanged.  Plain pointers and sizes only; nothing here throws or
+ * aborts across the boundary; there is NO CPU fallback: every decode entry point needs a CUDA
+ * device and returns ZSB_E_CUDA if none is usable.
+ */
+#ifndef ZSB_H
+#define ZSB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes -------------------------------------------------------------------------
+ * 1..62 are the reference's error variants, same numbering as the CPU oracle (oracle/refcpu.h) so
+ * parity tests compare codes directly.  >= 100 are conditions the reference has no variant for. */
+enum {
+    ZSB_OK = 0,
+    ZSB_E_NOT_ENOUGH_BYTES = 1,        /* parsing::Error::NotEnoughBytes          parsing.rs:14 */
+    ZSB_E_NOT_ENOUGH_BITS = 2,         /* parsing::Error::NotEnoughBits           parsing.rs:16 */
+    ZSB_E_EMPTY_INPUT_DATA = 4,        /* parsing::Error::EmptyInputData          parsing.rs:20 */
+    ZSB_E_NULL_BYTE = 5,               /* parsing::Error::NullByte                parsing.rs:22 */
+    ZSB_E_EMPTY_SLICE = 6,             /* parsing::Error::EmptySliceError (ZSB_REFERENCE_QUIRKS only) */
+    ZSB_E_LARGE_ACCURACY_LOG = 10,     /* decoders::Error::LargeAccuracyLog       decoders/mod.rs:18 */
+    ZSB_E_CORRUPTED_TABLE = 11,        /* decoders::Error::CorruptedTable         decoders/mod.rs:20 */
+    ZSB_E_SEQ_CODE_MAX = 12,           /* decoders::Error::SequenceCodeMaxValueExceeded */
+    ZSB_E_HUFFMAN_MISSING = 20,        /* literals::Error::HuffmanDecoderMissing  literals.rs:14 */
+    ZSB_E_STREAMS_TOO_BIG = 21,        /* literals::Error::CorruptedStreamsSizeTooBig */
+    ZSB_E_SEQ_RESERVED = 30,           /* sequences::Error::ReservedSet           sequences.rs:18 */
+    ZSB_E_NO_PREVIOUS_DECODER = 31,    /* sequences::Error::NoPreviousDecoder     sequences.rs:22 */
+    ZSB_E_WINDOW_TOO_BIG = 40,         /* frame::Error::WindowSizeTooBig          frame.rs:32 */
+    ZSB_E_NULL_OFFSET = 41,            /* decoding_context::Error::NullOffsetError */
+    ZSB_E_IMPOSSIBLE_VALUE = 42,       /* decoding_context::Error::ImpossibleValue decoding_context.rs:14 */
+    ZSB_E_RESERVED_BLOCK = 50,         /* block::Error::ReservedBlockType         block.rs:14 */
+    ZSB_E_UNRECOGNIZED_MAGIC = 60,     /* frame::Error::UnrecognizedMagic         frame.rs:16 */
+    ZSB_E_FRAME_RESERVED = 61,         /* frame::Error::ReservedSet               frame.rs:20 */
+    ZSB_E_MISSING_CHECKSUM = 62,       /* frame::Error::MissingChecksum           frame.rs:28 */
+    /* no reference variant: RFC 8878 violations the reference would panic on or silently accept */
+    ZSB_E_CORRUPT = 100,               /* malformed entropy data (bad weights, stream length mismatch ...) */
+    ZSB_E_BLOCK_TOO_LARGE = 101,       /* a compressed block regenerates more than 128 KiB */
+    ZSB_E_CONTENT_SIZE = 102,          /* decoded size != Frame_Content_Size */
+    ZSB_E_DST_TOO_SMALL = 103,
+    ZSB_E_DICTIONARY = 104,            /* frame needs a dictionary (only when ZSB_STRICT_DICT) */
+    ZSB_E_PREVIOUS_FRAME = 105,        /* frame not decoded because the scan stopped at an earlier error */
+    ZSB_E_CUDA = 200,                  /* no device / CUDA runtime failure: see zsb_last_cuda_error */
+    ZSB_E_ARG = 201,
+    ZSB_E_NOMEM = 202
+};
+
+/* ---- flags ---------------------------------------------------------------------------------- */
+#define ZSB_PRINT_SKIPPABLE   0x01u  /* src/main.rs:22-24,45-49 : skippable payloads become output      */
+#define ZSB_VERIFY_CHECKSUM   0x02u  /* compute XXH64 of every frame that stores one (frame.rs:239-259) */
+#define ZSB_REFERENCE_QUIRKS  0x04u  /* reject exactly what the reference rejects */
+#define ZSB_SRC_ON_DEVICE     0x08u  /* src is a device pointer (compressed bytes resident in HBM)      */
+#define ZSB_DST_ON_DEVICE     0x10u  /* dst is a device pointer (output stays in HBM)                   */
+#define ZSB_STRICT_DICT       0x20u  /* fail frames carrying a dict id (the reference ignores it)       */
+
+#define ZSB_MAX_WINDOW_DEFAULT ((uint64_t)8 << 20)   /* frame::MAX_WIN_SIZE frame.rs:44 */
+#define ZSB_BLOCK_MAX 131072u
+
+/* ---- frame / block descriptors: result of walking the container ------------------------------
+ * == enum Frame { ZStandardFrame, SkippableFrame } frame.rs:47-56 and struct Header frame.rs:103-108,
+ *    enum Block block.rs:29-40 (type + extent only; section parsing happens on the GPU). */
+typedef struct zsb_frame {
+    uint32_t kind;              /* 0 = ZStandardFrame, 1 = SkippableFrame */
+    uint32_t magic;
+    uint64_t src_off, src_len;  /* whole frame, magic to checksum */
+    uint64_t window_size;       /* Header::window_size (descriptor, else content size) */
+    uint64_t content_size;      /* Header::content_size, valid if has_content_size */
+    uint64_t dict_id;           /* Header::dictionnary_id, valid if has_dict_id (parsed, ignored) */
+    uint32_t stored_checksum;   /* ZStandard::checksum(), valid if has_checksum */
+    uint32_t first_block, n_blocks;
+    int32_t  status;            /* scan status of this frame */
+    uint8_t  has_content_size, has_checksum, has_dict_id, single_segment;
+    uint32_t reserved;
+} zsb_frame;
+
+typedef struct zsb_block {
+    uint64_t src_off;           /* payload (after the 3-byte header); skippable frame: its data */
+    uint32_t size;              /* Block_Size field: payload bytes, or repeat count for RLE */
+    uint32_t frame;             /* owning frame index */
+    uint8_t  type;              /* 0 raw, 1 RLE, 2 compressed (block.rs:51-69); 4 = skippable payload */
+    uint8_t  last;
+    uint8_t  pad[6];
+} zsb_block;
+
+/* == ForwardByteParser::new(data).iter() + Frame::parse for every frame (parsing.rs:30-36,
+ *    frame.rs:61-100,198-230 minus the section parsing).  Host only, never touches the GPU.
+ * Walks until the buffer is exhausted or a frame is malformed.  On a malformed frame the walk
+ * stops (like the reference's iterator, whose cursor is undefined after an error): that frame is
+ * appended with its error in `status`, *err_pos is the byte offset the reference's error payload
+ * refers to, and the function returns that status.  Arrays are malloc'd; free with zsb_free.
+ * max_window = 0 means ZSB_MAX_WINDOW_DEFAULT.  flags: ZSB_REFERENCE_QUIRKS, ZSB_STRICT_DICT. */
+int zsb_scan(const uint8_t *src, size_t n, uint32_t flags, uint64_t max_window,
+             zsb_frame **frames, size_t *n_frames, zsb_block **blocks, size_t *n_blocks,
+             uint64_t *err_a, uint64_t *err_b);
+void zsb_free(void *p);
+
+/* ---- decode context: owns a CUDA stream and the device scratch of one GPU ---------------------
+ * == DecodingContext (decoding_context.rs:17-47), except that one zsb_ctx serves a whole batch of
+ *    frames: the per-frame state (repeat offsets [1,4,8], Huffman table, repeat tables, output)
+ *    lives in device arrays indexed by frame/block. */
+typedef struct zsb_ctx zsb_ctx;
+int  zsb_ctx_create(zsb_ctx **ctx, int device);
+void zsb_ctx_destroy(zsb_ctx *ctx);
+/* Run all kernels on an existing CUDA stream (cudaStream_t cast to void*), e.g. torch's current
+ * stream so that the caller can bracket the call with its own events.  NULL = the ctx's stream. */
+int  zsb_ctx_set_stream(zsb_ctx *ctx, void *cuda_stream);
+const char *zsb_last_cuda_error(const zsb_ctx *ctx);
+
+/* == Frame::decode(self) -> Result<Vec<u8>> for every frame of the batch (frame.rs:79-84,232-260
+ *    -> block.rs:74-99 -> literals.rs:49-86, sequences.rs:191-237, decoding_context.rs:50-106).
+ * src/n: the same buffer zsb_scan walked (host, or device with ZSB_SRC_ON_DEVICE).
+ * dst/dst_cap: output, frames are written back to back in order (skippable payloads only with
+ * ZSB_PRINT_SKIPPABLE, as src/main.rs:43-53 concatenates them).
+ * Per frame (arrays of n_frames, host memory, any may be NULL): dst_off/dst_len = where its bytes
+ * are; status = ZSB_OK or the first error of the frame (one bad frame does not fail the batch;
+ * its dst_len is 0); xxh32 = low 32 bits of XXH64(seed 0) of its content when ZSB_VERIFY_CHECKSUM
+ * and the frame stores a checksum; checksum_ok = 1 if equal to the stored value (a mismatch is
+ * reported, not an error -- the reference only prints a warning, frame.rs:251-254).
+ * *dst_total = bytes produced.  Returns ZSB_OK if the batch ran (inspect status[]), else an error. */
+int zsb_decode(zsb_ctx *ctx, const uint8_t *src, size_t n,
+               const zsb_frame *frames, size_t n_frames, const zsb_block *blocks, size_t n_blocks,
+               uint8_t *dst, size_t dst_cap, uint64_t *dst_off, uint64_t *dst_len,
+               int32_t *status, uint32_t *xxh32, uint8_t *checksum_ok,
+               uint64_t *dst_total, uint32_t flags);
+
+/* Split zsb_decode for callers that keep data resident and time the GPU work only:
+ * prepare uploads descriptors (and src unless ZSB_SRC_ON_DEVICE) and sizes the scratch;
+ * launch enqueues every kernel of the batch on the ctx stream and returns without synchronising;
+ * finish synchronises and returns the per-frame results. */
+int zsb_decode_prepare(zsb_ctx *ctx, const uint8_t *src, size_t n,
+                       const zsb_frame *frames, size_t n_frames, const zsb_block *blocks, size_t n_blocks,
+                       uint8_t *dst, size_t dst_cap, uint32_t flags);
+int zsb_decode_launch(zsb_ctx *ctx);
+int zsb_decode_finish(zsb_ctx *ctx, uint64_t *dst_off, uint64_t *dst_len, int32_t *status,
+                      uint32_t *xxh32, uint8_t *checksum_ok, uint64_t *dst_total);
+/* Number of kernels enqueued by the last zsb_decode_launch, and per-kernel device times (ms) of the
+ * last launch when profiling was enabled with zsb_ctx_set_profile(ctx, 1).  names[i] are static. */
+int zsb_ctx_set_profile(zsb_ctx *ctx, int enable);
+int zsb_last_launch_count(const zsb_ctx *ctx);
+int zsb_last_kernel_times(const zsb_ctx *ctx, const char **names, float *ms, int cap);
+
+/* == whole-program behaviour of src/main.rs:42-58 : scan + decode + concatenate into a malloc'd
+ *    buffer; all-or-nothing like the CLI (first error => no output).  Convenience for bindings. */
+int zsb_decompress(zsb_ctx *ctx, const uint8_t *src, size_t n, uint32_t flags,
+                   uint8_t **out, size_t *out_len, uint64_t *err_a, uint64_t *err_b);
+
+/* ---- stage-level entry points (the reference's tests call these stages directly) -------------- */
+/* == parse_fse_table (fse.rs:16-69) + FseTable::from_distribution (fse.rs:110-202) on the GPU.
+ *    in: description bytes; out: al, table of (1<<al) x {output, baseline, bits_to_read} u16 triples,
+ *    consumed = ForwardBitParser::bytes_read().  dist (optional, 64 entries) gets the counts. */
+int zsb_fse_table_parse(zsb_ctx *ctx, const uint8_t *desc, size_t n, int max_symbols,
+                        uint8_t *al, uint16_t *table, size_t *consumed, int16_t *dist, size_t *n_dist);
+/* == FseTable::from_distribution (fse.rs:110-202) on the GPU */
+int zsb_fse_table_from_distribution(zsb_ctx *ctx, uint8_t al, const int16_t *dist, size_t n_dist, uint16_t *table);
+/* == HuffmanDecoder::parse (huffman.rs:80-130) + from_weights (huffman.rs:177-203) on the GPU:
+ *    per symbol code length (0 = absent) and canonical code value, as the reference's tree assigns. */
+int zsb_huffman_parse(zsb_ctx *ctx, const uint8_t *desc, size_t n, uint8_t lens[256], uint16_t codes[256],
+                      size_t *consumed, uint8_t *max_bits);
+/* == DecodingContext::execute_sequences (decoding_context.rs:78-106) on the GPU with a fresh context
+ *    (offsets [1,4,8]); seqs = n_seq triples (literal_length, offset_value, match_length) as u32. */
+int zsb_execute_sequences(zsb_ctx *ctx, const uint32_t *seqs, size_t n_seq, const uint8_t *literals, size_t n_lit,
+                          uint8_t *out, size_t out_cap, size_t *out_len);
+/* XXH64 (seed 0) of a host buffer, computed on the GPU (twox_hash::XxHash64 at frame.rs:240-244) */
+int zsb_xxh64(zsb_ctx *ctx, const uint8_t *data, size_t n, uint64_t *hash);
+
+const char *zsb_strerror(int status);
+const char *zsb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZSB_H */

@@ -1,0 +1,135 @@
+// emul.cpp -- CPU-only TEST HARNESS for the lane-serial device code (test infrastructure, not product).
+//
+// The CUDA kernels run one lane per block / per stream over host+device inline functions
+// (zsb_parse.h, zsb_fse.h, zsb_huf.h, zsb_seq.h).  This file compiles those same functions with g++
+// and drives them serially, so that `pytest -m "not gpu"` can diff every intermediate product
+// (tables, weights, literals, sequence records, statuses) against the CPU oracle without a GPU.
+// It is never loaded by the product package, bench.py's GPU arm or smoke().
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../zstd-decompressor_b200/csrc/zsb_parse.h"
+#include "../../zstd-decompressor_b200/csrc/zsb_huf.h"
+
+extern "C" {
+
+int emul_fse_parse(const uint8_t *desc, size_t n, int type, int *al_out, int *nsym_out, int16_t *dist, uint32_t *cells, uint32_t *consumed) {
+    FwdBits f; fwd_init(f, desc, n);
+    int16_t cnt[256]; int al = 0, nsym = 0;
+    int rc = fse_read_ncount(f, cnt, 1, 256, al, nsym);
+    if (rc) return rc;
+    *al_out = al; *nsym_out = nsym; *consumed = fwd_bytes_read(f);
+    if (dist) memcpy(dist, cnt, sizeof(int16_t) * (size_t)nsym);
+    return fse_build_table(cnt, 1, nsym, al, cells, 1, type);
+}
+int emul_fse_build(int type, int al, const int16_t *dist, int nsym, uint32_t *cells, int stride) {
+    std::vector<int16_t> cnt(256 * (size_t)stride, 0);
+    for (int i = 0; i < nsym; i++) cnt[(size_t)i * stride] = dist[i];
+    return fse_build_table(cnt.data(), stride, nsym, al, cells, stride, type);
+}
+int emul_huf_parse(const uint8_t *desc, size_t n, uint8_t *lens, uint16_t *lut, int *maxbits, uint32_t *consumed, uint8_t *weights_out, int *nw_out) {
+    uint8_t weights[260]; uint32_t ftbl[512]; int16_t cnt[16]; uint32_t rank[16];
+    int nw = 0, mb = 0; uint32_t dl = 0;
+    std::vector<uint8_t> padded(desc, desc + n); padded.resize(n + 16, 0);
+    int rc = huf_read_weights(padded.data(), n, weights, 1, nw, dl, ftbl, 1, cnt, 1, n, false);
+    if (rc) return rc;
+    if (weights_out) { memcpy(weights_out, weights, (size_t)nw); *nw_out = nw; }
+    rc = huf_build_lut(weights, 1, nw, lut, rank, 1, mb, lens);
+    *maxbits = mb; *consumed = dl;
+    return rc;
+}
+
+// Whole pipeline, serially: scan -> parse -> chain -> huffman -> sequences -> plan -> execute.
+// out/out_cap: output buffer; per-frame arrays sized n_frames as reported by zsb_scan.
+// Intermediates of the LAST compressed block that ran are exported for stage-level diffs when the
+// pointers are non-null (lits: literals, recs: packed sequence records).
+int emul_decode(const uint8_t *src_in, size_t n, uint32_t flags, uint8_t *out, size_t out_cap, uint64_t *out_len,
+                int32_t *status, uint64_t *foff, uint64_t *flen, size_t frames_cap, size_t *n_frames_out, uint64_t *err_a, uint64_t *err_b) {
+    std::vector<uint8_t> srcv(src_in, src_in + n); srcv.resize(n + 64, 0);   // same padding as the device copy
+    const uint8_t *src = srcv.data();
+    zsb_frame *frames = nullptr; zsb_block *blocks = nullptr; size_t nf = 0, nb = 0;
+    int scan_rc = zsb_scan(src, n, flags, 0, &frames, &nf, &blocks, &nb, err_a, err_b);
+    *n_frames_out = nf;
+    if (nf > frames_cap) { zsb_free(frames); zsb_free(blocks); return ZSB_E_ARG; }
+    std::vector<ZsbBlockWork> work(nb + 1);
+    for (size_t i = 0; i < nb; i++) parse_block(src, blocks[i], work[i], flags);                        // k_parse
+    std::vector<int> fstatus(nf, 0);
+    for (size_t f = 0; f < nf; f++) {                                                                     // k_plan1 (a)
+        fstatus[f] = frames[f].status; uint32_t ea = 0, eb = 0;
+        if (!fstatus[f] && frames[f].kind == 0) fstatus[f] = chain_frame(frames[f], blocks, work.data(), flags, ea, eb);
+    }
+    std::vector<std::vector<uint8_t>> lits(nb);
+    std::vector<std::vector<uint64_t>> recs(nb);
+    for (size_t i = 0; i < nb; i++) {
+        ZsbBlockWork &w = work[i];
+        if (blocks[i].type != ZSB_BT_COMPRESSED || w.status) continue;
+        if (w.lit_type >= ZSB_LT_COMPRESSED) {                                                            // k_huf
+            uint8_t weights[260]; uint32_t ftbl[512]; int16_t cnt[16]; uint32_t rank[16]; static uint16_t lut[2048];
+            int nw = 0, mb = 0; uint32_t dl = 0;
+            int rc = huf_read_weights(src + w.huf_desc, w.huf_desc_end - w.huf_desc, weights, 1, nw, dl, ftbl, 1, cnt, 1, n - w.huf_desc,
+                                      (flags & ZSB_REFERENCE_QUIRKS) != 0);
+            if (!rc) rc = huf_build_lut(weights, 1, nw, lut, rank, 1, mb, nullptr);
+            lits[i].assign(w.lit_regen + 16, 0);
+            uint64_t start = w.lit_src; uint32_t seg = (w.lit_regen + 3) / 4;
+            for (uint32_t s = 0; s < w.n_streams && !rc; s++) {
+                uint32_t expect = w.n_streams == 1 ? w.lit_regen : (s < 3 ? seg : w.lit_regen - 3 * seg);
+                rc = huf_decode_stream(src, start, start + w.stream_size[s], n, lut, mb, lits[i].data() + (w.n_streams == 1 ? 0 : s * seg), expect);
+                start += w.stream_size[s];
+            }
+            if (rc) { w.status = rc; continue; }
+        }
+        if (w.nseq) {                                                                                     // k_seq (interleaved layout, lane 5 of 32)
+            const int TS = 32, LANE = 5;
+            std::vector<uint32_t> tbl(3 * 512 * TS, 0xDEADBEEF); std::vector<int16_t> cnt(256 * TS, 0);
+            uint32_t bases[89];
+            for (uint32_t k = 0; k < 89; k++) bases[k] = k < 36 ? zsb_ll_base(k) : zsb_ml_base(k - 36);
+            SeqTables T; T.ts = TS; T.tbl[0] = tbl.data() + LANE; T.tbl[1] = tbl.data() + 512 * TS + LANE; T.tbl[2] = tbl.data() + 2 * 512 * TS + LANE;
+            recs[i].assign(w.nseq + 1, 0);
+            int rc = seq_build_tables(src, w, T, cnt.data() + LANE, TS);
+            if (!rc) rc = seq_decode(src, n, w, T, bases, bases + 36, recs[i].data());
+            if (rc) { w.status = rc; continue; }
+        }
+    }
+    uint64_t pos = 0;
+    for (size_t f = 0; f < nf; f++) {                                                                     // k_plan2 + k_rawrle + k_exec
+        uint64_t len = 0; int st = fstatus[f];
+        if (!st) {
+            if (frames[f].kind == 1) len = (flags & ZSB_PRINT_SKIPPABLE) ? blocks[frames[f].first_block].size : 0;
+            else {
+                st = plan_frame(frames[f], blocks, work.data(), len);
+                if (!st && frames[f].has_content_size && len != frames[f].content_size && !(flags & ZSB_REFERENCE_QUIRKS)) st = ZSB_E_CONTENT_SIZE;
+                if (st) len = 0;
+            }
+        }
+        if (!st && pos + len > out_cap) { st = ZSB_E_DST_TOO_SMALL; }
+        if (st) len = 0;
+        foff[f] = pos; flen[f] = len; status[f] = st;
+        if (st || !len) continue;
+        uint8_t *fd = out + pos;
+        for (uint32_t k = 0; k < frames[f].n_blocks && !st; k++) {
+            const uint32_t bi = frames[f].first_block + k; const zsb_block &b = blocks[bi]; ZsbBlockWork &w = work[bi];
+            uint8_t *o = fd + w.out_off;
+            if (b.type == ZSB_BT_RLE) { memset(o, src[b.src_off], b.size); continue; }
+            if (b.type != ZSB_BT_COMPRESSED) { memcpy(o, src + b.src_off, b.size); continue; }
+            auto lit = [&](uint32_t i) -> uint8_t { return w.lit_type == ZSB_LT_RAW ? src[w.lit_src + i] : w.lit_type == ZSB_LT_RLE ? src[w.lit_src] : lits[bi][i]; };
+            uint32_t oe = 0, le = 0;
+            for (uint32_t s = 0; s < w.nseq; s++) {
+                const uint64_t r = recs[bi][s];
+                const uint32_t out_end = (uint32_t)r & ZSB_REC_POS_MASK, lit_end = (uint32_t)(r >> 18) & ZSB_REC_POS_MASK;
+                const uint32_t off = seq_real_offset((uint32_t)(r >> 36), w.rep_in);
+                const uint32_t ll = lit_end - le, ml = out_end - oe - ll;
+                if (off == 0 || off > w.out_off + oe + ll) { st = ZSB_E_IMPOSSIBLE_VALUE; break; }
+                for (uint32_t i = 0; i < ll; i++) o[oe + i] = lit(le + i);
+                for (uint32_t i = 0; i < ml; i++) o[oe + ll + i] = o[(int64_t)oe + ll + i - off];
+                oe = out_end; le = lit_end;
+            }
+            for (uint32_t i = 0; !st && i < w.lit_regen - le; i++) o[oe + i] = lit(le + i);
+        }
+        if (st) { status[f] = st; flen[f] = 0; }
+        pos += len;
+    }
+    *out_len = pos;
+    zsb_free(frames); zsb_free(blocks);
+    return scan_rc;
+}
+}  // extern "C"

@@ -1,0 +1,155 @@
+"""CPU-only differential tests: the lane-serial device code (compiled with g++ by tests/emul) against
+the CPU oracle.  Same functions the sm_100a kernels run one lane per block / per stream."""
+import random
+
+import pytest
+
+import corpora
+import emul_lib as E
+import refcpu as R
+
+Q, SKIP = 4, 1   # ZSB_REFERENCE_QUIRKS, ZSB_PRINT_SKIPPABLE
+
+
+def as_states(cells):
+    return [(c >> 26, (c >> 16) & 0x3FF, c & 0xFF) for c in cells]   # (output, baseline, bits_to_read)
+
+
+# ---------------------------------------------------------------- FSE tables (fse.rs)
+def test_fse_reference_vectors():
+    rc, t = E.fse_parse([0x30, 0x6f, 0x9b, 0x03])
+    assert rc == 0 and t["al"] == 5 and t["dist"] == [18, 6, 2, 2, 2, 1, 1] and as_states(t["cells"])[0xc] == (1, 0x18, 3)
+    rc, t = E.fse_parse([0x21, 0x9d, 0x51, 0xcc, 0x18, 0x42, 0x44, 0x81, 0x8c, 0x94, 0xb4, 0x50, 0x1e])
+    s = as_states(t["cells"])
+    assert rc == 0 and t["al"] == 6 and s[0x3f] == (24, 0x10, 4) and s[0x2c] == (0, 0x34, 2) and t["consumed"] == 13
+
+
+def random_distribution(r, al, max_sym):
+    n = 1 << al
+    nsym = r.randrange(2, max_sym + 1)
+    dist = [0] * nsym
+    remaining = n
+    low = r.randrange(0, min(nsym, 8))
+    for _ in range(low):
+        s = r.randrange(nsym)
+        if dist[s] == 0 and remaining > 1:
+            dist[s] = -1; remaining -= 1
+    while remaining:
+        s = r.randrange(nsym)
+        if dist[s] == -1:
+            continue
+        k = r.randrange(1, max(2, remaining // 2 + 1)) if r.random() < 0.3 else 1
+        k = min(k, remaining)
+        dist[s] += k; remaining -= k
+    return dist
+
+
+@pytest.mark.parametrize("stride", [1, 32])
+def test_fse_build_equals_reference_grouping(stride):
+    """closed form next/nb/base == the reference's per-symbol grouping (fse.rs:169-189) on random distributions"""
+    r = random.Random(7)
+    for it in range(300):
+        al = r.randrange(5, 10)
+        dist = random_distribution(r, al, r.choice([8, 29, 36, 53, 60]))
+        want = R.fse_from_distribution(al, dist)
+        rc, cells = E.fse_build(3, al, dist, stride)
+        assert rc == 0 and as_states(cells) == want, (al, dist)
+
+
+def test_fse_predefined_tables_and_xbits():
+    LL = [4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1]
+    rc, cells = E.fse_build(0, 6, LL)
+    assert rc == 0 and as_states(cells) == R.fse_from_distribution(6, LL)
+    ll_bits = [0] * 16 + [1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
+    assert all(((c >> 8) & 0xFF) == ll_bits[c >> 26] for c in cells)
+
+
+def test_fse_errors():
+    assert E.fse_parse([0x05, 0, 0, 0])[0] == R.LargeAccuracyLog
+    assert E.fse_parse([0x00])[0] == R.NotEnoughBits
+    rc, _ = E.fse_build(3, 5, [10, 10])          # 20 of 32 cells
+    assert rc == R.CorruptedTable
+
+
+# ---------------------------------------------------------------- Huffman (huffman.rs)
+def test_huffman_direct_weights_vector():
+    w = [0] * 65 + [1, 2]
+    packed = [(w[i] << 4) + (w[i + 1] if i + 1 < len(w) else 0) for i in range(0, len(w), 2)]
+    rc, t = E.huf_parse(bytes([127 + 67] + packed))
+    assert rc == 0 and t["codes"] == {65: (2, 0), 67: (2, 1), 66: (1, 1)} and t["maxbits"] == 2
+
+
+def test_huffman_descriptions_from_real_frames():
+    """every Huffman tree description found in the corpora: same codes as the reference's tree"""
+    import zstd_inspect as I
+    blob = corpora.c4()[0] + corpora.fixture("moby-dick.txt.zst")
+    n = 0
+    for f in I.inspect(blob):
+        for k in f.blocks:
+            if k.type == "compressed" and k.lit_type == "compressed":
+                hdr = 1 + (2 if k.lit_streams == 1 or (k.lit_regen < 1024 and k.lit_csize < 1024) else 3 if k.lit_regen < 16384 and k.lit_csize < 16384 else 4)
+                desc = blob[k.src_off + hdr:k.src_off + hdr + k.lit_csize]
+                want, consumed, weights = R.huffman_parse(desc)
+                rc, t = E.huf_parse(desc)
+                assert rc == 0 and t["codes"] == want and t["consumed"] == consumed and t["weights"] == weights
+                n += 1
+    assert n > 20
+
+
+# ---------------------------------------------------------------- whole path
+@pytest.mark.parametrize("name", corpora.FIXTURE_NAMES)
+@pytest.mark.parametrize("skip", [0, SKIP])
+def test_fixtures(name, skip):
+    d = corpora.fixture(name)
+    rc, out, frames, _ = E.decode(d, Q | skip)
+    assert rc == 0 and all(f[0] == 0 for f in frames)
+    assert out == R.main_decode(d, print_skippable=bool(skip))
+
+
+def test_c4_all_modes():
+    blob, exp, exp_skip, _ = corpora.c4()
+    rc, out, frames, _ = E.decode(blob, Q)
+    assert rc == 0 and out == exp == R.main_decode(blob)
+    rc, out, frames, _ = E.decode(blob, SKIP)      # RFC mode accepts the same inputs
+    assert rc == 0 and out == exp_skip
+
+
+def test_c2_small_and_multiblock():
+    blob, exp = corpora.c2_small(16)
+    rc, out, frames, _ = E.decode(blob, Q)
+    assert rc == 0 and out == exp
+    blob, exp = corpora.c3_small(3 << 20)
+    rc, out, frames, _ = E.decode(blob, Q)
+    assert rc == 0 and out == exp
+
+
+def test_rfc_only_inputs_follow_libzstd():
+    """inputs the reference rejects: default mode decodes them like libzstd,
+    ZSB_REFERENCE_QUIRKS rejects them like the reference"""
+    for frame, plain in corpora.rfc_only():
+        rc, out, frames, _ = E.decode(frame, 0)
+        assert rc == 0 and all(f[0] == 0 for f in frames) and out == plain
+        _, _, oerr = R.decode_frames(frame, quirks=True)
+        rc, out, frames, _ = E.decode(frame, Q)
+        got = rc or next((f[0] for f in frames if f[0]), 0)
+        assert oerr is not None and got != 0
+
+
+def test_mutations_never_crash_and_agree_when_both_accept():
+    r = random.Random(11)
+    n_ok = n_same_err = 0
+    for name, d in corpora.mutation_sources().items():
+        for _ in range(120):
+            b = corpora.mutate(r, d)
+            want, _, oerr = R.decode_frames(b, quirks=True)
+            rc, out, frames, _ = E.decode(b, Q | SKIP)
+            got = rc or next((f[0] for f in frames if f[0]), 0)
+            if oerr is None and got == 0:
+                assert out == want
+                n_ok += 1
+            elif oerr is not None and got == oerr.code:
+                n_same_err += 1
+            # a frame the reference accepts may be refused here only as RFC-invalid data
+            if oerr is None and got:
+                assert got in (100, 101, 102), (name, got)
+    assert n_ok > 100 and n_same_err > 100

@@ -1,0 +1,420 @@
+// zsb_host.cu -- C ABI (include/zsb.h): container walk on the host, device context, batch decode.
+//
+// Host work is limited to what the reference does before any entropy decoding: finding frame and
+// block boundaries (frame.rs:61-230, block.rs:43-72 minus section parsing).  Everything below a
+// block header runs in the kernels of zsb_kernels.cu.  There is no CPU decode path in this file.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <string>
+#include <vector>
+#include "zsb_kernels.h"
+
+// ======================================================================================= context
+namespace {
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); want = bytes; e = cudaMalloc(&p, want); }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+const int kMaxKernels = 12;
+}  // namespace
+
+struct zsb_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    DevBuf src, frames, blocks, work, fout, huf_list, seq_list, rawrle_list, exec_list, xxh_list, lit_pool, seq_pool, counters, dst, stage;
+    std::string last_err;
+    // prepared batch
+    const uint8_t *d_src = nullptr; uint8_t *d_dst = nullptr; uint8_t *h_dst = nullptr;
+    size_t src_len = 0, dst_cap = 0;
+    uint32_t nf = 0, nb = 0, ncomp = 0, n_rawrle = 0, n_exec = 0, n_xxh = 0, flags = 0;
+    uint64_t lit_cap = 0, seq_cap = 0;
+    std::vector<zsb_frame> h_frames;
+    std::vector<uint32_t> h_xxh_list;
+    bool prepared = false, launched = false;
+    // profiling
+    bool profile = false;
+    cudaEvent_t ev[kMaxKernels + 1] = {};
+    const char *kname[kMaxKernels] = {};
+    float kms[kMaxKernels] = {};
+    int nk = 0, launches = 0;
+};
+
+#define CK(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { (ctx)->last_err = std::string(#call) + ": " + cudaGetErrorString(e__); (void)cudaGetLastError(); return ZSB_E_CUDA; } } while (0)
+
+extern "C" int zsb_ctx_create(zsb_ctx **out, int device) {
+    if (!out) return ZSB_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { (void)cudaGetLastError(); return ZSB_E_CUDA; }
+    zsb_ctx *c = new (std::nothrow) zsb_ctx();
+    if (!c) return ZSB_E_NOMEM;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        zsbk_init() != cudaSuccess) { (void)cudaGetLastError(); delete c; return ZSB_E_CUDA; }
+    c->stream = c->own_stream;
+    for (int i = 0; i <= kMaxKernels; i++) cudaEventCreate(&c->ev[i]);
+    *out = c;
+    return ZSB_OK;
+}
+extern "C" void zsb_ctx_destroy(zsb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list,
+                     &c->xxh_list, &c->lit_pool, &c->seq_pool, &c->counters, &c->dst, &c->stage};
+    for (DevBuf *b : all) b->release();
+    for (int i = 0; i <= kMaxKernels; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+extern "C" int zsb_ctx_set_stream(zsb_ctx *c, void *s) { if (!c) return ZSB_E_ARG; c->stream = s ? (cudaStream_t)s : c->own_stream; return ZSB_OK; }
+extern "C" const char *zsb_last_cuda_error(const zsb_ctx *c) { return c ? c->last_err.c_str() : "no context"; }
+extern "C" int zsb_ctx_set_profile(zsb_ctx *c, int en) { if (!c) return ZSB_E_ARG; c->profile = en != 0; return ZSB_OK; }
+extern "C" int zsb_last_launch_count(const zsb_ctx *c) { return c ? c->launches : 0; }
+extern "C" int zsb_last_kernel_times(const zsb_ctx *c, const char **names, float *ms, int cap) {
+    if (!c) return 0;
+    int n = c->nk < cap ? c->nk : cap;
+    for (int i = 0; i < n; i++) { if (names) names[i] = c->kname[i]; if (ms) ms[i] = c->kms[i]; }
+    return n;
+}
+
+// ======================================================================================= batch decode
+extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_frame *frames, size_t nf,
+                                  const zsb_block *blocks, size_t nb, uint8_t *dst, size_t dst_cap, uint32_t flags) {
+    if (!c || (!src && n) || (!frames && nf) || (!blocks && nb) || nf > 0x7FFFFFFFu || nb > 0x7FFFFFFFu) return ZSB_E_ARG;
+    CK(c, cudaSetDevice(c->device));
+    c->prepared = false; c->launched = false;
+    cudaStream_t st = c->stream;
+    // compressed bytes: resident already, or uploaded once (padded so that aligned 8-byte loads near the end stay inside)
+    if (flags & ZSB_SRC_ON_DEVICE) c->d_src = src;
+    else {
+        CK(c, c->src.ensure(n + 64));
+        if (n) CK(c, cudaMemcpyAsync(c->src.p, src, n, cudaMemcpyHostToDevice, st));
+        CK(c, cudaMemsetAsync((uint8_t *)c->src.p + n, 0, 64, st));
+        c->d_src = (const uint8_t *)c->src.p;
+    }
+    if (flags & ZSB_DST_ON_DEVICE) { c->d_dst = dst; c->h_dst = nullptr; }
+    else { CK(c, c->dst.ensure(dst_cap + 64)); c->d_dst = (uint8_t *)c->dst.p; c->h_dst = dst; }
+    c->src_len = n; c->dst_cap = dst_cap; c->nf = (uint32_t)nf; c->nb = (uint32_t)nb; c->flags = flags;
+    c->h_frames.assign(frames, frames + nf);
+    // host-side work lists (block types and frame kinds are known from the scan)
+    std::vector<uint32_t> rawrle, execl;
+    c->h_xxh_list.clear();
+    uint64_t ncomp = 0, lit_cap = 0, seq_cap = 0;
+    for (size_t i = 0; i < nb; i++) {
+        const zsb_block &b = blocks[i];
+        if (b.type == ZSB_BT_COMPRESSED) {
+            ncomp++;
+            uint64_t lc = (uint64_t)b.size * 4; if (lc > ZSB_BLOCK_MAX) lc = ZSB_BLOCK_MAX;
+            lit_cap += lc + 16;
+            seq_cap += b.size < ZSB_MAX_NSEQ_PER_BLOCK ? b.size : ZSB_MAX_NSEQ_PER_BLOCK;
+        } else if (b.type == ZSB_BT_SKIPPABLE) { if (flags & ZSB_PRINT_SKIPPABLE) rawrle.push_back((uint32_t)i); }
+        else rawrle.push_back((uint32_t)i);
+    }
+    for (size_t f = 0; f < nf; f++) {
+        if (frames[f].kind != 0 || frames[f].status != ZSB_OK) continue;
+        bool has_c = false;
+        for (uint32_t k = 0; k < frames[f].n_blocks && !has_c; k++) has_c = blocks[frames[f].first_block + k].type == ZSB_BT_COMPRESSED;
+        if (has_c) execl.push_back((uint32_t)f);
+        if ((flags & ZSB_VERIFY_CHECKSUM) && frames[f].has_checksum) c->h_xxh_list.push_back((uint32_t)f);
+    }
+    c->ncomp = (uint32_t)ncomp; c->n_rawrle = (uint32_t)rawrle.size(); c->n_exec = (uint32_t)execl.size(); c->n_xxh = (uint32_t)c->h_xxh_list.size();
+    if (lit_cap > c->lit_cap) c->lit_cap = lit_cap;
+    if (seq_cap > c->seq_cap) c->seq_cap = seq_cap;
+    CK(c, c->frames.ensure(sizeof(zsb_frame) * (nf + 1)));
+    CK(c, c->blocks.ensure(sizeof(zsb_block) * (nb + 1)));
+    CK(c, c->work.ensure(sizeof(ZsbBlockWork) * (nb + 1)));
+    CK(c, c->fout.ensure(sizeof(ZsbFrameOut) * (nf + 1)));
+    CK(c, c->huf_list.ensure(4 * (ncomp + 1)));
+    CK(c, c->seq_list.ensure(4 * (ncomp + 1)));
+    CK(c, c->rawrle_list.ensure(4 * (rawrle.size() + 1)));
+    CK(c, c->exec_list.ensure(4 * (execl.size() + 1)));
+    CK(c, c->xxh_list.ensure(4 * (c->h_xxh_list.size() + 1)));
+    CK(c, c->counters.ensure(sizeof(ZsbCounters)));
+    CK(c, c->lit_pool.ensure(c->lit_cap + 64));
+    CK(c, c->seq_pool.ensure(8 * (c->seq_cap + 8)));
+    if (nf) CK(c, cudaMemcpyAsync(c->frames.p, frames, sizeof(zsb_frame) * nf, cudaMemcpyHostToDevice, st));
+    if (nb) CK(c, cudaMemcpyAsync(c->blocks.p, blocks, sizeof(zsb_block) * nb, cudaMemcpyHostToDevice, st));
+    if (!rawrle.empty()) CK(c, cudaMemcpyAsync(c->rawrle_list.p, rawrle.data(), 4 * rawrle.size(), cudaMemcpyHostToDevice, st));
+    if (!execl.empty()) CK(c, cudaMemcpyAsync(c->exec_list.p, execl.data(), 4 * execl.size(), cudaMemcpyHostToDevice, st));
+    if (!c->h_xxh_list.empty()) CK(c, cudaMemcpyAsync(c->xxh_list.p, c->h_xxh_list.data(), 4 * c->h_xxh_list.size(), cudaMemcpyHostToDevice, st));
+    CK(c, cudaStreamSynchronize(st));   // the host vectors above go out of scope
+    c->prepared = true;
+    return ZSB_OK;
+}
+
+#define MARK(ctx, name) do { if ((ctx)->profile && (ctx)->nk < kMaxKernels) { (ctx)->kname[(ctx)->nk] = name; cudaEventRecord((ctx)->ev[(ctx)->nk], st); (ctx)->nk++; } } while (0)
+
+extern "C" int zsb_decode_launch(zsb_ctx *c) {
+    if (!c || !c->prepared) return ZSB_E_ARG;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const uint8_t *src = c->d_src;
+    zsb_frame *frames = (zsb_frame *)c->frames.p; zsb_block *blocks = (zsb_block *)c->blocks.p;
+    ZsbBlockWork *work = (ZsbBlockWork *)c->work.p; ZsbFrameOut *fout = (ZsbFrameOut *)c->fout.p;
+    ZsbCounters *cnt = (ZsbCounters *)c->counters.p;
+    c->nk = 0; c->launches = 0;
+    CK(c, cudaMemsetAsync(cnt, 0, sizeof(ZsbCounters), st));
+    MARK(c, "k_parse");  zsbk_parse(st, src, blocks, work, c->nb, c->flags); c->launches += c->nb ? 1 : 0;
+    MARK(c, "k_plan1");  zsbk_plan1(st, frames, c->nf, blocks, c->nb, work, fout, (uint32_t *)c->huf_list.p, (uint32_t *)c->seq_list.p, cnt,
+                                    c->lit_cap, c->seq_cap, c->flags); c->launches++;
+    MARK(c, "k_huf");    zsbk_huf(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags); c->launches += c->ncomp ? 1 : 0;
+    MARK(c, "k_seq");    zsbk_seq(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p); c->launches += c->ncomp ? 1 : 0;
+    MARK(c, "k_plan2");  zsbk_plan2(st, frames, c->nf, blocks, work, fout, cnt, c->dst_cap, c->flags); c->launches++;
+    MARK(c, "k_rawrle"); zsbk_rawrle(st, c->n_rawrle, src, blocks, work, fout, (const uint32_t *)c->rawrle_list.p, cnt, c->d_dst); c->launches += c->n_rawrle ? 1 : 0;
+    MARK(c, "k_exec");   zsbk_exec(st, c->n_exec, src, frames, blocks, work, fout, (const uint32_t *)c->exec_list.p, cnt, (const uint64_t *)c->seq_pool.p,
+                                   (const uint8_t *)c->lit_pool.p, c->d_dst); c->launches += c->n_exec ? 1 : 0;
+    MARK(c, "k_xxh");    zsbk_xxh(st, c->n_xxh, c->d_dst, fout, (const uint32_t *)c->xxh_list.p, cnt); c->launches += c->n_xxh ? 1 : 0;
+    if (c->profile) cudaEventRecord(c->ev[c->nk], st);
+    CK(c, cudaGetLastError());
+    c->launched = true;
+    return ZSB_OK;
+}
+
+extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_len, int32_t *status, uint32_t *xxh32,
+                                 uint8_t *checksum_ok, uint64_t *dst_total) {
+    if (!c || !c->launched) return ZSB_E_ARG;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    ZsbCounters hc;
+    for (int attempt = 0;; attempt++) {
+        CK(c, cudaMemcpyAsync(&hc, c->counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaStreamSynchronize(st));
+        if (!hc.overflow) break;
+        if (attempt >= 2) { c->last_err = "scratch overflow persists"; return ZSB_E_NOMEM; }
+        // the entropy scratch was too small for this input: size it exactly and run the batch again
+        c->lit_cap = hc.lit_total + 64; c->seq_cap = hc.seq_total + 8;
+        CK(c, c->lit_pool.ensure(c->lit_cap + 64));
+        CK(c, c->seq_pool.ensure(8 * (c->seq_cap + 8)));
+        int rc = zsb_decode_launch(c);
+        if (rc) return rc;
+    }
+    if (c->profile) for (int i = 0; i < c->nk; i++) cudaEventElapsedTime(&c->kms[i], c->ev[i], c->ev[i + 1]);
+    std::vector<ZsbFrameOut> fo(c->nf);
+    if (c->nf) CK(c, cudaMemcpyAsync(fo.data(), c->fout.p, sizeof(ZsbFrameOut) * c->nf, cudaMemcpyDeviceToHost, st));
+    if (c->h_dst && hc.dst_total) CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, hc.dst_total, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    for (uint32_t f = 0; f < c->nf; f++) {
+        const bool ok = fo[f].status == ZSB_OK;
+        if (dst_off) dst_off[f] = fo[f].dst_off;
+        if (dst_len) dst_len[f] = ok ? fo[f].dst_len : 0;
+        if (status) status[f] = fo[f].status;
+        const bool hashed = ok && (c->flags & ZSB_VERIFY_CHECKSUM) && c->h_frames[f].kind == 0 && c->h_frames[f].has_checksum;
+        if (xxh32) xxh32[f] = hashed ? (uint32_t)fo[f].xxh64 : 0;
+        if (checksum_ok) checksum_ok[f] = hashed ? ((uint32_t)fo[f].xxh64 == c->h_frames[f].stored_checksum) : 0;
+    }
+    if (dst_total) *dst_total = hc.dst_total;
+    return ZSB_OK;
+}
+
+extern "C" int zsb_decode(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_frame *frames, size_t nf, const zsb_block *blocks, size_t nb,
+                          uint8_t *dst, size_t dst_cap, uint64_t *dst_off, uint64_t *dst_len, int32_t *status, uint32_t *xxh32,
+                          uint8_t *checksum_ok, uint64_t *dst_total, uint32_t flags) {
+    int rc = zsb_decode_prepare(c, src, n, frames, nf, blocks, nb, dst, dst_cap, flags);
+    if (rc) return rc;
+    rc = zsb_decode_launch(c);
+    if (rc) return rc;
+    return zsb_decode_finish(c, dst_off, dst_len, status, xxh32, checksum_ok, dst_total);
+}
+
+// src/main.rs:42-58 : all-or-nothing whole-buffer decode
+extern "C" int zsb_decompress(zsb_ctx *c, const uint8_t *src, size_t n, uint32_t flags, uint8_t **out, size_t *out_len,
+                              uint64_t *err_a, uint64_t *err_b) {
+    if (!c || !out || !out_len) return ZSB_E_ARG;
+    *out = nullptr; *out_len = 0;
+    flags &= ~(ZSB_SRC_ON_DEVICE | ZSB_DST_ON_DEVICE);
+    zsb_frame *frames = nullptr; zsb_block *blocks = nullptr; size_t nf = 0, nb = 0;
+    int rc = zsb_scan(src, n, flags, 0, &frames, &nf, &blocks, &nb, err_a, err_b);
+    if (rc) { zsb_free(frames); zsb_free(blocks); return rc; }
+    // capacity: content sizes where declared; otherwise blocks regenerate at most 128 KiB each
+    uint64_t cap = 0;
+    for (size_t f = 0; f < nf; f++) {
+        if (frames[f].kind == 1) { cap += blocks[frames[f].first_block].size; continue; }
+        if (frames[f].has_content_size) { cap += frames[f].content_size; continue; }
+        for (uint32_t k = 0; k < frames[f].n_blocks; k++) {
+            const zsb_block &b = blocks[frames[f].first_block + k];
+            cap += b.type == ZSB_BT_COMPRESSED ? ZSB_BLOCK_MAX : b.size;
+        }
+    }
+    uint8_t *dst = (uint8_t *)malloc(cap ? cap : 1);
+    std::vector<int32_t> status(nf);
+    std::vector<uint64_t> off(nf), len(nf);
+    uint64_t total = 0;
+    if (!dst) { zsb_free(frames); zsb_free(blocks); return ZSB_E_NOMEM; }
+    rc = zsb_decode(c, src, n, frames, nf, blocks, nb, dst, cap, off.data(), len.data(), status.data(), nullptr, nullptr, &total, flags);
+    if (!rc) for (size_t f = 0; f < nf && !rc; f++) rc = status[f];      // main.rs:51 first error aborts, no partial output
+    zsb_free(frames); zsb_free(blocks);
+    if (rc) { free(dst); return rc; }
+    *out = dst; *out_len = total;
+    return ZSB_OK;
+}
+
+// ======================================================================================= stage-level entry points
+namespace {
+int stage_sync(zsb_ctx *c) { CK(c, cudaGetLastError()); CK(c, cudaStreamSynchronize(c->stream)); return ZSB_OK; }
+}
+static int fse_stage(zsb_ctx *c, const uint8_t *desc, size_t n, int max_symbols, const int16_t *dist_in, size_t nd_in, int al_in,
+                     uint8_t *al, uint16_t *table, size_t *consumed, int16_t *dist, size_t *n_dist) {
+    CK(c, cudaSetDevice(c->device));
+    const size_t off_res = 0, off_cells = 64, off_dist = off_cells + 512 * 4, off_in = off_dist + 256 * 2, total = off_in + (desc ? n : nd_in * 2) + 64;
+    CK(c, c->stage.ensure(total));
+    uint8_t *base = (uint8_t *)c->stage.p; cudaStream_t st = c->stream;
+    if (desc) CK(c, cudaMemcpyAsync(base + off_in, desc, n, cudaMemcpyHostToDevice, st));
+    else CK(c, cudaMemcpyAsync(base + off_in, dist_in, nd_in * 2, cudaMemcpyHostToDevice, st));
+    zsbk_stage_fse(st, desc ? base + off_in : nullptr, (uint32_t)n, max_symbols, desc ? nullptr : (const int16_t *)(base + off_in), (int)nd_in, al_in,
+                   (int *)(base + off_res), (uint32_t *)(base + off_cells), (int16_t *)(base + off_dist));
+    int res[4]; uint32_t cells[512]; int16_t d[256];
+    CK(c, cudaMemcpyAsync(res, base + off_res, sizeof res, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(cells, base + off_cells, sizeof cells, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(d, base + off_dist, sizeof d, cudaMemcpyDeviceToHost, st));
+    int rc = stage_sync(c); if (rc) return rc;
+    if (res[0]) return res[0];
+    if (al) *al = (uint8_t)res[1];
+    if (consumed) *consumed = (size_t)res[3];
+    if (dist) { for (int i = 0; i < res[2] && i < 256; i++) dist[i] = d[i]; }
+    if (n_dist) *n_dist = (size_t)res[2];
+    if (table) for (int i = 0; i < (1 << res[1]); i++) {
+        table[3 * i] = (uint16_t)ZSB_CELL_CODE(cells[i]); table[3 * i + 1] = (uint16_t)ZSB_CELL_BASE(cells[i]); table[3 * i + 2] = (uint16_t)ZSB_CELL_NB(cells[i]);
+    }
+    return ZSB_OK;
+}
+extern "C" int zsb_fse_table_parse(zsb_ctx *c, const uint8_t *desc, size_t n, int max_symbols, uint8_t *al, uint16_t *table,
+                                   size_t *consumed, int16_t *dist, size_t *n_dist) {
+    if (!c || !desc || !n) return c && !n ? ZSB_E_EMPTY_INPUT_DATA : ZSB_E_ARG;
+    if (max_symbols <= 0 || max_symbols > 64) max_symbols = 64;       // the cell's code field holds 0..63
+    return fse_stage(c, desc, n, max_symbols, nullptr, 0, 0, al, table, consumed, dist, n_dist);
+}
+extern "C" int zsb_fse_table_from_distribution(zsb_ctx *c, uint8_t al, const int16_t *dist, size_t n_dist, uint16_t *table) {
+    if (!c || !dist || n_dist == 0 || n_dist > 64) return ZSB_E_ARG;
+    return fse_stage(c, nullptr, 0, 64, dist, n_dist, al, nullptr, table, nullptr, nullptr, nullptr);
+}
+extern "C" int zsb_huffman_parse(zsb_ctx *c, const uint8_t *desc, size_t n, uint8_t lens[256], uint16_t codes[256], size_t *consumed, uint8_t *max_bits) {
+    if (!c || !desc || !n) return ZSB_E_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const size_t off_res = 0, off_lens = 64, off_lut = off_lens + 256, off_in = off_lut + 4096, total = off_in + n + 64;
+    CK(c, c->stage.ensure(total));
+    uint8_t *base = (uint8_t *)c->stage.p; cudaStream_t st = c->stream;
+    CK(c, cudaMemcpyAsync(base + off_in, desc, n, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemsetAsync(base + off_in + n, 0, 64, st));
+    zsbk_stage_huf(st, base + off_in, (uint32_t)n, (int *)(base + off_res), base + off_lens, (uint16_t *)(base + off_lut));
+    int res[3]; uint8_t l[256]; static thread_local uint16_t lut[2048];
+    CK(c, cudaMemcpyAsync(res, base + off_res, sizeof res, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(l, base + off_lens, 256, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(lut, base + off_lut, 4096, cudaMemcpyDeviceToHost, st));
+    int rc = stage_sync(c); if (rc) return rc;
+    if (res[0]) return res[0];
+    const int mb = res[1];
+    if (lens) memcpy(lens, l, 256);
+    if (codes) {
+        // code of a symbol = index of its first LUT cell, shortened to its length
+        memset(codes, 0, 512);
+        for (int i = (1 << mb) - 1; i >= 0; i--) { const int s = lut[i] & 255, nb = lut[i] >> 8; codes[s] = (uint16_t)(i >> (mb - nb)); }
+    }
+    if (consumed) *consumed = (size_t)res[2];
+    if (max_bits) *max_bits = (uint8_t)mb;
+    return ZSB_OK;
+}
+extern "C" int zsb_execute_sequences(zsb_ctx *c, const uint32_t *seqs, size_t n_seq, const uint8_t *literals, size_t n_lit,
+                                     uint8_t *out, size_t out_cap, size_t *out_len) {
+    if (!c || (!seqs && n_seq) || (!literals && n_lit) || !out_len) return ZSB_E_ARG;
+    if (n_lit > ZSB_BLOCK_MAX || n_seq > ZSB_MAX_NSEQ_PER_BLOCK) return ZSB_E_BLOCK_TOO_LARGE;
+    CK(c, cudaSetDevice(c->device));
+    // one synthetic frame holding one compressed block with raw literals; the records come from the device too
+    const size_t off_work = 0, off_fout = 512, off_frame = 640, off_block = 768, off_cnt = 832, off_list = 896, off_tri = 1024,
+                 off_rec = off_tri + ((12 * n_seq + 15) & ~(size_t)15), off_lit = off_rec + 8 * (n_seq + 2), off_out = (off_lit + n_lit + 79) & ~(size_t)15,
+                 total = off_out + ZSB_BLOCK_MAX + 64;
+    CK(c, c->stage.ensure(total));
+    uint8_t *base = (uint8_t *)c->stage.p; cudaStream_t st = c->stream;
+    CK(c, cudaMemsetAsync(base, 0, off_tri, st));
+    if (n_seq) CK(c, cudaMemcpyAsync(base + off_tri, seqs, 12 * n_seq, cudaMemcpyHostToDevice, st));
+    if (n_lit) CK(c, cudaMemcpyAsync(base + off_lit, literals, n_lit, cudaMemcpyHostToDevice, st));
+    ZsbBlockWork *w = (ZsbBlockWork *)(base + off_work);
+    zsbk_stage_records(st, (const uint32_t *)(base + off_tri), (uint32_t)n_seq, (uint32_t)n_lit, (uint64_t *)(base + off_rec), w);
+    ZsbBlockWork hw;
+    CK(c, cudaMemcpyAsync(&hw, w, sizeof hw, cudaMemcpyDeviceToHost, st));
+    int rc = stage_sync(c); if (rc) return rc;
+    if (hw.status) return hw.status;
+    hw.lit_type = ZSB_LT_RAW; hw.lit_regen = (uint32_t)n_lit; hw.lit_src = off_lit; hw.nseq = (uint32_t)n_seq; hw.seq_buf = 0; hw.out_off = 0;
+    zsb_frame fr; memset(&fr, 0, sizeof fr); fr.kind = 0; fr.first_block = 0; fr.n_blocks = 1;
+    zsb_block bl; memset(&bl, 0, sizeof bl); bl.type = ZSB_BT_COMPRESSED; bl.last = 1;
+    ZsbFrameOut fo; memset(&fo, 0, sizeof fo); fo.dst_len = hw.out_size;
+    uint32_t zero = 0;
+    CK(c, cudaMemcpyAsync(w, &hw, sizeof hw, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(base + off_frame, &fr, sizeof fr, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(base + off_block, &bl, sizeof bl, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(base + off_fout, &fo, sizeof fo, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(base + off_list, &zero, 4, cudaMemcpyHostToDevice, st));
+    zsbk_exec(st, 1, base, (const zsb_frame *)(base + off_frame), (const zsb_block *)(base + off_block), w, (ZsbFrameOut *)(base + off_fout),
+              (const uint32_t *)(base + off_list), (const ZsbCounters *)(base + off_cnt), (const uint64_t *)(base + off_rec), base, base + off_out);
+    CK(c, cudaMemcpyAsync(&fo, base + off_fout, sizeof fo, cudaMemcpyDeviceToHost, st));
+    rc = stage_sync(c); if (rc) return rc;
+    if (fo.status) return fo.status;
+    *out_len = hw.out_size;
+    if (hw.out_size > out_cap) return ZSB_E_DST_TOO_SMALL;
+    if (hw.out_size) CK(c, cudaMemcpy(out, base + off_out, hw.out_size, cudaMemcpyDeviceToHost));
+    return ZSB_OK;
+}
+extern "C" int zsb_xxh64(zsb_ctx *c, const uint8_t *data, size_t n, uint64_t *hash) {
+    if (!c || (!data && n) || !hash) return ZSB_E_ARG;
+    CK(c, cudaSetDevice(c->device));
+    const size_t off_fout = 0, off_cnt = 64, off_list = 128, off_data = 256, total = off_data + n + 64;
+    CK(c, c->stage.ensure(total));
+    uint8_t *base = (uint8_t *)c->stage.p; cudaStream_t st = c->stream;
+    CK(c, cudaMemsetAsync(base, 0, off_data, st));
+    ZsbFrameOut fo; memset(&fo, 0, sizeof fo); fo.dst_off = off_data; fo.dst_len = n;
+    CK(c, cudaMemcpyAsync(base + off_fout, &fo, sizeof fo, cudaMemcpyHostToDevice, st));
+    if (n) CK(c, cudaMemcpyAsync(base + off_data, data, n, cudaMemcpyHostToDevice, st));
+    zsbk_xxh(st, 1, base, (ZsbFrameOut *)(base + off_fout), (const uint32_t *)(base + off_list), (const ZsbCounters *)(base + off_cnt));
+    CK(c, cudaMemcpyAsync(&fo, base + off_fout, sizeof fo, cudaMemcpyDeviceToHost, st));
+    int rc = stage_sync(c); if (rc) return rc;
+    *hash = fo.xxh64;
+    return ZSB_OK;
+}
+
+extern "C" const char *zsb_strerror(int s) {
+    switch (s) {
+    case ZSB_OK: return "ok";
+    case ZSB_E_NOT_ENOUGH_BYTES: return "parsing::Error::NotEnoughBytes";
+    case ZSB_E_NOT_ENOUGH_BITS: return "parsing::Error::NotEnoughBits";
+    case ZSB_E_EMPTY_INPUT_DATA: return "parsing::Error::EmptyInputData";
+    case ZSB_E_NULL_BYTE: return "parsing::Error::NullByte";
+    case ZSB_E_EMPTY_SLICE: return "parsing::Error::EmptySliceError";
+    case ZSB_E_LARGE_ACCURACY_LOG: return "decoders::Error::LargeAccuracyLog";
+    case ZSB_E_CORRUPTED_TABLE: return "decoders::Error::CorruptedTable";
+    case ZSB_E_SEQ_CODE_MAX: return "decoders::Error::SequenceCodeMaxValueExceeded";
+    case ZSB_E_HUFFMAN_MISSING: return "literals::Error::HuffmanDecoderMissing";
+    case ZSB_E_STREAMS_TOO_BIG: return "literals::Error::CorruptedStreamsSizeTooBig";
+    case ZSB_E_SEQ_RESERVED: return "sequences::Error::ReservedSet";
+    case ZSB_E_NO_PREVIOUS_DECODER: return "sequences::Error::NoPreviousDecoder";
+    case ZSB_E_WINDOW_TOO_BIG: return "frame::Error::WindowSizeTooBig";
+    case ZSB_E_NULL_OFFSET: return "decoding_context::Error::NullOffsetError";
+    case ZSB_E_IMPOSSIBLE_VALUE: return "decoding_context::Error::ImpossibleValue";
+    case ZSB_E_RESERVED_BLOCK: return "block::Error::ReservedBlockType";
+    case ZSB_E_UNRECOGNIZED_MAGIC: return "frame::Error::UnrecognizedMagic";
+    case ZSB_E_FRAME_RESERVED: return "frame::Error::ReservedSet";
+    case ZSB_E_MISSING_CHECKSUM: return "frame::Error::MissingChecksum";
+    case ZSB_E_CORRUPT: return "corrupt entropy data (RFC 8878)";
+    case ZSB_E_BLOCK_TOO_LARGE: return "block regenerates more than 128 KiB";
+    case ZSB_E_CONTENT_SIZE: return "decoded size differs from Frame_Content_Size";
+    case ZSB_E_DST_TOO_SMALL: return "destination too small";
+    case ZSB_E_DICTIONARY: return "frame needs a dictionary";
+    case ZSB_E_PREVIOUS_FRAME: return "not decoded: an earlier error stopped the frame";
+    case ZSB_E_CUDA: return "CUDA error";
+    case ZSB_E_ARG: return "bad argument";
+    case ZSB_E_NOMEM: return "out of memory";
+    default: return "unknown status";
+    }
+}
+extern "C" const char *zsb_version(void) { return "zsb 0.1 (sm_100a)"; }

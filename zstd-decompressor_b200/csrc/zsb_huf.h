@@ -1,0 +1,133 @@
+// zsb_huf.h -- Huffman tree description -> flat decoding LUT -> stream decode, one lane per stream.
+//
+//  huf_read_weights  == HuffmanDecoder::parse / parse_direct / parse_fse (huffman.rs:80-130)
+//                       with AlternatingDecoder (alternating.rs:8-69)
+//  huf_build_lut     == HuffmanDecoder::from_weights / from_number_of_bits (huffman.rs:161-203):
+//                       the reference builds a boxed binary tree and walks it one bit at a time
+//                       (huffman.rs:205-218); the same canonical code (longest codes first, ascending
+//                       symbol within a length, counting up from 0) is laid out here as a
+//                       2^maxbits-entry LUT {symbol, nbits} indexed by the next maxbits bits.
+//  huf_decode_stream == the per-stream loop of LiteralsSection::decode (literals.rs:70-81)
+#pragma once
+#include "zsb_fse.h"
+
+#define ZSB_HUF_WEIGHT_SYMS 16   // weights 0..15 can be described (legal ones are <= 11)
+
+// Scratch needed by huf_read_weights: FSE table for the weights (<= 512 cells) and counts (16).
+// weights[]: up to 256 entries; returns the number of explicit weights in nw (last one is implied).
+// desc = first byte of the description (header byte); limit = bytes available from desc.
+ZSB_HDN int huf_read_weights(const uint8_t *desc, uint64_t limit, uint8_t *weights, int ws, int &nw, uint32_t &desc_len,
+                             uint32_t *ftbl, int fts, int16_t *cnt, int cs, uint64_t src_end_from_desc, bool quirks) {
+    if (limit < 1) return ZSB_E_NOT_ENOUGH_BYTES;
+    uint32_t hb = desc[0];
+    if (hb >= 128) {                                                     // parse_direct huffman.rs:92-106
+        int n = (int)hb - 127;
+        uint32_t nb = (uint32_t)(n + 1) / 2;
+        if (limit < 1 + (uint64_t)nb) return ZSB_E_NOT_ENOUGH_BYTES;
+        for (int i = 0; i < n; i++) {
+            uint32_t b = desc[1 + (i >> 1)];
+            weights[i * ws] = (uint8_t)((i & 1) ? (b & 15) : (b >> 4));  // high nibble first
+        }
+        nw = n; desc_len = 1 + nb;
+        return ZSB_OK;
+    }
+    // parse_fse huffman.rs:108-130
+    if (hb == 0) return quirks ? ZSB_E_EMPTY_SLICE : ZSB_E_CORRUPT;
+    if (limit < 1 + (uint64_t)hb) return ZSB_E_NOT_ENOUGH_BYTES;
+    FwdBits f; fwd_init(f, desc + 1, hb);
+    int al, nsym;
+    int rc = fse_read_ncount(f, cnt, cs, ZSB_HUF_WEIGHT_SYMS, al, nsym);
+    if (rc) return rc;
+    rc = fse_build_table(cnt, cs, nsym, al, ftbl, fts, 3);
+    if (rc) return rc;
+    uint32_t br = fwd_bytes_read(f);
+    BackWin b;
+    rc = back_init(b, desc, 1 + br, 1 + hb, src_end_from_desc);          // BackwardBitParser::new(&data[bytes_read..])
+    if (rc) return rc;
+    // AlternatingDecoder::initialize: first then second state (alternating.rs:28-34)
+    uint32_t s1 = back_take(b, (uint32_t)al);
+    uint32_t s2 = back_take(b, (uint32_t)al);
+    if (b.rem < 0) return ZSB_E_NOT_ENOUGH_BITS;
+    int n = 0;
+    // while decoder.expected_bits() <= bitstream.len() { push(symbol); update_bits } (huffman.rs:121-124)
+    for (;;) {
+        uint32_t e1 = ftbl[s1 * fts];
+        if ((int64_t)ZSB_CELL_NB(e1) > b.rem) break;
+        if (n >= 255) return ZSB_E_CORRUPT;
+        weights[n * ws] = (uint8_t)ZSB_CELL_CODE(e1); n++;
+        s1 = ZSB_CELL_BASE(e1) + back_take(b, ZSB_CELL_NB(e1));
+        uint32_t t = s1; s1 = s2; s2 = t;                                 // the other state is next
+    }
+    if (n > 254) return ZSB_E_CORRUPT;
+    weights[n * ws] = (uint8_t)ZSB_CELL_CODE(ftbl[s1 * fts]); n++;        // flush both pending symbols (huffman.rs:125-126)
+    weights[n * ws] = (uint8_t)ZSB_CELL_CODE(ftbl[s2 * fts]); n++;
+    nw = n; desc_len = 1 + hb;
+    return ZSB_OK;
+}
+
+// weights -> LUT.  lut: 1<<maxbits uint16 entries: symbol | nbits << 8.  rank[16] scratch (strided).
+// lens_out (optional, 256 entries, stride 1): code length per symbol for the stage-level API.
+ZSB_HDN int huf_build_lut(uint8_t *weights, int ws, int nw, uint16_t *lut, uint32_t *rank, int rs, int &maxbits, uint8_t *lens_out) {
+    uint32_t sum = 0;
+    for (int i = 0; i < nw; i++) {
+        uint32_t w = weights[i * ws];
+        if (w > ZSB_HUF_MAX_BITS + 1) return ZSB_E_CORRUPT;
+        if (w) sum += 1u << (w - 1);
+    }
+    if (sum == 0) return ZSB_E_CORRUPT;                                   // reference: discrete_log2(0) panics (huffman.rs:184)
+    int mb = zsb_flog2(sum) + 1;                                          // RFC 8878 4.2.1.1 (reference is off by one when sum is 2^k)
+    if (mb > ZSB_HUF_MAX_BITS) return ZSB_E_CORRUPT;
+    uint32_t rest = (1u << mb) - sum;
+    if (rest & (rest - 1)) return ZSB_E_CORRUPT;                          // implied weight must be a power of two
+    uint32_t lastw = (uint32_t)zsb_flog2(rest) + 1;
+    if (nw >= 256) return ZSB_E_CORRUPT;
+    weights[nw * ws] = (uint8_t)lastw;
+    int n = nw + 1;
+    // rank[w] = first LUT cell of weight class w: lowest weights (longest codes) first (huffman.rs:161-175)
+    for (int w = 0; w <= ZSB_HUF_MAX_BITS + 1; w++) rank[w * rs] = 0;
+    for (int i = 0; i < n; i++) rank[weights[i * ws] * rs] += 1;
+    uint32_t start = 0;
+    for (int w = 1; w <= mb; w++) { uint32_t c = rank[w * rs]; rank[w * rs] = start; start += c << (w - 1); }
+    if (start != (1u << mb)) return ZSB_E_CORRUPT;
+    if (lens_out) for (int i = 0; i < 256; i++) lens_out[i] = 0;
+    for (int i = 0; i < n; i++) {
+        uint32_t w = weights[i * ws];
+        if (!w) continue;
+        uint32_t nbits = (uint32_t)mb + 1 - w, len = 1u << (w - 1), at = rank[w * rs];
+        rank[w * rs] = at + len;
+        uint16_t cell = (uint16_t)(i | (nbits << 8));
+        for (uint32_t k = 0; k < len; k++) lut[at + k] = cell;
+        if (lens_out) lens_out[i] = (uint8_t)nbits;
+    }
+    maxbits = mb;
+    return ZSB_OK;
+}
+
+// Decode one backward stream src[start,end) into out[0..expect).  The reference decodes "until the
+// reader is empty" and ignores Regenerated_Size (literals.rs:55,78-80); a symbol cut short is
+// NotEnoughBits.  Here the stream must additionally regenerate exactly `expect` symbols (RFC 8878
+// 3.1.1.3.1.6), otherwise ZSB_E_CORRUPT -- identical on every valid stream.
+ZSB_HDN int huf_decode_stream(const uint8_t *src, uint64_t start, uint64_t end, uint64_t src_end,
+                              const uint16_t *lut, int maxbits, uint8_t *out, uint32_t expect) {
+    BackWin b;
+    int rc = back_init(b, src, start, end, src_end);
+    if (rc) return rc;
+    uint32_t n = 0;
+    const uint32_t sh = 64u - (uint32_t)maxbits;
+    while (b.rem > 0) {
+        back_refill(b);
+        // up to 5 symbols per refill: 5 * 11 = 55 <= 64 valid bits
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+        for (int k = 0; k < 5 && b.rem > 0; k++) {
+            uint32_t cell = lut[(uint32_t)(b.hi >> sh)];
+            uint32_t nb = cell >> 8;
+            if ((int64_t)nb > b.rem) return ZSB_E_NOT_ENOUGH_BITS;
+            if (n >= expect) return ZSB_E_CORRUPT;
+            out[n++] = (uint8_t)cell;
+            back_consume(b, nb);
+        }
+    }
+    return n == expect ? ZSB_OK : ZSB_E_CORRUPT;
+}
