@@ -147,6 +147,9 @@ int zsb_decode_finish(zsb_ctx *ctx, uint64_t *dst_off, uint64_t *dst_len, int32_
 int zsb_ctx_set_profile(zsb_ctx *ctx, int enable);
 int zsb_last_launch_count(const zsb_ctx *ctx);
 int zsb_last_kernel_times(const zsb_ctx *ctx, const char **names, float *ms, int cap);
+/* Synchronises, then averages each kernel over the launches recorded since profiling was switched on
+ * (at most the last 32). */
+int zsb_kernel_times_avg(zsb_ctx *ctx, const char **names, float *ms, int cap, int *n_launches);
 
 /* == whole-program behaviour of src/main.rs:42-58 : scan + decode + concatenate into a malloc'd
  *    buffer; all-or-nothing like the CLI (first error => no output).  Convenience for bindings. */

@@ -1,0 +1,251 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the
+CPU oracle on the same inputs -- bit-exact output, same statuses, verified checksums."""
+import hashlib
+import random
+
+import pytest
+
+import corpora
+import refcpu as R
+import zstd_decompressor_b200 as Z
+
+pytestmark = pytest.mark.gpu
+Q, SKIP, VER = Z.REFERENCE_QUIRKS, Z.PRINT_SKIPPABLE, Z.VERIFY_CHECKSUM
+
+
+@pytest.fixture(scope="module")
+def dec():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return Z.Decoder(Z.Context(0))
+
+
+def first_status(sc, r):
+    return sc.status or next((r.status[i] for i in range(sc.n_frames) if r.status[i]), 0)
+
+
+# ---------------------------------------------------------------- stage level (mirrors the reference's tests)
+def test_fse_reference_vectors():                       # tests/decoders/fse.rs
+    al, dist, table, consumed = Z.fse_table_parse([0x30, 0x6f, 0x9b, 0x03])
+    assert al == 5 and dist == [18, 6, 2, 2, 2, 1, 1] and table[0xc] == (1, 0x18, 3)
+    assert Z.fse_table_from_distribution(5, [18, 6, 2, 2, 2, 1, 1])[0xc] == (1, 0x18, 3)
+    al, dist, table, consumed = Z.fse_table_parse([0x21, 0x9d, 0x51, 0xcc, 0x18, 0x42, 0x44, 0x81, 0x8c, 0x94, 0xb4, 0x50, 0x1e])
+    assert al == 6 and table[0x3f] == (24, 0x10, 4) and table[0x2c] == (0, 0x34, 2) and consumed == 13
+    with pytest.raises(Z.ZsbError) as ei:
+        Z.fse_table_parse([0x05, 0, 0, 0])
+    assert ei.value.code == R.LargeAccuracyLog
+
+
+def test_fse_tables_equal_oracle_on_random_distributions():
+    from test_emul import random_distribution
+    r = random.Random(5)
+    for _ in range(40):
+        al = r.randrange(5, 10)
+        dist = random_distribution(r, al, r.choice([8, 29, 36, 53, 60]))
+        assert Z.fse_table_from_distribution(al, dist) == R.fse_from_distribution(al, dist)
+
+
+def test_huffman_reference_vectors():                   # tests/decoders/huffman.rs
+    w = [0] * 65 + [1, 2]
+    packed = [(w[i] << 4) + (w[i + 1] if i + 1 < len(w) else 0) for i in range(0, len(w), 2)]
+    codes, consumed, mb = Z.huffman_parse(bytes([127 + 67] + packed))
+    assert codes == {65: (2, 0), 67: (2, 1), 66: (1, 1)} and consumed == 35 and mb == 2
+
+
+def test_huffman_tables_equal_oracle_on_real_descriptions():
+    import zstd_inspect as I
+    blob = corpora.c4()[0] + corpora.fixture("moby-dick.txt.zst")
+    n = 0
+    for f in I.inspect(blob):
+        for k in f.blocks:
+            if k.type == "compressed" and k.lit_type == "compressed" and n < 24:
+                hdr = 1 + (2 if k.lit_streams == 1 or (k.lit_regen < 1024 and k.lit_csize < 1024) else 3 if k.lit_regen < 16384 and k.lit_csize < 16384 else 4)
+                desc = blob[k.src_off + hdr:k.src_off + hdr + k.lit_csize]
+                want, consumed, _ = R.huffman_parse(desc)
+                got, c2, _ = Z.huffman_parse(desc)
+                assert got == want and c2 == consumed
+                n += 1
+    assert n >= 10
+
+
+def test_execute_sequences_reference_vector():          # decoding_context.rs:109-122
+    ctx = Z.DecodingContext(0x42)
+    ctx.execute_sequences([(3, 5, 3), (2, 11, 1)], b"abcdefgh")
+    assert ctx.decoded == bytes([0x61, 0x62, 0x63, 0x62, 0x63, 0x62, 0x64, 0x65, 0x61, 0x66, 0x67, 0x68])
+    with pytest.raises(Z.ZsbError) as ei:
+        Z.DecodingContext((8 << 20) + 1)
+    assert ei.value.code == R.WindowSizeTooBig
+
+
+def test_execute_sequences_random_against_oracle():
+    r = random.Random(9)
+    for case in range(30):
+        lits = bytes(r.randrange(97, 123) for _ in range(r.randrange(50, 4000)))
+        seqs, produced, left = [], 0, len(lits)
+        style = case % 3
+        while left > 8 and produced < 100000:
+            ll = r.randrange(0, min(left, 40 if style else 300))
+            if produced + ll == 0:
+                ll = 1
+            if style == 0:      # short matches, any distance
+                off, ml = r.randrange(1, produced + ll + 1), r.randrange(3, 24)
+            elif style == 1:    # overlapping (offset < match length) and long matches
+                off, ml = r.randrange(1, min(produced + ll, 12) + 1), r.randrange(3, 3000)
+            else:               # repeat-offset codes
+                off, ml = None, r.randrange(3, 70)
+            ov = off + 3 if off is not None else r.randrange(1, 4)
+            seqs.append((ll, ov, ml)); left -= ll; produced += ll + ml
+        try:
+            want = R.execute_sequences(0x42, seqs, lits)
+        except R.RefError as e:
+            with pytest.raises(Z.ZsbError):
+                Z.DecodingContext(0x42).execute_sequences(seqs, lits)
+            continue
+        ctx = Z.DecodingContext(0x42)
+        ctx.execute_sequences(seqs, lits)
+        assert ctx.decoded == want, case
+
+
+def test_xxh64_against_oracle():
+    r = random.Random(1)
+    for n in list(range(0, 70)) + [255, 256, 1000, 4097, 131072, 131073 + 13]:
+        d = bytes(r.randrange(256) for _ in range(n))
+        assert Z.xxh64(d) == R.xxh64(d), n
+
+
+# ---------------------------------------------------------------- whole frames
+@pytest.mark.parametrize("name", corpora.FIXTURE_NAMES)
+@pytest.mark.parametrize("skip", [0, SKIP])
+def test_fixtures_bit_exact(dec, name, skip):           # BASELINE config C1 + the other reference fixtures
+    d = corpora.fixture(name)
+    out, sc, r = dec.decode(d, Q | VER | skip)
+    assert first_status(sc, r) == 0
+    assert out == R.main_decode(d, print_skippable=bool(skip))
+    _, oframes, _ = R.decode_frames(d)
+    for i, of in enumerate(oframes):
+        if of["kind"] == 0 and of["has_checksum"]:
+            assert r.xxh32[i] == of["computed_xxh64_low32"] == of["stored_checksum"] and r.checksum_ok[i] == 1
+
+
+def test_moby_dick_sha256(dec):
+    out, _, _ = dec.decode(corpora.fixture("moby-dick.txt.zst"), Q | VER)
+    assert len(out) == 1276235 and hashlib.sha256(out).hexdigest().startswith("61d5ab6a3910fab6")
+
+
+def test_reference_api_shapes(dec):                     # src/main.rs flow through the mirrored names
+    res = b""
+    for frame in Z.ForwardByteParser(corpora.fixture("welcome.zst")).iter():
+        if not frame.is_skippable:
+            res += frame.decode()
+            assert frame.checksum_ok
+    assert res == R.main_decode(corpora.fixture("welcome.zst"))
+    assert Z.decompress(corpora.fixture("romeo3.txt.zst")) == R.main_decode(corpora.fixture("romeo3.txt.zst"))
+
+
+def test_c4_all_modes(dec):                             # BASELINE config C4
+    blob, exp, exp_skip, parts = corpora.c4()
+    out, sc, r = dec.decode(blob, Q | VER)
+    assert first_status(sc, r) == 0 and out == exp == R.main_decode(blob)
+    out, sc, r = dec.decode(blob, VER | SKIP)
+    assert first_status(sc, r) == 0 and out == exp_skip
+    bad = [i for i in range(sc.n_frames) if sc.frames[i].kind == 0 and sc.frames[i].has_checksum and not r.checksum_ok[i]]
+    assert bad == []
+
+
+def test_c4_frame_by_frame_statuses(dec):
+    _, _, _, parts = corpora.c4()
+    for frame, plain, is_skip in parts:
+        out, sc, r = dec.decode(frame, Q | VER | SKIP)
+        assert first_status(sc, r) == 0 and out == plain
+
+
+def test_c2_batch_of_text_frames(dec):                  # BASELINE config C2, 256 frames vs the oracle
+    blob, exp = corpora.c2_small(256)
+    out, sc, r = dec.decode(blob, Q | VER)
+    assert first_status(sc, r) == 0 and sc.n_frames == 256 and all(r.checksum_ok[i] for i in range(256))
+    assert out == exp
+    assert R.main_decode(blob[:sc.frames[8].src_off]) == out[:8 * 131072]
+
+
+def test_c3_multi_block_frame_with_far_matches(dec):    # BASELINE config C3 at 16 MiB (window 8 MiB)
+    import gen_corpus as G
+    blob, exp = G.make_c3(total=16 << 20)
+    out, sc, r = dec.decode(blob, Q | VER)
+    assert first_status(sc, r) == 0 and sc.n_frames == 1 and sc.frames[0].n_blocks >= 128 and r.checksum_ok[0] == 1
+    assert hashlib.sha256(out).digest() == hashlib.sha256(exp).digest()
+    small, sexp = corpora.c3_small(3 << 20)
+    out, sc, r = dec.decode(small, Q | VER)
+    assert out == sexp == R.main_decode(small)
+
+
+def test_rfc_only_inputs(dec):                          # classes the reference rejects
+    for frame, plain in corpora.rfc_only():
+        out, sc, r = dec.decode(frame, VER | SKIP)
+        assert first_status(sc, r) == 0 and out == plain
+        out, sc, r = dec.decode(frame, Q | VER | SKIP)
+        _, _, oerr = R.decode_frames(frame, quirks=True)
+        assert oerr is not None and first_status(sc, r) != 0
+
+
+def test_one_bad_frame_does_not_fail_the_batch(dec):
+    good = corpora.fixture("romeo.txt.zst")
+    bad = bytearray(good); bad[300] ^= 0x55
+    blob = good + bytes(bad) + good
+    out, sc, r = dec.decode(blob, Q | VER)
+    assert sc.status == 0 and r.status[0] == 0 and r.status[2] == 0
+    want = R.main_decode(good)
+    assert out[r.dst_off[0]:r.dst_off[0] + r.dst_len[0]] == want and out[r.dst_off[2]:r.dst_off[2] + r.dst_len[2]] == want
+    assert r.status[1] != 0 or r.checksum_ok[1] == 0
+
+
+def test_dst_too_small_is_reported(dec):
+    d = corpora.fixture("romeo.txt.zst")
+    out, sc, r = dec.decode(d, Q | VER, dst_cap=100)
+    assert r.status[0] == 103 and out == b""
+
+
+def test_mutations_error_or_identical(dec):
+    r = random.Random(21)
+    n_ok = n_same = 0
+    for name, d in corpora.mutation_sources().items():
+        for _ in range(60):
+            b = corpora.mutate(r, d)
+            want, _, oerr = R.decode_frames(b, quirks=True)
+            out, sc, res = dec.decode(b, Q | SKIP | VER)
+            got = first_status(sc, res)
+            if oerr is None and got == 0:
+                assert out == want
+                n_ok += 1
+            elif oerr is not None and got == oerr.code:
+                n_same += 1
+            if oerr is None and got:
+                assert got in (100, 101, 102), (name, got)
+    assert n_ok > 50 and n_same > 50
+
+
+def test_gpu_matches_cpu_build_of_device_code(dec):
+    """the kernels and the g++ build of the same lane-serial code agree on statuses for malformed input"""
+    import emul_lib as E
+    r = random.Random(33)
+    for name, d in corpora.mutation_sources().items():
+        for _ in range(25):
+            b = corpora.mutate(r, d)
+            rc, eout, eframes, _ = E.decode(b, Q | SKIP)
+            out, sc, res = dec.decode(b, Q | SKIP | VER)
+            assert sc.status == rc and [res.status[i] for i in range(sc.n_frames)] == [f[0] for f in eframes], name
+            assert out == eout
+
+
+# ---------------------------------------------------------------- BASELINE full size (C2: 4096 x 128 KiB)
+def test_c2_full_size_round_trip(dec):
+    import gen_corpus as G
+    blob, exp = G.make_c2(4096, seed=2)
+    out, sc, r = dec.decode(blob, Q | VER)
+    assert first_status(sc, r) == 0 and sc.n_frames == 4096 and len(out) == 4096 * 131072
+    assert hashlib.sha256(out).digest() == hashlib.sha256(exp).digest()
+    assert all(r.checksum_ok[i] for i in range(4096))          # a checksum of checksums: every stored XXH64 verified on the GPU
+    # seeded 1/64 sample of the frames re-decoded by the oracle
+    rr = random.Random(64)
+    for i in rr.sample(range(4096), 64):
+        f = sc.frames[i]
+        assert R.main_decode(blob[f.src_off:f.src_off + f.src_len]) == out[r.dst_off[i]:r.dst_off[i] + r.dst_len[i]]

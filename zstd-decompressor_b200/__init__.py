@@ -90,6 +90,7 @@ def lib():
     L.zsb_ctx_set_profile.argtypes = [vp, C.c_int]
     L.zsb_last_launch_count.argtypes = [vp]
     L.zsb_last_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    L.zsb_kernel_times_avg.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     L.zsb_decode.argtypes = [vp, vp, sz, C.POINTER(ZsbFrame), sz, C.POINTER(ZsbBlock), sz, vp, sz, u64p, u64p, i32p, u32p, u8p, u64p, C.c_uint32]
     L.zsb_decode_prepare.argtypes = [vp, vp, sz, C.POINTER(ZsbFrame), sz, C.POINTER(ZsbBlock), sz, vp, sz, C.c_uint32]
     L.zsb_decode_launch.argtypes = [vp]
@@ -108,7 +109,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "zsb_scan", "zsb_free", "zsb_ctx_create", "zsb_ctx_destroy", "zsb_ctx_set_stream", "zsb_last_cuda_error", "zsb_ctx_set_profile",
-    "zsb_last_launch_count", "zsb_last_kernel_times", "zsb_decode", "zsb_decode_prepare", "zsb_decode_launch", "zsb_decode_finish",
+    "zsb_last_launch_count", "zsb_last_kernel_times", "zsb_kernel_times_avg", "zsb_decode", "zsb_decode_prepare", "zsb_decode_launch", "zsb_decode_finish",
     "zsb_decompress", "zsb_fse_table_parse", "zsb_fse_table_from_distribution", "zsb_huffman_parse", "zsb_execute_sequences",
     "zsb_xxh64", "zsb_strerror", "zsb_version"]
 
@@ -173,6 +174,12 @@ class Context:
         names = (C.c_char_p * 16)(); ms = (C.c_float * 16)()
         n = lib().zsb_last_kernel_times(self.h, names, ms, 16)
         return [(names[i].decode(), ms[i]) for i in range(n)]
+
+    def kernel_times_avg(self):
+        """[(kernel, mean ms)] over the launches since set_profile(True), and how many launches that was"""
+        names = (C.c_char_p * 16)(); ms = (C.c_float * 16)(); nl = C.c_int()
+        n = lib().zsb_kernel_times_avg(self.h, names, ms, 16, C.byref(nl))
+        return [(names[i].decode(), ms[i]) for i in range(n)], nl.value
 
     def cuda_error(self):
         return lib().zsb_last_cuda_error(self.h).decode()

@@ -28,6 +28,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 const int kMaxKernels = 12;
+const int kProfRing = 32;     // launches whose per-kernel events are kept
 }  // namespace
 
 struct zsb_ctx {
@@ -45,10 +46,11 @@ struct zsb_ctx {
     bool prepared = false, launched = false;
     // profiling
     bool profile = false;
-    cudaEvent_t ev[kMaxKernels + 1] = {};
+    cudaEvent_t ev[kProfRing][kMaxKernels + 1] = {};
     const char *kname[kMaxKernels] = {};
     float kms[kMaxKernels] = {};
     int nk = 0, launches = 0;
+    int prof_slot = 0, prof_count = 0;   // ring position / launches recorded since profiling was switched on
 };
 
 #define CK(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { (ctx)->last_err = std::string(#call) + ": " + cudaGetErrorString(e__); (void)cudaGetLastError(); return ZSB_E_CUDA; } } while (0)
@@ -64,7 +66,7 @@ extern "C" int zsb_ctx_create(zsb_ctx **out, int device) {
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         zsbk_init() != cudaSuccess) { (void)cudaGetLastError(); delete c; return ZSB_E_CUDA; }
     c->stream = c->own_stream;
-    for (int i = 0; i <= kMaxKernels; i++) cudaEventCreate(&c->ev[i]);
+    for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) cudaEventCreate(&c->ev[r][i]);
     *out = c;
     return ZSB_OK;
 }
@@ -75,18 +77,33 @@ extern "C" void zsb_ctx_destroy(zsb_ctx *c) {
     DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list,
                      &c->xxh_list, &c->lit_pool, &c->seq_pool, &c->counters, &c->dst, &c->stage};
     for (DevBuf *b : all) b->release();
-    for (int i = 0; i <= kMaxKernels; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) if (c->ev[r][i]) cudaEventDestroy(c->ev[r][i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 extern "C" int zsb_ctx_set_stream(zsb_ctx *c, void *s) { if (!c) return ZSB_E_ARG; c->stream = s ? (cudaStream_t)s : c->own_stream; return ZSB_OK; }
 extern "C" const char *zsb_last_cuda_error(const zsb_ctx *c) { return c ? c->last_err.c_str() : "no context"; }
-extern "C" int zsb_ctx_set_profile(zsb_ctx *c, int en) { if (!c) return ZSB_E_ARG; c->profile = en != 0; return ZSB_OK; }
+extern "C" int zsb_ctx_set_profile(zsb_ctx *c, int en) { if (!c) return ZSB_E_ARG; c->profile = en != 0; c->prof_slot = 0; c->prof_count = 0; return ZSB_OK; }
 extern "C" int zsb_last_launch_count(const zsb_ctx *c) { return c ? c->launches : 0; }
 extern "C" int zsb_last_kernel_times(const zsb_ctx *c, const char **names, float *ms, int cap) {
     if (!c) return 0;
     int n = c->nk < cap ? c->nk : cap;
     for (int i = 0; i < n; i++) { if (names) names[i] = c->kname[i]; if (ms) ms[i] = c->kms[i]; }
+    return n;
+}
+extern "C" int zsb_kernel_times_avg(zsb_ctx *c, const char **names, float *ms, int cap, int *n_launches) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    const int L = c->prof_count < kProfRing ? c->prof_count : kProfRing;
+    int n = c->nk < cap ? c->nk : cap;
+    for (int i = 0; i < n; i++) {
+        double sum = 0;
+        for (int r = 0; r < L; r++) { float t = 0; if (cudaEventElapsedTime(&t, c->ev[r][i], c->ev[r][i + 1]) == cudaSuccess) sum += t; else (void)cudaGetLastError(); }
+        if (names) names[i] = c->kname[i];
+        if (ms) ms[i] = L ? (float)(sum / L) : 0.f;
+    }
+    if (n_launches) *n_launches = L;
     return n;
 }
 
@@ -155,7 +172,7 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     return ZSB_OK;
 }
 
-#define MARK(ctx, name) do { if ((ctx)->profile && (ctx)->nk < kMaxKernels) { (ctx)->kname[(ctx)->nk] = name; cudaEventRecord((ctx)->ev[(ctx)->nk], st); (ctx)->nk++; } } while (0)
+#define MARK(ctx, name) do { if ((ctx)->profile && (ctx)->nk < kMaxKernels) { (ctx)->kname[(ctx)->nk] = name; cudaEventRecord((ctx)->ev[(ctx)->prof_slot][(ctx)->nk], st); (ctx)->nk++; } } while (0)
 
 extern "C" int zsb_decode_launch(zsb_ctx *c) {
     if (!c || !c->prepared) return ZSB_E_ARG;
@@ -177,7 +194,7 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     MARK(c, "k_exec");   zsbk_exec(st, c->n_exec, src, frames, blocks, work, fout, (const uint32_t *)c->exec_list.p, cnt, (const uint64_t *)c->seq_pool.p,
                                    (const uint8_t *)c->lit_pool.p, c->d_dst); c->launches += c->n_exec ? 1 : 0;
     MARK(c, "k_xxh");    zsbk_xxh(st, c->n_xxh, c->d_dst, fout, (const uint32_t *)c->xxh_list.p, cnt); c->launches += c->n_xxh ? 1 : 0;
-    if (c->profile) cudaEventRecord(c->ev[c->nk], st);
+    if (c->profile) { cudaEventRecord(c->ev[c->prof_slot][c->nk], st); c->prof_slot = (c->prof_slot + 1) % kProfRing; c->prof_count++; }
     CK(c, cudaGetLastError());
     c->launched = true;
     return ZSB_OK;
@@ -201,7 +218,7 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
         int rc = zsb_decode_launch(c);
         if (rc) return rc;
     }
-    if (c->profile) for (int i = 0; i < c->nk; i++) cudaEventElapsedTime(&c->kms[i], c->ev[i], c->ev[i + 1]);
+    if (c->profile) { const int r = (c->prof_slot + kProfRing - 1) % kProfRing; for (int i = 0; i < c->nk; i++) cudaEventElapsedTime(&c->kms[i], c->ev[r][i], c->ev[r][i + 1]); }
     std::vector<ZsbFrameOut> fo(c->nf);
     if (c->nf) CK(c, cudaMemcpyAsync(fo.data(), c->fout.p, sizeof(ZsbFrameOut) * c->nf, cudaMemcpyDeviceToHost, st));
     if (c->h_dst && hc.dst_total) CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, hc.dst_total, cudaMemcpyDeviceToHost, st));

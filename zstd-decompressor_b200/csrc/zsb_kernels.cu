@@ -327,7 +327,8 @@ __device__ __forceinline__ void exec_batch(uint32_t batch, uint32_t nseq, const 
     // match output; only [a0, e) below out_start comes from earlier sequences and must be awaited.
     const int e = min(src + (int)ml, (int)out_start);
     const uint32_t a0 = src > 0 ? (uint32_t)src : 0u;
-    for (;;) {
+    for (uint32_t spins = 0;; spins++) {
+        if (spins > (1u << 20)) { *s_err = ZSB_E_CORRUPT; break; }   // watchdog: a dependency that never resolves is a bug, not a hang
         bool didm = false;
         if (pend && !longM) {
             const bool ready = (e <= (int)a0) || range_ready(bm, a0, (uint32_t)e);
