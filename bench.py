@@ -169,7 +169,10 @@ def run_ours(args):
     flags = Z.VERIFY_CHECKSUM | Z.REFERENCE_QUIRKS
     ctx = Z.Context(local)
     dec = Z.Decoder(ctx)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: zsb_ctx_set_stream(NULL) would select the context's own stream and
+    # the events below would not bracket the kernels
+    stream = torch.cuda.Stream()
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     # ---- resident arm: compressed bytes and output stay in HBM
@@ -190,6 +193,7 @@ def run_ours(args):
     del got
     launches_per_step = ctx.last_launch_count()
 
+    torch.cuda.synchronize()
     for _ in range(args.warmup):
         dec.launch()
     torch.cuda.synchronize()

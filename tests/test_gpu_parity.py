@@ -233,7 +233,9 @@ def test_gpu_matches_cpu_build_of_device_code(dec):
             rc, eout, eframes, _ = E.decode(b, Q | SKIP)
             out, sc, res = dec.decode(b, Q | SKIP | VER)
             assert sc.status == rc and [res.status[i] for i in range(sc.n_frames)] == [f[0] for f in eframes], name
-            assert out == eout
+            for i, (st, off, ln) in enumerate(eframes):            # bytes of a failed frame are unspecified
+                if st == 0:
+                    assert (res.dst_off[i], res.dst_len[i]) == (off, ln) and out[off:off + ln] == eout[off:off + ln], name
 
 
 # ---------------------------------------------------------------- BASELINE full size (C2: 4096 x 128 KiB)
