@@ -10,6 +10,49 @@
 #include <vector>
 #include "../../zstd-decompressor_b200/csrc/zsb_parse.h"
 #include "../../zstd-decompressor_b200/csrc/zsb_huf.h"
+#include "../../zstd-decompressor_b200/csrc/zsb_seqfast.h"
+
+// fast-path bookkeeping for tests: blocks where the fast sequence path ran / agreed / asked for the careful path / disagreed
+static long g_fast_ran = 0, g_fast_same = 0, g_fast_slow = 0, g_fast_diff = 0;
+
+// The fast sequence path as the kernels run it (phase 1 per lane, phase 2 folded serially with the same
+// per-sequence functions and the same history composition) against the careful decoder's results.
+static void check_fast_path(const uint8_t *src, const ZsbBlockWork &w0, const SeqTables &T, int careful_rc, const ZsbBlockWork &wc,
+                            const std::vector<uint64_t> &rec_c) {
+    const int WS = 3;   // any stride
+    std::vector<uint32_t> words((size_t)w0.nseq * WS + 1, 0xABABABAB);
+    uint32_t rem0 = 0;
+    g_fast_ran++;
+    int rc = seq_fast_phase1(src, w0, T, words.data(), WS, rem0, 0);
+    if (rc > 0) { if (rc == careful_rc) g_fast_same++; else g_fast_diff++; return; }
+    int bad = 0;
+    std::vector<uint64_t> rec(w0.nseq, 0);
+    uint32_t lit = 0, out = 0; Hist H = hist_identity();
+    if (rc == ZSB_OK) {
+        uint32_t lltab[36], mltab[53];
+        for (uint32_t c = 0; c < 36; c++) lltab[c] = zsb_ll_entry(c);
+        for (uint32_t c = 0; c < 53; c++) mltab[c] = zsb_ml_entry(c);
+        const uint32_t mis = (uint32_t)((uintptr_t)src & 7);
+        int64_t top = (int64_t)(w0.bs_off + mis) * 8 + rem0;
+        for (uint32_t i = 0; i < w0.nseq; i++) {
+            const uint32_t word = words[(size_t)i * WS];
+            uint32_t ll, ml, ov, px;
+            seq_fast_values(src - mis, top, word, lltab, mltab, ll, ml, ov, px, bad);
+            if (bad) break;
+            top -= px + ZSB_W_NB(word);
+            Hist F = hist_of_sequence(ov, ll, bad);
+            H = hist_compose(F, H, bad);
+            lit += ll; out += ll + ml;
+            if (lit > w0.lit_regen || out + (w0.lit_regen - lit) > ZSB_BLOCK_MAX) { bad = 1; break; }
+            rec[i] = (uint64_t)out | ((uint64_t)lit << ZSB_REC_POS_BITS) | ((uint64_t)H.h0 << (2 * ZSB_REC_POS_BITS));
+        }
+    }
+    if (rc == ZSB_NEEDS_SLOW || bad) { if (careful_rc != ZSB_OK) g_fast_slow++; else g_fast_diff++; return; }
+    bool same = careful_rc == ZSB_OK && wc.lit_used == lit && wc.out_size == out + (w0.lit_regen - lit) &&
+                wc.rep_out[0] == H.h0 && wc.rep_out[1] == H.h1 && wc.rep_out[2] == H.h2;
+    for (uint32_t i = 0; same && i < w0.nseq; i++) same = rec[i] == rec_c[i];
+    if (same) g_fast_same++; else g_fast_diff++;
+}
 
 extern "C" {
 
@@ -83,10 +126,13 @@ int emul_decode(const uint8_t *src_in, size_t n, uint32_t flags, uint8_t *out, s
             std::vector<uint32_t> tbl(3 * 512 * TS, 0xDEADBEEF); std::vector<int16_t> cnt(256 * TS, 0);
             uint32_t bases[89];
             for (uint32_t k = 0; k < 89; k++) bases[k] = k < 36 ? zsb_ll_base(k) : zsb_ml_base(k - 36);
-            SeqTables T; T.ts = TS; T.tbl[0] = tbl.data() + LANE; T.tbl[1] = tbl.data() + 512 * TS + LANE; T.tbl[2] = tbl.data() + 2 * 512 * TS + LANE;
+            SeqTables T; T.ts = TS; T.max_al[0] = T.max_al[1] = T.max_al[2] = 0; T.tbl[0] = tbl.data() + LANE; T.tbl[1] = tbl.data() + 512 * TS + LANE; T.tbl[2] = tbl.data() + 2 * 512 * TS + LANE;
             recs[i].assign(w.nseq + 1, 0);
             int rc = seq_build_tables(src, w, T, cnt.data() + LANE, TS);
+            const ZsbBlockWork w0 = w;
+            const int trc = rc;
             if (!rc) rc = seq_decode(src, n, w, T, bases, bases + 36, recs[i].data());
+            if (!trc) check_fast_path(src, w0, T, rc, w, recs[i]);
             if (rc) { w.status = rc; continue; }
         }
     }
@@ -131,5 +177,27 @@ int emul_decode(const uint8_t *src_in, size_t n, uint32_t flags, uint8_t *out, s
     *out_len = pos;
     zsb_free(frames); zsb_free(blocks);
     return scan_rc;
+}
+void emul_fast_stats(long *ran, long *same, long *slow, long *diff) { *ran = g_fast_ran; *same = g_fast_same; *slow = g_fast_slow; *diff = g_fast_diff; }
+
+// associativity of the history composition on random transforms: returns the number of violations
+static uint32_t rnd(uint64_t &s) { s = s * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(s >> 33); }
+static Hist rnd_hist(uint64_t &s) {
+    int bad = 0;
+    uint32_t ov = (rnd(s) % 3 == 0) ? 1 + rnd(s) % 3 : 4 + rnd(s) % 100000;
+    return hist_of_sequence(ov, rnd(s) % 2, bad);
+}
+int emul_hist_assoc(uint64_t seed, int n) {
+    int viol = 0;
+    for (int i = 0; i < n; i++) {
+        Hist a = rnd_hist(seed), b = rnd_hist(seed), c = rnd_hist(seed), d = rnd_hist(seed), e = rnd_hist(seed);
+        int b1 = 0, b2 = 0;
+        // ((a.b).(c.d)).e  vs  a.(b.(c.(d.e)))
+        Hist l = hist_compose(hist_compose(hist_compose(a, b, b1), hist_compose(c, d, b1), b1), e, b1);
+        Hist r = hist_compose(a, hist_compose(b, hist_compose(c, hist_compose(d, e, b2), b2), b2), b2);
+        if (b1 || b2) continue;      // an offset reached zero: the careful path takes over
+        if (l.h0 != r.h0 || l.h1 != r.h1 || l.h2 != r.h2) viol++;
+    }
+    return viol;
 }
 }  // extern "C"

@@ -32,7 +32,7 @@ def fse_build(type_, al, dist, stride=1):
 
 def cell_fields(c):
     """(code, base, nb, xb)"""
-    return (c >> 26, (c >> 16) & 0x3FF, c & 0xFF, (c >> 8) & 0xFF)
+    return ((c >> 16) & 0x3F, c >> 22, c & 0x1F, (c >> 8) & 0x3F)
 
 
 def huf_parse(desc):
@@ -59,3 +59,17 @@ def decode(data, flags=0, cap=None):
     rc = L.emul_decode(data, len(data), flags, out, cap, C.byref(ol), st, fo, fl, nfc, C.byref(nf), C.byref(ea), C.byref(eb))
     frames = [(st[i], fo[i], fl[i]) for i in range(nf.value)]
     return rc, out.raw[:ol.value], frames, (ea.value, eb.value)
+
+
+def fast_stats():
+    """(ran, same, slow, diff): blocks on which the fast sequence path ran, agreed with the careful decoder,
+    asked for the careful decoder on a stream the careful decoder also rejects, or disagreed"""
+    v = [C.c_long() for _ in range(4)]
+    lib().emul_fast_stats(*[C.byref(x) for x in v])
+    return tuple(x.value for x in v)
+
+
+def hist_assoc(seed, n):
+    L = lib()
+    L.emul_hist_assoc.argtypes = [C.c_uint64, C.c_int]
+    return L.emul_hist_assoc(seed, n)

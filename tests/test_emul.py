@@ -12,7 +12,7 @@ Q, SKIP = 4, 1   # ZSB_REFERENCE_QUIRKS, ZSB_PRINT_SKIPPABLE
 
 
 def as_states(cells):
-    return [(c >> 26, (c >> 16) & 0x3FF, c & 0xFF) for c in cells]   # (output, baseline, bits_to_read)
+    return [((c >> 16) & 0x3F, c >> 22, c & 0x1F) for c in cells]   # (output, baseline, bits_to_read)
 
 
 # ---------------------------------------------------------------- FSE tables (fse.rs)
@@ -61,7 +61,7 @@ def test_fse_predefined_tables_and_xbits():
     rc, cells = E.fse_build(0, 6, LL)
     assert rc == 0 and as_states(cells) == R.fse_from_distribution(6, LL)
     ll_bits = [0] * 16 + [1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
-    assert all(((c >> 8) & 0xFF) == ll_bits[c >> 26] for c in cells)
+    assert all(((c >> 8) & 0x3F) == ll_bits[(c >> 16) & 0x3F] for c in cells)
 
 
 def test_fse_errors():
@@ -153,3 +153,24 @@ def test_mutations_never_crash_and_agree_when_both_accept():
             if oerr is None and got:
                 assert got in (100, 101, 102), (name, got)
     assert n_ok > 100 and n_same_err > 100
+
+
+# ---------------------------------------------------------------- fast sequence path (zsb_seqfast.h)
+def test_history_composition_is_associative():
+    assert E.hist_assoc(12345, 200000) == 0
+
+
+def test_fast_sequence_path_equals_careful_decoder():
+    """every block decoded above also went through phase 1 + phase 2 of the fast path: identical records,
+    sizes and repeat offsets, or a request for the careful decoder exactly where that one fails"""
+    for name in corpora.FIXTURE_NAMES:
+        E.decode(corpora.fixture(name), Q)
+    E.decode(corpora.c4()[0], Q)
+    E.decode(corpora.c2_small(16)[0], Q)
+    E.decode(corpora.c3_small(3 << 20)[0], Q)
+    r = random.Random(5)
+    for name, d in corpora.mutation_sources().items():
+        for _ in range(60):
+            E.decode(corpora.mutate(r, d), Q | SKIP)
+    ran, same, slow, diff = E.fast_stats()
+    assert diff == 0 and same > 200 and slow > 5 and ran == same + slow, (ran, same, slow, diff)

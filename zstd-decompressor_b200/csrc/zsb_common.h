@@ -58,13 +58,16 @@
 #define ZSB_OFF_MAX 0x7FFFFFFu   // largest real offset representable (128 MiB - 1)
 
 // FSE decoding-table cell, one 32-bit word (sequence tables and Huffman-weight table):
-//   bits 0..7 nb (state bits to read)  8..15 xb (extra bits of the symbol's code)
-//   bits 16..25 base (next-state baseline)  26..31 code (symbol, 63 = not a legal code)
-#define ZSB_CELL(nb, xb, base, code) ((uint32_t)(nb) | ((uint32_t)(xb) << 8) | ((uint32_t)(base) << 16) | ((uint32_t)(code) << 26))
-#define ZSB_CELL_NB(e) ((e) & 0xFFu)
-#define ZSB_CELL_XB(e) (((e) >> 8) & 0xFFu)
-#define ZSB_CELL_BASE(e) (((e) >> 16) & 0x3FFu)
-#define ZSB_CELL_CODE(e) ((e) >> 26)
+//   bits 0..4 nb (state bits to read)   8..13 xb (extra bits of the symbol's code)
+//   bits 16..21 code (symbol, 63 = not a legal code)   22..31 base (next-state baseline)
+// The layout serves the fast sequence path (zsb_seqfast.h): the sum of three cells has the total state
+// bits in byte 0 and the total extra bits in byte 1 (no carries: <= 27 and <= 63); nb sits where a
+// funnel shift takes its 5-bit shift amount; base comes out with one shift.
+#define ZSB_CELL(nb, xb, base, code) ((uint32_t)(nb) | ((uint32_t)(xb) << 8) | ((uint32_t)(code) << 16) | ((uint32_t)(base) << 22))
+#define ZSB_CELL_NB(e) ((e) & 0x1Fu)
+#define ZSB_CELL_XB(e) (((e) >> 8) & 0x3Fu)
+#define ZSB_CELL_CODE(e) (((e) >> 16) & 0x3Fu)
+#define ZSB_CELL_BASE(e) ((e) >> 22)
 
 // Per-block working record in HBM (one per zsb_block).  Filled by the section-header parse, the
 // per-frame chain pass, the entropy kernels and the output planner, in that order.
@@ -96,6 +99,7 @@ struct ZsbBlockWork {
     uint32_t rep_in[3];      // actual repeat offsets at block start
     int32_t  status;
     uint32_t err_a, err_b;   // payload of the reference's error variant where it has one
+    uint32_t seq_rem0;       // fast sequence path: unread bits of the bitstream once the three initial states are read
 };
 
 // Per-frame result record in HBM.

@@ -27,19 +27,20 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
-const int kMaxKernels = 12;
+const int kMaxKernels = 16;
 const int kProfRing = 32;     // launches whose per-kernel events are kept
+const uint32_t kBigFrameBlocks = 64;   // frames with more blocks than this are executed by a whole CTA (k_exec), not a warp (k_exec2)
 }  // namespace
 
 struct zsb_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    DevBuf src, frames, blocks, work, fout, huf_list, seq_list, rawrle_list, exec_list, xxh_list, lit_pool, seq_pool, counters, dst, stage;
+    DevBuf src, frames, blocks, work, fout, huf_list, seq_list, rawrle_list, exec_list, exec2_list, xxh_list, lit_pool, seq_pool, word_pool, slow_list, counters, dst, stage;
     std::string last_err;
     // prepared batch
     const uint8_t *d_src = nullptr; uint8_t *d_dst = nullptr; uint8_t *h_dst = nullptr;
     size_t src_len = 0, dst_cap = 0;
-    uint32_t nf = 0, nb = 0, ncomp = 0, n_rawrle = 0, n_exec = 0, n_xxh = 0, flags = 0;
+    uint32_t nf = 0, nb = 0, ncomp = 0, n_rawrle = 0, n_exec = 0, n_exec2 = 0, n_xxh = 0, flags = 0;
     uint64_t lit_cap = 0, seq_cap = 0;
     std::vector<zsb_frame> h_frames;
     std::vector<uint32_t> h_xxh_list;
@@ -74,8 +75,8 @@ extern "C" void zsb_ctx_destroy(zsb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list,
-                     &c->xxh_list, &c->lit_pool, &c->seq_pool, &c->counters, &c->dst, &c->stage};
+    DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list, &c->exec2_list,
+                     &c->xxh_list, &c->lit_pool, &c->seq_pool, &c->word_pool, &c->slow_list, &c->counters, &c->dst, &c->stage};
     for (DevBuf *b : all) b->release();
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) if (c->ev[r][i]) cudaEventDestroy(c->ev[r][i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -127,7 +128,7 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     c->src_len = n; c->dst_cap = dst_cap; c->nf = (uint32_t)nf; c->nb = (uint32_t)nb; c->flags = flags;
     c->h_frames.assign(frames, frames + nf);
     // host-side work lists (block types and frame kinds are known from the scan)
-    std::vector<uint32_t> rawrle, execl;
+    std::vector<uint32_t> rawrle, execl, exec2l;
     c->h_xxh_list.clear();
     uint64_t ncomp = 0, lit_cap = 0, seq_cap = 0;
     for (size_t i = 0; i < nb; i++) {
@@ -144,10 +145,11 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
         if (frames[f].kind != 0 || frames[f].status != ZSB_OK) continue;
         bool has_c = false;
         for (uint32_t k = 0; k < frames[f].n_blocks && !has_c; k++) has_c = blocks[frames[f].first_block + k].type == ZSB_BT_COMPRESSED;
-        if (has_c) execl.push_back((uint32_t)f);
+        // frames of many blocks: one CTA per frame (k_exec); all others: one warp per frame (k_exec2)
+        if (has_c) (frames[f].n_blocks > kBigFrameBlocks ? execl : exec2l).push_back((uint32_t)f);
         if ((flags & ZSB_VERIFY_CHECKSUM) && frames[f].has_checksum) c->h_xxh_list.push_back((uint32_t)f);
     }
-    c->ncomp = (uint32_t)ncomp; c->n_rawrle = (uint32_t)rawrle.size(); c->n_exec = (uint32_t)execl.size(); c->n_xxh = (uint32_t)c->h_xxh_list.size();
+    c->ncomp = (uint32_t)ncomp; c->n_rawrle = (uint32_t)rawrle.size(); c->n_exec = (uint32_t)execl.size(); c->n_exec2 = (uint32_t)exec2l.size(); c->n_xxh = (uint32_t)c->h_xxh_list.size();
     if (lit_cap > c->lit_cap) c->lit_cap = lit_cap;
     if (seq_cap > c->seq_cap) c->seq_cap = seq_cap;
     CK(c, c->frames.ensure(sizeof(zsb_frame) * (nf + 1)));
@@ -156,16 +158,20 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     CK(c, c->fout.ensure(sizeof(ZsbFrameOut) * (nf + 1)));
     CK(c, c->huf_list.ensure(4 * (ncomp + 1)));
     CK(c, c->seq_list.ensure(4 * (ncomp + 1)));
+    CK(c, c->slow_list.ensure(4 * (ncomp + 1)));
     CK(c, c->rawrle_list.ensure(4 * (rawrle.size() + 1)));
     CK(c, c->exec_list.ensure(4 * (execl.size() + 1)));
+    CK(c, c->exec2_list.ensure(4 * (exec2l.size() + 1)));
     CK(c, c->xxh_list.ensure(4 * (c->h_xxh_list.size() + 1)));
     CK(c, c->counters.ensure(sizeof(ZsbCounters)));
     CK(c, c->lit_pool.ensure(c->lit_cap + 64));
     CK(c, c->seq_pool.ensure(8 * (c->seq_cap + 8)));
+    CK(c, c->word_pool.ensure(4 * (c->seq_cap + 8)));
     if (nf) CK(c, cudaMemcpyAsync(c->frames.p, frames, sizeof(zsb_frame) * nf, cudaMemcpyHostToDevice, st));
     if (nb) CK(c, cudaMemcpyAsync(c->blocks.p, blocks, sizeof(zsb_block) * nb, cudaMemcpyHostToDevice, st));
     if (!rawrle.empty()) CK(c, cudaMemcpyAsync(c->rawrle_list.p, rawrle.data(), 4 * rawrle.size(), cudaMemcpyHostToDevice, st));
     if (!execl.empty()) CK(c, cudaMemcpyAsync(c->exec_list.p, execl.data(), 4 * execl.size(), cudaMemcpyHostToDevice, st));
+    if (!exec2l.empty()) CK(c, cudaMemcpyAsync(c->exec2_list.p, exec2l.data(), 4 * exec2l.size(), cudaMemcpyHostToDevice, st));
     if (!c->h_xxh_list.empty()) CK(c, cudaMemcpyAsync(c->xxh_list.p, c->h_xxh_list.data(), 4 * c->h_xxh_list.size(), cudaMemcpyHostToDevice, st));
     CK(c, cudaStreamSynchronize(st));   // the host vectors above go out of scope
     c->prepared = true;
@@ -188,9 +194,15 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     MARK(c, "k_plan1");  zsbk_plan1(st, frames, c->nf, blocks, c->nb, work, fout, (uint32_t *)c->huf_list.p, (uint32_t *)c->seq_list.p, cnt,
                                     c->lit_cap, c->seq_cap, c->flags); c->launches++;
     MARK(c, "k_huf");    zsbk_huf(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags); c->launches += c->ncomp ? 1 : 0;
-    MARK(c, "k_seq");    zsbk_seq(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p); c->launches += c->ncomp ? 1 : 0;
+    MARK(c, "k_seq1");   zsbk_seq1(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint32_t *)c->word_pool.p, (uint32_t *)c->slow_list.p);
+    MARK(c, "k_seq2");   zsbk_seq2(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (const uint32_t *)c->word_pool.p, (uint64_t *)c->seq_pool.p,
+                                   (uint32_t *)c->slow_list.p);
+    MARK(c, "k_seq_slow"); zsbk_seq_slow(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->slow_list.p, cnt, (uint64_t *)c->seq_pool.p);
+    c->launches += c->ncomp ? 3 : 0;
     MARK(c, "k_plan2");  zsbk_plan2(st, frames, c->nf, blocks, work, fout, cnt, c->dst_cap, c->flags); c->launches++;
     MARK(c, "k_rawrle"); zsbk_rawrle(st, c->n_rawrle, src, blocks, work, fout, (const uint32_t *)c->rawrle_list.p, cnt, c->d_dst); c->launches += c->n_rawrle ? 1 : 0;
+    MARK(c, "k_exec2");  zsbk_exec2(st, c->n_exec2, src, frames, blocks, work, fout, (const uint32_t *)c->exec2_list.p, cnt, (const uint64_t *)c->seq_pool.p,
+                                    (const uint8_t *)c->lit_pool.p, c->d_dst); c->launches += c->n_exec2 ? 1 : 0;
     MARK(c, "k_exec");   zsbk_exec(st, c->n_exec, src, frames, blocks, work, fout, (const uint32_t *)c->exec_list.p, cnt, (const uint64_t *)c->seq_pool.p,
                                    (const uint8_t *)c->lit_pool.p, c->d_dst); c->launches += c->n_exec ? 1 : 0;
     MARK(c, "k_xxh");    zsbk_xxh(st, c->n_xxh, c->d_dst, fout, (const uint32_t *)c->xxh_list.p, cnt); c->launches += c->n_xxh ? 1 : 0;
@@ -215,6 +227,7 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
         c->lit_cap = hc.lit_total + 64; c->seq_cap = hc.seq_total + 8;
         CK(c, c->lit_pool.ensure(c->lit_cap + 64));
         CK(c, c->seq_pool.ensure(8 * (c->seq_cap + 8)));
+        CK(c, c->word_pool.ensure(4 * (c->seq_cap + 8)));
         int rc = zsb_decode_launch(c);
         if (rc) return rc;
     }
@@ -373,7 +386,7 @@ extern "C" int zsb_execute_sequences(zsb_ctx *c, const uint32_t *seqs, size_t n_
     CK(c, cudaMemcpyAsync(base + off_block, &bl, sizeof bl, cudaMemcpyHostToDevice, st));
     CK(c, cudaMemcpyAsync(base + off_fout, &fo, sizeof fo, cudaMemcpyHostToDevice, st));
     CK(c, cudaMemcpyAsync(base + off_list, &zero, 4, cudaMemcpyHostToDevice, st));
-    zsbk_exec(st, 1, base, (const zsb_frame *)(base + off_frame), (const zsb_block *)(base + off_block), w, (ZsbFrameOut *)(base + off_fout),
+    zsbk_exec2(st, 1, base, (const zsb_frame *)(base + off_frame), (const zsb_block *)(base + off_block), w, (ZsbFrameOut *)(base + off_fout),
               (const uint32_t *)(base + off_list), (const ZsbCounters *)(base + off_cnt), (const uint64_t *)(base + off_rec), base, base + off_out);
     CK(c, cudaMemcpyAsync(&fo, base + off_fout, sizeof fo, cudaMemcpyDeviceToHost, st));
     rc = stage_sync(c); if (rc) return rc;

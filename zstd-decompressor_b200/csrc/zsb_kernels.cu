@@ -5,7 +5,9 @@
 //   k_parse   1 lane / block      section headers                       (literals.rs:135-206, sequences.rs:52-143)
 //   k_plan1   1 CTA               per-frame table/tree chaining + scratch placement (scan) + work lists
 //   k_huf     1 lane / stream     Huffman weights -> LUT (smem) -> 4-stream literal decode   (huffman.rs, literals.rs:49-86)
-//   k_seq     1 lane / block      FSE tables (interleaved smem) + 3-state sequence decode     (fse.rs, sequence.rs, sequences.rs:191-237)
+//   k_seq1    1 lane / block      FSE tables (interleaved smem) + the serial 3-state chain      (fse.rs, sequence.rs, sequences.rs:191-237)
+//   k_seq2    1 lane / sequence   extra bits, positions, repeat-offset history -> packed records (sequence.rs:41-55, decoding_context.rs:50-75)
+//   k_seq_slow 1 lane / block     careful decoder for blocks the fast path handed over (exact error order)
 //   k_plan2   1 CTA               block/frame output offsets (scan), repeat-offset history, size checks
 //   k_rawrle  1 CTA / block       raw / RLE block expansion, skippable payloads              (block.rs:76-79)
 //   k_exec    1 CTA / frame       sequence execution in a 128 KiB shared-memory block image   (decoding_context.rs:78-106)
@@ -18,6 +20,7 @@
 #include "zsb_kernels.h"
 #include "zsb_parse.h"
 #include "zsb_huf.h"
+#include "zsb_seqfast.h"
 
 #define FULL 0xFFFFFFFFu
 
@@ -153,35 +156,150 @@ __global__ void __launch_bounds__(32) k_huf(const uint8_t *__restrict__ src, uin
     }
 }
 
-// ======================================================================================= k_seq
-// One warp per CTA, one block per lane.  Tables are interleaved across lanes (cell i of lane l at word
-// i*32 + l), so the three table reads of every decode step are bank-conflict free.
+// ======================================================================================= k_seq1 / k_seq2 / k_seq_slow
+// The sequence stage in two phases (zsb_seqfast.h).
+//
+// k_seq1: the serial three-state FSE chain, one lane per block, SEQ1_LANES blocks per one-warp CTA.  The chain is
+// latency bound (table cell -> bit count -> bit position -> next state: one shared-memory load and ~8
+// dependent ALU operations per sequence), so the kernel wants as many independent chains per scheduler as the
+// batch offers and as few instructions on the chain as possible: tables interleaved across the lanes of the
+// CTA (cell i of lane l at word i*SEQ1_LANES + l: bank = 8*(i%4) + l, conflict free), the bit window reloaded
+// from L1 every step (two aligned 64-bit loads, off the chain), one 32-bit word out per sequence.
 #define SEQ_TBL_CELLS 512
+#define SEQ1_LANES 8
+#define SEQ1_OF_CELLS 256     // offset tables have accuracy log <= 8 (RFC 8878); a log-9 one (the reference accepts it) takes the careful path
+#define SEQ1_TBL_BYTES ((2 * SEQ_TBL_CELLS + SEQ1_OF_CELLS) * SEQ1_LANES * 4)
+#define SEQ1_SMEM_BYTES (SEQ1_TBL_BYTES + 256 * SEQ1_LANES * 2)     // counts (table build), then the stream rings (512 B per lane)
+__global__ void __launch_bounds__(32) k_seq1(const uint8_t *__restrict__ src, ZsbBlockWork *work, const uint32_t *__restrict__ seq_list,
+                                             ZsbCounters *cnt, uint32_t *word_pool, uint32_t *slow_list) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    if (cnt->overflow) return;
+    uint32_t *tbl = reinterpret_cast<uint32_t *>(smem);
+    int16_t *counts = reinterpret_cast<int16_t *>(smem + SEQ1_TBL_BYTES);
+    const uint32_t lane = threadIdx.x;
+    const uint32_t n = cnt->n_seq, idx = blockIdx.x * SEQ1_LANES + lane;
+    bool active = lane < SEQ1_LANES && idx < n;
+    const uint32_t bi = active ? seq_list[idx] : 0;
+    ZsbBlockWork w;
+    if (active) { w = work[bi]; active = w.status == ZSB_OK; }      // else: a literal stream of this block already failed
+    SeqTables T;
+    T.ts = SEQ1_LANES;
+    T.tbl[0] = tbl + lane; T.tbl[1] = tbl + SEQ_TBL_CELLS * SEQ1_LANES + lane; T.tbl[2] = tbl + (SEQ_TBL_CELLS + SEQ1_OF_CELLS) * SEQ1_LANES + lane;
+    T.max_al[0] = 9; T.max_al[1] = 8; T.max_al[2] = 9;
+    int rc = ZSB_OK;
+    if (active) rc = seq_build_tables(src, w, T, counts + lane, SEQ1_LANES);
+    __syncwarp();                                  // the count area becomes the stream rings
+    if (!active) return;
+    uint32_t rem0 = 0;
+    if (!rc) rc = seq_fast_phase1(src, w, T, word_pool + w.seq_buf, 1, rem0, (uint32_t)__cvta_generic_to_shared(smem + SEQ1_TBL_BYTES) + lane * 512u);
+    if (rc == ZSB_TABLE_TOO_SMALL) rc = ZSB_NEEDS_SLOW;
+    if (rc == ZSB_NEEDS_SLOW) slow_list[atomicAdd(&cnt->n_slow, 1u)] = bi;
+    if (rc) work[bi].status = rc; else work[bi].seq_rem0 = rem0;
+}
+
+// k_seq2: one warp per block, one lane per sequence, 32 sequences per step: bit positions, extra-bit values,
+// literal/output positions and the repeat-offset history all by warp prefix operations; packed records out.
+#define SEQ2_WARPS 4
+__device__ __forceinline__ Hist hist_shfl_up(const Hist &h, int d) {
+    Hist r; r.h0 = __shfl_up_sync(FULL, h.h0, d); r.h1 = __shfl_up_sync(FULL, h.h1, d); r.h2 = __shfl_up_sync(FULL, h.h2, d); return r;
+}
+__device__ __forceinline__ Hist hist_bcast(const Hist &h, int l) {
+    Hist r; r.h0 = __shfl_sync(FULL, h.h0, l); r.h1 = __shfl_sync(FULL, h.h1, l); r.h2 = __shfl_sync(FULL, h.h2, l); return r;
+}
+__global__ void __launch_bounds__(32 * SEQ2_WARPS) k_seq2(const uint8_t *__restrict__ src, ZsbBlockWork *work, const uint32_t *__restrict__ seq_list,
+                                                          ZsbCounters *cnt, const uint32_t *__restrict__ word_pool, uint64_t *seq_pool,
+                                                          uint32_t *slow_list) {
+    __shared__ uint32_t s_tab[36 + 53];
+    if (cnt->overflow) return;
+    for (uint32_t k = threadIdx.x; k < 36 + 53; k += blockDim.x) s_tab[k] = k < 36 ? zsb_ll_entry(k) : zsb_ml_entry(k - 36);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, gw = blockIdx.x * SEQ2_WARPS + (threadIdx.x >> 5);
+    if (gw >= cnt->n_seq) return;
+    const uint32_t bi = seq_list[gw];
+    ZsbBlockWork &w = work[bi];
+    if (w.status != ZSB_OK) return;
+    const uint32_t nseq = w.nseq, regen = w.lit_regen;
+    const uint32_t mis = (uint32_t)((uintptr_t)src & 7);
+    const uint8_t *base8 = src - mis;
+    int64_t top = (int64_t)(w.bs_off + mis) * 8 + w.seq_rem0;
+    const uint32_t *words = word_pool + w.seq_buf;
+    uint64_t *rec = seq_pool + w.seq_buf;
+    uint32_t lit_acc = 0, out_acc = 0;
+    Hist H = hist_identity();
+    int bad = 0;
+    for (uint32_t b0 = 0; b0 < nseq; b0 += 32) {
+        const uint32_t i = b0 + lane;
+        const bool valid = i < nseq;
+        const uint32_t word = valid ? __ldg(words + i) : 0u;
+        // bit position: exclusive prefix of the bits consumed (extra bits follow from the codes)
+        uint32_t cL = ZSB_W_CL(word), cO = ZSB_W_CO(word), cM = ZSB_W_CM(word);
+        if (cL > ZSB_MAX_LL_CODE || cO > ZSB_MAX_OF_CODE || cM > ZSB_MAX_ML_CODE) { bad = 1; cL = cO = cM = 0; }    // sequence.rs:46-48
+        const uint32_t eL = s_tab[cL], eM = s_tab[36 + cM];
+        const uint32_t xL = eL >> 24, xM = eM >> 24, px = valid ? xL + xM + cO : 0u;
+        const uint32_t tot = px + ZSB_W_NB(word);
+        uint32_t inc = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += t; }
+        uint32_t ll = 0, ml = 0, ov = 1;
+        if (valid) {
+            const uint64_t Wx = px ? fast_win_at(base8, top - (int64_t)(inc - tot) - px, px) : 0ull;
+            ll = (eL & 0xFFFFFFu) + ((uint32_t)Wx & ((1u << xL) - 1u));
+            ml = (eM & 0xFFFFFFu) + ((uint32_t)(Wx >> xL) & ((1u << xM) - 1u));
+            ov = (1u << cO) + ((uint32_t)(Wx >> (xL + xM)) & ((1u << cO) - 1u));
+        }
+        top -= (int64_t)__shfl_sync(FULL, inc, 31);
+        // literal / output positions
+        uint64_t pos = (uint64_t)ll | ((uint64_t)(ll + ml) << 32);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(FULL, pos, d); if (lane >= (uint32_t)d) pos += t; }
+        const uint32_t lit_end = lit_acc + (uint32_t)pos, out_end = out_acc + (uint32_t)(pos >> 32);
+        if (valid && (lit_end > regen || out_end + (regen - lit_end) > ZSB_BLOCK_MAX)) bad = 1;     // decoding_context.rs:86-90, Block_Maximum_Size
+        lit_acc = __shfl_sync(FULL, lit_end, 31); out_acc = __shfl_sync(FULL, out_end, 31);
+        // repeat-offset history: inclusive prefix over the per-sequence transforms, then the block-level carry
+        Hist G = valid ? hist_of_sequence(ov, ll, bad) : hist_identity();
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const Hist E = hist_shfl_up(G, d); if (lane >= (uint32_t)d) G = hist_compose(G, E, bad); }
+        G = hist_compose(G, H, bad);
+        H = hist_bcast(G, 31);
+        if (valid) rec[i] = (uint64_t)out_end | ((uint64_t)lit_end << ZSB_REC_POS_BITS) | ((uint64_t)G.h0 << (2 * ZSB_REC_POS_BITS));
+    }
+    if (__any_sync(FULL, bad)) {
+        if (lane == 0) { w.status = ZSB_NEEDS_SLOW; slow_list[atomicAdd(&cnt->n_slow, 1u)] = bi; }
+        return;
+    }
+    if (lane == 0) {
+        w.lit_used = lit_acc; w.out_size = out_acc + (regen - lit_acc);
+        w.rep_out[0] = H.h0; w.rep_out[1] = H.h1; w.rep_out[2] = H.h2;
+    }
+}
+
+// k_seq_slow: the careful decoder (zsb_seq.h, the reference's exact error order) for the blocks the fast path
+// handed over.  One warp per CTA, one block per lane, tables interleaved across the 32 lanes.
 #define SEQ_SMEM_BYTES (3 * SEQ_TBL_CELLS * 32 * 4 + 256 * 32 * 2 + 96 * 4)
-__global__ void __launch_bounds__(32, 1) k_seq(const uint8_t *__restrict__ src, uint64_t src_len, ZsbBlockWork *work,
-                                               const uint32_t *__restrict__ seq_list, const ZsbCounters *__restrict__ cnt,
-                                               uint64_t *seq_pool) {
+__global__ void __launch_bounds__(32, 1) k_seq_slow(const uint8_t *__restrict__ src, uint64_t src_len, ZsbBlockWork *work,
+                                                    const uint32_t *__restrict__ slow_list, const ZsbCounters *__restrict__ cnt,
+                                                    uint64_t *seq_pool) {
     extern __shared__ __align__(128) uint8_t smem[];
     if (cnt->overflow) return;
     uint32_t *tbl = reinterpret_cast<uint32_t *>(smem);
     int16_t *counts = reinterpret_cast<int16_t *>(smem + 3 * SEQ_TBL_CELLS * 32 * 4);
     uint32_t *bases = reinterpret_cast<uint32_t *>(smem + 3 * SEQ_TBL_CELLS * 32 * 4 + 256 * 32 * 2);   // [0..35] LL, [36..88] ML
     const uint32_t lane = threadIdx.x;
-    const uint32_t n = cnt->n_seq, idx = blockIdx.x * 32 + lane;
+    const uint32_t n = cnt->n_slow, idx = blockIdx.x * 32 + lane;
     if (blockIdx.x * 32 >= n) return;
     for (uint32_t k = lane; k < 36 + 53; k += 32) bases[k] = k < 36 ? zsb_ll_base(k) : zsb_ml_base(k - 36);
     __syncwarp();
     if (idx >= n) return;
-    const uint32_t bi = seq_list[idx];
+    const uint32_t bi = slow_list[idx];
     ZsbBlockWork w = work[bi];
-    if (w.status != ZSB_OK) return;            // a literal stream of this block already failed
     SeqTables T;
-    T.ts = 32;
+    T.ts = 32; T.max_al[0] = T.max_al[1] = T.max_al[2] = 0;
     T.tbl[0] = tbl + lane; T.tbl[1] = tbl + SEQ_TBL_CELLS * 32 + lane; T.tbl[2] = tbl + 2 * SEQ_TBL_CELLS * 32 + lane;
     int rc = seq_build_tables(src, w, T, counts + lane, 32);
     if (!rc) rc = seq_decode(src, src_len, w, T, bases, bases + 36, seq_pool + w.seq_buf);
-    if (rc) { work[bi].status = rc; return; }
     ZsbBlockWork &g = work[bi];
+    g.status = rc;
+    if (rc) return;
     g.out_size = w.out_size; g.lit_used = w.lit_used;
     g.rep_out[0] = w.rep_out[0]; g.rep_out[1] = w.rep_out[1]; g.rep_out[2] = w.rep_out[2];
 }
@@ -454,6 +572,183 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
     }
 }
 
+// ======================================================================================= k_exec2
+// Sequence execution, one WARP per frame, blocks and sequences strictly in order (decoding_context.rs:78-106).
+//
+// Why a warp and not a CTA per frame.  Text at level 3 is ~15 000 sequences of ~8.5 bytes per 128 KiB block and
+// every batch of 32 of them has a few matches whose source is only a few hundred bytes back, so the batches of
+// one block form a dependency chain whatever the number of warps working on the block; spreading a block over a
+// CTA only adds polling (k_exec, kept for frames of many blocks).  The chain is hidden across frames instead:
+// the warp keeps the last EX2_RING bytes of its frame in shared memory (near sources, resolved with __syncwarp
+// only), older sources are read back from HBM/L2 (they were flushed with 16-byte stores), and a SM holds 32
+// such warps.
+//
+// Positions are 32-bit and relative to the start of the current block (negative = earlier blocks of the frame);
+// the ring index of a position is its global address modulo EX2_RING, so that frames and blocks continue
+// seamlessly and 16-byte units of the ring and of HBM coincide.
+#define EX2_RING 4096u
+#define EX2_MASK (EX2_RING - 1u)
+#define EX2_WARPS 4
+#define EX2_LONG 32u
+#define EX2_GIANT (EX2_RING / 2)
+
+struct Ex2Lit { const uint8_t *p; uint32_t rle; bool is_rle; };
+__device__ __forceinline__ uint8_t ex2_lit(const Ex2Lit &L, uint32_t i) { return L.is_rle ? (uint8_t)L.rle : __ldg(L.p + i); }
+
+// ring -> HBM for positions [lo, hi): bytes up to the first 16-byte boundary of the global address, 16-byte units, tail bytes
+__device__ __forceinline__ void ex2_flush(const uint8_t *ring, uint8_t *gblk, uint32_t g0, int32_t lo, int32_t hi, uint32_t lane) {
+    if (hi <= lo) return;
+    int32_t a = lo + (int32_t)((16u - ((g0 + (uint32_t)lo) & 15u)) & 15u); if (a > hi) a = hi;
+    for (int32_t p = lo + (int32_t)lane; p < a; p += 32) gblk[p] = ring[(g0 + (uint32_t)p) & EX2_MASK];
+    int32_t b = hi - (int32_t)((g0 + (uint32_t)hi) & 15u); if (b < a) b = a;
+    for (int32_t p = a + 16 * (int32_t)lane; p < b; p += 512)
+        *reinterpret_cast<uint4 *>(gblk + p) = *reinterpret_cast<const uint4 *>(ring + ((g0 + (uint32_t)p) & EX2_MASK));
+    for (int32_t p = b + (int32_t)lane; p < hi; p += 32) gblk[p] = ring[(g0 + (uint32_t)p) & EX2_MASK];
+}
+// one already produced byte of the frame: from the ring if it is still there, else from HBM
+__device__ __forceinline__ uint8_t ex2_src(const uint8_t *ring, const uint8_t *gblk, uint32_t g0, int32_t ring_lo, int32_t p) {
+    return p >= ring_lo ? ring[(g0 + (uint32_t)p) & EX2_MASK] : __ldcg(gblk + p);
+}
+
+__global__ void __launch_bounds__(32 * EX2_WARPS, 8) k_exec2(const uint8_t *__restrict__ src, const zsb_frame *__restrict__ frames,
+                                                             const zsb_block *__restrict__ blocks, const ZsbBlockWork *__restrict__ work,
+                                                             ZsbFrameOut *fout, const uint32_t *__restrict__ exec_list, uint32_t n,
+                                                             const ZsbCounters *__restrict__ cnt, const uint64_t *__restrict__ seq_pool,
+                                                             const uint8_t *__restrict__ lit_pool, uint8_t *dst) {
+    __shared__ __align__(128) uint8_t rings[EX2_WARPS][EX2_RING];
+    if (cnt->overflow) return;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * EX2_WARPS + warp;
+    if (gw >= n) return;
+    uint8_t *ring = rings[warp];
+    const uint32_t f = exec_list[gw];
+    const ZsbFrameOut fo = fout[f];
+    if (fo.status != ZSB_OK) return;
+    const zsb_frame fr = frames[f];
+    uint8_t *fdst = dst + fo.dst_off;
+    int err = 0;
+    int32_t flushed = 0, ring_lo = 0;          // [ring_lo, ..) is in the ring, [.., flushed) is in HBM; ring_lo <= flushed always
+    for (uint32_t k = 0; k < fr.n_blocks && !err; k++) {
+        const uint32_t bi = fr.first_block + k;
+        const ZsbBlockWork &W = work[bi];
+        const uint32_t out_size = W.out_size;
+        uint8_t *gblk = fdst + W.out_off;
+        const uint32_t g0 = (uint32_t)(uintptr_t)gblk;
+        if (blocks[bi].type != ZSB_BT_COMPRESSED) {
+            ex2_flush(ring, gblk, g0, flushed, 0, lane);               // what earlier blocks left in the ring
+            flushed = ring_lo = (int32_t)out_size;                     // raw / RLE blocks were written by k_rawrle
+        } else {
+            const uint32_t nseq = W.nseq, regen = W.lit_regen;
+            Ex2Lit L;
+            L.is_rle = W.lit_type == ZSB_LT_RLE; L.rle = L.is_rle ? src[W.lit_src] : 0u;
+            L.p = W.lit_type == ZSB_LT_RAW ? src + W.lit_src : lit_pool + W.lit_buf;
+            const uint64_t *seqs = seq_pool + W.seq_buf;
+            const uint64_t P0 = W.out_off;
+            const uint32_t items = nseq + 1;   // the last item is the literal tail (decoding_context.rs:101-103); all there is when nseq == 0
+            uint32_t c_out = 0, c_lit = 0;
+            uint64_t rec_next = lane < nseq ? __ldg(seqs + lane) : 0ull;
+            for (uint32_t b0 = 0; b0 < items; b0 += 32) {
+                const uint32_t i = b0 + lane;
+                const uint64_t rec = rec_next;
+                if (i + 32 < nseq) rec_next = __ldg(seqs + i + 32);
+                const bool is_seq = i < nseq;
+                const uint32_t out_end = is_seq ? (uint32_t)rec & ZSB_REC_POS_MASK : out_size;
+                const uint32_t lit_end = is_seq ? (uint32_t)(rec >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK : regen;
+                uint32_t p_out = __shfl_up_sync(FULL, out_end, 1), p_lit = __shfl_up_sync(FULL, lit_end, 1);
+                if (lane == 0) { p_out = c_out; p_lit = c_lit; }
+                c_out = __shfl_sync(FULL, out_end, 31); c_lit = __shfl_sync(FULL, lit_end, 31);
+                const uint32_t ll = lit_end - p_lit;
+                uint32_t ml = out_end - p_out - ll;
+                const uint32_t off = is_seq ? seq_real_offset((uint32_t)(rec >> (2 * ZSB_REC_POS_BITS)), W.rep_in) : 1u;
+                const uint32_t dstm = p_out + ll;
+                if (is_seq && (off == 0 || (uint64_t)off > P0 + dstm)) { err = ZSB_E_IMPOSSIBLE_VALUE; ml = 0; }    // decoding_context.rs:86-90
+                const int32_t srcp = (int32_t)dstm - (int32_t)off;
+                const uint32_t B0 = __shfl_sync(FULL, p_out, 0), B1 = c_out;
+                if (B1 - B0 > EX2_GIANT) {
+                    // a batch too large for the ring (a very long literal run or match): sequence by sequence, straight to HBM
+                    ex2_flush(ring, gblk, g0, flushed, (int32_t)B0, lane);
+                    __syncwarp();
+                    for (int j = 0; j < 32; j++) {
+                        const uint32_t jo = __shfl_sync(FULL, p_out, j), jll = __shfl_sync(FULL, ll, j), jml = __shfl_sync(FULL, ml, j);
+                        const uint32_t jl = __shfl_sync(FULL, p_lit, j), joff = __shfl_sync(FULL, off, j);
+                        const int32_t js = __shfl_sync(FULL, srcp, j);
+                        const uint32_t jd = jo + jll;
+                        for (uint32_t q = lane; q < jll; q += 32) gblk[jo + q] = ex2_lit(L, jl + q);
+                        __syncwarp();
+                        if (joff >= 32) {
+                            for (uint32_t k0 = 0; k0 < jml; k0 += 32) {           // 32 bytes at a time: a unit never reads what it writes
+                                if (k0 + lane < jml) gblk[jd + k0 + lane] = __ldcg(gblk + js + (int32_t)(k0 + lane));
+                                __syncwarp();
+                            }
+                        } else {
+                            for (uint32_t q = lane; q < jml; q += 32) gblk[jd + q] = __ldcg(gblk + js + (int32_t)(q % joff));   // periodic with period off
+                        }
+                        __syncwarp();
+                    }
+                    flushed = ring_lo = (int32_t)B1;
+                    continue;
+                }
+                ring_lo = max(ring_lo, (int32_t)B1 - (int32_t)EX2_RING);
+                // ---- literals (no dependency on earlier output, decoding_context.rs:92-93)
+                if (ll && ll <= EX2_LONG)
+                    for (uint32_t q = 0; q < ll; q++) ring[(g0 + p_out + q) & EX2_MASK] = ex2_lit(L, p_lit + q);
+                for (uint32_t m = __ballot_sync(FULL, ll > EX2_LONG); m; m &= m - 1) {
+                    const int j = __ffs(m) - 1;
+                    const uint32_t jo = __shfl_sync(FULL, p_out, j), jll = __shfl_sync(FULL, ll, j), jl = __shfl_sync(FULL, p_lit, j);
+                    for (uint32_t q = lane; q < jll; q += 32) ring[(g0 + jo + q) & EX2_MASK] = ex2_lit(L, jl + q);
+                }
+                __syncwarp();
+                // ---- matches (decoding_context.rs:95-98): a lane goes once everything it needs from other sequences is written,
+                // i.e. lies below the match start of the lowest sequence still pending
+                bool pend = ml != 0;
+                const int32_t send = srcp + (int32_t)ml;
+                const int32_t need = min(send, (int32_t)p_out);
+                for (;;) {
+                    const uint32_t pm = __ballot_sync(FULL, pend);
+                    if (!pm) break;
+                    const int32_t done = (int32_t)__shfl_sync(FULL, dstm, __ffs(pm) - 1);
+                    const bool ready = pend && need <= done;
+                    if (ready && ml <= EX2_LONG) {
+                        if (srcp >= ring_lo) {
+                            for (uint32_t q = 0; q < ml; q++) ring[(g0 + dstm + q) & EX2_MASK] = ring[(g0 + (uint32_t)srcp + q) & EX2_MASK];
+                        } else if (send <= ring_lo) {
+#pragma unroll 4
+                            for (uint32_t q = 0; q < ml; q++) ring[(g0 + dstm + q) & EX2_MASK] = __ldcg(gblk + srcp + (int32_t)q);
+                        } else {
+                            for (uint32_t q = 0; q < ml; q++) ring[(g0 + dstm + q) & EX2_MASK] = ex2_src(ring, gblk, g0, ring_lo, srcp + (int32_t)q);
+                        }
+                        pend = false;
+                    }
+                    for (uint32_t m = __ballot_sync(FULL, ready && ml > EX2_LONG); m; m &= m - 1) {
+                        const int j = __ffs(m) - 1;
+                        const uint32_t jml = __shfl_sync(FULL, ml, j), jd = __shfl_sync(FULL, dstm, j), joff = __shfl_sync(FULL, off, j);
+                        const int32_t js = __shfl_sync(FULL, srcp, j);
+                        if (joff >= 32) {
+                            for (uint32_t k0 = 0; k0 < jml; k0 += 32) {
+                                if (k0 + lane < jml) ring[(g0 + jd + k0 + lane) & EX2_MASK] = ex2_src(ring, gblk, g0, ring_lo, js + (int32_t)(k0 + lane));
+                                __syncwarp();
+                            }
+                        } else {
+                            for (uint32_t q = lane; q < jml; q += 32) ring[(g0 + jd + q) & EX2_MASK] = ex2_src(ring, gblk, g0, ring_lo, js + (int32_t)(q % joff));
+                        }
+                        if ((int)lane == j) pend = false;
+                    }
+                    __syncwarp();
+                }
+                // ---- whole 16-byte units of the batch go to HBM
+                const int32_t hi = (int32_t)B1 - (int32_t)((g0 + B1) & 15u);
+                if (hi > flushed) { ex2_flush(ring, gblk, g0, flushed, hi, lane); flushed = hi; }
+                if (__any_sync(FULL, err != 0)) { err = ZSB_E_IMPOSSIBLE_VALUE; break; }
+            }
+        }
+        flushed -= (int32_t)out_size; ring_lo -= (int32_t)out_size;   // positions become relative to the next block
+        __syncwarp();
+    }
+    if (__any_sync(FULL, err != 0)) { if (lane == 0) { fout[f].status = ZSB_E_IMPOSSIBLE_VALUE; fout[f].dst_len = 0; } return; }
+    uint8_t *gend = fdst + fo.dst_len;
+    ex2_flush(ring, gend, (uint32_t)(uintptr_t)gend, flushed, 0, lane);
+}
+
 // ======================================================================================= k_xxh
 #define XP1 0x9E3779B185EBCA87ull
 #define XP2 0xC2B2AE3D27D4EB4Full
@@ -559,7 +854,9 @@ static cudaError_t set_smem(const void *fn, size_t bytes) {
     return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 cudaError_t zsbk_init() {
-    cudaError_t e = set_smem((const void *)k_seq, SEQ_SMEM_BYTES);
+    cudaError_t e = set_smem((const void *)k_seq_slow, SEQ_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = set_smem((const void *)k_seq1, SEQ1_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     return set_smem((const void *)k_exec, EXEC_SMEM_BYTES);
 }
@@ -574,9 +871,17 @@ void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_
               const ZsbCounters *cnt, uint8_t *lit_pool, uint32_t flags) {
     if (ncomp) k_huf<<<(ncomp + HUF_SLOTS - 1) / HUF_SLOTS, 32, 0, st>>>(src, src_len, work, huf_list, cnt, lit_pool, flags);
 }
-void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *seq_list,
-              const ZsbCounters *cnt, uint64_t *seq_pool) {
-    if (ncomp) k_seq<<<(ncomp + 31) / 32, 32, SEQ_SMEM_BYTES, st>>>(src, src_len, work, seq_list, cnt, seq_pool);
+void zsbk_seq1(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
+               uint32_t *word_pool, uint32_t *slow_list) {
+    if (ncomp) k_seq1<<<(ncomp + SEQ1_LANES - 1) / SEQ1_LANES, 32, SEQ1_SMEM_BYTES, st>>>(src, work, seq_list, cnt, word_pool, slow_list);
+}
+void zsbk_seq2(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
+               const uint32_t *word_pool, uint64_t *seq_pool, uint32_t *slow_list) {
+    if (ncomp) k_seq2<<<(ncomp + SEQ2_WARPS - 1) / SEQ2_WARPS, 32 * SEQ2_WARPS, 0, st>>>(src, work, seq_list, cnt, word_pool, seq_pool, slow_list);
+}
+void zsbk_seq_slow(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *slow_list,
+                   const ZsbCounters *cnt, uint64_t *seq_pool) {
+    if (ncomp) k_seq_slow<<<(ncomp + 31) / 32, 32, SEQ_SMEM_BYTES, st>>>(src, src_len, work, slow_list, cnt, seq_pool);
 }
 void zsbk_plan2(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb_block *blocks, ZsbBlockWork *work, ZsbFrameOut *fout,
                 ZsbCounters *cnt, uint64_t dst_cap, uint32_t flags) {
@@ -589,6 +894,10 @@ void zsbk_rawrle(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_bloc
 void zsbk_exec(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
                ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst) {
     if (n) k_exec<<<n, EXEC_THREADS, EXEC_SMEM_BYTES, st>>>(src, frames, blocks, work, fout, exec_list, cnt, seq_pool, lit_pool, dst);
+}
+void zsbk_exec2(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
+                ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst) {
+    if (n) k_exec2<<<(n + EX2_WARPS - 1) / EX2_WARPS, 32 * EX2_WARPS, 0, st>>>(src, frames, blocks, work, fout, exec_list, n, cnt, seq_pool, lit_pool, dst);
 }
 void zsbk_xxh(cudaStream_t st, uint32_t n, const uint8_t *dst, ZsbFrameOut *fout, const uint32_t *list, const ZsbCounters *cnt) {
     if (n) k_xxh<<<(n * 4 + 127) / 128, 128, 0, st>>>(dst, fout, list, n, cnt);

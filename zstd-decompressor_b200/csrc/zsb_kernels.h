@@ -10,7 +10,7 @@ struct ZsbCounters {
     uint32_t n_huf;       // blocks with Huffman-coded literals
     uint32_t n_seq;       // blocks with at least one sequence
     uint32_t overflow;    // scratch too small: every later kernel exits, the host grows it and relaunches
-    uint32_t pad;
+    uint32_t n_slow;      // blocks the fast sequence path handed to the careful decoder
 };
 
 cudaError_t zsbk_init();
@@ -19,14 +19,20 @@ void zsbk_plan1(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb
                 ZsbFrameOut *fout, uint32_t *huf_list, uint32_t *seq_list, ZsbCounters *cnt, uint64_t lit_cap, uint64_t seq_cap, uint32_t flags);
 void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *huf_list,
               const ZsbCounters *cnt, uint8_t *lit_pool, uint32_t flags);
-void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *seq_list,
-              const ZsbCounters *cnt, uint64_t *seq_pool);
+void zsbk_seq1(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
+               uint32_t *word_pool, uint32_t *slow_list);
+void zsbk_seq2(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
+               const uint32_t *word_pool, uint64_t *seq_pool, uint32_t *slow_list);
+void zsbk_seq_slow(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *slow_list,
+                   const ZsbCounters *cnt, uint64_t *seq_pool);
 void zsbk_plan2(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb_block *blocks, ZsbBlockWork *work, ZsbFrameOut *fout,
                 ZsbCounters *cnt, uint64_t dst_cap, uint32_t flags);
 void zsbk_rawrle(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_block *blocks, const ZsbBlockWork *work, const ZsbFrameOut *fout,
                  const uint32_t *list, const ZsbCounters *cnt, uint8_t *dst);
 void zsbk_exec(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
                ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst);
+void zsbk_exec2(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
+                ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst);
 void zsbk_xxh(cudaStream_t st, uint32_t n, const uint8_t *dst, ZsbFrameOut *fout, const uint32_t *list, const ZsbCounters *cnt);
 void zsbk_stage_fse(cudaStream_t st, const uint8_t *desc, uint32_t n, int max_sym, const int16_t *dist_in, int ndist_in, int al_in,
                     int *res, uint32_t *cells, int16_t *dist_out);

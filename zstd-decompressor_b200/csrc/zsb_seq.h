@@ -22,7 +22,9 @@ struct SeqTables {
     uint32_t *tbl[3];   // LL, OF, ML cells; cell i at tbl[t][i*ts]
     int ts;
     int al[3];
+    int max_al[3];      // largest accuracy log each table has room for (0 = ZSB_MAX_AL)
 };
+#define ZSB_TABLE_TOO_SMALL (-2)   // internal: seq_build_tables met a table larger than the caller's storage
 
 // Builds the three tables of block `w` (modes already resolved, never ZSB_M_REPEAT).
 ZSB_HDN int seq_build_tables(const uint8_t *src, const ZsbBlockWork &w, SeqTables &T, int16_t *cnt, int cs) {
@@ -36,6 +38,7 @@ ZSB_HDN int seq_build_tables(const uint8_t *src, const ZsbBlockWork &w, SeqTable
             rc = fse_read_ncount(f, cnt, cs, 256, al, nsym);
             if (rc) return rc;
         } else return ZSB_E_NO_PREVIOUS_DECODER;
+        if (T.max_al[t] && al > T.max_al[t]) return ZSB_TABLE_TOO_SMALL;
         rc = fse_build_table(cnt, cs, nsym, al, T.tbl[t], T.ts, t);
         if (rc) return rc;
         T.al[t] = al;

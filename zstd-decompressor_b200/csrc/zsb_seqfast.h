@@ -1,0 +1,253 @@
+// zsb_seqfast.h -- the fast sequence path: the serial FSE chain stripped to its dependency core
+// (phase 1, one lane per block) and everything else moved to a lane-per-sequence pass (phase 2).
+//
+// Why two phases.  Sequences::decode (sequences.rs:191-237) is one dependent chain per block:
+// state -> table cell -> number of bits -> bit position -> next state, three states sharing one bit
+// cursor.  Nothing else in the loop of SequenceDecoder::decode (decoders/sequence.rs:41-88) -- the
+// extra-bit values, the code -> baseline tables, literal/match positions, the repeat-offset history
+// of DecodingContext::decode_offset (decoding_context.rs:50-75) -- feeds back into that chain.  So
+//
+//   phase 1 (seq_fast_phase1)  walks the chain only and emits one 32-bit word per sequence:
+//                              the three codes and how many bits the sequence consumed;
+//   phase 2 (seq_fast_values, hist_*) turns 32 words at a time into (ll, ml, offset_value) with one
+//                              lane per sequence: bit positions by prefix sum, extra bits by direct
+//                              extraction, positions by prefix sum, the repeat-offset history as a
+//                              prefix "sum" over composable history transforms.
+//
+// Both phases only ever produce results for streams on which nothing unusual happened.  Any anomaly
+// (illegal code, over-read, a literal or output overrun, an offset that reaches zero or exceeds the
+// representable range) returns ZSB_NEEDS_SLOW and the block is decoded again by the careful
+// seq_decode (zsb_seq.h), which reproduces the reference's error order exactly.
+#pragma once
+#include "zsb_seq.h"
+
+#define ZSB_NEEDS_SLOW (-1)
+
+// phase-1 word, one byte per field: LL code | OF code | ML code | state bits consumed (LL+ML+OF).
+// The code bytes carry two stray high bits (the low bits of the cell's base field): mask with 63.
+#define ZSB_W_CL(w) ((w) & 63u)
+#define ZSB_W_CO(w) (((w) >> 8) & 63u)
+#define ZSB_W_CM(w) (((w) >> 16) & 63u)
+#define ZSB_W_NB(w) (((w) >> 24) & 31u)
+ZSB_HD uint32_t zsb_prmt(uint32_t a, uint32_t b, uint32_t sel) {      // PTX prmt.b32, default mode
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a; uint32_t r = 0;
+    for (int k = 0; k < 4; k++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * k)) & 7))) & 0xFF) << (8 * k);
+    return r;
+#endif
+}
+// high word of (hi:lo) << (n & 31)
+ZSB_HD uint32_t zsb_fsl(uint32_t lo, uint32_t hi, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, n);
+#else
+    n &= 31; return n ? (hi << n) | (lo >> (32 - n)) : hi;
+#endif
+}
+ZSB_HD uint32_t seq_fast_word(uint32_t eL, uint32_t eO, uint32_t eM, uint32_t nbs) {
+    return zsb_prmt(zsb_prmt(eL, eO, 0x0062), zsb_prmt(eM, nbs, 0x0042), 0x5410);
+}
+
+// code -> baseline | extra bits << 24 (sequence.rs:98-191)
+ZSB_HD uint32_t zsb_ll_entry(uint32_t c) { return zsb_ll_base(c) | (zsb_ll_bits(c) << 24); }
+ZSB_HD uint32_t zsb_ml_entry(uint32_t c) { return zsb_ml_base(c) | (zsb_ml_bits(c) << 24); }
+
+// `need` (<= 63) stream bits starting at absolute bit a >= 0, in the low bits of the result
+ZSB_HD uint64_t fast_win_at(const uint8_t *base8, int64_t a, uint32_t need) {
+    const int64_t wi = a >> 6; const uint32_t sh = (uint32_t)(a & 63);
+    const uint64_t lo = zsb_ld64(base8, wi);
+    const uint64_t hi = (sh + need > 64) ? zsb_ld64(base8, wi + 1) : 0ull;
+    return zsb_shr64(lo, sh) | zsb_shl64(hi, 64 - sh);
+}
+
+// ---- phase 1 ---------------------------------------------------------------------------------------
+// Walks the three-state chain of block w and writes words[0..nseq) (stride ws).  rem0 = unread bits
+// after the three initial states, i.e. where sequence 0 starts.  Returns ZSB_OK, an initialisation
+// error identical to the careful path's (BackwardBitParser::new parsing.rs:200-220, the initial
+// states sequence.rs:59-65), or ZSB_NEEDS_SLOW.
+//
+// Bit positions are 32-bit and relative to `pw`, the aligned 64-bit word just BELOW the word holding
+// the first stream byte, so that the 64-bit window ending at any position inside the stream starts at
+// a non-negative bit.  The two window words of the next step are requested as soon as the bit count of
+// the current one is known and are only combined after the next step's table cells were requested.
+struct FastWin { uint64_t lo, hi; uint32_t sh; };
+ZSB_HD void fast_win_load(FastWin &f, const uint8_t *pw, int32_t top) {
+    int32_t a = top - 64; a = a < 0 ? 0 : a;        // below the stream only after an over-read (reported at the end)
+    const uint32_t wi = (uint32_t)a >> 6;
+    f.sh = (uint32_t)a & 63u;
+    f.lo = zsb_ld64(pw, wi);
+    f.hi = f.sh ? zsb_ld64(pw, wi + 1) : 0ull;      // word wi+1 holds bit top-1, a stream bit, exactly when sh != 0
+}
+ZSB_HD uint64_t fast_win_get(const FastWin &f) { return zsb_shr64(f.lo, f.sh) | zsb_shl64(f.hi, 64 - f.sh); }
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint32_t zsb_lds32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint64_t zsb_lds64v(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
+
+// The bitstream of one lane staged through a 512-byte shared-memory ring of four 128-byte lines, filled with
+// cp.async two lines ahead of the (backward moving) cursor: the window loads of the chain become shared-memory
+// loads with a fixed latency instead of global loads whose misses would stall every chain of the warp.
+// Bit positions are relative to `pl`, a 128-byte aligned address at least 8 bytes below the stream.
+struct StreamRing { uint32_t sa; const uint8_t *pl; int32_t low; };   // ring address, line base, lowest line requested
+__device__ __forceinline__ void sr_fetch(const StreamRing &r, int32_t line) {
+    const uint8_t *g = r.pl + (size_t)(uint32_t)line * 128u;
+    const uint32_t d = r.sa + ((uint32_t)line & 3u) * 128u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 16 * k), "l"(g + 16 * k) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void sr_init(StreamRing &r, int32_t top) {
+    const int32_t l0 = (top - 1) >> 10;
+    r.low = l0 - 2 < 0 ? 0 : l0 - 2;
+    for (int32_t l = l0; l >= r.low; l--) sr_fetch(r, l);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+// window words for the 64 bits ending at `top`; entering line X requests line X-2 and waits for X-1
+__device__ __forceinline__ void sr_load(StreamRing &r, FastWin &f, int32_t top) {
+    int32_t a = top - 64; a = a < 0 ? 0 : a;          // below the stream only after an over-read (reported at the end)
+    const uint32_t wi = (uint32_t)a >> 6;
+    f.sh = (uint32_t)a & 63u;
+    if ((int32_t)(wi >> 4) <= r.low + 1 && r.low > 0) { r.low--; sr_fetch(r, r.low); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    f.lo = zsb_lds64v(r.sa + (wi & 63u) * 8u);
+    f.hi = f.sh ? zsb_lds64v(r.sa + ((wi + 1) & 63u) * 8u) : 0ull;
+}
+#endif
+
+ZSB_HDN int seq_fast_phase1(const uint8_t *src, const ZsbBlockWork &w, const SeqTables &T, uint32_t *words, int ws, uint32_t &rem0,
+                            uint32_t ring_sa) {
+    const uint64_t start = w.bs_off, end = w.bs_off + w.bs_len;
+    if (end <= start) return ZSB_E_EMPTY_INPUT_DATA;
+    const uint32_t lastb = src[end - 1];
+    if (lastb == 0) return ZSB_E_NULL_BYTE;
+    if (start < 8 || w.bs_len > (1u << 24)) return ZSB_NEEDS_SLOW;            // no word below the stream / positions would not fit
+    const uint32_t a0 = (uint32_t)T.al[0], a1 = (uint32_t)T.al[1], a2 = (uint32_t)T.al[2];
+    const uint32_t nseq = w.nseq;
+    FastWin F;
+#if defined(__CUDA_ARCH__)
+    StreamRing R;
+    R.sa = ring_sa;
+    R.pl = (const uint8_t *)(((uintptr_t)(src + start) - 8) & ~(uintptr_t)127);
+    const uint32_t d0 = (uint32_t)((src + start) - R.pl);                     // 8 .. 135
+    int32_t top = (int32_t)((d0 + w.bs_len - 1) * 8) + zsb_flog2(lastb);
+    const int32_t startbit = (int32_t)(d0 * 8);
+    if (top - startbit < (int32_t)(a0 + a1 + a2)) return ZSB_E_NOT_ENOUGH_BITS;
+    sr_init(R, top);
+    sr_load(R, F, top);
+#define FAST_LOAD(t_) sr_load(R, F, t_)
+#else
+    (void)ring_sa;
+    const uint32_t mis = (uint32_t)((uintptr_t)src & 7);
+    const uint64_t w0 = ((start + mis) & ~7ull) - 8;                          // byte offset of pw from the aligned base
+    const uint8_t *pw = src - mis + w0;
+    int32_t top = (int32_t)((end - 1 + mis - w0) * 8) + zsb_flog2(lastb);
+    const int32_t startbit = (int32_t)((start + mis - w0) * 8);
+    if (top - startbit < (int32_t)(a0 + a1 + a2)) return ZSB_E_NOT_ENOUGH_BITS;
+    fast_win_load(F, pw, top);
+#define FAST_LOAD(t_) fast_win_load(F, pw, t_)
+#endif
+    uint64_t W = fast_win_get(F);
+    uint32_t sL = (uint32_t)zsb_shr64(W, 64 - a0);
+    uint32_t sO = (uint32_t)zsb_shr64(zsb_shl64(W, a0), 64 - a1);
+    uint32_t sM = (uint32_t)zsb_shr64(zsb_shl64(W, a0 + a1), 64 - a2);
+    top -= (int32_t)(a0 + a1 + a2);
+    rem0 = (uint32_t)(top - startbit);
+    FAST_LOAD(top);
+#if defined(__CUDA_ARCH__)
+    // states are kept as shared-memory byte addresses of their cells: next = (table + base*stride) + bits*stride
+    const uint32_t stride = (uint32_t)T.ts * 4u;
+    const uint32_t tbL = (uint32_t)__cvta_generic_to_shared(T.tbl[0]), tbO = (uint32_t)__cvta_generic_to_shared(T.tbl[1]),
+                   tbM = (uint32_t)__cvta_generic_to_shared(T.tbl[2]);
+    uint32_t aL = tbL + sL * stride, aO = tbO + sO * stride, aM = tbM + sM * stride;
+#define FAST_CELLS() const uint32_t eL = zsb_lds32(aL), eO = zsb_lds32(aO), eM = zsb_lds32(aM)
+#define FAST_NEXT() aL = tbL + (ZSB_CELL_BASE(eL) + bL) * stride; aM = tbM + (ZSB_CELL_BASE(eM) + bM) * stride; aO = tbO + (ZSB_CELL_BASE(eO) + bO) * stride
+#else
+    const int ts = T.ts;
+    const uint32_t *tL = T.tbl[0], *tO = T.tbl[1], *tM = T.tbl[2];
+#define FAST_CELLS() const uint32_t eL = tL[sL * ts], eO = tO[sO * ts], eM = tM[sM * ts]
+#define FAST_NEXT() sL = ZSB_CELL_BASE(eL) + bL; sM = ZSB_CELL_BASE(eM) + bM; sO = ZSB_CELL_BASE(eO) + bO
+#endif
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
+    for (uint32_t i = 0; i + 1 < nseq; i++) {
+        FAST_CELLS();
+        W = fast_win_get(F);
+        const uint32_t sum = eL + eO + eM;                        // byte 0: state bits, byte 1: extra bits (no carries: <= 27, <= 63)
+        const uint32_t nbs = sum & 0xFFu, px = zsb_prmt(sum, 0, 0x4441);
+        uint32_t skip = px;
+        if (px + nbs > 64) { top -= (int32_t)px; FAST_LOAD(top); W = fast_win_get(F); skip = 0; }   // state bits past the window: rare
+        const uint32_t t = (uint32_t)(zsb_shl64(W, skip) >> 32);  // the <= 27 state bits, top-aligned
+        // the funnel shifts take their 5-bit amounts straight from the cells (nb in bits 0..4)
+        const uint32_t bL = zsb_fsl(t, 0, eL), t2 = zsb_fsl(0, t, eL), bM = zsb_fsl(t2, 0, eM), bO = zsb_fsl(zsb_fsl(0, t2, eM), 0, eO);
+        top -= (int32_t)(skip + nbs);
+        FAST_LOAD(top);
+        FAST_NEXT();                                              // sequence.rs:80-88
+        words[i * ws] = seq_fast_word(eL, eO, eM, nbs);
+    }
+    {   // last sequence: no state update (sequence.rs:80)
+        FAST_CELLS();
+        words[(nseq - 1) * ws] = seq_fast_word(eL, eO, eM, 0);
+        top -= (int32_t)zsb_prmt(eL + eO + eM, 0, 0x4441);
+    }
+#undef FAST_LOAD
+#undef FAST_CELLS
+#undef FAST_NEXT
+    // an over-read shows as a cursor below the stream start; illegal codes are caught by phase 2, which sees every code
+    if (top < startbit) return ZSB_NEEDS_SLOW;
+    return ZSB_OK;
+}
+
+// ---- phase 2 ---------------------------------------------------------------------------------------
+// (ll, ml, offset_value) of one sequence from its word and `top`, the absolute bit just above its
+// first bit (sequence.rs:50-55: OF extra, then ML extra, then LL extra, MSB first).
+ZSB_HD void seq_fast_values(const uint8_t *base8, int64_t top, uint32_t word, const uint32_t *lltab, const uint32_t *mltab,
+                            uint32_t &ll, uint32_t &ml, uint32_t &ov, uint32_t &px, int &bad) {
+    uint32_t cL = ZSB_W_CL(word), cO = ZSB_W_CO(word), cM = ZSB_W_CM(word);
+    if (cL > ZSB_MAX_LL_CODE || cO > ZSB_MAX_OF_CODE || cM > ZSB_MAX_ML_CODE) { bad = 1; cL = cO = cM = 0; }   // sequence.rs:46-48
+    const uint32_t eL = lltab[cL], eM = mltab[cM];
+    const uint32_t xL = eL >> 24, xM = eM >> 24;
+    px = xL + xM + cO;
+    const uint64_t W = px ? fast_win_at(base8, top - px, px) : 0ull;
+    ll = (eL & 0xFFFFFFu) + ((uint32_t)W & ((1u << xL) - 1u));
+    ml = (eM & 0xFFFFFFu) + ((uint32_t)(W >> xL) & ((1u << xM) - 1u));
+    ov = (1u << cO) + ((uint32_t)(W >> (xL + xM)) & ((1u << cO) - 1u));
+}
+
+// Repeat-offset history as a composable transform.  Each of the three slots is a coded offset in
+// the sense of zsb_common.h: a constant, or (ZSB_OFF_SYM) "incoming slot k minus d".
+struct Hist { uint32_t h0, h1, h2; };
+#define ZSB_HSLOT(k) (ZSB_OFF_SYM | ((uint32_t)(k) << 25))
+ZSB_HD Hist hist_identity() { Hist h; h.h0 = ZSB_HSLOT(0); h.h1 = ZSB_HSLOT(1); h.h2 = ZSB_HSLOT(2); return h; }
+// what decode_offset (decoding_context.rs:50-75) does to the history for one sequence; h0 of the
+// result is the offset the sequence uses
+ZSB_HD Hist hist_of_sequence(uint32_t ov, uint32_t ll, int &bad) {
+    Hist h;
+    if (ov > 3) {
+        uint32_t off = ov - 3;
+        if (off > ZSB_OFF_MAX) { bad = 1; off = 1; }
+        h.h0 = off; h.h1 = ZSB_HSLOT(0); h.h2 = ZSB_HSLOT(1);
+        return h;
+    }
+    const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
+    if (idx == 0) return hist_identity();
+    if (idx == 1) { h.h0 = ZSB_HSLOT(1); h.h1 = ZSB_HSLOT(0); h.h2 = ZSB_HSLOT(2); }
+    else if (idx == 2) { h.h0 = ZSB_HSLOT(2); h.h1 = ZSB_HSLOT(0); h.h2 = ZSB_HSLOT(1); }
+    else { h.h0 = ZSB_HSLOT(0) + 1u; h.h1 = ZSB_HSLOT(0); h.h2 = ZSB_HSLOT(1); }
+    return h;
+}
+// value of coded slot f once the history it refers to is g
+ZSB_HD uint32_t hist_pick(const Hist &g, uint32_t f, int &bad) {
+    if (!(f & ZSB_OFF_SYM)) return f;
+    const uint32_t k = ZSB_OFF_SLOT(f), d = ZSB_OFF_DEC(f);
+    const uint32_t x = k == 0 ? g.h0 : k == 1 ? g.h1 : g.h2;
+    if (x & ZSB_OFF_SYM) return x + d;
+    if (x <= d) { bad = 1; return 1u; }
+    return x - d;
+}
+// f after g
+ZSB_HD Hist hist_compose(const Hist &f, const Hist &g, int &bad) {
+    Hist r; r.h0 = hist_pick(g, f.h0, bad); r.h1 = hist_pick(g, f.h1, bad); r.h2 = hist_pick(g, f.h2, bad);
+    return r;
+}
