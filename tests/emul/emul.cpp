@@ -14,6 +14,7 @@
 
 // fast-path bookkeeping for tests: blocks where the fast sequence path ran / agreed / asked for the careful path / disagreed
 static long g_fast_ran = 0, g_fast_same = 0, g_fast_slow = 0, g_fast_diff = 0;
+static long g_huf_ran = 0, g_huf_same = 0, g_huf_slow = 0, g_huf_diff = 0;
 
 // The fast sequence path as the kernels run it (phase 1 per lane, phase 2 folded serially with the same
 // per-sequence functions and the same history composition) against the careful decoder's results.
@@ -116,7 +117,17 @@ int emul_decode(const uint8_t *src_in, size_t n, uint32_t flags, uint8_t *out, s
             uint64_t start = w.lit_src; uint32_t seg = (w.lit_regen + 3) / 4;
             for (uint32_t s = 0; s < w.n_streams && !rc; s++) {
                 uint32_t expect = w.n_streams == 1 ? w.lit_regen : (s < 3 ? seg : w.lit_regen - 3 * seg);
-                rc = huf_decode_stream(src, start, start + w.stream_size[s], n, lut, mb, lits[i].data() + (w.n_streams == 1 ? 0 : s * seg), expect);
+                uint8_t *o = lits[i].data() + (w.n_streams == 1 ? 0 : s * seg);
+                rc = huf_decode_stream(src, start, start + w.stream_size[s], n, lut, mb, o, expect);
+                {   // the fast stream decode on the same stream: same bytes, or a request for the careful decoder where that one fails
+                    std::vector<uint8_t> fo((size_t)expect + 16, 0xEE);
+                    uint8_t *fa = fo.data() + ((4 - ((uintptr_t)fo.data() & 3)) & 3) + ((uintptr_t)o & 3);   // same alignment as the real output
+                    int frc = huf_fast_stream(src, start, start + w.stream_size[s], lut, mb, fa, expect, 0);
+                    g_huf_ran++;
+                    if (frc == ZSB_OK) { if (rc == ZSB_OK && memcmp(fa, o, expect) == 0) g_huf_same++; else g_huf_diff++; }
+                    else if (frc == ZSB_NEEDS_SLOW) { if (rc != ZSB_OK) g_huf_slow++; else g_huf_diff++; }
+                    else g_huf_diff++;
+                }
                 start += w.stream_size[s];
             }
             if (rc) { w.status = rc; continue; }
@@ -178,6 +189,7 @@ int emul_decode(const uint8_t *src_in, size_t n, uint32_t flags, uint8_t *out, s
     zsb_free(frames); zsb_free(blocks);
     return scan_rc;
 }
+void emul_huf_stats(long *ran, long *same, long *slow, long *diff) { *ran = g_huf_ran; *same = g_huf_same; *slow = g_huf_slow; *diff = g_huf_diff; }
 void emul_fast_stats(long *ran, long *same, long *slow, long *diff) { *ran = g_fast_ran; *same = g_fast_same; *slow = g_fast_slow; *diff = g_fast_diff; }
 
 // associativity of the history composition on random transforms: returns the number of violations

@@ -73,3 +73,10 @@ def hist_assoc(seed, n):
     L = lib()
     L.emul_hist_assoc.argtypes = [C.c_uint64, C.c_int]
     return L.emul_hist_assoc(seed, n)
+
+
+def huf_stats():
+    """like fast_stats, for the fast Huffman stream decode (one count per stream)"""
+    v = [C.c_long() for _ in range(4)]
+    lib().emul_huf_stats(*[C.byref(x) for x in v])
+    return tuple(x.value for x in v)

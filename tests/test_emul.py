@@ -174,3 +174,5 @@ def test_fast_sequence_path_equals_careful_decoder():
             E.decode(corpora.mutate(r, d), Q | SKIP)
     ran, same, slow, diff = E.fast_stats()
     assert diff == 0 and same > 200 and slow > 5 and ran == same + slow, (ran, same, slow, diff)
+    ran, same, slow, diff = E.huf_stats()          # fast Huffman stream decode (zsb_huf.h), one count per stream
+    assert diff == 0 and same > 500 and slow > 5 and ran == same + slow, (ran, same, slow, diff)

@@ -25,6 +25,9 @@
 #define ZSB_HUF_MAX_BITS 11
 #define ZSB_MAX_NSEQ_PER_BLOCK 43691u   // ml >= 3 and a block regenerates <= 128 KiB
 
+// internal status: a fast path met something unusual and the careful (reference-order) path must decide
+#define ZSB_NEEDS_SLOW (-1)
+
 // block types in zsb_block.type
 #define ZSB_BT_RAW 0
 #define ZSB_BT_RLE 1
@@ -100,6 +103,7 @@ struct ZsbBlockWork {
     int32_t  status;
     uint32_t err_a, err_b;   // payload of the reference's error variant where it has one
     uint32_t seq_rem0;       // fast sequence path: unread bits of the bitstream once the three initial states are read
+    int32_t  lit_status;     // status of the literals stage (runs concurrently with the sequence stage; wins over `status`, literals.rs:49 runs first)
 };
 
 // Per-frame result record in HBM.

@@ -34,7 +34,9 @@ const uint32_t kBigFrameBlocks = 64;   // frames with more blocks than this are 
 
 struct zsb_ctx {
     int device = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, aux_stream = nullptr;   // aux: the literals stage runs beside the sequence stage
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_huf[kProfRing][2] = {};
     DevBuf src, frames, blocks, work, fout, huf_list, seq_list, rawrle_list, exec_list, exec2_list, xxh_list, lit_pool, seq_pool, word_pool, slow_list, counters, dst, stage;
     std::string last_err;
     // prepared batch
@@ -45,6 +47,7 @@ struct zsb_ctx {
     std::vector<zsb_frame> h_frames;
     std::vector<uint32_t> h_xxh_list;
     bool prepared = false, launched = false;
+    bool overlap = true;       // literals stage on the auxiliary stream (ZSB_NO_OVERLAP=1 serialises it for per-kernel timing)
     // profiling
     bool profile = false;
     cudaEvent_t ev[kProfRing][kMaxKernels + 1] = {};
@@ -67,7 +70,11 @@ extern "C" int zsb_ctx_create(zsb_ctx **out, int device) {
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         zsbk_init() != cudaSuccess) { (void)cudaGetLastError(); delete c; return ZSB_E_CUDA; }
     c->stream = c->own_stream;
+    { const char *e = getenv("ZSB_NO_OVERLAP"); c->overlap = !(e && *e && *e != '0'); }
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) cudaEventCreate(&c->ev[r][i]);
+    for (int r = 0; r < kProfRing; r++) { cudaEventCreate(&c->ev_huf[r][0]); cudaEventCreate(&c->ev_huf[r][1]); }
+    if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); zsb_ctx_destroy(c); return ZSB_E_CUDA; }
     *out = c;
     return ZSB_OK;
 }
@@ -79,6 +86,10 @@ extern "C" void zsb_ctx_destroy(zsb_ctx *c) {
                      &c->xxh_list, &c->lit_pool, &c->seq_pool, &c->word_pool, &c->slow_list, &c->counters, &c->dst, &c->stage};
     for (DevBuf *b : all) b->release();
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) if (c->ev[r][i]) cudaEventDestroy(c->ev[r][i]);
+    for (int r = 0; r < kProfRing; r++) for (int i = 0; i < 2; i++) if (c->ev_huf[r][i]) cudaEventDestroy(c->ev_huf[r][i]);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -103,6 +114,13 @@ extern "C" int zsb_kernel_times_avg(zsb_ctx *c, const char **names, float *ms, i
         for (int r = 0; r < L; r++) { float t = 0; if (cudaEventElapsedTime(&t, c->ev[r][i], c->ev[r][i + 1]) == cudaSuccess) sum += t; else (void)cudaGetLastError(); }
         if (names) names[i] = c->kname[i];
         if (ms) ms[i] = L ? (float)(sum / L) : 0.f;
+    }
+    if (n < cap && c->nk) {       // the literals stage ran on the auxiliary stream, beside k_seq1/k_seq2
+        double sum = 0;
+        for (int r = 0; r < L; r++) { float t = 0; if (cudaEventElapsedTime(&t, c->ev_huf[r][0], c->ev_huf[r][1]) == cudaSuccess) sum += t; else (void)cudaGetLastError(); }
+        if (names) names[n] = "k_huf(aux stream)";
+        if (ms) ms[n] = L ? (float)(sum / L) : 0.f;
+        n++;
     }
     if (n_launches) *n_launches = L;
     return n;
@@ -193,12 +211,21 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     MARK(c, "k_parse");  zsbk_parse(st, src, blocks, work, c->nb, c->flags); c->launches += c->nb ? 1 : 0;
     MARK(c, "k_plan1");  zsbk_plan1(st, frames, c->nf, blocks, c->nb, work, fout, (uint32_t *)c->huf_list.p, (uint32_t *)c->seq_list.p, cnt,
                                     c->lit_cap, c->seq_cap, c->flags); c->launches++;
-    MARK(c, "k_huf");    zsbk_huf(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags); c->launches += c->ncomp ? 1 : 0;
+    // the literals stage (k_huf) and the sequence stage (k_seq1/2) read the same blocks and write disjoint results: both are
+    // latency bound, so they share the SMs.  k_seq1 is enqueued first: its CTAs need the larger shared-memory slice.
+    cudaStream_t hst = c->overlap ? c->aux_stream : st;
+    CK(c, cudaEventRecord(c->ev_fork, st));
+    CK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
     MARK(c, "k_seq1");   zsbk_seq1(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint32_t *)c->word_pool.p, (uint32_t *)c->slow_list.p);
+    if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][0], hst);
+    zsbk_huf(hst, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags); c->launches += c->ncomp ? 1 : 0;
+    if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][1], hst);
+    CK(c, cudaEventRecord(c->ev_join, c->aux_stream));
     MARK(c, "k_seq2");   zsbk_seq2(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (const uint32_t *)c->word_pool.p, (uint64_t *)c->seq_pool.p,
                                    (uint32_t *)c->slow_list.p);
     MARK(c, "k_seq_slow"); zsbk_seq_slow(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->slow_list.p, cnt, (uint64_t *)c->seq_pool.p);
     c->launches += c->ncomp ? 3 : 0;
+    MARK(c, "wait k_huf"); CK(c, cudaStreamWaitEvent(st, c->ev_join, 0));
     MARK(c, "k_plan2");  zsbk_plan2(st, frames, c->nf, blocks, work, fout, cnt, c->dst_cap, c->flags); c->launches++;
     MARK(c, "k_rawrle"); zsbk_rawrle(st, c->n_rawrle, src, blocks, work, fout, (const uint32_t *)c->rawrle_list.p, cnt, c->d_dst); c->launches += c->n_rawrle ? 1 : 0;
     MARK(c, "k_exec2");  zsbk_exec2(st, c->n_exec2, src, frames, blocks, work, fout, (const uint32_t *)c->exec2_list.p, cnt, (const uint64_t *)c->seq_pool.p,

@@ -10,6 +10,7 @@
 //  huf_decode_stream == the per-stream loop of LiteralsSection::decode (literals.rs:70-81)
 #pragma once
 #include "zsb_fse.h"
+#include "zsb_stream.h"
 
 #define ZSB_HUF_WEIGHT_SYMS 16   // weights 0..15 can be described (legal ones are <= 11)
 
@@ -130,4 +131,63 @@ ZSB_HDN int huf_decode_stream(const uint8_t *src, uint64_t start, uint64_t end, 
         }
     }
     return n == expect ? ZSB_OK : ZSB_E_CORRUPT;
+}
+
+
+// ---- fast stream decode ------------------------------------------------------------------------------
+// The same chain as huf_decode_stream with everything that is not on it removed: the window is reloaded once
+// per four symbols (4 x 11 bits fit), four symbols leave as one aligned 32-bit store, and the stream is decoded
+// for exactly `expect` symbols and must then be exactly empty.  Anything else (empty stream, missing end mark,
+// over-read, bits left over, a stream too close to the buffer start) returns ZSB_NEEDS_SLOW and the caller runs
+// huf_decode_stream, which reports what the reference reports.  On the GPU the stream is staged through a
+// shared-memory ring (ring_sa, zsb_stream.h); the host build reads it in place.
+ZSB_HDN int huf_fast_stream(const uint8_t *src, uint64_t start, uint64_t end, const uint16_t *lut, int maxbits, uint8_t *out, uint32_t expect,
+                            uint32_t ring_sa) {
+    if (end <= start || start < 16 || end - start > (1u << 24)) return ZSB_NEEDS_SLOW;
+    const uint32_t lastb = src[end - 1];
+    if (lastb == 0) return ZSB_NEEDS_SLOW;
+    FastWin F;
+#if defined(__CUDA_ARCH__)
+    StreamRing R;
+    R.sa = ring_sa;
+    R.pl = (const uint8_t *)(((uintptr_t)(src + start) - 16) & ~(uintptr_t)63);
+    const uint32_t d0 = (uint32_t)((src + start) - R.pl);                     // 16 .. 79
+    int32_t top = (int32_t)((d0 + (uint32_t)(end - start) - 1) * 8) + zsb_flog2(lastb);
+    const int32_t startbit = (int32_t)(d0 * 8);
+    sr_init<6>(R, top);
+#define HUF_LOAD(t_) sr_load<6>(R, F, t_)
+#else
+    (void)ring_sa;
+    const uint32_t mis = (uint32_t)((uintptr_t)src & 7);
+    const uint64_t w0 = ((start + mis) & ~7ull) - 8;
+    const uint8_t *pw = src - mis + w0;
+    int32_t top = (int32_t)((end - 1 + mis - w0) * 8) + zsb_flog2(lastb);
+    const int32_t startbit = (int32_t)((start + mis - w0) * 8);
+#define HUF_LOAD(t_) fast_win_load(F, pw, t_)
+#endif
+    const uint32_t sh = 64u - (uint32_t)maxbits;
+    uint32_t n = 0;
+    // single symbols until the output is 4-byte aligned
+    while (n < expect && (((uintptr_t)(out + n)) & 3)) {
+        HUF_LOAD(top);
+        const uint32_t cell = lut[(uint32_t)(fast_win_get(F) >> sh)];
+        out[n++] = (uint8_t)cell; top -= (int32_t)(cell >> 8);
+    }
+    for (; n + 4 <= expect; n += 4) {
+        HUF_LOAD(top);
+        uint64_t W = fast_win_get(F);
+        const uint32_t c0 = lut[(uint32_t)(W >> sh)]; W <<= (c0 >> 8);
+        const uint32_t c1 = lut[(uint32_t)(W >> sh)]; W <<= (c1 >> 8);
+        const uint32_t c2 = lut[(uint32_t)(W >> sh)]; W <<= (c2 >> 8);
+        const uint32_t c3 = lut[(uint32_t)(W >> sh)];
+        top -= (int32_t)((c0 >> 8) + (c1 >> 8) + (c2 >> 8) + (c3 >> 8));
+        *reinterpret_cast<uint32_t *>(out + n) = (c0 & 0xFFu) | (c1 & 0xFFu) << 8 | (c2 & 0xFFu) << 16 | c3 << 24;
+    }
+    while (n < expect) {
+        HUF_LOAD(top);
+        const uint32_t cell = lut[(uint32_t)(fast_win_get(F) >> sh)];
+        out[n++] = (uint8_t)cell; top -= (int32_t)(cell >> 8);
+    }
+#undef HUF_LOAD
+    return top == startbit ? ZSB_OK : ZSB_NEEDS_SLOW;
 }

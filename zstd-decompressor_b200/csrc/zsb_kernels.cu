@@ -101,7 +101,9 @@ __global__ void __launch_bounds__(1024) k_plan1(const zsb_frame *__restrict__ fr
 
 // ======================================================================================= k_huf
 // One warp per CTA, 8 blocks per warp: lane = 4 * slot + stream.  Per slot: LUT (4 KiB, aliased with the
-// weight FSE table while the weights are being decoded), weights, counts, ranks.
+// weight FSE table while the weights are being decoded), weights, counts, ranks.  Per lane: a 256-byte ring
+// through which cp.async feeds its stream (zsb_stream.h).  The decode is one dependent chain per stream (LUT cell ->
+// code length -> next LUT index), so like k_seq1 the kernel is latency bound and shares the SMs with k_seq1.
 #define HUF_SLOTS 8
 #define HUF_LUT_BYTES (2u << ZSB_HUF_MAX_BITS)   // 4096
 struct HufSlot {
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(32) k_huf(const uint8_t *__restrict__ src, uin
                                             const uint32_t *__restrict__ huf_list, const ZsbCounters *__restrict__ cnt,
                                             uint8_t *lit_pool, uint32_t flags) {
     __shared__ HufSlot slots[HUF_SLOTS];
+    __shared__ __align__(128) uint8_t rings[32][256];
     if (cnt->overflow) return;
     const uint32_t lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
     const uint32_t n = cnt->n_huf, idx = blockIdx.x * HUF_SLOTS + slot;
@@ -145,14 +148,17 @@ __global__ void __launch_bounds__(32) k_huf(const uint8_t *__restrict__ src, uin
                 seg = (regen + 3) / 4; ooff = stream * seg; expect = stream < 3 ? seg : regen - 3 * seg;
                 for (uint32_t k = 0; k < stream; k++) start += w.stream_size[k];
             }
-            rc = huf_decode_stream(src, start, start + w.stream_size[stream], src_len, S.u.lut, S.maxbits, lit_pool + w.lit_buf + ooff, expect);
+            rc = huf_fast_stream(src, start, start + w.stream_size[stream], S.u.lut, S.maxbits, lit_pool + w.lit_buf + ooff, expect,
+                                 (uint32_t)__cvta_generic_to_shared(rings[lane]));
+            if (rc == ZSB_NEEDS_SLOW)    // the reference's verdict on this stream (literals.rs:70-81)
+                rc = huf_decode_stream(src, start, start + w.stream_size[stream], src_len, S.u.lut, S.maxbits, lit_pool + w.lit_buf + ooff, expect);
         }
     }
     // first failing stream of the block decides its status
     const int r1 = __shfl_sync(FULL, rc, (lane & ~3u) + 1), r2 = __shfl_sync(FULL, rc, (lane & ~3u) + 2), r3 = __shfl_sync(FULL, rc, (lane & ~3u) + 3);
     if (active && stream == 0) {
         int st = rc ? rc : r1 ? r1 : r2 ? r2 : r3;
-        if (st) work[bi].status = st;
+        if (st) work[bi].lit_status = st;
     }
 }
 
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(32) k_seq1(const uint8_t *__restrict__ src, Zs
     bool active = lane < SEQ1_LANES && idx < n;
     const uint32_t bi = active ? seq_list[idx] : 0;
     ZsbBlockWork w;
-    if (active) { w = work[bi]; active = w.status == ZSB_OK; }      // else: a literal stream of this block already failed
+    if (active) { w = work[bi]; active = w.status == ZSB_OK; }
     SeqTables T;
     T.ts = SEQ1_LANES;
     T.tbl[0] = tbl + lane; T.tbl[1] = tbl + SEQ_TBL_CELLS * SEQ1_LANES + lane; T.tbl[2] = tbl + (SEQ_TBL_CELLS + SEQ1_OF_CELLS) * SEQ1_LANES + lane;
@@ -610,6 +616,43 @@ __device__ __forceinline__ uint8_t ex2_src(const uint8_t *ring, const uint8_t *g
     return p >= ring_lo ? ring[(g0 + (uint32_t)p) & EX2_MASK] : __ldcg(gblk + p);
 }
 
+// ---- copies in units of up to 8 bytes: three aligned source words, two funnel shifts, byte stores
+// store the low n (<= 8) bytes of v1:v0 at ring position d (unmasked)
+__device__ __forceinline__ void ex2_store8(uint8_t *ring, uint32_t d, uint32_t v0, uint32_t v1, uint32_t n) {
+    d &= EX2_MASK;
+    if (d + 8 <= EX2_RING) {
+        uint8_t *p = ring + d;
+        if (n > 0) p[0] = (uint8_t)v0;
+        if (n > 1) p[1] = (uint8_t)(v0 >> 8);
+        if (n > 2) p[2] = (uint8_t)(v0 >> 16);
+        if (n > 3) p[3] = (uint8_t)(v0 >> 24);
+        if (n > 4) p[4] = (uint8_t)v1;
+        if (n > 5) p[5] = (uint8_t)(v1 >> 8);
+        if (n > 6) p[6] = (uint8_t)(v1 >> 16);
+        if (n > 7) p[7] = (uint8_t)(v1 >> 24);
+    } else {
+        const uint64_t v = ((uint64_t)v1 << 32) | v0;
+        for (uint32_t t = 0; t < n; t++) ring[(d + t) & EX2_MASK] = (uint8_t)(v >> (8 * t));
+    }
+}
+// n (<= 8) bytes starting at ring position s (unmasked)
+__device__ __forceinline__ void ex2_load8_ring(const uint8_t *ring, uint32_t s, uint32_t n, uint32_t &v0, uint32_t &v1) {
+    const uint32_t a = s & EX2_MASK & ~3u, sh = (s & 3u) * 8u;
+    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(ring + a);
+    const uint32_t w1 = *reinterpret_cast<const uint32_t *>(ring + ((a + 4) & EX2_MASK));
+    const uint32_t w2 = *reinterpret_cast<const uint32_t *>(ring + ((a + 8) & EX2_MASK));
+    v0 = __funnelshift_r(w0, w1, sh); v1 = __funnelshift_r(w1, w2, sh);
+}
+// n (<= 8) bytes starting at global address g; only words that hold a wanted byte are touched
+__device__ __forceinline__ void ex2_load8_glob(const uint8_t *g, uint32_t n, uint32_t &v0, uint32_t &v1, bool cg) {
+    const uint32_t m = (uint32_t)(uintptr_t)g & 3u, sh = m * 8u;
+    const uint32_t *a = reinterpret_cast<const uint32_t *>(g - m);
+    uint32_t w0, w1 = 0, w2 = 0;
+    if (cg) { w0 = __ldcg(a); if (m + n > 4) w1 = __ldcg(a + 1); if (m + n > 8) w2 = __ldcg(a + 2); }
+    else { w0 = __ldg(a); if (m + n > 4) w1 = __ldg(a + 1); if (m + n > 8) w2 = __ldg(a + 2); }
+    v0 = __funnelshift_r(w0, w1, sh); v1 = __funnelshift_r(w1, w2, sh);
+}
+
 __global__ void __launch_bounds__(32 * EX2_WARPS, 8) k_exec2(const uint8_t *__restrict__ src, const zsb_frame *__restrict__ frames,
                                                              const zsb_block *__restrict__ blocks, const ZsbBlockWork *__restrict__ work,
                                                              ZsbFrameOut *fout, const uint32_t *__restrict__ exec_list, uint32_t n,
@@ -690,8 +733,14 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 8) k_exec2(const uint8_t *__re
                 }
                 ring_lo = max(ring_lo, (int32_t)B1 - (int32_t)EX2_RING);
                 // ---- literals (no dependency on earlier output, decoding_context.rs:92-93)
-                if (ll && ll <= EX2_LONG)
-                    for (uint32_t q = 0; q < ll; q++) ring[(g0 + p_out + q) & EX2_MASK] = ex2_lit(L, p_lit + q);
+                if (ll && ll <= EX2_LONG) {
+                    if (L.is_rle) { const uint32_t v = L.rle * 0x01010101u; for (uint32_t q = 0; q < ll; q += 8) ex2_store8(ring, g0 + p_out + q, v, v, min(ll - q, 8u)); }
+                    else for (uint32_t q = 0; q < ll; q += 8) {
+                        const uint32_t c = min(ll - q, 8u); uint32_t v0, v1;
+                        ex2_load8_glob(L.p + p_lit + q, c, v0, v1, false);
+                        ex2_store8(ring, g0 + p_out + q, v0, v1, c);
+                    }
+                }
                 for (uint32_t m = __ballot_sync(FULL, ll > EX2_LONG); m; m &= m - 1) {
                     const int j = __ffs(m) - 1;
                     const uint32_t jo = __shfl_sync(FULL, p_out, j), jll = __shfl_sync(FULL, ll, j), jl = __shfl_sync(FULL, p_lit, j);
@@ -709,11 +758,20 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 8) k_exec2(const uint8_t *__re
                     const int32_t done = (int32_t)__shfl_sync(FULL, dstm, __ffs(pm) - 1);
                     const bool ready = pend && need <= done;
                     if (ready && ml <= EX2_LONG) {
-                        if (srcp >= ring_lo) {
-                            for (uint32_t q = 0; q < ml; q++) ring[(g0 + dstm + q) & EX2_MASK] = ring[(g0 + (uint32_t)srcp + q) & EX2_MASK];
-                        } else if (send <= ring_lo) {
-#pragma unroll 4
-                            for (uint32_t q = 0; q < ml; q++) ring[(g0 + dstm + q) & EX2_MASK] = __ldcg(gblk + srcp + (int32_t)q);
+                        if (off < 8 && off < ml) {                     // overlapping with a short period: byte by byte
+                            for (uint32_t q = 0; q < ml; q++) ring[(g0 + dstm + q) & EX2_MASK] = ex2_src(ring, gblk, g0, ring_lo, srcp + (int32_t)q);
+                        } else if (srcp >= ring_lo) {                  // source still in the ring; a unit never reads what it writes (off >= 8)
+                            for (uint32_t q = 0; q < ml; q += 8) {
+                                const uint32_t c = min(ml - q, 8u); uint32_t v0, v1;
+                                ex2_load8_ring(ring, g0 + (uint32_t)srcp + q, c, v0, v1);
+                                ex2_store8(ring, g0 + dstm + q, v0, v1, c);
+                            }
+                        } else if (send <= ring_lo) {                  // source already in HBM only
+                            for (uint32_t q = 0; q < ml; q += 8) {
+                                const uint32_t c = min(ml - q, 8u); uint32_t v0, v1;
+                                ex2_load8_glob(gblk + srcp + (int32_t)q, c, v0, v1, true);
+                                ex2_store8(ring, g0 + dstm + q, v0, v1, c);
+                            }
                         } else {
                             for (uint32_t q = 0; q < ml; q++) ring[(g0 + dstm + q) & EX2_MASK] = ex2_src(ring, gblk, g0, ring_lo, srcp + (int32_t)q);
                         }
@@ -768,26 +826,81 @@ __device__ __forceinline__ uint64_t ld64_any(const uint8_t *p) {
     uint64_t w1 = __ldcg(q + 1);
     return (w0 >> sh) | (w1 << (64 - sh));
 }
-// Four lanes per frame: lane q owns accumulator v(q+1) and reads 8 of every 32 bytes.
-__global__ void __launch_bounds__(128) k_xxh(const uint8_t *__restrict__ dst, ZsbFrameOut *fout, const uint32_t *__restrict__ list,
-                                             uint32_t n, const ZsbCounters *__restrict__ cnt) {
+// XXH64 has no combine step: a frame is four dependent accumulator chains over its 32-byte stripes
+// (round = rotl(acc + x*P2, 31) * P1, ~25 cycles), so a frame is four lanes and the kernel is bound by that
+// chain as long as the bytes arrive in time.  One warp hashes 8 frames (4 lanes each).  The frames' bytes are
+// staged through shared memory with cp.async, 512 bytes per frame and step, double buffered: coalesced 16-byte
+// requests, no registers held across the latency, and the lanes read their 8 bytes per stripe from shared memory
+// at any alignment (two aligned 64-bit loads and a funnel).
+#define XXH_FRAMES 8                 // frames per warp
+#define XXH_CHUNK 512u               // bytes of one frame staged per step (16 stripes)
+#define XXH_BUF 544u                 // chunk + 16 bytes of overhang for unaligned frames, padded to spread the banks
+#define XXH_WARPS 4
+__global__ void __launch_bounds__(32 * XXH_WARPS) k_xxh(const uint8_t *__restrict__ dst, ZsbFrameOut *fout, const uint32_t *__restrict__ list,
+                                                        uint32_t n, const ZsbCounters *__restrict__ cnt) {
+    __shared__ __align__(16) uint8_t s_buf[XXH_WARPS][2][XXH_FRAMES][XXH_BUF];
+    __shared__ unsigned long long s_pal[XXH_WARPS][XXH_FRAMES];     // 16-byte aligned base of each frame
+    __shared__ uint32_t s_tot[XXH_WARPS][XXH_FRAMES];               // bytes to stage from that base (stripes only)
     if (cnt->overflow) return;
-    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x, gq = gt >> 2, q = gt & 3, lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = lane & 3, fj = lane >> 2;
+    const uint32_t gq = (blockIdx.x * XXH_WARPS + warp) * XXH_FRAMES + fj;
     const bool active = gq < n;
     const uint32_t f = active ? list[gq] : 0;
     const bool ok = active && fout[f].status == ZSB_OK;
     const uint8_t *p = dst + (ok ? fout[f].dst_off : 0);
     const uint64_t len = ok ? fout[f].dst_len : 0;
-    uint64_t v = q == 0 ? XP1 + XP2 : q == 1 ? XP2 : q == 2 ? 0ull : 0ull - XP1;
     const uint64_t nstripes = len >> 5;
-    const uint8_t *pp = p + 8 * q;
-    uint64_t i = 0;
-    for (; i + 4 <= nstripes; i += 4) {
-        const uint64_t x0 = ld64_any(pp), x1 = ld64_any(pp + 32), x2 = ld64_any(pp + 64), x3 = ld64_any(pp + 96);
-        v = xround(v, x0); v = xround(v, x1); v = xround(v, x2); v = xround(v, x3);
-        pp += 128;
+    const uint32_t m = (uint32_t)(uintptr_t)p & 15u;
+    // a frame longer than 4 GiB would overflow the 32-bit staging offsets: hash it in 2 GiB sections
+    uint64_t v = q == 0 ? XP1 + XP2 : q == 1 ? XP2 : q == 2 ? 0ull : 0ull - XP1;
+    const uint64_t SECT = 1ull << 26;                               // stripes per section (2 GiB)
+    for (uint64_t s0 = 0; __any_sync(FULL, s0 < nstripes); s0 += SECT) {
+        const uint64_t left = s0 < nstripes ? nstripes - s0 : 0;
+        const uint32_t ns = (uint32_t)(left < SECT ? left : SECT);  // stripes of this section for this frame
+        const uint8_t *ps = p + (s0 << 5);
+        __syncwarp();
+        if (q == 0) { s_pal[warp][fj] = (unsigned long long)(uintptr_t)(ps - m); s_tot[warp][fj] = ns ? m + (ns << 5) : 0u; }
+        __syncwarp();
+        uint32_t nch = (ns + 15) >> 4;                              // steps this frame needs
+#pragma unroll
+        for (int d = 16; d; d >>= 1) nch = max(nch, __shfl_xor_sync(FULL, nch, d));
+        const uint32_t sh = (m & 7u) * 8u;
+        // stage step c of all 8 frames into buffer b: lane l copies 16-byte unit l of every frame, lane 0 also the overhang unit
+        auto stage = [&](uint32_t c, uint32_t b) {
+#pragma unroll
+            for (int j = 0; j < XXH_FRAMES; j++) {
+                const uint8_t *g = reinterpret_cast<const uint8_t *>((uintptr_t)s_pal[warp][j]);
+                const uint32_t tot = s_tot[warp][j];
+                const uint32_t A = c * XXH_CHUNK + 16u * lane;
+                const uint32_t sa = (uint32_t)__cvta_generic_to_shared(&s_buf[warp][b][j][16u * lane]);
+                const uint32_t sz = A < tot ? 16u : 0u;             // 0: nothing is read from global, the unit is zero filled
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(g + (sz ? A : 0u)), "r"(sz) : "memory");
+                if (lane == 0) {
+                    const uint32_t A2 = c * XXH_CHUNK + XXH_CHUNK, sz2 = A2 < tot ? 16u : 0u;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sa + XXH_CHUNK), "l"(g + (sz2 ? A2 : 0u)), "r"(sz2) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (nch) stage(0, 0);
+        for (uint32_t c = 0; c < nch; c++) {
+            __syncwarp();                                           // buffer (c+1)&1 was fully read in step c-1
+            if (c + 1 < nch) { stage(c + 1, (c + 1) & 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const uint8_t *bp = &s_buf[warp][c & 1][fj][0];
+            const uint32_t s_lo = c << 4;
+#pragma unroll 4
+            for (uint32_t s = 0; s < 16; s++) {
+                if (s_lo + s < ns) {
+                    const uint32_t B = m + 32u * s + 8u * q;
+                    const unsigned long long *w = reinterpret_cast<const unsigned long long *>(bp + (B & ~7u));
+                    const uint64_t x = zsb_shr64(w[0], sh) | zsb_shl64(w[1], 64 - sh);
+                    v = xround(v, x);
+                }
+            }
+        }
     }
-    for (; i < nstripes; i++) { v = xround(v, ld64_any(pp)); pp += 32; }
     __syncwarp();
     const uint32_t qb = lane & ~3u;
     const uint64_t v1 = __shfl_sync(FULL, v, qb), v2 = __shfl_sync(FULL, v, qb + 1), v3 = __shfl_sync(FULL, v, qb + 2), v4 = __shfl_sync(FULL, v, qb + 3);
@@ -900,7 +1013,7 @@ void zsbk_exec2(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame
     if (n) k_exec2<<<(n + EX2_WARPS - 1) / EX2_WARPS, 32 * EX2_WARPS, 0, st>>>(src, frames, blocks, work, fout, exec_list, n, cnt, seq_pool, lit_pool, dst);
 }
 void zsbk_xxh(cudaStream_t st, uint32_t n, const uint8_t *dst, ZsbFrameOut *fout, const uint32_t *list, const ZsbCounters *cnt) {
-    if (n) k_xxh<<<(n * 4 + 127) / 128, 128, 0, st>>>(dst, fout, list, n, cnt);
+    if (n) k_xxh<<<(n + XXH_WARPS * XXH_FRAMES - 1) / (XXH_WARPS * XXH_FRAMES), 32 * XXH_WARPS, 0, st>>>(dst, fout, list, n, cnt);
 }
 void zsbk_stage_fse(cudaStream_t st, const uint8_t *desc, uint32_t n, int max_sym, const int16_t *dist_in, int ndist_in, int al_in,
                     int *res, uint32_t *cells, int16_t *dist_out) {

@@ -18,7 +18,7 @@
 
 ZSB_HDN void parse_block(const uint8_t *src, const zsb_block &blk, ZsbBlockWork &w, uint32_t flags) {
     const bool quirks = (flags & ZSB_REFERENCE_QUIRKS) != 0;
-    w.status = ZSB_OK; w.err_a = w.err_b = 0;
+    w.status = ZSB_OK; w.lit_status = ZSB_OK; w.err_a = w.err_b = 0; w.seq_rem0 = 0;
     w.nseq = 0; w.lit_type = ZSB_LT_NONE; w.lit_regen = 0; w.n_streams = 0; w.raw_modes = 0;
     w.lit_used = 0; w.out_off = 0; w.lit_buf = 0; w.seq_buf = 0;
     w.mode[0] = w.mode[1] = w.mode[2] = ZSB_M_REPEAT;
@@ -185,6 +185,7 @@ ZSB_HDN int plan_frame(const zsb_frame &fr, const zsb_block *blocks, ZsbBlockWor
     for (uint32_t k = 0; k < fr.n_blocks; k++) {
         const uint32_t bi = fr.first_block + k;
         ZsbBlockWork &w = work[bi];
+        if (w.lit_status != ZSB_OK) { total = pos; return w.lit_status; }       // Block::decode: literals first (block.rs:83-85)
         if (w.status != ZSB_OK) { total = pos; return w.status; }
         w.out_off = pos;
         w.rep_in[0] = rep[0]; w.rep_in[1] = rep[1]; w.rep_in[2] = rep[2];

@@ -20,8 +20,8 @@
 // seq_decode (zsb_seq.h), which reproduces the reference's error order exactly.
 #pragma once
 #include "zsb_seq.h"
+#include "zsb_stream.h"
 
-#define ZSB_NEEDS_SLOW (-1)
 
 // phase-1 word, one byte per field: LL code | OF code | ML code | state bits consumed (LL+ML+OF).
 // The code bytes carry two stray high bits (the low bits of the cell's base field): mask with 63.
@@ -29,23 +29,6 @@
 #define ZSB_W_CO(w) (((w) >> 8) & 63u)
 #define ZSB_W_CM(w) (((w) >> 16) & 63u)
 #define ZSB_W_NB(w) (((w) >> 24) & 31u)
-ZSB_HD uint32_t zsb_prmt(uint32_t a, uint32_t b, uint32_t sel) {      // PTX prmt.b32, default mode
-#if defined(__CUDA_ARCH__)
-    return __byte_perm(a, b, sel);
-#else
-    const uint64_t v = ((uint64_t)b << 32) | a; uint32_t r = 0;
-    for (int k = 0; k < 4; k++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * k)) & 7))) & 0xFF) << (8 * k);
-    return r;
-#endif
-}
-// high word of (hi:lo) << (n & 31)
-ZSB_HD uint32_t zsb_fsl(uint32_t lo, uint32_t hi, uint32_t n) {
-#if defined(__CUDA_ARCH__)
-    return __funnelshift_l(lo, hi, n);
-#else
-    n &= 31; return n ? (hi << n) | (lo >> (32 - n)) : hi;
-#endif
-}
 ZSB_HD uint32_t seq_fast_word(uint32_t eL, uint32_t eO, uint32_t eM, uint32_t nbs) {
     return zsb_prmt(zsb_prmt(eL, eO, 0x0062), zsb_prmt(eM, nbs, 0x0042), 0x5410);
 }
@@ -53,14 +36,6 @@ ZSB_HD uint32_t seq_fast_word(uint32_t eL, uint32_t eO, uint32_t eM, uint32_t nb
 // code -> baseline | extra bits << 24 (sequence.rs:98-191)
 ZSB_HD uint32_t zsb_ll_entry(uint32_t c) { return zsb_ll_base(c) | (zsb_ll_bits(c) << 24); }
 ZSB_HD uint32_t zsb_ml_entry(uint32_t c) { return zsb_ml_base(c) | (zsb_ml_bits(c) << 24); }
-
-// `need` (<= 63) stream bits starting at absolute bit a >= 0, in the low bits of the result
-ZSB_HD uint64_t fast_win_at(const uint8_t *base8, int64_t a, uint32_t need) {
-    const int64_t wi = a >> 6; const uint32_t sh = (uint32_t)(a & 63);
-    const uint64_t lo = zsb_ld64(base8, wi);
-    const uint64_t hi = (sh + need > 64) ? zsb_ld64(base8, wi + 1) : 0ull;
-    return zsb_shr64(lo, sh) | zsb_shl64(hi, 64 - sh);
-}
 
 // ---- phase 1 ---------------------------------------------------------------------------------------
 // Walks the three-state chain of block w and writes words[0..nseq) (stride ws).  rem0 = unread bits
@@ -72,70 +47,27 @@ ZSB_HD uint64_t fast_win_at(const uint8_t *base8, int64_t a, uint32_t need) {
 // the first stream byte, so that the 64-bit window ending at any position inside the stream starts at
 // a non-negative bit.  The two window words of the next step are requested as soon as the bit count of
 // the current one is known and are only combined after the next step's table cells were requested.
-struct FastWin { uint64_t lo, hi; uint32_t sh; };
-ZSB_HD void fast_win_load(FastWin &f, const uint8_t *pw, int32_t top) {
-    int32_t a = top - 64; a = a < 0 ? 0 : a;        // below the stream only after an over-read (reported at the end)
-    const uint32_t wi = (uint32_t)a >> 6;
-    f.sh = (uint32_t)a & 63u;
-    f.lo = zsb_ld64(pw, wi);
-    f.hi = f.sh ? zsb_ld64(pw, wi + 1) : 0ull;      // word wi+1 holds bit top-1, a stream bit, exactly when sh != 0
-}
-ZSB_HD uint64_t fast_win_get(const FastWin &f) { return zsb_shr64(f.lo, f.sh) | zsb_shl64(f.hi, 64 - f.sh); }
-
-#if defined(__CUDA_ARCH__)
-__device__ __forceinline__ uint32_t zsb_lds32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint64_t zsb_lds64v(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
-
-// The bitstream of one lane staged through a 512-byte shared-memory ring of four 128-byte lines, filled with
-// cp.async two lines ahead of the (backward moving) cursor: the window loads of the chain become shared-memory
-// loads with a fixed latency instead of global loads whose misses would stall every chain of the warp.
-// Bit positions are relative to `pl`, a 128-byte aligned address at least 8 bytes below the stream.
-struct StreamRing { uint32_t sa; const uint8_t *pl; int32_t low; };   // ring address, line base, lowest line requested
-__device__ __forceinline__ void sr_fetch(const StreamRing &r, int32_t line) {
-    const uint8_t *g = r.pl + (size_t)(uint32_t)line * 128u;
-    const uint32_t d = r.sa + ((uint32_t)line & 3u) * 128u;
-#pragma unroll
-    for (int k = 0; k < 8; k++) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 16 * k), "l"(g + 16 * k) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void sr_init(StreamRing &r, int32_t top) {
-    const int32_t l0 = (top - 1) >> 10;
-    r.low = l0 - 2 < 0 ? 0 : l0 - 2;
-    for (int32_t l = l0; l >= r.low; l--) sr_fetch(r, l);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-// window words for the 64 bits ending at `top`; entering line X requests line X-2 and waits for X-1
-__device__ __forceinline__ void sr_load(StreamRing &r, FastWin &f, int32_t top) {
-    int32_t a = top - 64; a = a < 0 ? 0 : a;          // below the stream only after an over-read (reported at the end)
-    const uint32_t wi = (uint32_t)a >> 6;
-    f.sh = (uint32_t)a & 63u;
-    if ((int32_t)(wi >> 4) <= r.low + 1 && r.low > 0) { r.low--; sr_fetch(r, r.low); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-    f.lo = zsb_lds64v(r.sa + (wi & 63u) * 8u);
-    f.hi = f.sh ? zsb_lds64v(r.sa + ((wi + 1) & 63u) * 8u) : 0ull;
-}
-#endif
-
 ZSB_HDN int seq_fast_phase1(const uint8_t *src, const ZsbBlockWork &w, const SeqTables &T, uint32_t *words, int ws, uint32_t &rem0,
                             uint32_t ring_sa) {
     const uint64_t start = w.bs_off, end = w.bs_off + w.bs_len;
     if (end <= start) return ZSB_E_EMPTY_INPUT_DATA;
     const uint32_t lastb = src[end - 1];
     if (lastb == 0) return ZSB_E_NULL_BYTE;
-    if (start < 8 || w.bs_len > (1u << 24)) return ZSB_NEEDS_SLOW;            // no word below the stream / positions would not fit
+    if (start < 16 || w.bs_len > (1u << 24)) return ZSB_NEEDS_SLOW;            // no word below the stream / positions would not fit
     const uint32_t a0 = (uint32_t)T.al[0], a1 = (uint32_t)T.al[1], a2 = (uint32_t)T.al[2];
     const uint32_t nseq = w.nseq;
     FastWin F;
 #if defined(__CUDA_ARCH__)
     StreamRing R;
     R.sa = ring_sa;
-    R.pl = (const uint8_t *)(((uintptr_t)(src + start) - 8) & ~(uintptr_t)127);
-    const uint32_t d0 = (uint32_t)((src + start) - R.pl);                     // 8 .. 135
+    R.pl = (const uint8_t *)(((uintptr_t)(src + start) - 16) & ~(uintptr_t)127);
+    const uint32_t d0 = (uint32_t)((src + start) - R.pl);                     // 16 .. 143
     int32_t top = (int32_t)((d0 + w.bs_len - 1) * 8) + zsb_flog2(lastb);
     const int32_t startbit = (int32_t)(d0 * 8);
     if (top - startbit < (int32_t)(a0 + a1 + a2)) return ZSB_E_NOT_ENOUGH_BITS;
-    sr_init(R, top);
-    sr_load(R, F, top);
-#define FAST_LOAD(t_) sr_load(R, F, t_)
+    sr_init<7>(R, top);
+    sr_load<7>(R, F, top);
+#define FAST_LOAD(t_) sr_load<7>(R, F, t_)
 #else
     (void)ring_sa;
     const uint32_t mis = (uint32_t)((uintptr_t)src & 7);
