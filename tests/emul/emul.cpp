@@ -24,7 +24,7 @@ static void check_fast_path(const uint8_t *src, const ZsbBlockWork &w0, const Se
     std::vector<uint32_t> words((size_t)w0.nseq * WS + 1, 0xABABABAB);
     uint32_t rem0 = 0;
     g_fast_ran++;
-    int rc = seq_fast_phase1(src, w0, T, words.data(), WS, rem0, 0);
+    int rc = seq_fast_phase1(src, w0, T, words.data(), WS, rem0);
     if (rc > 0) { if (rc == careful_rc) g_fast_same++; else g_fast_diff++; return; }
     int bad = 0;
     std::vector<uint64_t> rec(w0.nseq, 0);

@@ -37,7 +37,7 @@ struct zsb_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr, aux_stream = nullptr;   // aux: the literals stage runs beside the sequence stage
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_huf[kProfRing][2] = {};
-    DevBuf src, frames, blocks, work, fout, huf_list, seq_list, rawrle_list, exec_list, exec2_list, xxh_list, lit_pool, seq_pool, word_pool, slow_list, counters, dst, stage;
+    DevBuf src, frames, blocks, work, fout, huf_list, seq_list, rawrle_list, exec_list, exec2_list, xxh_list, lit_pool, seq_pool, slow_list, counters, dst, stage;
     std::string last_err;
     // prepared batch
     const uint8_t *d_src = nullptr; uint8_t *d_dst = nullptr; uint8_t *h_dst = nullptr;
@@ -47,7 +47,7 @@ struct zsb_ctx {
     std::vector<zsb_frame> h_frames;
     std::vector<uint32_t> h_xxh_list;
     bool prepared = false, launched = false;
-    bool overlap = true;       // literals stage on the auxiliary stream (ZSB_NO_OVERLAP=1 serialises it for per-kernel timing)
+    bool overlap = false;      // ZSB_OVERLAP=1: literals stage on the auxiliary stream beside k_seq (measured slower: both are latency bound and share schedulers)
     // profiling
     bool profile = false;
     cudaEvent_t ev[kProfRing][kMaxKernels + 1] = {};
@@ -70,7 +70,7 @@ extern "C" int zsb_ctx_create(zsb_ctx **out, int device) {
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         zsbk_init() != cudaSuccess) { (void)cudaGetLastError(); delete c; return ZSB_E_CUDA; }
     c->stream = c->own_stream;
-    { const char *e = getenv("ZSB_NO_OVERLAP"); c->overlap = !(e && *e && *e != '0'); }
+    { const char *e = getenv("ZSB_OVERLAP"); c->overlap = e && *e && *e != '0'; }
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) cudaEventCreate(&c->ev[r][i]);
     for (int r = 0; r < kProfRing; r++) { cudaEventCreate(&c->ev_huf[r][0]); cudaEventCreate(&c->ev_huf[r][1]); }
     if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -83,7 +83,7 @@ extern "C" void zsb_ctx_destroy(zsb_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list, &c->exec2_list,
-                     &c->xxh_list, &c->lit_pool, &c->seq_pool, &c->word_pool, &c->slow_list, &c->counters, &c->dst, &c->stage};
+                     &c->xxh_list, &c->lit_pool, &c->seq_pool, &c->slow_list, &c->counters, &c->dst, &c->stage};
     for (DevBuf *b : all) b->release();
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) if (c->ev[r][i]) cudaEventDestroy(c->ev[r][i]);
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i < 2; i++) if (c->ev_huf[r][i]) cudaEventDestroy(c->ev_huf[r][i]);
@@ -184,7 +184,6 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     CK(c, c->counters.ensure(sizeof(ZsbCounters)));
     CK(c, c->lit_pool.ensure(c->lit_cap + 64));
     CK(c, c->seq_pool.ensure(8 * (c->seq_cap + 8)));
-    CK(c, c->word_pool.ensure(4 * (c->seq_cap + 8)));
     if (nf) CK(c, cudaMemcpyAsync(c->frames.p, frames, sizeof(zsb_frame) * nf, cudaMemcpyHostToDevice, st));
     if (nb) CK(c, cudaMemcpyAsync(c->blocks.p, blocks, sizeof(zsb_block) * nb, cudaMemcpyHostToDevice, st));
     if (!rawrle.empty()) CK(c, cudaMemcpyAsync(c->rawrle_list.p, rawrle.data(), 4 * rawrle.size(), cudaMemcpyHostToDevice, st));
@@ -211,20 +210,18 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     MARK(c, "k_parse");  zsbk_parse(st, src, blocks, work, c->nb, c->flags); c->launches += c->nb ? 1 : 0;
     MARK(c, "k_plan1");  zsbk_plan1(st, frames, c->nf, blocks, c->nb, work, fout, (uint32_t *)c->huf_list.p, (uint32_t *)c->seq_list.p, cnt,
                                     c->lit_cap, c->seq_cap, c->flags); c->launches++;
-    // the literals stage (k_huf) and the sequence stage (k_seq1/2) read the same blocks and write disjoint results: both are
-    // latency bound, so they share the SMs.  k_seq1 is enqueued first: its CTAs need the larger shared-memory slice.
+    // the literals stage (k_huf) and the sequence stage (k_seq) read the same blocks and write disjoint results; with ZSB_OVERLAP=1
+    // k_huf runs on the auxiliary stream beside k_seq (enqueued first: its CTAs need the larger shared-memory slice).
     cudaStream_t hst = c->overlap ? c->aux_stream : st;
     CK(c, cudaEventRecord(c->ev_fork, st));
     CK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-    MARK(c, "k_seq1");   zsbk_seq1(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint32_t *)c->word_pool.p, (uint32_t *)c->slow_list.p);
+    MARK(c, "k_seq");    zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p);
     if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][0], hst);
     zsbk_huf(hst, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags); c->launches += c->ncomp ? 1 : 0;
     if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][1], hst);
     CK(c, cudaEventRecord(c->ev_join, c->aux_stream));
-    MARK(c, "k_seq2");   zsbk_seq2(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (const uint32_t *)c->word_pool.p, (uint64_t *)c->seq_pool.p,
-                                   (uint32_t *)c->slow_list.p);
     MARK(c, "k_seq_slow"); zsbk_seq_slow(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->slow_list.p, cnt, (uint64_t *)c->seq_pool.p);
-    c->launches += c->ncomp ? 3 : 0;
+    c->launches += c->ncomp ? 2 : 0;
     MARK(c, "wait k_huf"); CK(c, cudaStreamWaitEvent(st, c->ev_join, 0));
     MARK(c, "k_plan2");  zsbk_plan2(st, frames, c->nf, blocks, work, fout, cnt, c->dst_cap, c->flags); c->launches++;
     MARK(c, "k_rawrle"); zsbk_rawrle(st, c->n_rawrle, src, blocks, work, fout, (const uint32_t *)c->rawrle_list.p, cnt, c->d_dst); c->launches += c->n_rawrle ? 1 : 0;
@@ -254,8 +251,7 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
         c->lit_cap = hc.lit_total + 64; c->seq_cap = hc.seq_total + 8;
         CK(c, c->lit_pool.ensure(c->lit_cap + 64));
         CK(c, c->seq_pool.ensure(8 * (c->seq_cap + 8)));
-        CK(c, c->word_pool.ensure(4 * (c->seq_cap + 8)));
-        int rc = zsb_decode_launch(c);
+            int rc = zsb_decode_launch(c);
         if (rc) return rc;
     }
     if (c->profile) { const int r = (c->prof_slot + kProfRing - 1) % kProfRing; for (int i = 0; i < c->nk; i++) cudaEventElapsedTime(&c->kms[i], c->ev[r][i], c->ev[r][i + 1]); }

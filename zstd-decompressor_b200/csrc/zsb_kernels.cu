@@ -5,8 +5,8 @@
 //   k_parse   1 lane / block      section headers                       (literals.rs:135-206, sequences.rs:52-143)
 //   k_plan1   1 CTA               per-frame table/tree chaining + scratch placement (scan) + work lists
 //   k_huf     1 lane / stream     Huffman weights -> LUT (smem) -> 4-stream literal decode   (huffman.rs, literals.rs:49-86)
-//   k_seq1    1 lane / block      FSE tables (interleaved smem) + the serial 3-state chain      (fse.rs, sequence.rs, sequences.rs:191-237)
-//   k_seq2    1 lane / sequence   extra bits, positions, repeat-offset history -> packed records (sequence.rs:41-55, decoding_context.rs:50-75)
+//   k_seq     1 lane / block      FSE tables (interleaved smem) + the serial 3-state chain      (fse.rs, sequence.rs, sequences.rs:191-237)
+//           + 1 lane / sequence   extra bits, positions, repeat-offset history -> packed records (sequence.rs:41-55, decoding_context.rs:50-75)
 //   k_seq_slow 1 lane / block     careful decoder for blocks the fast path handed over (exact error order)
 //   k_plan2   1 CTA               block/frame output offsets (scan), repeat-offset history, size checks
 //   k_rawrle  1 CTA / block       raw / RLE block expansion, skippable payloads              (block.rs:76-79)
@@ -162,126 +162,259 @@ __global__ void __launch_bounds__(32) k_huf(const uint8_t *__restrict__ src, uin
     }
 }
 
-// ======================================================================================= k_seq1 / k_seq2 / k_seq_slow
-// The sequence stage in two phases (zsb_seqfast.h).
+// ======================================================================================= k_seq / k_seq_slow
+// The sequence stage in two phases (zsb_seqfast.h), fused in one CTA:
 //
-// k_seq1: the serial three-state FSE chain, one lane per block, SEQ1_LANES blocks per one-warp CTA.  The chain is
-// latency bound (table cell -> bit count -> bit position -> next state: one shared-memory load and ~8
-// dependent ALU operations per sequence), so the kernel wants as many independent chains per scheduler as the
-// batch offers and as few instructions on the chain as possible: tables interleaved across the lanes of the
-// CTA (cell i of lane l at word i*SEQ1_LANES + l: bank = 8*(i%4) + l, conflict free), the bit window reloaded
-// from L1 every step (two aligned 64-bit loads, off the chain), one 32-bit word out per sequence.
+//   warp 0 (producer)  the serial three-state FSE chain, one lane per block, SEQ_CHAINS blocks per CTA.  The chain is
+//                      latency bound (table cell -> bit count -> bit position -> next state: one shared-memory load and
+//                      ~8 dependent ALU operations per sequence), so it carries as little else as possible: tables
+//                      interleaved across the lanes (cell i of lane l at word i*SEQ_CHAINS + l: bank = 8*(i%4) + l,
+//                      conflict free), the bit window fed from a cp.async stream ring, one 32-bit word per sequence
+//                      into a shared-memory ring.
+//   warps 1..H (phase 2) one lane per sequence, 32 sequences per step and block: bit positions, extra-bit values,
+//                      literal/output positions and the repeat-offset history by warp prefix operations; packed
+//                      records to HBM.  They run in the issue slots the producers leave empty (~70 %).
+//
+// Hand-over: the chains advance in lockstep, 32 sequences (one batch per chain) at a time; the word ring holds two
+// batches per chain; named barriers (full / free, two of each) pass the batches on, so a waiting warp costs no issue slot.
 #define SEQ_TBL_CELLS 512
-#define SEQ1_LANES 8
-#define SEQ1_OF_CELLS 256     // offset tables have accuracy log <= 8 (RFC 8878); a log-9 one (the reference accepts it) takes the careful path
-#define SEQ1_TBL_BYTES ((2 * SEQ_TBL_CELLS + SEQ1_OF_CELLS) * SEQ1_LANES * 4)
-#define SEQ1_SMEM_BYTES (SEQ1_TBL_BYTES + 256 * SEQ1_LANES * 2)     // counts (table build), then the stream rings (512 B per lane)
-__global__ void __launch_bounds__(32) k_seq1(const uint8_t *__restrict__ src, ZsbBlockWork *work, const uint32_t *__restrict__ seq_list,
-                                             ZsbCounters *cnt, uint32_t *word_pool, uint32_t *slow_list) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    if (cnt->overflow) return;
-    uint32_t *tbl = reinterpret_cast<uint32_t *>(smem);
-    int16_t *counts = reinterpret_cast<int16_t *>(smem + SEQ1_TBL_BYTES);
-    const uint32_t lane = threadIdx.x;
-    const uint32_t n = cnt->n_seq, idx = blockIdx.x * SEQ1_LANES + lane;
-    bool active = lane < SEQ1_LANES && idx < n;
-    const uint32_t bi = active ? seq_list[idx] : 0;
-    ZsbBlockWork w;
-    if (active) { w = work[bi]; active = w.status == ZSB_OK; }
-    SeqTables T;
-    T.ts = SEQ1_LANES;
-    T.tbl[0] = tbl + lane; T.tbl[1] = tbl + SEQ_TBL_CELLS * SEQ1_LANES + lane; T.tbl[2] = tbl + (SEQ_TBL_CELLS + SEQ1_OF_CELLS) * SEQ1_LANES + lane;
-    T.max_al[0] = 9; T.max_al[1] = 8; T.max_al[2] = 9;
-    int rc = ZSB_OK;
-    if (active) rc = seq_build_tables(src, w, T, counts + lane, SEQ1_LANES);
-    __syncwarp();                                  // the count area becomes the stream rings
-    if (!active) return;
-    uint32_t rem0 = 0;
-    if (!rc) rc = seq_fast_phase1(src, w, T, word_pool + w.seq_buf, 1, rem0, (uint32_t)__cvta_generic_to_shared(smem + SEQ1_TBL_BYTES) + lane * 512u);
-    if (rc == ZSB_TABLE_TOO_SMALL) rc = ZSB_NEEDS_SLOW;
-    if (rc == ZSB_NEEDS_SLOW) slow_list[atomicAdd(&cnt->n_slow, 1u)] = bi;
-    if (rc) work[bi].status = rc; else work[bi].seq_rem0 = rem0;
-}
+#define SEQ_CHAINS 8
+#define SEQ_HELPERS 8
+#define SEQ_CPH (SEQ_CHAINS / SEQ_HELPERS)       // chains per phase-2 warp
+#define SEQ_OF_CELLS 256      // offset tables have accuracy log <= 8 (RFC 8878); a log-9 one (the reference accepts it) takes the careful path
+#define SEQ_TBL_BYTES ((2 * SEQ_TBL_CELLS + SEQ_OF_CELLS) * SEQ_CHAINS * 4)
+#define SEQ_WSTRIDE 65        // words per chain in the ring (64) + 1 to spread the banks
+struct SeqShared {
+    uint32_t words[SEQ_CHAINS][SEQ_WSTRIDE];
+    uint32_t tab[36 + 53];                       // code -> baseline | extra bits << 24
+    uint32_t nseq[SEQ_CHAINS];                   // 0: chain not running (no block, or it failed before the first sequence)
+    uint32_t regen[SEQ_CHAINS], bi[SEQ_CHAINS];
+    unsigned long long top0[SEQ_CHAINS], rec[SEQ_CHAINS];   // absolute bit position of sequence 0, record pointer
+    int final_rc[SEQ_CHAINS];
+};
+// named barriers of the hand-over (0 is __syncthreads): FULL+parity: batch written, FREE+parity: batch consumed; every thread of the CTA takes part
+#define SEQ_BAR_FULL 1u
+#define SEQ_BAR_FREE 3u
+__device__ __forceinline__ void seq_bar_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(32u * (1 + SEQ_HELPERS)) : "memory"); }
+__device__ __forceinline__ void seq_bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(32u * (1 + SEQ_HELPERS)) : "memory"); }
+#define SEQ_SMEM_FUSED (SEQ_TBL_BYTES + 256 * SEQ_CHAINS * 2 + sizeof(SeqShared))   // tables | counts, then stream rings | hand-over
 
-// k_seq2: one warp per block, one lane per sequence, 32 sequences per step: bit positions, extra-bit values,
-// literal/output positions and the repeat-offset history all by warp prefix operations; packed records out.
-#define SEQ2_WARPS 4
 __device__ __forceinline__ Hist hist_shfl_up(const Hist &h, int d) {
     Hist r; r.h0 = __shfl_up_sync(FULL, h.h0, d); r.h1 = __shfl_up_sync(FULL, h.h1, d); r.h2 = __shfl_up_sync(FULL, h.h2, d); return r;
 }
 __device__ __forceinline__ Hist hist_bcast(const Hist &h, int l) {
     Hist r; r.h0 = __shfl_sync(FULL, h.h0, l); r.h1 = __shfl_sync(FULL, h.h1, l); r.h2 = __shfl_sync(FULL, h.h2, l); return r;
 }
-__global__ void __launch_bounds__(32 * SEQ2_WARPS) k_seq2(const uint8_t *__restrict__ src, ZsbBlockWork *work, const uint32_t *__restrict__ seq_list,
-                                                          ZsbCounters *cnt, const uint32_t *__restrict__ word_pool, uint64_t *seq_pool,
-                                                          uint32_t *slow_list) {
-    __shared__ uint32_t s_tab[36 + 53];
+// phase 2 for 32 consecutive sequences of one block; C carries the block-level state from batch to batch (warp uniform, but `bad`)
+struct Seq2Carry { int64_t top; uint32_t lit_acc, out_acc; Hist H; int bad; };
+__device__ __forceinline__ void seq2_batch(const uint8_t *base8, const uint32_t *tab, uint32_t word, bool valid, uint32_t i, uint32_t regen,
+                                           uint64_t *rec, Seq2Carry &C, uint32_t lane) {
+    // bit position: exclusive prefix of the bits consumed (the extra bits follow from the codes)
+    uint32_t cL = ZSB_W_CL(word), cO = ZSB_W_CO(word), cM = ZSB_W_CM(word);
+    if (cL > ZSB_MAX_LL_CODE || cO > ZSB_MAX_OF_CODE || cM > ZSB_MAX_ML_CODE) { C.bad = 1; cL = cO = cM = 0; }    // sequence.rs:46-48
+    const uint32_t eL = tab[cL], eM = tab[36 + cM];
+    const uint32_t xL = eL >> 24, xM = eM >> 24, px = valid ? xL + xM + cO : 0u;
+    const uint32_t tot = valid ? px + ZSB_W_NB(word) : 0u;
+    uint32_t inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += t; }
+    uint32_t ll = 0, ml = 0, ov = 1;
+    if (valid) {
+        int64_t a = C.top - (int64_t)(inc - tot) - px;
+        if (a < 0) { C.bad = 1; a = 0; }                          // only after an over-read (the producer reports it too)
+        const uint64_t Wx = px ? fast_win_at(base8, a, px) : 0ull;
+        ll = (eL & 0xFFFFFFu) + ((uint32_t)Wx & ((1u << xL) - 1u));
+        ml = (eM & 0xFFFFFFu) + ((uint32_t)(Wx >> xL) & ((1u << xM) - 1u));
+        ov = (1u << cO) + ((uint32_t)(Wx >> (xL + xM)) & ((1u << cO) - 1u));
+    }
+    C.top -= (int64_t)__shfl_sync(FULL, inc, 31);
+    // literal / output positions
+    uint64_t pos = (uint64_t)ll | ((uint64_t)(ll + ml) << 32);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(FULL, pos, d); if (lane >= (uint32_t)d) pos += t; }
+    const uint32_t lit_end = C.lit_acc + (uint32_t)pos, out_end = C.out_acc + (uint32_t)(pos >> 32);
+    if (valid && (lit_end > regen || out_end + (regen - lit_end) > ZSB_BLOCK_MAX)) C.bad = 1;     // decoding_context.rs:86-90, Block_Maximum_Size
+    C.lit_acc = __shfl_sync(FULL, lit_end, 31); C.out_acc = __shfl_sync(FULL, out_end, 31);
+    // repeat-offset history: inclusive prefix over the per-sequence transforms, then the block-level carry
+    Hist G = valid ? hist_of_sequence(ov, ll, C.bad) : hist_identity();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const Hist E = hist_shfl_up(G, d); if (lane >= (uint32_t)d) G = hist_compose(G, E, C.bad); }
+    G = hist_compose(G, C.H, C.bad);
+    C.H = hist_bcast(G, 31);
+    if (valid) rec[i] = (uint64_t)out_end | ((uint64_t)lit_end << ZSB_REC_POS_BITS) | ((uint64_t)G.h0 << (2 * ZSB_REC_POS_BITS));
+}
+
+__global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 4) k_seq(const uint8_t *__restrict__ src, ZsbBlockWork *work, const uint32_t *__restrict__ seq_list,
+                                                                ZsbCounters *cnt, uint64_t *seq_pool, uint32_t *slow_list) {
+    extern __shared__ __align__(128) uint8_t smem[];
     if (cnt->overflow) return;
-    for (uint32_t k = threadIdx.x; k < 36 + 53; k += blockDim.x) s_tab[k] = k < 36 ? zsb_ll_entry(k) : zsb_ml_entry(k - 36);
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, gw = blockIdx.x * SEQ2_WARPS + (threadIdx.x >> 5);
-    if (gw >= cnt->n_seq) return;
-    const uint32_t bi = seq_list[gw];
-    ZsbBlockWork &w = work[bi];
-    if (w.status != ZSB_OK) return;
-    const uint32_t nseq = w.nseq, regen = w.lit_regen;
+    uint32_t *tbl = reinterpret_cast<uint32_t *>(smem);
+    int16_t *counts = reinterpret_cast<int16_t *>(smem + SEQ_TBL_BYTES);
+    SeqShared &S = *reinterpret_cast<SeqShared *>(smem + SEQ_TBL_BYTES + 256 * SEQ_CHAINS * 2);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n = cnt->n_seq;
     const uint32_t mis = (uint32_t)((uintptr_t)src & 7);
     const uint8_t *base8 = src - mis;
-    int64_t top = (int64_t)(w.bs_off + mis) * 8 + w.seq_rem0;
-    const uint32_t *words = word_pool + w.seq_buf;
-    uint64_t *rec = seq_pool + w.seq_buf;
-    uint32_t lit_acc = 0, out_acc = 0;
-    Hist H = hist_identity();
-    int bad = 0;
-    for (uint32_t b0 = 0; b0 < nseq; b0 += 32) {
-        const uint32_t i = b0 + lane;
-        const bool valid = i < nseq;
-        const uint32_t word = valid ? __ldg(words + i) : 0u;
-        // bit position: exclusive prefix of the bits consumed (extra bits follow from the codes)
-        uint32_t cL = ZSB_W_CL(word), cO = ZSB_W_CO(word), cM = ZSB_W_CM(word);
-        if (cL > ZSB_MAX_LL_CODE || cO > ZSB_MAX_OF_CODE || cM > ZSB_MAX_ML_CODE) { bad = 1; cL = cO = cM = 0; }    // sequence.rs:46-48
-        const uint32_t eL = s_tab[cL], eM = s_tab[36 + cM];
-        const uint32_t xL = eL >> 24, xM = eM >> 24, px = valid ? xL + xM + cO : 0u;
-        const uint32_t tot = px + ZSB_W_NB(word);
-        uint32_t inc = tot;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += t; }
-        uint32_t ll = 0, ml = 0, ov = 1;
-        if (valid) {
-            const uint64_t Wx = px ? fast_win_at(base8, top - (int64_t)(inc - tot) - px, px) : 0ull;
-            ll = (eL & 0xFFFFFFu) + ((uint32_t)Wx & ((1u << xL) - 1u));
-            ml = (eM & 0xFFFFFFu) + ((uint32_t)(Wx >> xL) & ((1u << xM) - 1u));
-            ov = (1u << cO) + ((uint32_t)(Wx >> (xL + xM)) & ((1u << cO) - 1u));
+
+    // ---- set-up: the producer lanes build their tables and read the initial states; the other warps fill the code tables
+    SeqTables T;
+    ZsbBlockWork w;
+    bool active = false;
+    uint32_t bi = 0;
+    FastWin F; StreamRing R;
+    int32_t top = 0, startbit = 0;
+    uint32_t aL = 0, aO = 0, aM = 0, tbL = 0, tbO = 0, tbM = 0;
+    if (warp == 0) {
+        const uint32_t idx = blockIdx.x * SEQ_CHAINS + lane;
+        active = lane < SEQ_CHAINS && idx < n;
+        bi = active ? seq_list[idx] : 0;
+        if (active) { w = work[bi]; active = w.status == ZSB_OK; }
+        T.ts = SEQ_CHAINS;
+        T.tbl[0] = tbl + lane; T.tbl[1] = tbl + SEQ_TBL_CELLS * SEQ_CHAINS + lane; T.tbl[2] = tbl + (SEQ_TBL_CELLS + SEQ_OF_CELLS) * SEQ_CHAINS + lane;
+        T.max_al[0] = 9; T.max_al[1] = 8; T.max_al[2] = 9;
+        int rc = ZSB_OK;
+        if (active) rc = seq_build_tables(src, w, T, counts + lane, SEQ_CHAINS);
+        __syncwarp();                                  // the count area becomes the stream rings
+        if (active && !rc) {
+            // == seq_fast_phase1 up to the first sequence (zsb_seqfast.h), on the stream ring
+            const uint64_t start = w.bs_off;
+            const uint32_t lastb = w.bs_len ? src[start + w.bs_len - 1] : 0;
+            if (w.bs_len == 0) rc = ZSB_E_EMPTY_INPUT_DATA;
+            else if (lastb == 0) rc = ZSB_E_NULL_BYTE;
+            else if (start < 16 || w.bs_len > (1u << 24)) rc = ZSB_NEEDS_SLOW;
+            else {
+                R.sa = (uint32_t)__cvta_generic_to_shared(smem + SEQ_TBL_BYTES) + lane * 512u;
+                R.pl = (const uint8_t *)(((uintptr_t)(src + start) - 16) & ~(uintptr_t)127);
+                const uint32_t d0 = (uint32_t)((src + start) - R.pl);                     // 16 .. 143
+                top = (int32_t)((d0 + w.bs_len - 1) * 8) + zsb_flog2(lastb);
+                startbit = (int32_t)(d0 * 8);
+                const uint32_t a0 = (uint32_t)T.al[0], a1 = (uint32_t)T.al[1], a2 = (uint32_t)T.al[2];
+                if (top - startbit < (int32_t)(a0 + a1 + a2)) rc = ZSB_E_NOT_ENOUGH_BITS;
+                else {
+                    sr_init<7>(R, top);
+                    sr_load<7>(R, F, top);
+                    const uint64_t W = fast_win_get(F);
+                    const uint32_t sL = (uint32_t)zsb_shr64(W, 64 - a0), sO = (uint32_t)zsb_shr64(zsb_shl64(W, a0), 64 - a1),
+                                   sM = (uint32_t)zsb_shr64(zsb_shl64(W, a0 + a1), 64 - a2);
+                    top -= (int32_t)(a0 + a1 + a2);
+                    sr_load<7>(R, F, top);
+                    // states are kept as shared-memory byte addresses of their cells: next = (table + base*stride) + bits*stride
+                    tbL = (uint32_t)__cvta_generic_to_shared(T.tbl[0]); tbO = (uint32_t)__cvta_generic_to_shared(T.tbl[1]);
+                    tbM = (uint32_t)__cvta_generic_to_shared(T.tbl[2]);
+                    aL = tbL + sL * (SEQ_CHAINS * 4); aO = tbO + sO * (SEQ_CHAINS * 4); aM = tbM + sM * (SEQ_CHAINS * 4);
+                }
+            }
         }
-        top -= (int64_t)__shfl_sync(FULL, inc, 31);
-        // literal / output positions
-        uint64_t pos = (uint64_t)ll | ((uint64_t)(ll + ml) << 32);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(FULL, pos, d); if (lane >= (uint32_t)d) pos += t; }
-        const uint32_t lit_end = lit_acc + (uint32_t)pos, out_end = out_acc + (uint32_t)(pos >> 32);
-        if (valid && (lit_end > regen || out_end + (regen - lit_end) > ZSB_BLOCK_MAX)) bad = 1;     // decoding_context.rs:86-90, Block_Maximum_Size
-        lit_acc = __shfl_sync(FULL, lit_end, 31); out_acc = __shfl_sync(FULL, out_end, 31);
-        // repeat-offset history: inclusive prefix over the per-sequence transforms, then the block-level carry
-        Hist G = valid ? hist_of_sequence(ov, ll, bad) : hist_identity();
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const Hist E = hist_shfl_up(G, d); if (lane >= (uint32_t)d) G = hist_compose(G, E, bad); }
-        G = hist_compose(G, H, bad);
-        H = hist_bcast(G, 31);
-        if (valid) rec[i] = (uint64_t)out_end | ((uint64_t)lit_end << ZSB_REC_POS_BITS) | ((uint64_t)G.h0 << (2 * ZSB_REC_POS_BITS));
+        if (active && rc) {
+            if (rc == ZSB_TABLE_TOO_SMALL) rc = ZSB_NEEDS_SLOW;
+            if (rc == ZSB_NEEDS_SLOW) slow_list[atomicAdd(&cnt->n_slow, 1u)] = bi;
+            work[bi].status = rc;
+            active = false;
+        }
+        if (lane < SEQ_CHAINS) {
+            S.nseq[lane] = active ? w.nseq : 0u;
+            S.regen[lane] = w.lit_regen; S.bi[lane] = bi;
+            S.top0[lane] = (unsigned long long)((int64_t)(R.pl - base8) * 8 + top);
+            S.rec[lane] = (unsigned long long)(uintptr_t)(seq_pool + w.seq_buf);
+            S.final_rc[lane] = ZSB_OK;
+        }
+    } else {
+        for (uint32_t k = threadIdx.x - 32; k < 36 + 53; k += 32 * SEQ_HELPERS) S.tab[k] = k < 36 ? zsb_ll_entry(k) : zsb_ml_entry(k - 36);
     }
-    if (__any_sync(FULL, bad)) {
-        if (lane == 0) { w.status = ZSB_NEEDS_SLOW; slow_list[atomicAdd(&cnt->n_slow, 1u)] = bi; }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ---- producer: == the loop of seq_fast_phase1
+        const uint32_t nseq = active ? w.nseq : 0u;
+        uint32_t maxn = nseq;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) maxn = max(maxn, __shfl_xor_sync(FULL, maxn, d));
+        uint32_t *wrow = &S.words[lane < SEQ_CHAINS ? lane : 0][0];
+        // one step of the chain; LAST: no state update after the last sequence (sequence.rs:80)
+#define SEQ_STEP(i_, LAST)                                                                                                                  \
+        {                                                                                                                                   \
+            const uint32_t eL = zsb_lds32(aL), eO = zsb_lds32(aO), eM = zsb_lds32(aM);                                                      \
+            uint64_t W = fast_win_get(F);                                                                                                   \
+            const uint32_t sum = eL + eO + eM;                 /* byte 0: state bits, byte 1: extra bits (no carries: <= 27, <= 63) */     \
+            const uint32_t nbs = (LAST) ? 0u : sum & 0xFFu;                                                                                 \
+            const uint32_t px = zsb_prmt(sum, 0, 0x4441);                                                                                   \
+            uint32_t skip = px;                                                                                                             \
+            if (px + nbs > 64) { top -= (int32_t)px; sr_load<7>(R, F, top); W = fast_win_get(F); skip = 0; }   /* state bits past the window: rare */ \
+            const uint32_t t = (uint32_t)(zsb_shl64(W, skip) >> 32);   /* the <= 27 state bits, top-aligned */                              \
+            /* the funnel shifts take their 5-bit amounts straight from the cells (nb in bits 0..4) */                                      \
+            const uint32_t bL = zsb_fsl(t, 0, eL), t2 = zsb_fsl(0, t, eL), bM = zsb_fsl(t2, 0, eM), bO = zsb_fsl(zsb_fsl(0, t2, eM), 0, eO); \
+            top -= (int32_t)(skip + nbs);                                                                                                   \
+            sr_load<7>(R, F, top);                                                                                                          \
+            aL = tbL + (ZSB_CELL_BASE(eL) + bL) * (SEQ_CHAINS * 4); aM = tbM + (ZSB_CELL_BASE(eM) + bM) * (SEQ_CHAINS * 4);                 \
+            aO = tbO + (ZSB_CELL_BASE(eO) + bO) * (SEQ_CHAINS * 4);                                        /* sequence.rs:80-88 */          \
+            wrow[(i_) & 63u] = seq_fast_word(eL, eO, eM, nbs);                                                                              \
+        }
+        for (uint32_t i0 = 0; i0 < maxn; i0 += 32) {
+            const uint32_t B = i0 >> 5;
+            if (B >= 2) seq_bar_sync(SEQ_BAR_FREE + (B & 1u));      // the phase-2 warps are done with batch B-2, whose ring slots batch B overwrites
+            const bool full = i0 + 32 < nseq;                   // 32 more sequences, none of them the last
+            if (!__any_sync(FULL, !full && i0 < nseq)) {
+                if (full) {
+#pragma unroll 2
+                    for (uint32_t i = i0; i < i0 + 32; i++) SEQ_STEP(i, false)
+                }
+            } else {
+                for (uint32_t i = i0; i < i0 + 32; i++)
+                    if (i < nseq) SEQ_STEP(i, i + 1 == nseq)
+            }
+            __threadfence_block();
+            seq_bar_arrive(SEQ_BAR_FULL + (B & 1u));                // batch B is in the ring
+        }
+#undef SEQ_STEP
+        // an over-read shows as a cursor below the stream start; illegal codes are caught by phase 2, which sees every code
+        if (active && top < startbit) S.final_rc[lane] = ZSB_NEEDS_SLOW;
+    } else {
+        // ---- phase 2: this warp's chains, batch by batch as the producer delivers them
+        const uint32_t h = warp - 1, c0 = h * SEQ_CPH;
+        Seq2Carry C[SEQ_CPH];
+        uint32_t nsq[SEQ_CPH];
+#pragma unroll
+        for (int k = 0; k < SEQ_CPH; k++) {
+            nsq[k] = S.nseq[c0 + k];
+            C[k].top = (int64_t)S.top0[c0 + k]; C[k].lit_acc = 0; C[k].out_acc = 0; C[k].H = hist_identity(); C[k].bad = 0;
+        }
+        uint32_t nbat = 0;                                            // batches of the longest chain of the CTA: every warp takes part in every hand-over
+#pragma unroll
+        for (int c = 0; c < SEQ_CHAINS; c++) nbat = max(nbat, (S.nseq[c] + 31) >> 5);
+        for (uint32_t b = 0; b < nbat; b++) {
+            seq_bar_sync(SEQ_BAR_FULL + (b & 1u));
+#pragma unroll
+            for (int k = 0; k < SEQ_CPH; k++) {
+                if ((b << 5) < nsq[k]) {
+                    const uint32_t i = (b << 5) + lane;
+                    const uint32_t word = S.words[c0 + k][(i & 63u)];
+                    seq2_batch(base8, S.tab, word, i < nsq[k], i, S.regen[c0 + k], reinterpret_cast<uint64_t *>((uintptr_t)S.rec[c0 + k]), C[k], lane);
+                }
+            }
+            if (b + 2 < nbat) seq_bar_arrive(SEQ_BAR_FREE + (b & 1u));
+        }
+        __syncthreads();                           // the producer's final verdicts
+#pragma unroll
+        for (int k = 0; k < SEQ_CPH; k++) {
+            if (nsq[k] == 0) continue;
+            const bool bad = __any_sync(FULL, C[k].bad) || S.final_rc[c0 + k] != ZSB_OK;
+            if (lane == 0) {
+                ZsbBlockWork &g = work[S.bi[c0 + k]];
+                if (bad) { g.status = ZSB_NEEDS_SLOW; slow_list[atomicAdd(&cnt->n_slow, 1u)] = S.bi[c0 + k]; }
+                else {
+                    g.lit_used = C[k].lit_acc; g.out_size = C[k].out_acc + (S.regen[c0 + k] - C[k].lit_acc);
+                    g.rep_out[0] = C[k].H.h0; g.rep_out[1] = C[k].H.h1; g.rep_out[2] = C[k].H.h2;
+                }
+            }
+        }
         return;
     }
-    if (lane == 0) {
-        w.lit_used = lit_acc; w.out_size = out_acc + (regen - lit_acc);
-        w.rep_out[0] = H.h0; w.rep_out[1] = H.h1; w.rep_out[2] = H.h2;
-    }
+    __syncthreads();
 }
 
 // k_seq_slow: the careful decoder (zsb_seq.h, the reference's exact error order) for the blocks the fast path
 // handed over.  One warp per CTA, one block per lane, tables interleaved across the 32 lanes.
-#define SEQ_SMEM_BYTES (3 * SEQ_TBL_CELLS * 32 * 4 + 256 * 32 * 2 + 96 * 4)
+#define SEQ_SLOW_SMEM_BYTES (3 * SEQ_TBL_CELLS * 32 * 4 + 256 * 32 * 2 + 96 * 4)
 __global__ void __launch_bounds__(32, 1) k_seq_slow(const uint8_t *__restrict__ src, uint64_t src_len, ZsbBlockWork *work,
                                                     const uint32_t *__restrict__ slow_list, const ZsbCounters *__restrict__ cnt,
                                                     uint64_t *seq_pool) {
@@ -967,9 +1100,9 @@ static cudaError_t set_smem(const void *fn, size_t bytes) {
     return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 cudaError_t zsbk_init() {
-    cudaError_t e = set_smem((const void *)k_seq_slow, SEQ_SMEM_BYTES);
+    cudaError_t e = set_smem((const void *)k_seq_slow, SEQ_SLOW_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    e = set_smem((const void *)k_seq1, SEQ1_SMEM_BYTES);
+    e = set_smem((const void *)k_seq, SEQ_SMEM_FUSED);
     if (e != cudaSuccess) return e;
     return set_smem((const void *)k_exec, EXEC_SMEM_BYTES);
 }
@@ -984,17 +1117,13 @@ void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_
               const ZsbCounters *cnt, uint8_t *lit_pool, uint32_t flags) {
     if (ncomp) k_huf<<<(ncomp + HUF_SLOTS - 1) / HUF_SLOTS, 32, 0, st>>>(src, src_len, work, huf_list, cnt, lit_pool, flags);
 }
-void zsbk_seq1(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
-               uint32_t *word_pool, uint32_t *slow_list) {
-    if (ncomp) k_seq1<<<(ncomp + SEQ1_LANES - 1) / SEQ1_LANES, 32, SEQ1_SMEM_BYTES, st>>>(src, work, seq_list, cnt, word_pool, slow_list);
-}
-void zsbk_seq2(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
-               const uint32_t *word_pool, uint64_t *seq_pool, uint32_t *slow_list) {
-    if (ncomp) k_seq2<<<(ncomp + SEQ2_WARPS - 1) / SEQ2_WARPS, 32 * SEQ2_WARPS, 0, st>>>(src, work, seq_list, cnt, word_pool, seq_pool, slow_list);
+void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
+              uint64_t *seq_pool, uint32_t *slow_list) {
+    if (ncomp) k_seq<<<(ncomp + SEQ_CHAINS - 1) / SEQ_CHAINS, 32 * (1 + SEQ_HELPERS), SEQ_SMEM_FUSED, st>>>(src, work, seq_list, cnt, seq_pool, slow_list);
 }
 void zsbk_seq_slow(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *slow_list,
                    const ZsbCounters *cnt, uint64_t *seq_pool) {
-    if (ncomp) k_seq_slow<<<(ncomp + 31) / 32, 32, SEQ_SMEM_BYTES, st>>>(src, src_len, work, slow_list, cnt, seq_pool);
+    if (ncomp) k_seq_slow<<<(ncomp + 31) / 32, 32, SEQ_SLOW_SMEM_BYTES, st>>>(src, src_len, work, slow_list, cnt, seq_pool);
 }
 void zsbk_plan2(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb_block *blocks, ZsbBlockWork *work, ZsbFrameOut *fout,
                 ZsbCounters *cnt, uint64_t dst_cap, uint32_t flags) {

@@ -47,8 +47,10 @@ ZSB_HD uint32_t zsb_ml_entry(uint32_t c) { return zsb_ml_base(c) | (zsb_ml_bits(
 // the first stream byte, so that the 64-bit window ending at any position inside the stream starts at
 // a non-negative bit.  The two window words of the next step are requested as soon as the bit count of
 // the current one is known and are only combined after the next step's table cells were requested.
-ZSB_HDN int seq_fast_phase1(const uint8_t *src, const ZsbBlockWork &w, const SeqTables &T, uint32_t *words, int ws, uint32_t &rem0,
-                            uint32_t ring_sa) {
+// This is the reference form of phase 1 (the CPU build of the differential tests runs it); k_seq in
+// zsb_kernels.cu runs the same steps with the states kept as shared-memory addresses, the window fed from a
+// cp.async stream ring and the words handed to the phase-2 warps through shared memory.
+ZSB_HDN int seq_fast_phase1(const uint8_t *src, const ZsbBlockWork &w, const SeqTables &T, uint32_t *words, int ws, uint32_t &rem0) {
     const uint64_t start = w.bs_off, end = w.bs_off + w.bs_len;
     if (end <= start) return ZSB_E_EMPTY_INPUT_DATA;
     const uint32_t lastb = src[end - 1];
@@ -57,19 +59,6 @@ ZSB_HDN int seq_fast_phase1(const uint8_t *src, const ZsbBlockWork &w, const Seq
     const uint32_t a0 = (uint32_t)T.al[0], a1 = (uint32_t)T.al[1], a2 = (uint32_t)T.al[2];
     const uint32_t nseq = w.nseq;
     FastWin F;
-#if defined(__CUDA_ARCH__)
-    StreamRing R;
-    R.sa = ring_sa;
-    R.pl = (const uint8_t *)(((uintptr_t)(src + start) - 16) & ~(uintptr_t)127);
-    const uint32_t d0 = (uint32_t)((src + start) - R.pl);                     // 16 .. 143
-    int32_t top = (int32_t)((d0 + w.bs_len - 1) * 8) + zsb_flog2(lastb);
-    const int32_t startbit = (int32_t)(d0 * 8);
-    if (top - startbit < (int32_t)(a0 + a1 + a2)) return ZSB_E_NOT_ENOUGH_BITS;
-    sr_init<7>(R, top);
-    sr_load<7>(R, F, top);
-#define FAST_LOAD(t_) sr_load<7>(R, F, t_)
-#else
-    (void)ring_sa;
     const uint32_t mis = (uint32_t)((uintptr_t)src & 7);
     const uint64_t w0 = ((start + mis) & ~7ull) - 8;                          // byte offset of pw from the aligned base
     const uint8_t *pw = src - mis + w0;
@@ -77,55 +66,31 @@ ZSB_HDN int seq_fast_phase1(const uint8_t *src, const ZsbBlockWork &w, const Seq
     const int32_t startbit = (int32_t)((start + mis - w0) * 8);
     if (top - startbit < (int32_t)(a0 + a1 + a2)) return ZSB_E_NOT_ENOUGH_BITS;
     fast_win_load(F, pw, top);
-#define FAST_LOAD(t_) fast_win_load(F, pw, t_)
-#endif
     uint64_t W = fast_win_get(F);
     uint32_t sL = (uint32_t)zsb_shr64(W, 64 - a0);
     uint32_t sO = (uint32_t)zsb_shr64(zsb_shl64(W, a0), 64 - a1);
     uint32_t sM = (uint32_t)zsb_shr64(zsb_shl64(W, a0 + a1), 64 - a2);
     top -= (int32_t)(a0 + a1 + a2);
     rem0 = (uint32_t)(top - startbit);
-    FAST_LOAD(top);
-#if defined(__CUDA_ARCH__)
-    // states are kept as shared-memory byte addresses of their cells: next = (table + base*stride) + bits*stride
-    const uint32_t stride = (uint32_t)T.ts * 4u;
-    const uint32_t tbL = (uint32_t)__cvta_generic_to_shared(T.tbl[0]), tbO = (uint32_t)__cvta_generic_to_shared(T.tbl[1]),
-                   tbM = (uint32_t)__cvta_generic_to_shared(T.tbl[2]);
-    uint32_t aL = tbL + sL * stride, aO = tbO + sO * stride, aM = tbM + sM * stride;
-#define FAST_CELLS() const uint32_t eL = zsb_lds32(aL), eO = zsb_lds32(aO), eM = zsb_lds32(aM)
-#define FAST_NEXT() aL = tbL + (ZSB_CELL_BASE(eL) + bL) * stride; aM = tbM + (ZSB_CELL_BASE(eM) + bM) * stride; aO = tbO + (ZSB_CELL_BASE(eO) + bO) * stride
-#else
+    fast_win_load(F, pw, top);
     const int ts = T.ts;
     const uint32_t *tL = T.tbl[0], *tO = T.tbl[1], *tM = T.tbl[2];
-#define FAST_CELLS() const uint32_t eL = tL[sL * ts], eO = tO[sO * ts], eM = tM[sM * ts]
-#define FAST_NEXT() sL = ZSB_CELL_BASE(eL) + bL; sM = ZSB_CELL_BASE(eM) + bM; sO = ZSB_CELL_BASE(eO) + bO
-#endif
-#if defined(__CUDA_ARCH__)
-#pragma unroll 2
-#endif
-    for (uint32_t i = 0; i + 1 < nseq; i++) {
-        FAST_CELLS();
+    for (uint32_t i = 0; i < nseq; i++) {
+        const uint32_t eL = tL[sL * ts], eO = tO[sO * ts], eM = tM[sM * ts];
         W = fast_win_get(F);
         const uint32_t sum = eL + eO + eM;                        // byte 0: state bits, byte 1: extra bits (no carries: <= 27, <= 63)
-        const uint32_t nbs = sum & 0xFFu, px = zsb_prmt(sum, 0, 0x4441);
+        const uint32_t nbs = i + 1 == nseq ? 0u : sum & 0xFFu;    // no state update after the last sequence (sequence.rs:80)
+        const uint32_t px = zsb_prmt(sum, 0, 0x4441);
         uint32_t skip = px;
-        if (px + nbs > 64) { top -= (int32_t)px; FAST_LOAD(top); W = fast_win_get(F); skip = 0; }   // state bits past the window: rare
+        if (px + nbs > 64) { top -= (int32_t)px; fast_win_load(F, pw, top); W = fast_win_get(F); skip = 0; }   // state bits past the window: rare
         const uint32_t t = (uint32_t)(zsb_shl64(W, skip) >> 32);  // the <= 27 state bits, top-aligned
         // the funnel shifts take their 5-bit amounts straight from the cells (nb in bits 0..4)
         const uint32_t bL = zsb_fsl(t, 0, eL), t2 = zsb_fsl(0, t, eL), bM = zsb_fsl(t2, 0, eM), bO = zsb_fsl(zsb_fsl(0, t2, eM), 0, eO);
         top -= (int32_t)(skip + nbs);
-        FAST_LOAD(top);
-        FAST_NEXT();                                              // sequence.rs:80-88
+        fast_win_load(F, pw, top);
+        sL = ZSB_CELL_BASE(eL) + bL; sM = ZSB_CELL_BASE(eM) + bM; sO = ZSB_CELL_BASE(eO) + bO;      // sequence.rs:80-88
         words[i * ws] = seq_fast_word(eL, eO, eM, nbs);
     }
-    {   // last sequence: no state update (sequence.rs:80)
-        FAST_CELLS();
-        words[(nseq - 1) * ws] = seq_fast_word(eL, eO, eM, 0);
-        top -= (int32_t)zsb_prmt(eL + eO + eM, 0, 0x4441);
-    }
-#undef FAST_LOAD
-#undef FAST_CELLS
-#undef FAST_NEXT
     // an over-read shows as a cursor below the stream start; illegal codes are caught by phase 2, which sees every code
     if (top < startbit) return ZSB_NEEDS_SLOW;
     return ZSB_OK;

@@ -42,7 +42,7 @@ ZSB_HD void fast_win_load(FastWin &f, const uint8_t *pw, int32_t top) {
 }
 ZSB_HD uint64_t fast_win_get(const FastWin &f) { return zsb_shr64(f.lo, f.sh) | zsb_shl64(f.hi, 64 - f.sh); }
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 __device__ __forceinline__ uint32_t zsb_lds32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint64_t zsb_lds64v(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
 
