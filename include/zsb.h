@@ -103,6 +103,16 @@ int zsb_scan(const uint8_t *src, size_t n, uint32_t flags, uint64_t max_window,
              uint64_t *err_a, uint64_t *err_b);
 void zsb_free(void *p);
 
+/* ---- sharding by frame over the GPUs of one box (no reference counterpart: the crate is single threaded; frames are
+ *      independent because ZStandard::decode creates a fresh DecodingContext, frame.rs:233).  Host only.
+ * zsb_shard_plan: first[0..n_shards] = contiguous frame ranges [first[s], first[s+1]) balanced on decompressed bytes
+ * (Frame_Content_Size where declared, else 2.4 x compressed size).
+ * zsb_shard_extract: descriptors of frames [f0, f1) rebased onto the sub-buffer src[*src_off, +*src_len), ready for
+ * zsb_decode on one rank.  Arrays are malloc'd; free with zsb_free. */
+int zsb_shard_plan(const zsb_frame *frames, size_t n_frames, int n_shards, size_t *first);
+int zsb_shard_extract(const zsb_frame *frames, size_t n_frames, const zsb_block *blocks, size_t n_blocks, size_t f0, size_t f1,
+                      zsb_frame **out_frames, zsb_block **out_blocks, size_t *out_n_blocks, uint64_t *src_off, uint64_t *src_len);
+
 /* ---- decode context: owns a CUDA stream and the device scratch of one GPU ---------------------
  * == DecodingContext (decoding_context.rs:17-47), except that one zsb_ctx serves a whole batch of
  *    frames: the per-frame state (repeat offsets [1,4,8], Huffman table, repeat tables, output)

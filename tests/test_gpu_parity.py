@@ -251,3 +251,28 @@ def test_c2_full_size_round_trip(dec):
     for i in rr.sample(range(4096), 64):
         f = sc.frames[i]
         assert R.main_decode(blob[f.src_off:f.src_off + f.src_len]) == out[r.dst_off[i]:r.dst_off[i] + r.dst_len[i]]
+
+
+# ---------------------------------------------------------------- sharding by frame
+def test_shards_decode_independently_and_concatenate(dec):
+    """every rank's shard decoded on its own (here one after the other on cuda:0) gives the whole output in rank order"""
+    blob, exp = corpora.c2_small(64)
+    blob = corpora.fixture("welcome.zst") + blob + corpora.fixture("moby-dick.txt.zst")
+    want = R.main_decode(blob)
+    for world in (2, 3, 8):
+        parts = []
+        for rank in range(world):
+            out, sh, r = Z.decode_shard(blob, rank, world, Q | VER, ctx=dec.ctx)
+            assert r.first_error() is None
+            assert all(r.checksum_ok[i] for i in range(sh.n_frames) if sh.frames[i].kind == 0 and sh.frames[i].has_checksum)
+            parts.append(out)
+        assert b"".join(parts) == want
+
+
+def test_two_gpus_two_ranks():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    blob, exp = corpora.c2_small(64)
+    outs = [Z.decode_shard(blob, rank, 2, Q | VER, ctx=Z.Context(rank))[0] for rank in range(2)]
+    assert b"".join(outs) == exp

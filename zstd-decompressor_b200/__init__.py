@@ -101,6 +101,9 @@ def lib():
     L.zsb_huffman_parse.argtypes = [vp, C.c_char_p, sz, u8p, C.POINTER(C.c_uint16), C.POINTER(sz), u8p]
     L.zsb_execute_sequences.argtypes = [vp, u32p, sz, C.c_char_p, sz, vp, sz, C.POINTER(sz)]
     L.zsb_xxh64.argtypes = [vp, C.c_char_p, sz, u64p]
+    L.zsb_shard_plan.argtypes = [C.POINTER(ZsbFrame), sz, C.c_int, C.POINTER(sz)]
+    L.zsb_shard_extract.argtypes = [C.POINTER(ZsbFrame), sz, C.POINTER(ZsbBlock), sz, sz, sz, C.POINTER(C.POINTER(ZsbFrame)), C.POINTER(C.POINTER(ZsbBlock)),
+                                    C.POINTER(sz), u64p, u64p]
     L.zsb_strerror.restype = C.c_char_p; L.zsb_strerror.argtypes = [C.c_int]
     L.zsb_version.restype = C.c_char_p
     _lib = L
@@ -111,7 +114,7 @@ EXPORTED_SYMBOLS = [
     "zsb_scan", "zsb_free", "zsb_ctx_create", "zsb_ctx_destroy", "zsb_ctx_set_stream", "zsb_last_cuda_error", "zsb_ctx_set_profile",
     "zsb_last_launch_count", "zsb_last_kernel_times", "zsb_kernel_times_avg", "zsb_decode", "zsb_decode_prepare", "zsb_decode_launch", "zsb_decode_finish",
     "zsb_decompress", "zsb_fse_table_parse", "zsb_fse_table_from_distribution", "zsb_huffman_parse", "zsb_execute_sequences",
-    "zsb_xxh64", "zsb_strerror", "zsb_version"]
+    "zsb_xxh64", "zsb_strerror", "zsb_version", "zsb_shard_plan", "zsb_shard_extract"]
 
 
 # ------------------------------------------------------------------------------------------ scan
@@ -438,3 +441,66 @@ def decompress(data, print_skippable=False, quirks=True, verify=True, ctx=None):
     if e:
         raise ZsbError(e[1])
     return out
+
+
+# ------------------------------------------------------------------------------------------ sharding by frame (one process per GPU)
+def shard_plan(scan, n_shards):
+    """Contiguous frame ranges balanced on decompressed bytes: [first[s], first[s+1]) for shard s (zsb_shard_plan)."""
+    first = (C.c_size_t * (n_shards + 1))()
+    rc = lib().zsb_shard_plan(scan.frames, scan.n_frames, n_shards, first)
+    if rc:
+        raise ZsbError(rc)
+    return list(first)
+
+
+class Shard:
+    """Frames [f0, f1) of a scanned buffer as a self-contained batch: the sub-buffer and its rebased descriptors."""
+    def __init__(self, scan, f0, f1):
+        fp, bp = C.POINTER(ZsbFrame)(), C.POINTER(ZsbBlock)()
+        nb, off, ln = C.c_size_t(), C.c_uint64(), C.c_uint64()
+        rc = lib().zsb_shard_extract(scan.frames, scan.n_frames, scan.blocks, scan.n_blocks, f0, f1, C.byref(fp), C.byref(bp), C.byref(nb), C.byref(off), C.byref(ln))
+        if rc:
+            raise ZsbError(rc)
+        self.frames, self.blocks, self.n_frames, self.n_blocks = fp, bp, f1 - f0, nb.value
+        self.src_off, self.src_len, self.f0, self.f1 = off.value, ln.value, f0, f1
+        self.status = 0
+        base = C.cast(scan.buf, C.c_void_p).value or 0
+        self.buf, self.n = C.c_void_p(base + self.src_off), self.src_len
+        self._keep = scan
+
+    def __del__(self):
+        try:
+            if getattr(self, "frames", None): lib().zsb_free(self.frames)
+            if getattr(self, "blocks", None): lib().zsb_free(self.blocks)
+        except Exception:
+            pass
+
+
+def decode_shard(data, rank, world, flags=VERIFY_CHECKSUM, ctx=None, scan=None):
+    """What rank `rank` of `world` does with a buffer every rank holds: scan (host), take its frame range, decode it on
+    its own GPU.  Returns (output bytes of the shard, Shard, BatchResult).  No collective is involved."""
+    sc = scan or Scan(data, flags)
+    first = shard_plan(sc, world)
+    sh = Shard(sc, first[rank], first[rank + 1])
+    out, _, r = Decoder(ctx).decode(None, flags, scan=sh)
+    return out, sh, r
+
+
+def gather_outputs(local_bytes, group=None, device=None):
+    """Optional gather for a single-stream consumer: every rank receives the concatenation of all shards' outputs in rank
+    order (torch.distributed all_gather over NCCL/NVLink on GPUs, gloo on CPU).  Not part of the decode path."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = device or "cpu"
+    n = torch.tensor([len(local_bytes)], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    cap = max(max(sizes), 1)
+    mine = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    if len(local_bytes):
+        mine[:len(local_bytes)] = torch.frombuffer(bytearray(local_bytes), dtype=torch.uint8).to(dev)
+    parts = [torch.zeros(cap, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return b"".join(bytes(p[:sz].cpu().numpy().tobytes()) for p, sz in zip(parts, sizes))

@@ -135,3 +135,48 @@ extern "C" int zsb_scan(const uint8_t *src, size_t n, uint32_t flags, uint64_t m
 }
 extern "C" void zsb_free(void *p) { free(p); }
 
+
+// ======================================================================================= sharding by frame
+// Frames are independent (a fresh DecodingContext per frame, frame.rs:233), so a buffer shards over GPUs by contiguous
+// frame ranges with no exchange step.  Ranges are balanced on decompressed bytes: Frame_Content_Size where the header
+// declares it, else 2.4 x the compressed size (text at level 3); skippable frames weigh their payload.
+extern "C" int zsb_shard_plan(const zsb_frame *frames, size_t n_frames, int n_shards, size_t *first) {
+    if ((!frames && n_frames) || n_shards <= 0 || !first) return ZSB_E_ARG;
+    std::vector<double> cum(n_frames + 1, 0.0);
+    for (size_t f = 0; f < n_frames; f++) {
+        const zsb_frame &fr = frames[f];
+        const double wgt = fr.kind == 0 ? (fr.has_content_size ? (double)fr.content_size : 2.4 * (double)fr.src_len) : (double)fr.src_len;
+        cum[f + 1] = cum[f] + wgt + 1.0;     // +1: empty frames still cost a descriptor
+    }
+    first[0] = 0;
+    size_t f = 0;
+    for (int s = 1; s < n_shards; s++) {
+        const double target = cum[n_frames] * (double)s / (double)n_shards;
+        while (f < n_frames && cum[f + 1] <= target) f++;
+        // the frame that crosses the target goes to the side it mostly lies on
+        if (f < n_frames && target - cum[f] > cum[f + 1] - target) f++;
+        if (f < first[s - 1]) f = first[s - 1];
+        first[s] = f;
+    }
+    first[n_shards] = n_frames;
+    return ZSB_OK;
+}
+
+// Descriptors of frames [f0, f1) rebased so that they describe the sub-buffer src[*src_off, *src_off + *src_len) on its own:
+// what one rank uploads and hands to zsb_decode.  Arrays are malloc'd; free with zsb_free.
+extern "C" int zsb_shard_extract(const zsb_frame *frames, size_t n_frames, const zsb_block *blocks, size_t n_blocks, size_t f0, size_t f1,
+                                 zsb_frame **out_frames, zsb_block **out_blocks, size_t *out_n_blocks, uint64_t *src_off, uint64_t *src_len) {
+    if (!frames || f0 > f1 || f1 > n_frames || !out_frames || !out_blocks || !out_n_blocks || !src_off || !src_len) return ZSB_E_ARG;
+    *out_frames = nullptr; *out_blocks = nullptr; *out_n_blocks = 0; *src_off = 0; *src_len = 0;
+    if (f0 == f1) return ZSB_OK;
+    const uint64_t base = frames[f0].src_off, end = frames[f1 - 1].src_off + frames[f1 - 1].src_len;
+    const size_t b0 = frames[f0].first_block, b1 = (size_t)frames[f1 - 1].first_block + frames[f1 - 1].n_blocks;
+    if (b1 > n_blocks || b0 > b1) return ZSB_E_ARG;
+    zsb_frame *of = (zsb_frame *)malloc(sizeof(zsb_frame) * (f1 - f0));
+    zsb_block *ob = (zsb_block *)malloc(sizeof(zsb_block) * (b1 - b0 + 1));
+    if (!of || !ob) { free(of); free(ob); return ZSB_E_NOMEM; }
+    for (size_t f = f0; f < f1; f++) { of[f - f0] = frames[f]; of[f - f0].src_off -= base; of[f - f0].first_block -= (uint32_t)b0; }
+    for (size_t b = b0; b < b1; b++) { ob[b - b0] = blocks[b]; ob[b - b0].src_off -= base; ob[b - b0].frame -= (uint32_t)f0; }
+    *out_frames = of; *out_blocks = ob; *out_n_blocks = b1 - b0; *src_off = base; *src_len = end - base;
+    return ZSB_OK;
+}
