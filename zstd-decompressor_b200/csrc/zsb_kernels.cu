@@ -165,11 +165,11 @@ __global__ void __launch_bounds__(32) k_huf(const uint8_t *__restrict__ src, uin
 // ======================================================================================= k_seq / k_seq_slow
 // The sequence stage in two phases (zsb_seqfast.h), fused in one CTA:
 //
-//   warp 0 (producer)  the serial three-state FSE chain, one lane per block, SEQ_CHAINS blocks per CTA.  The chain is
+//   warp 0 (producer)  the serial three-state FSE chain, one lane per block, SEQ_CHAINS = 32 blocks per CTA (so that a SM
+//                      hosts one producer warp and the phase-2 warps mostly run on the other sub-cores).  The chain is
 //                      latency bound (table cell -> bit count -> bit position -> next state: one shared-memory load and
 //                      ~8 dependent ALU operations per sequence), so it carries as little else as possible: tables
-//                      interleaved across the lanes (cell i of lane l at word i*SEQ_CHAINS + l: bank = 8*(i%4) + l,
-//                      conflict free), the bit window fed from a cp.async stream ring, one 32-bit word per sequence
+//                      interleaved across the lanes (cell i of lane l at word i*32 + l: bank = l, conflict free), the bit window fed from a cp.async stream ring, one 32-bit word per sequence
 //                      into a shared-memory ring.
 //   warps 1..H (phase 2) one lane per sequence, 32 sequences per step and block: bit positions, extra-bit values,
 //                      literal/output positions and the repeat-offset history by warp prefix operations; packed
@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(32) k_huf(const uint8_t *__restrict__ src, uin
 // Hand-over: the chains advance in lockstep, 32 sequences (one batch per chain) at a time; the word ring holds two
 // batches per chain; named barriers (full / free, two of each) pass the batches on, so a waiting warp costs no issue slot.
 #define SEQ_TBL_CELLS 512
-#define SEQ_CHAINS 8
-#define SEQ_HELPERS 8
+#define SEQ_CHAINS 32
+#define SEQ_HELPERS 16
 #define SEQ_CPH (SEQ_CHAINS / SEQ_HELPERS)       // chains per phase-2 warp
 #define SEQ_OF_CELLS 256      // offset tables have accuracy log <= 8 (RFC 8878); a log-9 one (the reference accepts it) takes the careful path
 #define SEQ_TBL_BYTES ((2 * SEQ_TBL_CELLS + SEQ_OF_CELLS) * SEQ_CHAINS * 4)
@@ -244,9 +244,9 @@ __device__ __forceinline__ void seq2_batch(const uint8_t *base8, const uint32_t 
     if (valid) rec[i] = (uint64_t)out_end | ((uint64_t)lit_end << ZSB_REC_POS_BITS) | ((uint64_t)G.h0 << (2 * ZSB_REC_POS_BITS));
 }
 
-__global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 4) k_seq(const uint8_t *__restrict__ src, ZsbBlockWork *work, const uint32_t *__restrict__ seq_list,
+__global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t *__restrict__ src, ZsbBlockWork *work, const uint32_t *__restrict__ seq_list,
                                                                 ZsbCounters *cnt, uint64_t *seq_pool, uint32_t *slow_list) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];      // the stream rings must be 512-byte aligned (SEQ_STEP)
     if (cnt->overflow) return;
     uint32_t *tbl = reinterpret_cast<uint32_t *>(smem);
     int16_t *counts = reinterpret_cast<int16_t *>(smem + SEQ_TBL_BYTES);
@@ -297,7 +297,6 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 4) k_seq(const uint8_t
                     const uint32_t sL = (uint32_t)zsb_shr64(W, 64 - a0), sO = (uint32_t)zsb_shr64(zsb_shl64(W, a0), 64 - a1),
                                    sM = (uint32_t)zsb_shr64(zsb_shl64(W, a0 + a1), 64 - a2);
                     top -= (int32_t)(a0 + a1 + a2);
-                    sr_load<7>(R, F, top);
                     // states are kept as shared-memory byte addresses of their cells: next = (table + base*stride) + bits*stride
                     tbL = (uint32_t)__cvta_generic_to_shared(T.tbl[0]); tbO = (uint32_t)__cvta_generic_to_shared(T.tbl[1]);
                     tbM = (uint32_t)__cvta_generic_to_shared(T.tbl[2]);
@@ -330,21 +329,23 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 4) k_seq(const uint8_t
 #pragma unroll
         for (int d = 16; d; d >>= 1) maxn = max(maxn, __shfl_xor_sync(FULL, maxn, d));
         uint32_t *wrow = &S.words[lane < SEQ_CHAINS ? lane : 0][0];
-        // one step of the chain; LAST: no state update after the last sequence (sequence.rs:80)
+        // One step of the chain; LAST: no state update after the last sequence (sequence.rs:80).  The <= 27 state bits are
+        // fetched where they lie -- the 32 bits ending px bits below the cursor, two aligned ring words and one funnel
+        // shift -- so the step carries no window bookkeeping: ~35 instructions, of which two dependent shared-memory loads.
+        const uint32_t ring_sa = R.sa;                   // 512-byte aligned: ring byte address = ring_sa | (offset & 0x1FC)
 #define SEQ_STEP(i_, LAST)                                                                                                                  \
         {                                                                                                                                   \
             const uint32_t eL = zsb_lds32(aL), eO = zsb_lds32(aO), eM = zsb_lds32(aM);                                                      \
-            uint64_t W = fast_win_get(F);                                                                                                   \
             const uint32_t sum = eL + eO + eM;                 /* byte 0: state bits, byte 1: extra bits (no carries: <= 27, <= 63) */     \
-            const uint32_t nbs = (LAST) ? 0u : sum & 0xFFu;                                                                                 \
             const uint32_t px = zsb_prmt(sum, 0, 0x4441);                                                                                   \
-            uint32_t skip = px;                                                                                                             \
-            if (px + nbs > 64) { top -= (int32_t)px; sr_load<7>(R, F, top); W = fast_win_get(F); skip = 0; }   /* state bits past the window: rare */ \
-            const uint32_t t = (uint32_t)(zsb_shl64(W, skip) >> 32);   /* the <= 27 state bits, top-aligned */                              \
+            const uint32_t nbs = (LAST) ? 0u : sum & 0xFFu;                                                                                 \
+            const uint32_t e = (uint32_t)(top - 32) - px;      /* lowest bit of the 32 wanted; below the stream only after an over-read */ \
+            const uint32_t e3 = e >> 3;                                                                                                     \
+            const uint32_t w0 = zsb_lds32v((e3 & 0x1FCu) | ring_sa), w1 = zsb_lds32v(((e3 + 4u) & 0x1FCu) | ring_sa);                         \
+            const uint32_t t = __funnelshift_r(w0, w1, e);     /* the state bits, top-aligned */                                            \
             /* the funnel shifts take their 5-bit amounts straight from the cells (nb in bits 0..4) */                                      \
             const uint32_t bL = zsb_fsl(t, 0, eL), t2 = zsb_fsl(0, t, eL), bM = zsb_fsl(t2, 0, eM), bO = zsb_fsl(zsb_fsl(0, t2, eM), 0, eO); \
-            top -= (int32_t)(skip + nbs);                                                                                                   \
-            sr_load<7>(R, F, top);                                                                                                          \
+            top -= (int32_t)(px + nbs);                                                                                                     \
             aL = tbL + (ZSB_CELL_BASE(eL) + bL) * (SEQ_CHAINS * 4); aM = tbM + (ZSB_CELL_BASE(eM) + bM) * (SEQ_CHAINS * 4);                 \
             aO = tbO + (ZSB_CELL_BASE(eO) + bO) * (SEQ_CHAINS * 4);                                        /* sequence.rs:80-88 */          \
             wrow[(i_) & 63u] = seq_fast_word(eL, eO, eM, nbs);                                                                              \
@@ -353,14 +354,18 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 4) k_seq(const uint8_t
             const uint32_t B = i0 >> 5;
             if (B >= 2) seq_bar_sync(SEQ_BAR_FREE + (B & 1u));      // the phase-2 warps are done with batch B-2, whose ring slots batch B overwrites
             const bool full = i0 + 32 < nseq;                   // 32 more sequences, none of them the last
+            // the stream rings are topped up every 8 steps (8 x 89 + 95 bits < one 128-byte line), by all lanes in the same pass
             if (!__any_sync(FULL, !full && i0 < nseq)) {
                 if (full) {
+                    for (uint32_t i8 = i0; i8 < i0 + 32; i8 += 8) {
+                        sr_check<7>(R, top - 32);
 #pragma unroll 2
-                    for (uint32_t i = i0; i < i0 + 32; i++) SEQ_STEP(i, false)
+                        for (uint32_t i = i8; i < i8 + 8; i++) SEQ_STEP(i, false)
+                    }
                 }
             } else {
                 for (uint32_t i = i0; i < i0 + 32; i++)
-                    if (i < nseq) SEQ_STEP(i, i + 1 == nseq)
+                    if (i < nseq) { if ((i & 7u) == 0) sr_check<7>(R, top - 32); SEQ_STEP(i, i + 1 == nseq) }
             }
             __threadfence_block();
             seq_bar_arrive(SEQ_BAR_FULL + (B & 1u));                // batch B is in the ring
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 4) k_seq(const uint8_t
         if (active && top < startbit) S.final_rc[lane] = ZSB_NEEDS_SLOW;
     } else {
         // ---- phase 2: this warp's chains, batch by batch as the producer delivers them
-        const uint32_t h = warp - 1, c0 = h * SEQ_CPH;
+        const uint32_t h = warp - 1, c0 = h * SEQ_CPH;     // this warp's chains: c0 .. c0 + SEQ_CPH - 1
         Seq2Carry C[SEQ_CPH];
         uint32_t nsq[SEQ_CPH];
 #pragma unroll
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 4) k_seq(const uint8_t
 __global__ void __launch_bounds__(32, 1) k_seq_slow(const uint8_t *__restrict__ src, uint64_t src_len, ZsbBlockWork *work,
                                                     const uint32_t *__restrict__ slow_list, const ZsbCounters *__restrict__ cnt,
                                                     uint64_t *seq_pool) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     if (cnt->overflow) return;
     uint32_t *tbl = reinterpret_cast<uint32_t *>(smem);
     int16_t *counts = reinterpret_cast<int16_t *>(smem + 3 * SEQ_TBL_CELLS * 32 * 4);
@@ -645,7 +650,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
                                                           ZsbFrameOut *fout, const uint32_t *__restrict__ exec_list,
                                                           const ZsbCounters *__restrict__ cnt, const uint64_t *__restrict__ seq_pool,
                                                           const uint8_t *__restrict__ lit_pool, uint8_t *dst) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ int s_err;
     if (cnt->overflow) return;
     uint8_t *out_s = smem;

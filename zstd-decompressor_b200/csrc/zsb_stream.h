@@ -44,6 +44,7 @@ ZSB_HD uint64_t fast_win_get(const FastWin &f) { return zsb_shr64(f.lo, f.sh) | 
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ uint32_t zsb_lds32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t zsb_lds32v(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }   // ordered after the cp.async waits
 __device__ __forceinline__ uint64_t zsb_lds64v(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
 
 // The bitstream of one lane staged through a shared-memory ring of four lines (LB = log2 of the line size in
@@ -65,15 +66,26 @@ template <int LB> __device__ __forceinline__ void sr_init(StreamRing &r, int32_t
     for (int32_t l = l0; l >= r.low; l--) sr_fetch<LB>(r, l);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
-// window words for the 64 bits ending at `top`; entering line X requests line X-2 and waits for X-1
-template <int LB> __device__ __forceinline__ void sr_load(StreamRing &r, FastWin &f, int32_t top) {
+// Keeps the ring ahead of the cursor: when the window ending at `top` has entered line X (<= low+1), line X-2 is
+// requested and line X-1 awaited.  Must run at least once per line of progress: every step (sr_load), or every k steps
+// when k steps cannot consume a whole line (sr_check + sr_load_nocheck; all lanes of a warp then refill in the same
+// pass instead of diverging step by step).
+template <int LB> __device__ __forceinline__ void sr_check(StreamRing &r, int32_t top) {
+    int32_t a = top - 64; a = a < 0 ? 0 : a;
+    if ((a >> (LB + 3)) <= r.low + 1 && r.low > 0) { r.low--; sr_fetch<LB>(r, r.low); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+}
+// window words for the 64 bits ending at `top`
+template <int LB> __device__ __forceinline__ void sr_load_nocheck(const StreamRing &r, FastWin &f, int32_t top) {
     int32_t a = top - 64; a = a < 0 ? 0 : a;          // below the stream only after an over-read (reported at the end)
     const uint32_t wi = (uint32_t)a >> 6;
     f.sh = (uint32_t)a & 63u;
-    if ((int32_t)(wi >> (LB - 3)) <= r.low + 1 && r.low > 0) { r.low--; sr_fetch<LB>(r, r.low); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
     const uint32_t wm = (4u << (LB - 3)) - 1u;         // words in the ring - 1
     f.lo = zsb_lds64v(r.sa + (wi & wm) * 8u);
     f.hi = f.sh ? zsb_lds64v(r.sa + ((wi + 1) & wm) * 8u) : 0ull;
+}
+template <int LB> __device__ __forceinline__ void sr_load(StreamRing &r, FastWin &f, int32_t top) {
+    sr_check<LB>(r, top);
+    sr_load_nocheck<LB>(r, f, top);
 }
 #endif
 
