@@ -162,6 +162,104 @@ __global__ void __launch_bounds__(32) k_huf(const uint8_t *__restrict__ src, uin
     }
 }
 
+// ======================================================================================= FSE table build, one warp per table
+// == FseTable::from_distribution (fse.rs:110-202), lane parallel.  The serial form (fse_build_table, zsb_fse.h) walks the
+// table three times; here
+//   (1) the "less than one" symbols take the cells N-1, N-2, ... in symbol order: a ballot rank (fse.rs:120-133);
+//   (2) the spread visits position (k*step) & (N-1) at step k -- step is odd, so the N steps are a permutation -- and
+//       skips positions above the low-probability zone: the j-th visited position gets occurrence j, whose symbol is
+//       found by binary search in the prefix sums of the counts (fse.rs:136-157);
+//   (3) the next-state numbers go to a symbol's cells in index order: per 32 cells, __match_any_sync groups equal symbols,
+//       the rank inside the group plus a per-symbol running counter gives next = count + rank, then
+//       nb = AL - floor(log2(next)), base = (next << nb) - N  (fse.rs:169-189 in closed form, see zsb_fse.h).
+// Results are identical to fse_build_table cell for cell (tests: the reference's vectors and random distributions
+// through zsb_fse_table_from_distribution, which runs this code).
+struct FseWarpScratch { int16_t cnt[64]; uint16_t cum[66]; uint16_t next[64]; };
+// tab: code -> baseline | extra bits << 24 for LL ([0..35]) and ML ([36..88]); type 3: plain table (xb = 0, code = symbol)
+__device__ __forceinline__ int fse_build_table_warp(FseWarpScratch &X, int nsym, int al, uint32_t *tbl, int ts, int type, const uint32_t *tab, uint32_t lane) {
+    const int N = 1 << al, step = (N >> 1) + (N >> 3) + 3, mask = N - 1;
+    const uint32_t lt = (1u << lane) - 1u;
+    int nlow = 0, total = 0;
+    bool overflow = false;
+    for (int s0 = 0; s0 < nsym; s0 += 32) {
+        const int sy = s0 + (int)lane;
+        const int c = sy < nsym ? X.cnt[sy] : 0;
+        const bool low = c == -1;
+        const uint32_t lm = __ballot_sync(FULL, low);
+        const int p = c > 0 ? c : 0;
+        int inc = p;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, inc, d); if ((int)lane >= d) inc += t; }
+        if (sy < nsym) { X.cum[sy] = (uint16_t)(total + inc - p); X.next[sy] = (uint16_t)(low ? 1 : p); }
+        if (low) { const int cell = N - 1 - (nlow + __popc(lm & lt)); if (cell >= 0) tbl[cell * ts] = (uint32_t)sy; else overflow = true; }
+        nlow += __popc(lm); total += __shfl_sync(FULL, inc, 31);
+    }
+    const int high = N - 1 - nlow;
+    if (__any_sync(FULL, overflow) || total != high + 1) return ZSB_E_CORRUPTED_TABLE;       // fse.rs:160-166 and the guards of the serial form
+    if (lane == 0) X.cum[nsym] = (uint16_t)total;
+    __syncwarp();
+    int jbase = 0;
+    for (int k0 = 0; k0 < N; k0 += 32) {
+        const int pos = ((k0 + (int)lane) * step) & mask;
+        const bool valid = pos <= high;
+        const uint32_t b = __ballot_sync(FULL, valid);
+        const int j = jbase + __popc(b & lt);
+        jbase += __popc(b);
+        if (valid) {
+            int lo = 0, hi = nsym;                      // cum[lo] <= j < cum[hi]
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int)X.cum[mid] <= j) lo = mid; else hi = mid; }
+            tbl[pos * ts] = (uint32_t)lo;
+        }
+    }
+    __syncwarp();
+    for (int i0 = 0; i0 < N; i0 += 32) {
+        const int i = i0 + (int)lane;
+        const uint32_t sy = tbl[i * ts];
+        const uint32_t g = __match_any_sync(FULL, sy);
+        const uint32_t r = __popc(g & lt);
+        const uint32_t nx = (uint32_t)X.next[sy] + r;
+        __syncwarp();
+        if (r == 0) X.next[sy] = (uint16_t)(nx + __popc(g));
+        __syncwarp();
+        const uint32_t nb = (uint32_t)(al - zsb_flog2(nx));
+        const uint32_t base = (nx << nb) - (uint32_t)N;
+        uint32_t code = sy, xb = 0;
+        if (type != 3) {
+            const uint32_t mx = type == 0 ? ZSB_MAX_LL_CODE : type == 1 ? ZSB_MAX_OF_CODE : ZSB_MAX_ML_CODE;
+            if (sy > mx) code = 63u;
+            else xb = type == 1 ? sy : tab[(type == 2 ? 36 : 0) + sy] >> 24;
+        }
+        tbl[i * ts] = ZSB_CELL(nb, xb, base, code);
+    }
+    return ZSB_OK;
+}
+// Table t (0 LL, 1 OF, 2 ML) of block w by one warp: == seq_build_table (zsb_seq.h) with max_sym = 64.  All lanes return the same status.
+__device__ __forceinline__ int seq_build_table_warp(const uint8_t *src, const ZsbBlockWork &w, int t, uint32_t *tbl, int ts, FseWarpScratch &X,
+                                                    const uint32_t *tab, int max_al, int &al_out, uint32_t lane) {
+    const int mode = w.mode[t];
+    al_out = 0;
+    if (mode == ZSB_M_RLE) { if (lane == 0) fse_build_rle(w.rle_sym[t], tbl, t); return ZSB_OK; }
+    int al = 0, nsym = 0, rc = ZSB_OK;
+    if (mode == ZSB_M_PREDEFINED) {
+        nsym = zsb_predef_nsym(t); al = zsb_predef_al(t);
+        for (int sy = (int)lane; sy < nsym; sy += 32) X.cnt[sy] = (int16_t)zsb_predef_count(t, sy);
+    } else if (mode == ZSB_M_FSE) {
+        if (lane == 0) {
+            FwdBits f; fwd_init(f, src + w.tbl_desc[t], w.tbl_end - w.tbl_desc[t]);
+            rc = fse_read_ncount(f, X.cnt, 1, 64, al, nsym);
+            if (rc == ZSB_E_CORRUPT) rc = ZSB_TABLE_TOO_SMALL;            // more than 64 symbols described
+        }
+        rc = __shfl_sync(FULL, rc, 0); al = __shfl_sync(FULL, al, 0); nsym = __shfl_sync(FULL, nsym, 0);
+        if (rc) return rc;
+    } else return ZSB_E_NO_PREVIOUS_DECODER;
+    if (max_al && al > max_al) return ZSB_TABLE_TOO_SMALL;
+    __syncwarp();
+    rc = fse_build_table_warp(X, nsym, al, tbl, ts, t, tab, lane);
+    __syncwarp();
+    if (!rc) al_out = al;
+    return rc;
+}
+
 // ======================================================================================= k_seq / k_seq_slow
 // The sequence stage in two phases (zsb_seqfast.h), fused in one CTA:
 //
@@ -191,11 +289,14 @@ struct SeqShared {
     uint32_t regen[SEQ_CHAINS], bi[SEQ_CHAINS];
     unsigned long long top0[SEQ_CHAINS], rec[SEQ_CHAINS];   // absolute bit position of sequence 0, record pointer
     int final_rc[SEQ_CHAINS];
+    int tal[SEQ_CHAINS][3], trc[SEQ_CHAINS][3];  // accuracy log / build status of each table (built by the phase-2 warps during set-up)
 };
 // named barriers of the hand-over (0 is __syncthreads): FULL+parity: batch written, FREE+parity: batch consumed; every thread of the CTA takes part
 #define SEQ_BAR_FULL 1u
 #define SEQ_BAR_FREE 3u
 __device__ __forceinline__ void seq_bar_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(32u * (1 + SEQ_HELPERS)) : "memory"); }
+// the phase-2 warps among themselves (id 5)
+__device__ __forceinline__ void seq_bar_sync_helpers() { asm volatile("bar.sync 5, %0;" ::"r"(32u * SEQ_HELPERS) : "memory"); }
 __device__ __forceinline__ void seq_bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(32u * (1 + SEQ_HELPERS)) : "memory"); }
 #define SEQ_SMEM_FUSED (SEQ_TBL_BYTES + 256 * SEQ_CHAINS * 2 + sizeof(SeqShared))   // tables | counts, then stream rings | hand-over
 
@@ -256,7 +357,8 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
     const uint32_t mis = (uint32_t)((uintptr_t)src & 7);
     const uint8_t *base8 = src - mis;
 
-    // ---- set-up: the producer lanes build their tables and read the initial states; the other warps fill the code tables
+    // ---- set-up: the phase-2 warps fill the code tables and build the 3 x 32 FSE tables, one warp per table (6 tables per
+    // warp, fse_build_table_warp); then the producer lanes read their initial states
     SeqTables T;
     ZsbBlockWork w;
     bool active = false;
@@ -264,17 +366,40 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
     FastWin F; StreamRing R;
     int32_t top = 0, startbit = 0;
     uint32_t aL = 0, aO = 0, aM = 0, tbL = 0, tbO = 0, tbM = 0;
+    R.sa = 0; R.pl = base8; R.low = 0;
     if (warp == 0) {
         const uint32_t idx = blockIdx.x * SEQ_CHAINS + lane;
-        active = lane < SEQ_CHAINS && idx < n;
+        active = idx < n;
         bi = active ? seq_list[idx] : 0;
         if (active) { w = work[bi]; active = w.status == ZSB_OK; }
+    } else {
+        for (uint32_t k = threadIdx.x - 32; k < 36 + 53; k += 32 * SEQ_HELPERS) S.tab[k] = k < 36 ? zsb_ll_entry(k) : zsb_ml_entry(k - 36);
+        __syncwarp();
+        // the code tables are filled by all phase-2 warps together: wait for all of them
+        seq_bar_sync_helpers();
+        FseWarpScratch &X = reinterpret_cast<FseWarpScratch *>(counts)[warp - 1];
+        for (uint32_t q = 0; q < 3 * SEQ_CPH; q++) {
+            const uint32_t c = (warp - 1) * SEQ_CPH + q / 3, t = q % 3, idx = blockIdx.x * SEQ_CHAINS + c;
+            int rc = ZSB_OK, al = 0;
+            if (idx < n) {
+                const ZsbBlockWork &wb = work[seq_list[idx]];
+                if (wb.status == ZSB_OK) {
+                    uint32_t *tb = tbl + (t == 0 ? 0 : t == 1 ? SEQ_TBL_CELLS * SEQ_CHAINS : (SEQ_TBL_CELLS + SEQ_OF_CELLS) * SEQ_CHAINS) + c;
+                    rc = seq_build_table_warp(src, wb, (int)t, tb, SEQ_CHAINS, X, S.tab, t == 1 ? 8 : 9, al, lane);
+                }
+            }
+            if (lane == 0) { S.tal[c][t] = al; S.trc[c][t] = rc; }
+        }
+    }
+    __syncthreads();                                   // tables built; the count area becomes the stream rings
+    if (warp == 0) {
         T.ts = SEQ_CHAINS;
         T.tbl[0] = tbl + lane; T.tbl[1] = tbl + SEQ_TBL_CELLS * SEQ_CHAINS + lane; T.tbl[2] = tbl + (SEQ_TBL_CELLS + SEQ_OF_CELLS) * SEQ_CHAINS + lane;
-        T.max_al[0] = 9; T.max_al[1] = 8; T.max_al[2] = 9;
         int rc = ZSB_OK;
-        if (active) rc = seq_build_tables(src, w, T, counts + lane, SEQ_CHAINS);
-        __syncwarp();                                  // the count area becomes the stream rings
+        if (active) {
+            rc = S.trc[lane][0] ? S.trc[lane][0] : S.trc[lane][1] ? S.trc[lane][1] : S.trc[lane][2];     // the reference's order: LL, OF, ML
+            T.al[0] = S.tal[lane][0]; T.al[1] = S.tal[lane][1]; T.al[2] = S.tal[lane][2];
+        }
         if (active && !rc) {
             // == seq_fast_phase1 up to the first sequence (zsb_seqfast.h), on the stream ring
             const uint64_t start = w.bs_off;
@@ -310,15 +435,11 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
             work[bi].status = rc;
             active = false;
         }
-        if (lane < SEQ_CHAINS) {
-            S.nseq[lane] = active ? w.nseq : 0u;
-            S.regen[lane] = w.lit_regen; S.bi[lane] = bi;
-            S.top0[lane] = (unsigned long long)((int64_t)(R.pl - base8) * 8 + top);
-            S.rec[lane] = (unsigned long long)(uintptr_t)(seq_pool + w.seq_buf);
-            S.final_rc[lane] = ZSB_OK;
-        }
-    } else {
-        for (uint32_t k = threadIdx.x - 32; k < 36 + 53; k += 32 * SEQ_HELPERS) S.tab[k] = k < 36 ? zsb_ll_entry(k) : zsb_ml_entry(k - 36);
+        S.nseq[lane] = active ? w.nseq : 0u;
+        S.regen[lane] = w.lit_regen; S.bi[lane] = bi;
+        S.top0[lane] = (unsigned long long)((int64_t)(R.pl - base8) * 8 + top);
+        S.rec[lane] = (unsigned long long)(uintptr_t)(seq_pool + w.seq_buf);
+        S.final_rc[lane] = ZSB_OK;
     }
     __syncthreads();
 
@@ -1062,18 +1183,23 @@ __global__ void __launch_bounds__(32 * XXH_WARPS) k_xxh(const uint8_t *__restric
 }
 
 // ======================================================================================= stage kernels (one lane)
-__global__ void k_stage_fse(const uint8_t *desc, uint32_t n, int max_sym, const int16_t *dist_in, int ndist_in, int al_in,
-                            int *res /* rc, al, nsym, consumed */, uint32_t *cells, int16_t *dist_out) {
-    __shared__ int16_t cntbuf[256];
+__global__ void __launch_bounds__(32) k_stage_fse(const uint8_t *desc, uint32_t n, int max_sym, const int16_t *dist_in, int ndist_in, int al_in,
+                                                  int *res /* rc, al, nsym, consumed */, uint32_t *cells, int16_t *dist_out) {
+    __shared__ FseWarpScratch X;
+    const uint32_t lane = threadIdx.x;
     int al = al_in, nsym = ndist_in, rc = 0; uint32_t consumed = 0;
     if (desc) {
-        FwdBits f; fwd_init(f, desc, n);
-        rc = fse_read_ncount(f, cntbuf, 1, max_sym, al, nsym);
-        consumed = fwd_bytes_read(f);
-    } else for (int i = 0; i < nsym; i++) cntbuf[i] = dist_in[i];
-    if (!rc && dist_out) for (int i = 0; i < nsym && i < 256; i++) dist_out[i] = cntbuf[i];
-    if (!rc) { if (al > ZSB_MAX_AL) rc = ZSB_E_LARGE_ACCURACY_LOG; else rc = fse_build_table(cntbuf, 1, nsym, al, cells, 1, 3); }
-    res[0] = rc; res[1] = al; res[2] = nsym; res[3] = (int)consumed;
+        if (lane == 0) {
+            FwdBits f; fwd_init(f, desc, n);
+            rc = fse_read_ncount(f, X.cnt, 1, max_sym < 64 ? max_sym : 64, al, nsym);
+            consumed = fwd_bytes_read(f);
+        }
+        rc = __shfl_sync(FULL, rc, 0); al = __shfl_sync(FULL, al, 0); nsym = __shfl_sync(FULL, nsym, 0); consumed = __shfl_sync(FULL, consumed, 0);
+    } else for (int i = (int)lane; i < nsym; i += 32) X.cnt[i] = dist_in[i];
+    __syncwarp();
+    if (!rc && dist_out) for (int i = (int)lane; i < nsym; i += 32) dist_out[i] = X.cnt[i];
+    if (!rc) { if (al > ZSB_MAX_AL || al < 5) rc = al > ZSB_MAX_AL ? ZSB_E_LARGE_ACCURACY_LOG : ZSB_E_ARG; else rc = fse_build_table_warp(X, nsym, al, cells, 1, 3, nullptr, lane); }
+    if (lane == 0) { res[0] = rc; res[1] = al; res[2] = nsym; res[3] = (int)consumed; }
 }
 __global__ void k_stage_huf(const uint8_t *desc, uint32_t n, int *res /* rc, maxbits, consumed */, uint8_t *lens, uint16_t *lut_out) {
     __shared__ HufSlot S;
@@ -1151,7 +1277,7 @@ void zsbk_xxh(cudaStream_t st, uint32_t n, const uint8_t *dst, ZsbFrameOut *fout
 }
 void zsbk_stage_fse(cudaStream_t st, const uint8_t *desc, uint32_t n, int max_sym, const int16_t *dist_in, int ndist_in, int al_in,
                     int *res, uint32_t *cells, int16_t *dist_out) {
-    k_stage_fse<<<1, 1, 0, st>>>(desc, n, max_sym, dist_in, ndist_in, al_in, res, cells, dist_out);
+    k_stage_fse<<<1, 32, 0, st>>>(desc, n, max_sym, dist_in, ndist_in, al_in, res, cells, dist_out);
 }
 void zsbk_stage_huf(cudaStream_t st, const uint8_t *desc, uint32_t n, int *res, uint8_t *lens, uint16_t *lut) {
     k_stage_huf<<<1, 1, 0, st>>>(desc, n, res, lens, lut);

@@ -26,22 +26,32 @@ struct SeqTables {
 };
 #define ZSB_TABLE_TOO_SMALL (-2)   // internal: seq_build_tables met a table larger than the caller's storage
 
-// Builds the three tables of block `w` (modes already resolved, never ZSB_M_REPEAT).
+// Builds table t (0 LL, 1 OF, 2 ML) of block `w` (modes already resolved, never ZSB_M_REPEAT) into tbl (stride ts).
+// cnt: scratch for max_sym counts (stride cs); max_al: largest accuracy log tbl has room for (0 = ZSB_MAX_AL).
+// A description with more symbols than max_sym or a larger accuracy log returns ZSB_TABLE_TOO_SMALL.
+ZSB_HDN int seq_build_table(const uint8_t *src, const ZsbBlockWork &w, int t, uint32_t *tbl, int ts, int16_t *cnt, int cs, int max_sym, int max_al,
+                            int &al_out) {
+    const int mode = w.mode[t];
+    if (mode == ZSB_M_RLE) { fse_build_rle(w.rle_sym[t], tbl, t); al_out = 0; return ZSB_OK; }
+    int al, nsym, rc;
+    if (mode == ZSB_M_PREDEFINED) fse_predefined_counts(t, cnt, cs, al, nsym);
+    else if (mode == ZSB_M_FSE) {
+        FwdBits f; fwd_init(f, src + w.tbl_desc[t], w.tbl_end - w.tbl_desc[t]);
+        rc = fse_read_ncount(f, cnt, cs, max_sym, al, nsym);
+        if (rc == ZSB_E_CORRUPT && max_sym < 256) return ZSB_TABLE_TOO_SMALL;      // more symbols than the scratch holds
+        if (rc) return rc;
+    } else return ZSB_E_NO_PREVIOUS_DECODER;
+    if (max_al && al > max_al) return ZSB_TABLE_TOO_SMALL;
+    rc = fse_build_table(cnt, cs, nsym, al, tbl, ts, t);
+    if (rc) return rc;
+    al_out = al;
+    return ZSB_OK;
+}
+// Builds the three tables of block `w` in the reference's order (LL, OF, ML: sequences.rs:116-141).
 ZSB_HDN int seq_build_tables(const uint8_t *src, const ZsbBlockWork &w, SeqTables &T, int16_t *cnt, int cs) {
     for (int t = 0; t < 3; t++) {
-        int mode = w.mode[t];
-        if (mode == ZSB_M_RLE) { fse_build_rle(w.rle_sym[t], T.tbl[t], t); T.al[t] = 0; continue; }
-        int al, nsym, rc;
-        if (mode == ZSB_M_PREDEFINED) fse_predefined_counts(t, cnt, cs, al, nsym);
-        else if (mode == ZSB_M_FSE) {
-            FwdBits f; fwd_init(f, src + w.tbl_desc[t], w.tbl_end - w.tbl_desc[t]);
-            rc = fse_read_ncount(f, cnt, cs, 256, al, nsym);
-            if (rc) return rc;
-        } else return ZSB_E_NO_PREVIOUS_DECODER;
-        if (T.max_al[t] && al > T.max_al[t]) return ZSB_TABLE_TOO_SMALL;
-        rc = fse_build_table(cnt, cs, nsym, al, T.tbl[t], T.ts, t);
+        const int rc = seq_build_table(src, w, t, T.tbl[t], T.ts, cnt, cs, 256, T.max_al[t], T.al[t]);
         if (rc) return rc;
-        T.al[t] = al;
     }
     return ZSB_OK;
 }
