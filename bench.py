@@ -9,8 +9,8 @@ by libzstd from the moby-dick fixture with fixed seeds (tools/gen_corpus.py).  W
 rank decodes its own F-frame shard (frames shard by frame, no collective on the decode path): weak
 scaling, `value` = bytes all ranks produced / max-over-ranks device time.
 
-A step = one pass of the whole decode path (8 kernels: section parse, plan, Huffman literals, FSE
-sequences, plan, raw/RLE, sequence execution, XXH64) over the batch, checksums verified.
+A step = one pass of the whole decode path (section parse, plan, Huffman literals, FSE sequences (+ the
+careful re-decode of rejected blocks), plan, raw/RLE, sequence execution, XXH64) over the batch, checksums verified.
 `value`: compressed input and output resident in HBM, CUDA-event time on the launching stream.
 `e2e`  : the same through the C ABI with HOST buffers (zsb_scan + zsb_decode on pinned memory): the
          host walk, H2D of the compressed bytes and D2H of the output are inside the timed region.

@@ -115,7 +115,7 @@ extern "C" int zsb_kernel_times_avg(zsb_ctx *c, const char **names, float *ms, i
         if (names) names[i] = c->kname[i];
         if (ms) ms[i] = L ? (float)(sum / L) : 0.f;
     }
-    if (n < cap && c->nk) {       // the literals stage ran on the auxiliary stream, beside k_seq1/k_seq2
+    if (n < cap && c->nk && c->overlap) {       // the literals stage ran on the auxiliary stream, beside k_seq
         double sum = 0;
         for (int r = 0; r < L; r++) { float t = 0; if (cudaEventElapsedTime(&t, c->ev_huf[r][0], c->ev_huf[r][1]) == cudaSuccess) sum += t; else (void)cudaGetLastError(); }
         if (names) names[n] = "k_huf(aux stream)";
@@ -212,17 +212,22 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
                                     c->lit_cap, c->seq_cap, c->flags); c->launches++;
     // the literals stage (k_huf) and the sequence stage (k_seq) read the same blocks and write disjoint results; with ZSB_OVERLAP=1
     // k_huf runs on the auxiliary stream beside k_seq (enqueued first: its CTAs need the larger shared-memory slice).
-    cudaStream_t hst = c->overlap ? c->aux_stream : st;
-    CK(c, cudaEventRecord(c->ev_fork, st));
-    CK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-    MARK(c, "k_seq");    zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p);
-    if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][0], hst);
-    zsbk_huf(hst, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags); c->launches += c->ncomp ? 1 : 0;
-    if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][1], hst);
-    CK(c, cudaEventRecord(c->ev_join, c->aux_stream));
+    if (c->overlap) {
+        CK(c, cudaEventRecord(c->ev_fork, st));
+        CK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p);
+        if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][0], c->aux_stream);
+        zsbk_huf(c->aux_stream, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags);
+        if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][1], c->aux_stream);
+        CK(c, cudaEventRecord(c->ev_join, c->aux_stream));
+    } else {
+        MARK(c, "k_huf");  zsbk_huf(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags);
+        MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p);
+    }
+    c->launches += c->ncomp ? 1 : 0;
     MARK(c, "k_seq_slow"); zsbk_seq_slow(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->slow_list.p, cnt, (uint64_t *)c->seq_pool.p);
     c->launches += c->ncomp ? 2 : 0;
-    MARK(c, "wait k_huf"); CK(c, cudaStreamWaitEvent(st, c->ev_join, 0));
+    if (c->overlap) { MARK(c, "wait k_huf"); CK(c, cudaStreamWaitEvent(st, c->ev_join, 0)); }
     MARK(c, "k_plan2");  zsbk_plan2(st, frames, c->nf, blocks, work, fout, cnt, c->dst_cap, c->flags); c->launches++;
     MARK(c, "k_rawrle"); zsbk_rawrle(st, c->n_rawrle, src, blocks, work, fout, (const uint32_t *)c->rawrle_list.p, cnt, c->d_dst); c->launches += c->n_rawrle ? 1 : 0;
     MARK(c, "k_exec2");  zsbk_exec2(st, c->n_exec2, src, frames, blocks, work, fout, (const uint32_t *)c->exec2_list.p, cnt, (const uint64_t *)c->seq_pool.p,

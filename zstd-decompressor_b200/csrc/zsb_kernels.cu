@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(1024) k_plan1(const zsb_frame *__restrict__ fr
 // weight FSE table while the weights are being decoded), weights, counts, ranks.  Per lane: a 256-byte ring
 // through which cp.async feeds its stream (zsb_stream.h).  The decode is one dependent chain per stream (LUT cell ->
 // code length -> next LUT index), so like k_seq1 the kernel is latency bound and shares the SMs with k_seq1.
-#define HUF_SLOTS 8
+#define HUF_SLOTS 4
+#define HUF_THREADS (4 * HUF_SLOTS)
+#define HUF_MASK (HUF_THREADS == 32 ? 0xFFFFFFFFu : ((1u << HUF_THREADS) - 1u))
 #define HUF_LUT_BYTES (2u << ZSB_HUF_MAX_BITS)   // 4096
 struct HufSlot {
     union { uint16_t lut[1 << ZSB_HUF_MAX_BITS]; uint32_t ftbl[512]; } u;
@@ -114,11 +116,11 @@ struct HufSlot {
     int maxbits;
     int status;
 };
-__global__ void __launch_bounds__(32) k_huf(const uint8_t *__restrict__ src, uint64_t src_len, ZsbBlockWork *work,
+__global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__ src, uint64_t src_len, ZsbBlockWork *work,
                                             const uint32_t *__restrict__ huf_list, const ZsbCounters *__restrict__ cnt,
                                             uint8_t *lit_pool, uint32_t flags) {
     __shared__ HufSlot slots[HUF_SLOTS];
-    __shared__ __align__(128) uint8_t rings[32][256];
+    __shared__ __align__(128) uint8_t rings[HUF_THREADS][256];
     if (cnt->overflow) return;
     const uint32_t lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
     const uint32_t n = cnt->n_huf, idx = blockIdx.x * HUF_SLOTS + slot;
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(32) k_huf(const uint8_t *__restrict__ src, uin
         if (!rc) rc = huf_build_lut(S.weights, 1, nw, S.u.lut, S.rank, 1, mb, nullptr);
         S.maxbits = mb; S.status = rc;
     }
-    __syncwarp();
+    __syncwarp(HUF_MASK);
     int rc = 0;
     if (active) {
         rc = S.status;
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(32) k_huf(const uint8_t *__restrict__ src, uin
         }
     }
     // first failing stream of the block decides its status
-    const int r1 = __shfl_sync(FULL, rc, (lane & ~3u) + 1), r2 = __shfl_sync(FULL, rc, (lane & ~3u) + 2), r3 = __shfl_sync(FULL, rc, (lane & ~3u) + 3);
+    const int r1 = __shfl_sync(HUF_MASK, rc, (lane & ~3u) + 1), r2 = __shfl_sync(HUF_MASK, rc, (lane & ~3u) + 2), r3 = __shfl_sync(HUF_MASK, rc, (lane & ~3u) + 3);
     if (active && stream == 0) {
         int st = rc ? rc : r1 ? r1 : r2 ? r2 : r3;
         if (st) work[bi].lit_status = st;
@@ -1246,7 +1248,7 @@ void zsbk_plan1(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb
 }
 void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *huf_list,
               const ZsbCounters *cnt, uint8_t *lit_pool, uint32_t flags) {
-    if (ncomp) k_huf<<<(ncomp + HUF_SLOTS - 1) / HUF_SLOTS, 32, 0, st>>>(src, src_len, work, huf_list, cnt, lit_pool, flags);
+    if (ncomp) k_huf<<<(ncomp + HUF_SLOTS - 1) / HUF_SLOTS, HUF_THREADS, 0, st>>>(src, src_len, work, huf_list, cnt, lit_pool, flags);
 }
 void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
               uint64_t *seq_pool, uint32_t *slow_list) {
