@@ -276,3 +276,24 @@ def test_two_gpus_two_ranks():
     blob, exp = corpora.c2_small(64)
     outs = [Z.decode_shard(blob, rank, 2, Q | VER, ctx=Z.Context(rank))[0] for rank in range(2)]
     assert b"".join(outs) == exp
+
+
+# ---------------------------------------------------------------- BASELINE full sizes: C3 (one 1 GiB frame) and C5's per-GPU share
+def test_c3_full_size_single_frame(dec):
+    """one multi-segment 1 GiB frame, 8 192 blocks, window 8 MiB: executed block after block by one CTA (k_exec);
+    size-independent checks: SHA-256 against the plaintext and the stored XXH64 verified on the GPU"""
+    import gen_corpus as G
+    blob, exp = G.make_c3(total=1 << 30)
+    out, sc, r = dec.decode(blob, Q | VER)
+    assert first_status(sc, r) == 0 and sc.n_frames == 1 and sc.frames[0].n_blocks >= 8192 and sc.frames[0].single_segment == 0
+    assert len(out) == 1 << 30 and r.checksum_ok[0] == 1
+    assert hashlib.sha256(out).digest() == hashlib.sha256(exp).digest()
+
+
+def test_c5_per_gpu_share(dec):
+    """C5 = 65 536 frames over 8 GPUs: one GPU's share (8 192 frames, 1 GiB out) in one batch"""
+    import gen_corpus as G
+    blob, exp = G.make_c2(8192, seed=5)
+    out, sc, r = dec.decode(blob, Q | VER)
+    assert first_status(sc, r) == 0 and sc.n_frames == 8192 and all(r.checksum_ok[i] for i in range(8192))
+    assert hashlib.sha256(out).digest() == hashlib.sha256(exp).digest()
