@@ -856,7 +856,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
 #define EX2_RING 4096u
 #define EX2_MASK (EX2_RING - 1u)
 #define EX2_WARPS 4
-#define EX2_LONG 32u
+#define EX2_LONG 16u
 #define EX2_GIANT (EX2_RING / 2)
 
 struct Ex2Lit { const uint8_t *p; uint32_t rle; bool is_rle; };
@@ -877,20 +877,25 @@ __device__ __forceinline__ uint8_t ex2_src(const uint8_t *ring, const uint8_t *g
     return p >= ring_lo ? ring[(g0 + (uint32_t)p) & EX2_MASK] : __ldcg(gblk + p);
 }
 
-// ---- copies in units of up to 8 bytes: three aligned source words, two funnel shifts, byte stores
-// store the low n (<= 8) bytes of v1:v0 at ring position d (unmasked)
+// ---- copies in units of up to 8 bytes: three aligned source words, two funnel shifts, predicated byte stores
+// store the low n (1..8) bytes of v1:v0 at ring position d (unmasked)
 __device__ __forceinline__ void ex2_store8(uint8_t *ring, uint32_t d, uint32_t v0, uint32_t v1, uint32_t n) {
     d &= EX2_MASK;
     if (d + 8 <= EX2_RING) {
-        uint8_t *p = ring + d;
-        if (n > 0) p[0] = (uint8_t)v0;
-        if (n > 1) p[1] = (uint8_t)(v0 >> 8);
-        if (n > 2) p[2] = (uint8_t)(v0 >> 16);
-        if (n > 3) p[3] = (uint8_t)(v0 >> 24);
-        if (n > 4) p[4] = (uint8_t)v1;
-        if (n > 5) p[5] = (uint8_t)(v1 >> 8);
-        if (n > 6) p[6] = (uint8_t)(v1 >> 16);
-        if (n > 7) p[7] = (uint8_t)(v1 >> 24);
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(ring) + d;
+        asm volatile(
+            "{\n\t.reg .pred p1, p2, p3, p4, p5, p6, p7;\n\t.reg .b32 t;\n\t"
+            "setp.gt.u32 p1, %3, 1;\n\tsetp.gt.u32 p2, %3, 2;\n\tsetp.gt.u32 p3, %3, 3;\n\tsetp.gt.u32 p4, %3, 4;\n\t"
+            "setp.gt.u32 p5, %3, 5;\n\tsetp.gt.u32 p6, %3, 6;\n\tsetp.gt.u32 p7, %3, 7;\n\t"
+            "st.shared.u8 [%0], %1;\n\t"
+            "shr.u32 t, %1, 8;\n\t@p1 st.shared.u8 [%0+1], t;\n\t"
+            "shr.u32 t, %1, 16;\n\t@p2 st.shared.u8 [%0+2], t;\n\t"
+            "shr.u32 t, %1, 24;\n\t@p3 st.shared.u8 [%0+3], t;\n\t"
+            "@p4 st.shared.u8 [%0+4], %2;\n\t"
+            "shr.u32 t, %2, 8;\n\t@p5 st.shared.u8 [%0+5], t;\n\t"
+            "shr.u32 t, %2, 16;\n\t@p6 st.shared.u8 [%0+6], t;\n\t"
+            "shr.u32 t, %2, 24;\n\t@p7 st.shared.u8 [%0+7], t;\n\t}"
+            ::"r"(a), "r"(v0), "r"(v1), "r"(n) : "memory");
     } else {
         const uint64_t v = ((uint64_t)v1 << 32) | v0;
         for (uint32_t t = 0; t < n; t++) ring[(d + t) & EX2_MASK] = (uint8_t)(v >> (8 * t));
@@ -993,7 +998,16 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 8) k_exec2(const uint8_t *__re
                     continue;
                 }
                 ring_lo = max(ring_lo, (int32_t)B1 - (int32_t)EX2_RING);
-                // ---- literals (no dependency on earlier output, decoding_context.rs:92-93)
+                // ---- the HBM reads of the batch are requested first, so that their latencies overlap: the sources of short matches
+                // that lie entirely in HBM (<= 16 bytes: two units; they depend on nothing in this batch) ...
+                const int32_t send = srcp + (int32_t)ml;
+                const bool farm = ml && ml <= EX2_LONG && send <= ring_lo && !(off < 8 && off < ml);
+                uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+                if (farm) {
+                    ex2_load8_glob(gblk + srcp, min(ml, 8u), f0, f1, true);
+                    if (ml > 8) ex2_load8_glob(gblk + srcp + 8, ml - 8, f2, f3, true);
+                }
+                // ---- ... and the literals (no dependency on earlier output, decoding_context.rs:92-93)
                 if (ll && ll <= EX2_LONG) {
                     if (L.is_rle) { const uint32_t v = L.rle * 0x01010101u; for (uint32_t q = 0; q < ll; q += 8) ex2_store8(ring, g0 + p_out + q, v, v, min(ll - q, 8u)); }
                     else for (uint32_t q = 0; q < ll; q += 8) {
@@ -1010,8 +1024,9 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 8) k_exec2(const uint8_t *__re
                 __syncwarp();
                 // ---- matches (decoding_context.rs:95-98): a lane goes once everything it needs from other sequences is written,
                 // i.e. lies below the match start of the lowest sequence still pending
-                bool pend = ml != 0;
-                const int32_t send = srcp + (int32_t)ml;
+                if (farm) { ex2_store8(ring, g0 + dstm, f0, f1, min(ml, 8u)); if (ml > 8) ex2_store8(ring, g0 + dstm + 8, f2, f3, ml - 8); }
+                __syncwarp();
+                bool pend = ml != 0 && !farm;
                 const int32_t need = min(send, (int32_t)p_out);
                 for (;;) {
                     const uint32_t pm = __ballot_sync(FULL, pend);
@@ -1027,13 +1042,7 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 8) k_exec2(const uint8_t *__re
                                 ex2_load8_ring(ring, g0 + (uint32_t)srcp + q, c, v0, v1);
                                 ex2_store8(ring, g0 + dstm + q, v0, v1, c);
                             }
-                        } else if (send <= ring_lo) {                  // source already in HBM only
-                            for (uint32_t q = 0; q < ml; q += 8) {
-                                const uint32_t c = min(ml - q, 8u); uint32_t v0, v1;
-                                ex2_load8_glob(gblk + srcp + (int32_t)q, c, v0, v1, true);
-                                ex2_store8(ring, g0 + dstm + q, v0, v1, c);
-                            }
-                        } else {
+                        } else {                                       // straddles the ring floor (sources entirely in HBM were done above)
                             for (uint32_t q = 0; q < ml; q++) ring[(g0 + dstm + q) & EX2_MASK] = ex2_src(ring, gblk, g0, ring_lo, srcp + (int32_t)q);
                         }
                         pend = false;
