@@ -173,6 +173,24 @@ ZSB_HDN int huf_fast_stream(const uint8_t *src, uint64_t start, uint64_t end, co
         const uint32_t cell = lut[(uint32_t)(fast_win_get(F) >> sh)];
         out[n++] = (uint8_t)cell; top -= (int32_t)(cell >> 8);
     }
+#if defined(__CUDA_ARCH__)
+    // eight steps of four symbols consume at most 352 bits, less than a 64-byte line: the ring is topped up once per eight
+    // steps, by all lanes of the warp in the same pass
+    for (; n + 32 <= expect; n += 32) {
+        sr_check<6>(R, top);
+#pragma unroll 2
+        for (uint32_t k = 0; k < 32; k += 4) {
+            sr_load_nocheck<6>(R, F, top);
+            uint64_t W = fast_win_get(F);
+            const uint32_t c0 = lut[(uint32_t)(W >> sh)]; W <<= (c0 >> 8);
+            const uint32_t c1 = lut[(uint32_t)(W >> sh)]; W <<= (c1 >> 8);
+            const uint32_t c2 = lut[(uint32_t)(W >> sh)]; W <<= (c2 >> 8);
+            const uint32_t c3 = lut[(uint32_t)(W >> sh)];
+            top -= (int32_t)((c0 >> 8) + (c1 >> 8) + (c2 >> 8) + (c3 >> 8));
+            *reinterpret_cast<uint32_t *>(out + n + k) = (c0 & 0xFFu) | (c1 & 0xFFu) << 8 | (c2 & 0xFFu) << 16 | c3 << 24;
+        }
+    }
+#endif
     for (; n + 4 <= expect; n += 4) {
         HUF_LOAD(top);
         uint64_t W = fast_win_get(F);

@@ -1160,12 +1160,22 @@ __global__ void __launch_bounds__(32 * XXH_WARPS) k_xxh(const uint8_t *__restric
             __syncwarp();
             const uint8_t *bp = &s_buf[warp][c & 1][fj][0];
             const uint32_t s_lo = c << 4;
-#pragma unroll 4
-            for (uint32_t s = 0; s < 16; s++) {
-                if (s_lo + s < ns) {
-                    const uint32_t B = m + 32u * s + 8u * q;
-                    const unsigned long long *w = reinterpret_cast<const unsigned long long *>(bp + (B & ~7u));
-                    const uint64_t x = zsb_shr64(w[0], sh) | zsb_shl64(w[1], 64 - sh);
+            const unsigned long long *w = reinterpret_cast<const unsigned long long *>(bp + ((m + 8u * q) & ~7u));
+            if (s_lo + 16 <= ns) {
+                // a full step: the 16 (or 17) words are loaded first, x * P2 is off the chain, the chain is rotl(acc + y, 31) * P1
+                uint64_t y[16];
+                if (sh == 0) {
+#pragma unroll
+                    for (int s = 0; s < 16; s++) y[s] = w[4 * s] * XP2;
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 16; s++) y[s] = (zsb_shr64(w[4 * s], sh) | zsb_shl64(w[4 * s + 1], 64 - sh)) * XP2;
+                }
+#pragma unroll
+                for (int s = 0; s < 16; s++) v = rotl64(v + y[s], 31) * XP1;
+            } else {
+                for (uint32_t s = 0; s < 16 && s_lo + s < ns; s++) {
+                    const uint64_t x = zsb_shr64(w[4 * s], sh) | zsb_shl64(w[4 * s + 1], 64 - sh);
                     v = xround(v, x);
                 }
             }
