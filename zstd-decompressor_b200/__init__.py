@@ -63,6 +63,11 @@ def build(force=False, verbose=False):
     return _build_module().build(force=force, verbose=verbose)
 
 
+def build_cli(force=False):
+    """Build cli/zstd-decompressor (flag compatible with the reference's src/main.rs)."""
+    return _build_module().build_cli(force=force)
+
+
 _lib = None
 
 

@@ -40,5 +40,21 @@ def build(force=False, verbose=False):
     return OUT
 
 
+CLI_SRC = os.path.join(os.path.dirname(HERE), "cli", "zstd_decompressor.cpp")
+CLI_OUT = os.path.join(os.path.dirname(HERE), "cli", "zstd-decompressor")
+
+
+def build_cli(force=False):
+    """The command line front end (cli/zstd_decompressor.cpp), linked against libzsb.so next to the package."""
+    build()
+    if not force and os.path.exists(CLI_OUT) and os.path.getmtime(CLI_OUT) > max(os.path.getmtime(CLI_SRC), os.path.getmtime(OUT)):
+        return CLI_OUT
+    cmd = [shutil.which("g++") or "g++", "-O2", "-std=c++17", "-o", CLI_OUT, CLI_SRC, OUT, "-Wl,-rpath," + HERE]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return CLI_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
