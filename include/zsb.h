@@ -135,7 +135,10 @@ const char *zsb_last_cuda_error(const zsb_ctx *ctx);
  * its dst_len is 0); xxh32 = low 32 bits of XXH64(seed 0) of its content when ZSB_VERIFY_CHECKSUM
  * and the frame stores a checksum; checksum_ok = 1 if equal to the stored value (a mismatch is
  * reported, not an error -- the reference only prints a warning, frame.rs:251-254).
- * *dst_total = bytes produced.  Returns ZSB_OK if the batch ran (inspect status[]), else an error. */
+ * *dst_total = bytes produced.  Returns ZSB_OK if the batch ran (inspect status[]), else an error.
+ * With host buffers and >= 512 frames that all declare Frame_Content_Size the batch is cut into 8 shards by frame, each on its
+ * own stream: upload, kernels and download of different shards overlap (same results; pinned host memory makes the copies
+ * asynchronous). */
 int zsb_decode(zsb_ctx *ctx, const uint8_t *src, size_t n,
                const zsb_frame *frames, size_t n_frames, const zsb_block *blocks, size_t n_blocks,
                uint8_t *dst, size_t dst_cap, uint64_t *dst_off, uint64_t *dst_len,
@@ -143,7 +146,8 @@ int zsb_decode(zsb_ctx *ctx, const uint8_t *src, size_t n,
                uint64_t *dst_total, uint32_t flags);
 
 /* Split zsb_decode for callers that keep data resident and time the GPU work only:
- * prepare uploads descriptors (and src unless ZSB_SRC_ON_DEVICE) and sizes the scratch;
+ * prepare enqueues the upload of the descriptors (and of src unless ZSB_SRC_ON_DEVICE: src must stay unchanged until finish)
+ * and sizes the scratch;
  * launch enqueues every kernel of the batch on the ctx stream and returns without synchronising;
  * finish synchronises and returns the per-frame results. */
 int zsb_decode_prepare(zsb_ctx *ctx, const uint8_t *src, size_t n,

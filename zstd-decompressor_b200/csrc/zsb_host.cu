@@ -45,7 +45,11 @@ struct zsb_ctx {
     uint32_t nf = 0, nb = 0, ncomp = 0, n_rawrle = 0, n_exec = 0, n_exec2 = 0, n_xxh = 0, flags = 0;
     uint64_t lit_cap = 0, seq_cap = 0;
     std::vector<zsb_frame> h_frames;
-    std::vector<uint32_t> h_xxh_list;
+    std::vector<zsb_block> h_blocks;
+    std::vector<uint32_t> h_xxh_list, h_rawrle, h_exec, h_exec2;   // host copies stay alive while their uploads are in flight
+    std::vector<zsb_ctx *> subs;          // child contexts of the pipelined host path (own stream + scratch each)
+    bool is_sub = false;
+    uint64_t eager_d2h = 0;               // pipelined path: bytes of output to send to the host right behind the kernels (size known from the headers)
     bool prepared = false, launched = false;
     bool overlap = false;      // ZSB_OVERLAP=1: literals stage on the auxiliary stream beside k_seq (measured slower: both are latency bound and share schedulers)
     // profiling
@@ -80,6 +84,8 @@ extern "C" int zsb_ctx_create(zsb_ctx **out, int device) {
 }
 extern "C" void zsb_ctx_destroy(zsb_ctx *c) {
     if (!c) return;
+    for (zsb_ctx *sub : c->subs) zsb_ctx_destroy(sub);
+    c->subs.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list, &c->exec2_list,
@@ -145,8 +151,11 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     else { CK(c, c->dst.ensure(dst_cap + 64)); c->d_dst = (uint8_t *)c->dst.p; c->h_dst = dst; }
     c->src_len = n; c->dst_cap = dst_cap; c->nf = (uint32_t)nf; c->nb = (uint32_t)nb; c->flags = flags;
     c->h_frames.assign(frames, frames + nf);
+    c->h_blocks.assign(blocks, blocks + nb);
+    frames = c->h_frames.data(); blocks = c->h_blocks.data();      // the caller's arrays are not touched after this call returns
     // host-side work lists (block types and frame kinds are known from the scan)
-    std::vector<uint32_t> rawrle, execl, exec2l;
+    std::vector<uint32_t> &rawrle = c->h_rawrle, &execl = c->h_exec, &exec2l = c->h_exec2;
+    rawrle.clear(); execl.clear(); exec2l.clear();
     c->h_xxh_list.clear();
     uint64_t ncomp = 0, lit_cap = 0, seq_cap = 0;
     for (size_t i = 0; i < nb; i++) {
@@ -190,8 +199,7 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     if (!execl.empty()) CK(c, cudaMemcpyAsync(c->exec_list.p, execl.data(), 4 * execl.size(), cudaMemcpyHostToDevice, st));
     if (!exec2l.empty()) CK(c, cudaMemcpyAsync(c->exec2_list.p, exec2l.data(), 4 * exec2l.size(), cudaMemcpyHostToDevice, st));
     if (!c->h_xxh_list.empty()) CK(c, cudaMemcpyAsync(c->xxh_list.p, c->h_xxh_list.data(), 4 * c->h_xxh_list.size(), cudaMemcpyHostToDevice, st));
-    CK(c, cudaStreamSynchronize(st));   // the host vectors above go out of scope
-    c->prepared = true;
+    c->prepared = true;               // nothing waited for: the uploads read the context's own host copies, and `src` if it is host memory
     return ZSB_OK;
 }
 
@@ -236,6 +244,7 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
                                    (const uint8_t *)c->lit_pool.p, c->d_dst); c->launches += c->n_exec ? 1 : 0;
     MARK(c, "k_xxh");    zsbk_xxh(st, c->n_xxh, c->d_dst, fout, (const uint32_t *)c->xxh_list.p, cnt); c->launches += c->n_xxh ? 1 : 0;
     if (c->profile) { cudaEventRecord(c->ev[c->prof_slot][c->nk], st); c->prof_slot = (c->prof_slot + 1) % kProfRing; c->prof_count++; }
+    if (c->eager_d2h && c->h_dst) CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, c->eager_d2h, cudaMemcpyDeviceToHost, st));
     CK(c, cudaGetLastError());
     c->launched = true;
     return ZSB_OK;
@@ -262,7 +271,7 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
     if (c->profile) { const int r = (c->prof_slot + kProfRing - 1) % kProfRing; for (int i = 0; i < c->nk; i++) cudaEventElapsedTime(&c->kms[i], c->ev[r][i], c->ev[r][i + 1]); }
     std::vector<ZsbFrameOut> fo(c->nf);
     if (c->nf) CK(c, cudaMemcpyAsync(fo.data(), c->fout.p, sizeof(ZsbFrameOut) * c->nf, cudaMemcpyDeviceToHost, st));
-    if (c->h_dst && hc.dst_total) CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, hc.dst_total, cudaMemcpyDeviceToHost, st));
+    if (c->h_dst && hc.dst_total && hc.dst_total != c->eager_d2h) CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, hc.dst_total, cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     for (uint32_t f = 0; f < c->nf; f++) {
         const bool ok = fo[f].status == ZSB_OK;
@@ -277,9 +286,81 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
     return ZSB_OK;
 }
 
+// Host buffers, many frames: the batch is cut into shards by frame (zsb_shard_plan) and every shard runs on its own
+// stream and scratch -- upload of shard k+1, kernels of shard k and download of shard k-1 overlap (PCIe is ~3/4 of the
+// host-to-host time of a batch).  Output placement needs every frame's size before it is decoded, so this path is taken
+// only when all frames declare Frame_Content_Size, and its result is kept only if every frame decoded to exactly that
+// size; otherwise (return 1) the plain path runs and reports as usual.
+static const size_t kPipeMinFrames = 512;
+static const int kPipeShards = 8;
+static int decode_pipelined(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_frame *frames, size_t nf, const zsb_block *blocks, size_t nb,
+                            uint8_t *dst, size_t dst_cap, uint64_t *dst_off, uint64_t *dst_len, int32_t *status, uint32_t *xxh32,
+                            uint8_t *checksum_ok, uint64_t *dst_total, uint32_t flags) {
+    (void)n;
+    uint64_t expect_total = 0;
+    for (size_t f = 0; f < nf; f++) {
+        if (frames[f].status != ZSB_OK) return 1;
+        if (frames[f].kind == 1) { if (flags & ZSB_PRINT_SKIPPABLE) expect_total += blocks[frames[f].first_block].size; }
+        else if (!frames[f].has_content_size) return 1;
+        else expect_total += frames[f].content_size;
+    }
+    if (expect_total > dst_cap || expect_total < (32u << 20)) return 1;
+    size_t first[kPipeShards + 1];
+    if (zsb_shard_plan(frames, nf, kPipeShards, first) != ZSB_OK) return 1;
+    while (c->subs.size() < (size_t)kPipeShards) {
+        zsb_ctx *sub = nullptr;
+        if (zsb_ctx_create(&sub, c->device) != ZSB_OK) return 1;
+        sub->is_sub = true;
+        c->subs.push_back(sub);
+    }
+    struct Sh { zsb_frame *fr = nullptr; zsb_block *bl = nullptr; size_t nb = 0; uint64_t so = 0, sl = 0, doff = 0, dexp = 0; bool on = false; } sh[kPipeShards];
+    int rc = ZSB_OK; bool fallback = false;
+    uint64_t doff = 0;
+    for (int k = 0; k < kPipeShards && !fallback; k++) {
+        Sh &S = sh[k];
+        const size_t f0 = first[k], f1 = first[k + 1];
+        S.doff = doff;
+        if (f0 == f1) continue;
+        if (zsb_shard_extract(frames, nf, blocks, nb, f0, f1, &S.fr, &S.bl, &S.nb, &S.so, &S.sl) != ZSB_OK) { fallback = true; break; }
+        for (size_t f = f0; f < f1; f++)
+            S.dexp += frames[f].kind == 1 ? ((flags & ZSB_PRINT_SKIPPABLE) ? blocks[frames[f].first_block].size : 0) : frames[f].content_size;
+        doff += S.dexp;
+        zsb_ctx *sub = c->subs[k];
+        sub->eager_d2h = S.dexp;
+        if (zsb_decode_prepare(sub, src + S.so, S.sl, S.fr, f1 - f0, S.bl, S.nb, dst + S.doff, S.dexp, flags) != ZSB_OK ||
+            zsb_decode_launch(sub) != ZSB_OK) { fallback = true; break; }
+        S.on = true;
+    }
+    uint64_t total = 0;
+    for (int k = 0; k < kPipeShards; k++) {
+        Sh &S = sh[k];
+        if (S.on) {
+            const size_t f0 = first[k], f1 = first[k + 1];
+            uint64_t t = 0;
+            const int r = zsb_decode_finish(c->subs[k], dst_off ? dst_off + f0 : nullptr, dst_len ? dst_len + f0 : nullptr, status ? status + f0 : nullptr,
+                                            xxh32 ? xxh32 + f0 : nullptr, checksum_ok ? checksum_ok + f0 : nullptr, &t);
+            if (r != ZSB_OK) { rc = r; c->last_err = c->subs[k]->last_err; fallback = true; }
+            else {
+                if (t != S.dexp) fallback = true;                                   // a frame failed or disagreed with its declared size
+                if (dst_off) for (size_t f = f0; f < f1; f++) dst_off[f] += S.doff;
+                total += t;
+            }
+        }
+        zsb_free(S.fr); zsb_free(S.bl);
+    }
+    if (rc == ZSB_E_CUDA) return rc;
+    if (fallback) return 1;
+    if (dst_total) *dst_total = total;
+    return ZSB_OK;
+}
+
 extern "C" int zsb_decode(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_frame *frames, size_t nf, const zsb_block *blocks, size_t nb,
                           uint8_t *dst, size_t dst_cap, uint64_t *dst_off, uint64_t *dst_len, int32_t *status, uint32_t *xxh32,
                           uint8_t *checksum_ok, uint64_t *dst_total, uint32_t flags) {
+    if (c && !c->is_sub && !(flags & (ZSB_SRC_ON_DEVICE | ZSB_DST_ON_DEVICE)) && nf >= kPipeMinFrames && src && dst && frames && blocks) {
+        const int prc = decode_pipelined(c, src, n, frames, nf, blocks, nb, dst, dst_cap, dst_off, dst_len, status, xxh32, checksum_ok, dst_total, flags);
+        if (prc != 1) return prc;
+    }
     int rc = zsb_decode_prepare(c, src, n, frames, nf, blocks, nb, dst, dst_cap, flags);
     if (rc) return rc;
     rc = zsb_decode_launch(c);
