@@ -82,7 +82,7 @@ def lib():
     except Exception:
         if not os.path.exists(_SO):
             raise
-    L = C.CDLL(_SO)
+    L = C.CDLL(os.environ.get("ZSB_LIB_PATH") or _SO)      # ZSB_LIB_PATH: development knob, a differently tuned build of the same library
     u8p, sz, vp = C.POINTER(C.c_uint8), C.c_size_t, C.c_void_p
     u64p, i32p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
     L.zsb_scan.argtypes = [vp, sz, C.c_uint32, C.c_uint64, C.POINTER(C.POINTER(ZsbFrame)), C.POINTER(sz),

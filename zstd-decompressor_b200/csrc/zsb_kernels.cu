@@ -847,13 +847,14 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
 // one block form a dependency chain whatever the number of warps working on the block; spreading a block over a
 // CTA only adds polling (k_exec, kept for frames of many blocks).  The chain is hidden across frames instead:
 // the warp keeps the last EX2_RING bytes of its frame in shared memory (near sources, resolved with __syncwarp
-// only), older sources are read back from HBM/L2 (they were flushed with 16-byte stores), and a SM holds 32
-// such warps.
+// only), older sources are read back from HBM/L2 (they were flushed with 16-byte stores), and a SM holds 28
+// such warps (all 4 096 frames of a C2 batch are resident at once).  The ring is small on purpose: 1, 2 and 4 KiB
+// run equally fast, 8 KiB is twice as slow because the literal and record loads lose their L1.
 //
 // Positions are 32-bit and relative to the start of the current block (negative = earlier blocks of the frame);
 // the ring index of a position is its global address modulo EX2_RING, so that frames and blocks continue
 // seamlessly and 16-byte units of the ring and of HBM coincide.
-#define EX2_RING 4096u
+#define EX2_RING 2048u
 #define EX2_MASK (EX2_RING - 1u)
 #define EX2_WARPS 4
 #define EX2_LONG 16u
@@ -909,17 +910,33 @@ __device__ __forceinline__ void ex2_load8_ring(const uint8_t *ring, uint32_t s, 
     const uint32_t w2 = *reinterpret_cast<const uint32_t *>(ring + ((a + 8) & EX2_MASK));
     v0 = __funnelshift_r(w0, w1, sh); v1 = __funnelshift_r(w1, w2, sh);
 }
-// n (<= 8) bytes starting at global address g; only words that hold a wanted byte are touched
-__device__ __forceinline__ void ex2_load8_glob(const uint8_t *g, uint32_t n, uint32_t &v0, uint32_t &v1, bool cg) {
-    const uint32_t m = (uint32_t)(uintptr_t)g & 3u, sh = m * 8u;
+// n (<= 16) bytes starting at global address g, in two steps so that the loads of several sources are in flight together:
+// ex2_issue requests the aligned words that hold a wanted byte, ex2_unit shifts unit u (bytes 8u .. 8u+7) into place
+struct ExRaw { uint32_t w0, w1, w2, w3, w4, sh; };
+__device__ __forceinline__ void ex2_issue(const uint8_t *g, uint32_t n, ExRaw &r, bool cg) {
+    const uint32_t m = (uint32_t)(uintptr_t)g & 3u;
     const uint32_t *a = reinterpret_cast<const uint32_t *>(g - m);
-    uint32_t w0, w1 = 0, w2 = 0;
-    if (cg) { w0 = __ldcg(a); if (m + n > 4) w1 = __ldcg(a + 1); if (m + n > 8) w2 = __ldcg(a + 2); }
-    else { w0 = __ldg(a); if (m + n > 4) w1 = __ldg(a + 1); if (m + n > 8) w2 = __ldg(a + 2); }
-    v0 = __funnelshift_r(w0, w1, sh); v1 = __funnelshift_r(w1, w2, sh);
+    r.sh = m * 8u; r.w1 = r.w2 = r.w3 = r.w4 = 0;
+    if (cg) {
+        r.w0 = __ldcg(a);
+        if (m + n > 4) r.w1 = __ldcg(a + 1);
+        if (m + n > 8) r.w2 = __ldcg(a + 2);
+        if (m + n > 12) r.w3 = __ldcg(a + 3);
+        if (m + n > 16) r.w4 = __ldcg(a + 4);
+    } else {
+        r.w0 = __ldg(a);
+        if (m + n > 4) r.w1 = __ldg(a + 1);
+        if (m + n > 8) r.w2 = __ldg(a + 2);
+        if (m + n > 12) r.w3 = __ldg(a + 3);
+        if (m + n > 16) r.w4 = __ldg(a + 4);
+    }
+}
+__device__ __forceinline__ void ex2_unit(const ExRaw &r, int u, uint32_t &v0, uint32_t &v1) {
+    if (u == 0) { v0 = __funnelshift_r(r.w0, r.w1, r.sh); v1 = __funnelshift_r(r.w1, r.w2, r.sh); }
+    else { v0 = __funnelshift_r(r.w2, r.w3, r.sh); v1 = __funnelshift_r(r.w3, r.w4, r.sh); }
 }
 
-__global__ void __launch_bounds__(32 * EX2_WARPS, 8) k_exec2(const uint8_t *__restrict__ src, const zsb_frame *__restrict__ frames,
+__global__ void __launch_bounds__(32 * EX2_WARPS, 7) k_exec2(const uint8_t *__restrict__ src, const zsb_frame *__restrict__ frames,
                                                              const zsb_block *__restrict__ blocks, const ZsbBlockWork *__restrict__ work,
                                                              ZsbFrameOut *fout, const uint32_t *__restrict__ exec_list, uint32_t n,
                                                              const ZsbCounters *__restrict__ cnt, const uint64_t *__restrict__ seq_pool,
@@ -956,6 +973,7 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 8) k_exec2(const uint8_t *__re
             const uint32_t items = nseq + 1;   // the last item is the literal tail (decoding_context.rs:101-103); all there is when nseq == 0
             uint32_t c_out = 0, c_lit = 0;
             uint64_t rec_next = lane < nseq ? __ldg(seqs + lane) : 0ull;
+            ExRaw LR; bool lr_has = false;          // literal words of the current batch, requested during the previous one
             for (uint32_t b0 = 0; b0 < items; b0 += 32) {
                 const uint32_t i = b0 + lane;
                 const uint64_t rec = rec_next;
@@ -995,6 +1013,7 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 8) k_exec2(const uint8_t *__re
                         __syncwarp();
                     }
                     flushed = ring_lo = (int32_t)B1;
+                    lr_has = false;                 // nothing was requested for the next batch
                     continue;
                 }
                 ring_lo = max(ring_lo, (int32_t)B1 - (int32_t)EX2_RING);
@@ -1002,20 +1021,29 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 8) k_exec2(const uint8_t *__re
                 // that lie entirely in HBM (<= 16 bytes: two units; they depend on nothing in this batch) ...
                 const int32_t send = srcp + (int32_t)ml;
                 const bool farm = ml && ml <= EX2_LONG && send <= ring_lo && !(off < 8 && off < ml);
-                uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0;
-                if (farm) {
-                    ex2_load8_glob(gblk + srcp, min(ml, 8u), f0, f1, true);
-                    if (ml > 8) ex2_load8_glob(gblk + srcp + 8, ml - 8, f2, f3, true);
+                ExRaw FR;
+                if (farm) ex2_issue(gblk + srcp, ml, FR, true);
+                // ... and the literals of the NEXT batch (those of this batch were requested one batch ago)
+                ExRaw NR; bool n_has = false;
+                if (b0 + 32 < items && !L.is_rle) {
+                    const uint32_t n_end = (i + 32 < nseq) ? (uint32_t)(rec_next >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK : regen;
+                    uint32_t n_beg = __shfl_up_sync(FULL, n_end, 1);
+                    if (lane == 0) n_beg = c_lit;
+                    const uint32_t n_ll = n_end - n_beg;
+                    n_has = n_ll && n_ll <= EX2_LONG;
+                    if (n_has) ex2_issue(L.p + n_beg, n_ll, NR, false);
                 }
-                // ---- ... and the literals (no dependency on earlier output, decoding_context.rs:92-93)
+                // ---- literals (no dependency on earlier output, decoding_context.rs:92-93)
                 if (ll && ll <= EX2_LONG) {
                     if (L.is_rle) { const uint32_t v = L.rle * 0x01010101u; for (uint32_t q = 0; q < ll; q += 8) ex2_store8(ring, g0 + p_out + q, v, v, min(ll - q, 8u)); }
-                    else for (uint32_t q = 0; q < ll; q += 8) {
-                        const uint32_t c = min(ll - q, 8u); uint32_t v0, v1;
-                        ex2_load8_glob(L.p + p_lit + q, c, v0, v1, false);
-                        ex2_store8(ring, g0 + p_out + q, v0, v1, c);
+                    else {
+                        if (!lr_has) ex2_issue(L.p + p_lit, ll, LR, false);           // first batch of a block
+                        uint32_t v0, v1;
+                        ex2_unit(LR, 0, v0, v1); ex2_store8(ring, g0 + p_out, v0, v1, min(ll, 8u));
+                        if (ll > 8) { ex2_unit(LR, 1, v0, v1); ex2_store8(ring, g0 + p_out + 8, v0, v1, ll - 8); }
                     }
                 }
+                LR = NR; lr_has = n_has;
                 for (uint32_t m = __ballot_sync(FULL, ll > EX2_LONG); m; m &= m - 1) {
                     const int j = __ffs(m) - 1;
                     const uint32_t jo = __shfl_sync(FULL, p_out, j), jll = __shfl_sync(FULL, ll, j), jl = __shfl_sync(FULL, p_lit, j);
@@ -1024,7 +1052,11 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 8) k_exec2(const uint8_t *__re
                 __syncwarp();
                 // ---- matches (decoding_context.rs:95-98): a lane goes once everything it needs from other sequences is written,
                 // i.e. lies below the match start of the lowest sequence still pending
-                if (farm) { ex2_store8(ring, g0 + dstm, f0, f1, min(ml, 8u)); if (ml > 8) ex2_store8(ring, g0 + dstm + 8, f2, f3, ml - 8); }
+                if (farm) {
+                    uint32_t v0, v1;
+                    ex2_unit(FR, 0, v0, v1); ex2_store8(ring, g0 + dstm, v0, v1, min(ml, 8u));
+                    if (ml > 8) { ex2_unit(FR, 1, v0, v1); ex2_store8(ring, g0 + dstm + 8, v0, v1, ml - 8); }
+                }
                 __syncwarp();
                 bool pend = ml != 0 && !farm;
                 const int32_t need = min(send, (int32_t)p_out);
