@@ -38,7 +38,7 @@ def main():
         rows = page(rep, 'source', ('--print-source', 'sass'))
         hdr = rows[1]
         isrc, isamp, iex = hdr.index('Source'), hdr.index('# Samples'), hdr.index('Instructions Executed')
-        data = rows[2:]
+        data = [r for r in rows[2:] if len(r) > max(isrc, isamp, iex)]      # (a report with several kernels repeats the two header rows)
         tot = sum(int(r[isamp]) for r in data if r[isamp].isdigit())
         top = sorted(((int(r[isamp]), i) for i, r in enumerate(data) if r[isamp].isdigit()), reverse=True)[:hot]
         print('total samples', tot)
