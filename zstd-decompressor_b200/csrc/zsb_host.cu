@@ -164,7 +164,7 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
             ncomp++;
             uint64_t lc = (uint64_t)b.size * 4; if (lc > ZSB_BLOCK_MAX) lc = ZSB_BLOCK_MAX;
             lit_cap += lc + 16;
-            seq_cap += b.size < ZSB_MAX_NSEQ_PER_BLOCK ? b.size : ZSB_MAX_NSEQ_PER_BLOCK;
+            seq_cap += (b.size < ZSB_MAX_NSEQ_PER_BLOCK ? b.size : ZSB_MAX_NSEQ_PER_BLOCK) + 1;
         } else if (b.type == ZSB_BT_SKIPPABLE) { if (flags & ZSB_PRINT_SKIPPABLE) rawrle.push_back((uint32_t)i); }
         else rawrle.push_back((uint32_t)i);
     }

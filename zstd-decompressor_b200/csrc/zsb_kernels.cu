@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(1024) k_plan1(const zsb_frame *__restrict__ fr
         uint64_t lit_need = 0, seq_need = 0, hf = 0, sf = 0;
         if (i < nb && blocks[i].type == ZSB_BT_COMPRESSED && work[i].status == ZSB_OK) {
             if (work[i].lit_type >= ZSB_LT_COMPRESSED) { lit_need = ((uint64_t)work[i].lit_regen + 15) & ~15ull; hf = 1; }
-            if (work[i].nseq) { seq_need = work[i].nseq; sf = 1; }
+            if (work[i].nseq) { seq_need = ((uint64_t)work[i].nseq + 1) & ~1ull; sf = 1; }     // even: the records of a block start 16-byte aligned
         }
         uint64_t t0, t1, t2, t3;
         uint64_t a = cta_scan_excl(lit_need, s_warp, t0), b = cta_scan_excl(seq_need, s_warp, t1);
@@ -275,15 +275,16 @@ __device__ __forceinline__ int seq_build_table_warp(const uint8_t *src, const Zs
 //                      literal/output positions and the repeat-offset history by warp prefix operations; packed
 //                      records to HBM.  They run in the issue slots the producers leave empty (~70 %).
 //
-// Hand-over: the chains advance in lockstep, 32 sequences (one batch per chain) at a time; the word ring holds two
-// batches per chain; named barriers (full / free, two of each) pass the batches on, so a waiting warp costs no issue slot.
+// Hand-over: the chains advance in lockstep, 64 sequences (one window per chain) at a time; the word ring holds two
+// windows per chain; named barriers (full / free, two of each) pass the batches on, so a waiting warp costs no issue slot.
 #define SEQ_TBL_CELLS 512
 #define SEQ_CHAINS 32
 #define SEQ_HELPERS 16
 #define SEQ_CPH (SEQ_CHAINS / SEQ_HELPERS)       // chains per phase-2 warp
 #define SEQ_OF_CELLS 256      // offset tables have accuracy log <= 8 (RFC 8878); a log-9 one (the reference accepts it) takes the careful path
 #define SEQ_TBL_BYTES ((2 * SEQ_TBL_CELLS + SEQ_OF_CELLS) * SEQ_CHAINS * 4)
-#define SEQ_WSTRIDE 65        // words per chain in the ring (64) + 1 to spread the banks
+#define SEQ_WIN 64            // sequences per hand-over and chain (two per phase-2 lane)
+#define SEQ_WSTRIDE 130       // words per chain in the ring (two windows) + 2: rows stay 8-byte aligned, banks spread
 struct SeqShared {
     uint32_t words[SEQ_CHAINS][SEQ_WSTRIDE];
     uint32_t tab[36 + 53];                       // code -> baseline | extra bits << 24
@@ -310,41 +311,72 @@ __device__ __forceinline__ Hist hist_bcast(const Hist &h, int l) {
 }
 // phase 2 for 32 consecutive sequences of one block; C carries the block-level state from batch to batch (warp uniform, but `bad`)
 struct Seq2Carry { int64_t top; uint32_t lit_acc, out_acc; Hist H; int bad; };
-__device__ __forceinline__ void seq2_batch(const uint8_t *base8, const uint32_t *tab, uint32_t word, bool valid, uint32_t i, uint32_t regen,
-                                           uint64_t *rec, Seq2Carry &C, uint32_t lane) {
-    // bit position: exclusive prefix of the bits consumed (the extra bits follow from the codes)
-    uint32_t cL = ZSB_W_CL(word), cO = ZSB_W_CO(word), cM = ZSB_W_CM(word);
-    if (cL > ZSB_MAX_LL_CODE || cO > ZSB_MAX_OF_CODE || cM > ZSB_MAX_ML_CODE) { C.bad = 1; cL = cO = cM = 0; }    // sequence.rs:46-48
-    const uint32_t eL = tab[cL], eM = tab[36 + cM];
-    const uint32_t xL = eL >> 24, xM = eM >> 24, px = valid ? xL + xM + cO : 0u;
-    const uint32_t tot = valid ? px + ZSB_W_NB(word) : 0u;
-    uint32_t inc = tot;
+// codes -> (ll, ml, offset_value, bits consumed) of one sequence whose first bit lies just below absolute bit `top`
+struct Seq2One { uint32_t ll, ml, ov; };
+__device__ __forceinline__ void seq2_codes(const uint32_t *tab, uint32_t word, bool valid, uint32_t &eL, uint32_t &eM, uint32_t &cO, uint32_t &px,
+                                           uint32_t &tot, int &bad) {
+    uint32_t cL = ZSB_W_CL(word), cM = ZSB_W_CM(word);
+    cO = ZSB_W_CO(word);
+    if (cL > ZSB_MAX_LL_CODE || cO > ZSB_MAX_OF_CODE || cM > ZSB_MAX_ML_CODE) { bad = 1; cL = cO = cM = 0; }    // sequence.rs:46-48
+    eL = tab[cL]; eM = tab[36 + cM];
+    px = valid ? (eL >> 24) + (eM >> 24) + cO : 0u;
+    tot = valid ? px + ZSB_W_NB(word) : 0u;
+}
+__device__ __forceinline__ Seq2One seq2_values(const uint8_t *base8, int64_t top, bool valid, uint32_t eL, uint32_t eM, uint32_t cO, uint32_t px, int &bad) {
+    Seq2One r; r.ll = 0; r.ml = 0; r.ov = 1;
+    if (valid) {
+        const uint32_t xL = eL >> 24, xM = eM >> 24;
+        int64_t a = top - px;
+        if (a < 0) { bad = 1; a = 0; }                            // only after an over-read (the producer reports it too)
+        const uint64_t Wx = px ? fast_win_at(base8, a, px) : 0ull;
+        r.ll = (eL & 0xFFFFFFu) + ((uint32_t)Wx & ((1u << xL) - 1u));
+        r.ml = (eM & 0xFFFFFFu) + ((uint32_t)(Wx >> xL) & ((1u << xM) - 1u));
+        r.ov = (1u << cO) + ((uint32_t)(Wx >> (xL + xM)) & ((1u << cO) - 1u));
+    }
+    return r;
+}
+// Phase 2 for 64 consecutive sequences of one block, two per lane (lane l: sequences i0 + 2l and i0 + 2l + 1).  A lane folds
+// its two sequences locally and the warp prefix operations run once per 64 sequences: half the shuffles and compositions of a
+// one-per-lane layout, which matters because the shuffles share the SM's load/store path with the producer's table loads.
+__device__ __forceinline__ void seq2_window(const uint8_t *base8, const uint32_t *tab, uint32_t w0, uint32_t w1, uint32_t i0, uint32_t nseq, uint32_t regen,
+                                            uint64_t *rec, Seq2Carry &C, uint32_t lane) {
+    const uint32_t ia = i0 + 2 * lane;
+    const bool va = ia < nseq, vb = ia + 1 < nseq;
+    uint32_t eLa, eMa, cOa, pxa, tota, eLb, eMb, cOb, pxb, totb;
+    seq2_codes(tab, w0, va, eLa, eMa, cOa, pxa, tota, C.bad);
+    seq2_codes(tab, w1, vb, eLb, eMb, cOb, pxb, totb, C.bad);
+    // bit positions: exclusive prefix of the bits consumed
+    uint32_t inc = tota + totb;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += t; }
-    uint32_t ll = 0, ml = 0, ov = 1;
-    if (valid) {
-        int64_t a = C.top - (int64_t)(inc - tot) - px;
-        if (a < 0) { C.bad = 1; a = 0; }                          // only after an over-read (the producer reports it too)
-        const uint64_t Wx = px ? fast_win_at(base8, a, px) : 0ull;
-        ll = (eL & 0xFFFFFFu) + ((uint32_t)Wx & ((1u << xL) - 1u));
-        ml = (eM & 0xFFFFFFu) + ((uint32_t)(Wx >> xL) & ((1u << xM) - 1u));
-        ov = (1u << cO) + ((uint32_t)(Wx >> (xL + xM)) & ((1u << cO) - 1u));
-    }
+    const int64_t topa = C.top - (int64_t)(inc - tota - totb);
+    const Seq2One A = seq2_values(base8, topa, va, eLa, eMa, cOa, pxa, C.bad);
+    const Seq2One B = seq2_values(base8, topa - tota, vb, eLb, eMb, cOb, pxb, C.bad);
     C.top -= (int64_t)__shfl_sync(FULL, inc, 31);
     // literal / output positions
-    uint64_t pos = (uint64_t)ll | ((uint64_t)(ll + ml) << 32);
+    uint64_t pos = (uint64_t)(A.ll + B.ll) | ((uint64_t)(A.ll + A.ml + B.ll + B.ml) << 32);
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(FULL, pos, d); if (lane >= (uint32_t)d) pos += t; }
-    const uint32_t lit_end = C.lit_acc + (uint32_t)pos, out_end = C.out_acc + (uint32_t)(pos >> 32);
-    if (valid && (lit_end > regen || out_end + (regen - lit_end) > ZSB_BLOCK_MAX)) C.bad = 1;     // decoding_context.rs:86-90, Block_Maximum_Size
-    C.lit_acc = __shfl_sync(FULL, lit_end, 31); C.out_acc = __shfl_sync(FULL, out_end, 31);
-    // repeat-offset history: inclusive prefix over the per-sequence transforms, then the block-level carry
-    Hist G = valid ? hist_of_sequence(ov, ll, C.bad) : hist_identity();
+    const uint32_t lit_b = C.lit_acc + (uint32_t)pos, out_b = C.out_acc + (uint32_t)(pos >> 32);
+    const uint32_t lit_a = lit_b - B.ll, out_a = out_b - B.ll - B.ml;
+    if (va && (lit_a > regen || out_a + (regen - lit_a) > ZSB_BLOCK_MAX)) C.bad = 1;             // decoding_context.rs:86-90, Block_Maximum_Size
+    if (vb && (lit_b > regen || out_b + (regen - lit_b) > ZSB_BLOCK_MAX)) C.bad = 1;
+    C.lit_acc = __shfl_sync(FULL, lit_b, 31); C.out_acc = __shfl_sync(FULL, out_b, 31);
+    // repeat-offset history: the lane's two transforms folded, an inclusive prefix over the lanes, then the block-level carry
+    const Hist Fa = va ? hist_of_sequence(A.ov, A.ll, C.bad) : hist_identity();
+    const Hist Fb = vb ? hist_of_sequence(B.ov, B.ll, C.bad) : hist_identity();
+    Hist G = hist_compose(Fb, Fa, C.bad);
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const Hist E = hist_shfl_up(G, d); if (lane >= (uint32_t)d) G = hist_compose(G, E, C.bad); }
-    G = hist_compose(G, C.H, C.bad);
-    C.H = hist_bcast(G, 31);
-    if (valid) rec[i] = (uint64_t)out_end | ((uint64_t)lit_end << ZSB_REC_POS_BITS) | ((uint64_t)G.h0 << (2 * ZSB_REC_POS_BITS));
+    Hist E = hist_shfl_up(G, 1);                                   // history before this lane's first sequence, relative to the window start
+    if (lane == 0) E = hist_identity();
+    const uint32_t offa = hist_pick(C.H, hist_compose(Fa, E, C.bad).h0, C.bad);
+    const uint32_t offb = hist_pick(C.H, G.h0, C.bad);
+    C.H = hist_compose(hist_bcast(G, 31), C.H, C.bad);
+    const uint64_t ra = (uint64_t)out_a | ((uint64_t)lit_a << ZSB_REC_POS_BITS) | ((uint64_t)offa << (2 * ZSB_REC_POS_BITS));
+    const uint64_t rb = (uint64_t)out_b | ((uint64_t)lit_b << ZSB_REC_POS_BITS) | ((uint64_t)offb << (2 * ZSB_REC_POS_BITS));
+    if (vb) *reinterpret_cast<ulonglong2 *>(rec + ia) = make_ulonglong2(ra, rb);      // (records are 16-byte aligned: seq_buf is kept even)
+    else if (va) rec[ia] = ra;
 }
 
 __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t *__restrict__ src, ZsbBlockWork *work, const uint32_t *__restrict__ seq_list,
@@ -471,27 +503,27 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
             top -= (int32_t)(px + nbs);                                                                                                     \
             aL = tbL + (ZSB_CELL_BASE(eL) + bL) * (SEQ_CHAINS * 4); aM = tbM + (ZSB_CELL_BASE(eM) + bM) * (SEQ_CHAINS * 4);                 \
             aO = tbO + (ZSB_CELL_BASE(eO) + bO) * (SEQ_CHAINS * 4);                                        /* sequence.rs:80-88 */          \
-            wrow[(i_) & 63u] = seq_fast_word(eL, eO, eM, nbs);                                                                              \
+            wrow[(i_) & (2 * SEQ_WIN - 1)] = seq_fast_word(eL, eO, eM, nbs);                                                                              \
         }
-        for (uint32_t i0 = 0; i0 < maxn; i0 += 32) {
-            const uint32_t B = i0 >> 5;
-            if (B >= 2) seq_bar_sync(SEQ_BAR_FREE + (B & 1u));      // the phase-2 warps are done with batch B-2, whose ring slots batch B overwrites
-            const bool full = i0 + 32 < nseq;                   // 32 more sequences, none of them the last
+        for (uint32_t i0 = 0; i0 < maxn; i0 += SEQ_WIN) {
+            const uint32_t B = i0 / SEQ_WIN;
+            if (B >= 2) seq_bar_sync(SEQ_BAR_FREE + (B & 1u));      // the phase-2 warps are done with window B-2, whose ring slots window B overwrites
+            const bool full = i0 + SEQ_WIN < nseq;              // a whole window of sequences, none of them the last
             // the stream rings are topped up every 8 steps (8 x 89 + 95 bits < one 128-byte line), by all lanes in the same pass
             if (!__any_sync(FULL, !full && i0 < nseq)) {
                 if (full) {
-                    for (uint32_t i8 = i0; i8 < i0 + 32; i8 += 8) {
+                    for (uint32_t i8 = i0; i8 < i0 + SEQ_WIN; i8 += 8) {
                         sr_check<7>(R, top - 32);
 #pragma unroll 2
                         for (uint32_t i = i8; i < i8 + 8; i++) SEQ_STEP(i, false)
                     }
                 }
             } else {
-                for (uint32_t i = i0; i < i0 + 32; i++)
+                for (uint32_t i = i0; i < i0 + SEQ_WIN; i++)
                     if (i < nseq) { if ((i & 7u) == 0) sr_check<7>(R, top - 32); SEQ_STEP(i, i + 1 == nseq) }
             }
             __threadfence_block();
-            seq_bar_arrive(SEQ_BAR_FULL + (B & 1u));                // batch B is in the ring
+            seq_bar_arrive(SEQ_BAR_FULL + (B & 1u));                // window B is in the ring
         }
 #undef SEQ_STEP
         // an over-read shows as a cursor below the stream start; illegal codes are caught by phase 2, which sees every code
@@ -506,17 +538,16 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
             nsq[k] = S.nseq[c0 + k];
             C[k].top = (int64_t)S.top0[c0 + k]; C[k].lit_acc = 0; C[k].out_acc = 0; C[k].H = hist_identity(); C[k].bad = 0;
         }
-        uint32_t nbat = 0;                                            // batches of the longest chain of the CTA: every warp takes part in every hand-over
+        uint32_t nbat = 0;                                            // windows of the longest chain of the CTA: every warp takes part in every hand-over
 #pragma unroll
-        for (int c = 0; c < SEQ_CHAINS; c++) nbat = max(nbat, (S.nseq[c] + 31) >> 5);
+        for (int c = 0; c < SEQ_CHAINS; c++) nbat = max(nbat, (S.nseq[c] + SEQ_WIN - 1) / SEQ_WIN);
         for (uint32_t b = 0; b < nbat; b++) {
             seq_bar_sync(SEQ_BAR_FULL + (b & 1u));
 #pragma unroll
             for (int k = 0; k < SEQ_CPH; k++) {
-                if ((b << 5) < nsq[k]) {
-                    const uint32_t i = (b << 5) + lane;
-                    const uint32_t word = S.words[c0 + k][(i & 63u)];
-                    seq2_batch(base8, S.tab, word, i < nsq[k], i, S.regen[c0 + k], reinterpret_cast<uint64_t *>((uintptr_t)S.rec[c0 + k]), C[k], lane);
+                if (b * SEQ_WIN < nsq[k]) {
+                    const uint2 ww = *reinterpret_cast<const uint2 *>(&S.words[c0 + k][(b & 1u) * SEQ_WIN + 2 * lane]);
+                    seq2_window(base8, S.tab, ww.x, ww.y, b * SEQ_WIN, nsq[k], S.regen[c0 + k], reinterpret_cast<uint64_t *>((uintptr_t)S.rec[c0 + k]), C[k], lane);
                 }
             }
             if (b + 2 < nbat) seq_bar_arrive(SEQ_BAR_FREE + (b & 1u));
