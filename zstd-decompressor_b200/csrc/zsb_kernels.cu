@@ -283,8 +283,8 @@ __device__ __forceinline__ int seq_build_table_warp(const uint8_t *src, const Zs
 #define SEQ_CPH (SEQ_CHAINS / SEQ_HELPERS)       // chains per phase-2 warp
 #define SEQ_OF_CELLS 256      // offset tables have accuracy log <= 8 (RFC 8878); a log-9 one (the reference accepts it) takes the careful path
 #define SEQ_TBL_BYTES ((2 * SEQ_TBL_CELLS + SEQ_OF_CELLS) * SEQ_CHAINS * 4)
-#define SEQ_WIN 64            // sequences per hand-over and chain (two per phase-2 lane)
-#define SEQ_WSTRIDE 130       // words per chain in the ring (two windows) + 2: rows stay 8-byte aligned, banks spread
+#define SEQ_WIN 128           // sequences per hand-over and chain (SEQ_PER_LANE = 4 per phase-2 lane)
+#define SEQ_WSTRIDE 260       // words per chain in the ring (two windows) + 4: rows stay 16-byte aligned, banks spread
 struct SeqShared {
     uint32_t words[SEQ_CHAINS][SEQ_WSTRIDE];
     uint32_t tab[36 + 53];                       // code -> baseline | extra bits << 24
@@ -335,48 +335,62 @@ __device__ __forceinline__ Seq2One seq2_values(const uint8_t *base8, int64_t top
     }
     return r;
 }
-// Phase 2 for 64 consecutive sequences of one block, two per lane (lane l: sequences i0 + 2l and i0 + 2l + 1).  A lane folds
-// its two sequences locally and the warp prefix operations run once per 64 sequences: half the shuffles and compositions of a
-// one-per-lane layout, which matters because the shuffles share the SM's load/store path with the producer's table loads.
-__device__ __forceinline__ void seq2_window(const uint8_t *base8, const uint32_t *tab, uint32_t w0, uint32_t w1, uint32_t i0, uint32_t nseq, uint32_t regen,
+// Phase 2 for SEQ_WIN = 32 * SEQ_PER_LANE consecutive sequences of one block, SEQ_PER_LANE per lane (lane l: sequences
+// i0 + K*l .. i0 + K*l + K-1).  A lane folds its sequences locally and the warp prefix operations run once per window: a
+// fraction of the shuffles and compositions of a one-per-lane layout, which matters because the shuffles share the SM's
+// load/store path with the producer's table loads.
+#define SEQ_PER_LANE 4
+__device__ __forceinline__ void seq2_window(const uint8_t *base8, const uint32_t *tab, const uint32_t *wd, uint32_t i0, uint32_t nseq, uint32_t regen,
                                             uint64_t *rec, Seq2Carry &C, uint32_t lane) {
-    const uint32_t ia = i0 + 2 * lane;
-    const bool va = ia < nseq, vb = ia + 1 < nseq;
-    uint32_t eLa, eMa, cOa, pxa, tota, eLb, eMb, cOb, pxb, totb;
-    seq2_codes(tab, w0, va, eLa, eMa, cOa, pxa, tota, C.bad);
-    seq2_codes(tab, w1, vb, eLb, eMb, cOb, pxb, totb, C.bad);
+    constexpr int K = SEQ_PER_LANE;
+    const uint32_t ia = i0 + K * lane;
+    bool v[K]; uint32_t eL[K], eM[K], cO[K], px[K], tot[K];
+    uint32_t lane_tot = 0;
+#pragma unroll
+    for (int j = 0; j < K; j++) { v[j] = ia + j < nseq; seq2_codes(tab, wd[j], v[j], eL[j], eM[j], cO[j], px[j], tot[j], C.bad); lane_tot += tot[j]; }
     // bit positions: exclusive prefix of the bits consumed
-    uint32_t inc = tota + totb;
+    uint32_t inc = lane_tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += t; }
-    const int64_t topa = C.top - (int64_t)(inc - tota - totb);
-    const Seq2One A = seq2_values(base8, topa, va, eLa, eMa, cOa, pxa, C.bad);
-    const Seq2One B = seq2_values(base8, topa - tota, vb, eLb, eMb, cOb, pxb, C.bad);
+    int64_t tp = C.top - (int64_t)(inc - lane_tot);
+    Seq2One Q[K];
+    uint32_t sll = 0, sout = 0;
+#pragma unroll
+    for (int j = 0; j < K; j++) { Q[j] = seq2_values(base8, tp, v[j], eL[j], eM[j], cO[j], px[j], C.bad); tp -= tot[j]; sll += Q[j].ll; sout += Q[j].ll + Q[j].ml; }
     C.top -= (int64_t)__shfl_sync(FULL, inc, 31);
     // literal / output positions
-    uint64_t pos = (uint64_t)(A.ll + B.ll) | ((uint64_t)(A.ll + A.ml + B.ll + B.ml) << 32);
+    uint64_t pos = (uint64_t)sll | ((uint64_t)sout << 32);
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(FULL, pos, d); if (lane >= (uint32_t)d) pos += t; }
-    const uint32_t lit_b = C.lit_acc + (uint32_t)pos, out_b = C.out_acc + (uint32_t)(pos >> 32);
-    const uint32_t lit_a = lit_b - B.ll, out_a = out_b - B.ll - B.ml;
-    if (va && (lit_a > regen || out_a + (regen - lit_a) > ZSB_BLOCK_MAX)) C.bad = 1;             // decoding_context.rs:86-90, Block_Maximum_Size
-    if (vb && (lit_b > regen || out_b + (regen - lit_b) > ZSB_BLOCK_MAX)) C.bad = 1;
-    C.lit_acc = __shfl_sync(FULL, lit_b, 31); C.out_acc = __shfl_sync(FULL, out_b, 31);
-    // repeat-offset history: the lane's two transforms folded, an inclusive prefix over the lanes, then the block-level carry
-    const Hist Fa = va ? hist_of_sequence(A.ov, A.ll, C.bad) : hist_identity();
-    const Hist Fb = vb ? hist_of_sequence(B.ov, B.ll, C.bad) : hist_identity();
-    Hist G = hist_compose(Fb, Fa, C.bad);
+    uint32_t lit = C.lit_acc + (uint32_t)pos - sll, out = C.out_acc + (uint32_t)(pos >> 32) - sout;     // before this lane's first sequence
+    C.lit_acc = __shfl_sync(FULL, C.lit_acc + (uint32_t)pos, 31); C.out_acc = __shfl_sync(FULL, C.out_acc + (uint32_t)(pos >> 32), 31);
+    // repeat-offset history: the lane's transforms folded, an inclusive prefix over the lanes, then the block-level carry
+    Hist P[K];                                                     // P[j]: this lane's sequences 0..j applied in order
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const Hist F = v[j] ? hist_of_sequence(Q[j].ov, Q[j].ll, C.bad) : hist_identity();
+        P[j] = j ? hist_compose(F, P[j - 1], C.bad) : F;
+    }
+    Hist G = P[K - 1];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const Hist E = hist_shfl_up(G, d); if (lane >= (uint32_t)d) G = hist_compose(G, E, C.bad); }
     Hist E = hist_shfl_up(G, 1);                                   // history before this lane's first sequence, relative to the window start
     if (lane == 0) E = hist_identity();
-    const uint32_t offa = hist_pick(C.H, hist_compose(Fa, E, C.bad).h0, C.bad);
-    const uint32_t offb = hist_pick(C.H, G.h0, C.bad);
+    uint64_t r[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        lit += Q[j].ll; out += Q[j].ll + Q[j].ml;
+        if (v[j] && (lit > regen || out + (regen - lit) > ZSB_BLOCK_MAX)) C.bad = 1;               // decoding_context.rs:86-90, Block_Maximum_Size
+        const uint32_t off = hist_pick(C.H, hist_pick(E, P[j].h0, C.bad), C.bad);                  // the offset a sequence uses is slot 0 after it
+        r[j] = (uint64_t)out | ((uint64_t)lit << ZSB_REC_POS_BITS) | ((uint64_t)off << (2 * ZSB_REC_POS_BITS));
+    }
     C.H = hist_compose(hist_bcast(G, 31), C.H, C.bad);
-    const uint64_t ra = (uint64_t)out_a | ((uint64_t)lit_a << ZSB_REC_POS_BITS) | ((uint64_t)offa << (2 * ZSB_REC_POS_BITS));
-    const uint64_t rb = (uint64_t)out_b | ((uint64_t)lit_b << ZSB_REC_POS_BITS) | ((uint64_t)offb << (2 * ZSB_REC_POS_BITS));
-    if (vb) *reinterpret_cast<ulonglong2 *>(rec + ia) = make_ulonglong2(ra, rb);      // (records are 16-byte aligned: seq_buf is kept even)
-    else if (va) rec[ia] = ra;
+    // (records are 16-byte aligned: seq_buf is kept even and K is even)
+#pragma unroll
+    for (int j = 0; j < K; j += 2) {
+        if (v[j + 1]) *reinterpret_cast<ulonglong2 *>(rec + ia + j) = make_ulonglong2(r[j], r[j + 1]);
+        else if (v[j]) rec[ia + j] = r[j];
+    }
 }
 
 __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t *__restrict__ src, ZsbBlockWork *work, const uint32_t *__restrict__ seq_list,
@@ -546,8 +560,9 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
 #pragma unroll
             for (int k = 0; k < SEQ_CPH; k++) {
                 if (b * SEQ_WIN < nsq[k]) {
-                    const uint2 ww = *reinterpret_cast<const uint2 *>(&S.words[c0 + k][(b & 1u) * SEQ_WIN + 2 * lane]);
-                    seq2_window(base8, S.tab, ww.x, ww.y, b * SEQ_WIN, nsq[k], S.regen[c0 + k], reinterpret_cast<uint64_t *>((uintptr_t)S.rec[c0 + k]), C[k], lane);
+                    const uint4 ww = *reinterpret_cast<const uint4 *>(&S.words[c0 + k][(b & 1u) * SEQ_WIN + SEQ_PER_LANE * lane]);
+                    const uint32_t wd[4] = {ww.x, ww.y, ww.z, ww.w};
+                    seq2_window(base8, S.tab, wd, b * SEQ_WIN, nsq[k], S.regen[c0 + k], reinterpret_cast<uint64_t *>((uintptr_t)S.rec[c0 + k]), C[k], lane);
                 }
             }
             if (b + 2 < nbat) seq_bar_arrive(SEQ_BAR_FREE + (b & 1u));
