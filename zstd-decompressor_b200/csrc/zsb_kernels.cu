@@ -1143,7 +1143,13 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 7) k_exec2(const uint8_t *__re
                 }
                 // ---- whole 16-byte units of the batch go to HBM
                 const int32_t hi = (int32_t)B1 - (int32_t)((g0 + B1) & 15u);
-                if (hi > flushed) { ex2_flush(ring, gblk, g0, flushed, hi, lane); flushed = hi; }
+                if (hi > flushed) {
+                    if (((g0 + (uint32_t)flushed) & 15u) == 0) {           // the usual case: whole 16-byte units only, at most a few per lane
+                        for (int32_t p = flushed + 16 * (int32_t)lane; p < hi; p += 512)
+                            *reinterpret_cast<uint4 *>(gblk + p) = *reinterpret_cast<const uint4 *>(ring + ((g0 + (uint32_t)p) & EX2_MASK));
+                    } else ex2_flush(ring, gblk, g0, flushed, hi, lane);
+                    flushed = hi;
+                }
                 if (__any_sync(FULL, err != 0)) { err = ZSB_E_IMPOSSIBLE_VALUE; break; }
             }
         }
