@@ -1018,12 +1018,14 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 7) k_exec2(const uint8_t *__re
             const uint64_t P0 = W.out_off;
             const uint32_t items = nseq + 1;   // the last item is the literal tail (decoding_context.rs:101-103); all there is when nseq == 0
             uint32_t c_out = 0, c_lit = 0;
-            uint64_t rec_next = lane < nseq ? __ldg(seqs + lane) : 0ull;
+            // records are requested two batches ahead: the batch after this one is looked at early (its literals are prefetched)
+            uint64_t rec_next = lane < nseq ? __ldg(seqs + lane) : 0ull, rec_next2 = lane + 32 < nseq ? __ldg(seqs + lane + 32) : 0ull;
             ExRaw LR; bool lr_has = false;          // literal words of the current batch, requested during the previous one
             for (uint32_t b0 = 0; b0 < items; b0 += 32) {
                 const uint32_t i = b0 + lane;
                 const uint64_t rec = rec_next;
-                if (i + 32 < nseq) rec_next = __ldg(seqs + i + 32);
+                rec_next = rec_next2;
+                if (i + 64 < nseq) rec_next2 = __ldg(seqs + i + 64);
                 const bool is_seq = i < nseq;
                 const uint32_t out_end = is_seq ? (uint32_t)rec & ZSB_REC_POS_MASK : out_size;
                 const uint32_t lit_end = is_seq ? (uint32_t)(rec >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK : regen;
