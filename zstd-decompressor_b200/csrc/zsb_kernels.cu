@@ -318,7 +318,9 @@ __device__ __forceinline__ void seq2_codes(const uint32_t *tab, uint32_t word, b
     uint32_t cL = ZSB_W_CL(word), cM = ZSB_W_CM(word);
     cO = ZSB_W_CO(word);
     if (cL > ZSB_MAX_LL_CODE || cO > ZSB_MAX_OF_CODE || cM > ZSB_MAX_ML_CODE) { bad = 1; cL = cO = cM = 0; }    // sequence.rs:46-48
-    eL = tab[cL]; eM = tab[36 + cM];
+    // small codes carry no extra bits (sequence.rs:98-191: LL codes 0..15 are the length itself, ML codes 0..31 the length - 3):
+    // the table is only consulted for the rare larger ones, which keeps these loads off the SM's shared-memory path
+    eL = cL < 16 ? cL : tab[cL]; eM = cM < 32 ? cM + 3u : tab[36 + cM];
     px = valid ? (eL >> 24) + (eM >> 24) + cO : 0u;
     tot = valid ? px + ZSB_W_NB(word) : 0u;
 }
