@@ -116,6 +116,31 @@ def cpu_oracle_rate(blob, scan_frames, target_cpu_seconds, threads):
     return {"value": len(out) / dt / 1e9, "bytes": len(out), "seconds": dt, "frames": n, "single_thread_gbs": rate1 / 1e9, "sample_blob": sample}
 
 
+def libzstd_rate(blob, scan_frames, n_frames, threads):
+    """Context line: libzstd 1.5.5 (the system library, through ctypes, which releases the GIL) decoding the
+    first n_frames frames, frames spread over `threads` threads.  Not the reference and not the target."""
+    import concurrent.futures as cf
+    import gen_corpus as G
+    z = G.libzstd()
+    frames = [(o, l) for o, l in scan_frames[:n_frames]]
+    src = C.create_string_buffer(blob, len(blob))
+    base = C.addressof(src)
+
+    def work(part):
+        out = C.create_string_buffer(FRAME_SIZE + 64)
+        n = 0
+        for o, l in part:
+            r = z.ZSTD_decompress(out, FRAME_SIZE + 64, C.c_char_p(base + o), l)
+            assert not z.ZSTD_isError(r)
+            n += r
+        return n
+    parts = [frames[i::threads] for i in range(threads)]
+    t = time.perf_counter()
+    with cf.ThreadPoolExecutor(threads) as ex:
+        total = sum(ex.map(work, parts))
+    return total / (time.perf_counter() - t) / 1e9
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -305,6 +330,11 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": cb["value"], "unit": "GB/s", "cores": cores, "kind": "port",
                                 "sample": f"first {cb['frames']} frames of the workload ({cb['bytes']} bytes out) by oracle/refcpu.c, frame-parallel on {cores} threads "
                                           f"({cb['seconds']:.2f} s wall); single thread {cb['single_thread_gbs']:.4f} GB/s"}
+        try:   # context only: the production CPU decoder on the same frames
+            line["cpu_baseline"]["context_libzstd_1_5_5"] = {"unit": "GB/s", "threads_1": round(libzstd_rate(blob, fr, 512, 1), 3),
+                                                               f"threads_{cores}": round(libzstd_rate(blob, fr, frames_n, cores), 3)}
+        except Exception as e:
+            line["cpu_baseline"]["context_libzstd_1_5_5"] = {"unavailable": str(e)[:80]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
