@@ -10,12 +10,14 @@
 //   k_seq_slow 1 lane / block     careful decoder for blocks the fast path handed over (exact error order)
 //   k_plan2   1 CTA               block/frame output offsets (scan), repeat-offset history, size checks
 //   k_rawrle  1 CTA / block       raw / RLE block expansion, skippable payloads              (block.rs:76-79)
-//   k_exec    1 CTA / frame       sequence execution in a 128 KiB shared-memory block image   (decoding_context.rs:78-106)
+//   k_exec2   1 warp / frame      sequence execution through a 2 KiB shared-memory ring      (decoding_context.rs:78-106)
+//   k_exec    1 CTA / frame       the same for frames of many blocks: a 128 KiB block image in shared memory
 //   k_xxh     4 lanes / frame     XXH64 content checksum                                      (frame.rs:239-259)
 //
-// Nothing here is a dense contraction: no tensor cores.  The entropy stages are serial per stream,
-// so they run lane-per-stream with all tables in shared memory; the execution stage is the only one
-// that moves bulk data and keeps the whole block on chip, writing HBM once with 16-byte stores.
+// Nothing here is a dense contraction: no tensor cores.  The entropy stages are serial per stream, so they run
+// lane-per-stream with all tables in shared memory and everything that is not on the serial chain moved to other warps;
+// the execution stage runs a warp per frame and writes HBM with 16-byte stores.  DESIGN.md section 4 has the measurements
+// behind each of these choices.
 #include <cuda_runtime.h>
 #include "zsb_kernels.h"
 #include "zsb_parse.h"
