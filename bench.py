@@ -170,7 +170,7 @@ def run_reference(args):
                              "sample": f"{cal['frames']} of the workload's frames per step ({cal['bytes']} bytes out), oracle/refcpu.c frame-parallel on {cores} threads; "
                                        f"single thread {cal['single_thread_gbs']:.4f} GB/s; the Rust reference itself cannot be built in this image"},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -335,12 +335,27 @@ def run_ours(args):
                                                                f"threads_{cores}": round(libzstd_rate(blob, fr, frames_n, cores), 3)}
         except Exception as e:
             line["cpu_baseline"]["context_libzstd_1_5_5"] = {"unavailable": str(e)[:80]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there) must not add to it: file
+    descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved original."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    _claim_stdout()
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
