@@ -280,7 +280,9 @@ __device__ __forceinline__ int seq_build_table_warp(const uint8_t *src, const Zs
 // Hand-over: the chains advance in lockstep, 64 sequences (one window per chain) at a time; the word ring holds two
 // windows per chain; named barriers (full / free, two of each) pass the batches on, so a waiting warp costs no issue slot.
 #define SEQ_TBL_CELLS 512
-#define SEQ_CHAINS 32
+#define SEQ_CHAINS 32         // table columns / producer lanes of a CTA
+// (how many of them carry a block is chosen per launch so that the CTAs fill whole waves of one CTA per SM: 4 096 blocks on
+//  148 SMs run 28 chains per CTA in 147 CTAs; 32 would leave 20 SMs idle and load the others' phase-2 warps more)
 #define SEQ_HELPERS 16
 #define SEQ_CPH (SEQ_CHAINS / SEQ_HELPERS)       // chains per phase-2 warp
 #define SEQ_OF_CELLS 256      // offset tables have accuracy log <= 8 (RFC 8878); a log-9 one (the reference accepts it) takes the careful path
@@ -398,7 +400,7 @@ __device__ __forceinline__ void seq2_window(const uint8_t *base8, const uint32_t
 }
 
 __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t *__restrict__ src, ZsbBlockWork *work, const uint32_t *__restrict__ seq_list,
-                                                                ZsbCounters *cnt, uint64_t *seq_pool, uint32_t *slow_list) {
+                                                                ZsbCounters *cnt, uint64_t *seq_pool, uint32_t *slow_list, uint32_t used) {
     extern __shared__ __align__(1024) uint8_t smem[];      // the stream rings must be 512-byte aligned (SEQ_STEP)
     if (cnt->overflow) return;
     uint32_t *tbl = reinterpret_cast<uint32_t *>(smem);
@@ -420,8 +422,8 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
     uint32_t aL = 0, aO = 0, aM = 0, tbL = 0, tbO = 0, tbM = 0;
     R.sa = 0; R.pl = base8; R.low = 0;
     if (warp == 0) {
-        const uint32_t idx = blockIdx.x * SEQ_CHAINS + lane;
-        active = idx < n;
+        const uint32_t idx = blockIdx.x * used + lane;
+        active = lane < used && idx < n;
         bi = active ? seq_list[idx] : 0;
         if (active) { w = work[bi]; active = w.status == ZSB_OK; }
     } else {
@@ -431,9 +433,9 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
         seq_bar_sync_helpers();
         FseWarpScratch &X = reinterpret_cast<FseWarpScratch *>(counts)[warp - 1];
         for (uint32_t q = 0; q < 3 * SEQ_CPH; q++) {
-            const uint32_t c = (warp - 1) * SEQ_CPH + q / 3, t = q % 3, idx = blockIdx.x * SEQ_CHAINS + c;
+            const uint32_t c = (warp - 1) * SEQ_CPH + q / 3, t = q % 3, idx = blockIdx.x * used + c;
             int rc = ZSB_OK, al = 0;
-            if (idx < n) {
+            if (c < used && idx < n) {
                 const ZsbBlockWork &wb = work[seq_list[idx]];
                 if (wb.status == ZSB_OK) {
                     uint32_t *tb = tbl + (t == 0 ? 0 : t == 1 ? SEQ_TBL_CELLS * SEQ_CHAINS : (SEQ_TBL_CELLS + SEQ_OF_CELLS) * SEQ_CHAINS) + c;
@@ -1361,7 +1363,15 @@ void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_
 }
 void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
               uint64_t *seq_pool, uint32_t *slow_list) {
-    if (ncomp) k_seq<<<(ncomp + SEQ_CHAINS - 1) / SEQ_CHAINS, 32 * (1 + SEQ_HELPERS), SEQ_SMEM_FUSED, st>>>(src, work, seq_list, cnt, seq_pool, slow_list);
+    if (!ncomp) return;
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148; }
+    // one CTA per SM (shared memory): as few waves as possible, and the blocks spread evenly over the CTAs of those waves
+    const uint32_t waves = (ncomp + (uint32_t)n_sm * SEQ_CHAINS - 1) / ((uint32_t)n_sm * SEQ_CHAINS);
+    uint32_t used = (ncomp + waves * (uint32_t)n_sm - 1) / (waves * (uint32_t)n_sm);
+    if (used > SEQ_CHAINS) used = SEQ_CHAINS;
+    if (used < 1) used = 1;
+    k_seq<<<(ncomp + used - 1) / used, 32 * (1 + SEQ_HELPERS), SEQ_SMEM_FUSED, st>>>(src, work, seq_list, cnt, seq_pool, slow_list, used);
 }
 void zsbk_seq_slow(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *slow_list,
                    const ZsbCounters *cnt, uint64_t *seq_pool) {
