@@ -223,14 +223,14 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     if (c->overlap) {
         CK(c, cudaEventRecord(c->ev_fork, st));
         CK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-        MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p);
+        MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p, c->is_sub);
         if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][0], c->aux_stream);
         zsbk_huf(c->aux_stream, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags);
         if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][1], c->aux_stream);
         CK(c, cudaEventRecord(c->ev_join, c->aux_stream));
     } else {
         MARK(c, "k_huf");  zsbk_huf(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags);
-        MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p);
+        MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p, c->is_sub);
     }
     c->launches += c->ncomp ? 1 : 0;
     MARK(c, "k_seq_slow"); zsbk_seq_slow(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->slow_list.p, cnt, (uint64_t *)c->seq_pool.p);

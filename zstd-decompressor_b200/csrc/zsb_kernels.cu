@@ -1362,14 +1362,14 @@ void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_
     if (ncomp) k_huf<<<(ncomp + HUF_SLOTS - 1) / HUF_SLOTS, HUF_THREADS, 0, st>>>(src, src_len, work, huf_list, cnt, lit_pool, flags);
 }
 void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
-              uint64_t *seq_pool, uint32_t *slow_list) {
+              uint64_t *seq_pool, uint32_t *slow_list, bool shared_device) {
     if (!ncomp) return;
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148; }
     // one CTA per SM (shared memory): as few waves as possible, and the blocks spread evenly over the CTAs of those waves
     const uint32_t waves = (ncomp + (uint32_t)n_sm * SEQ_CHAINS - 1) / ((uint32_t)n_sm * SEQ_CHAINS);
     uint32_t used = (ncomp + waves * (uint32_t)n_sm - 1) / (waves * (uint32_t)n_sm);
-    if (used > SEQ_CHAINS) used = SEQ_CHAINS;
+    if (used > SEQ_CHAINS || shared_device) used = SEQ_CHAINS;     // (batches of other streams run beside this one: as few SMs as possible)
     if (used < 1) used = 1;
     k_seq<<<(ncomp + used - 1) / used, 32 * (1 + SEQ_HELPERS), SEQ_SMEM_FUSED, st>>>(src, work, seq_list, cnt, seq_pool, slow_list, used);
 }
