@@ -379,7 +379,13 @@ __device__ __forceinline__ void seq2_window(const uint8_t *base8, const uint32_t
     }
     Hist G = P[K - 1];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const Hist E = hist_shfl_up(G, d); if (lane >= (uint32_t)d) G = hist_compose(G, E, C.bad); }
+    for (int d = 1; d < 32; d <<= 1) {
+        // a transform whose three slots are constants is not changed by what came before it: once every lane that still has a
+        // partner (lane >= d) is closed, the remaining rounds are no-ops (after 8-16 sequences nearly every transform is closed)
+        if (!__any_sync(FULL, lane >= (uint32_t)d && ((G.h0 | G.h1 | G.h2) & ZSB_OFF_SYM))) break;
+        const Hist E = hist_shfl_up(G, d);
+        if (lane >= (uint32_t)d) G = hist_compose(G, E, C.bad);
+    }
     Hist E = hist_shfl_up(G, 1);                                   // history before this lane's first sequence, relative to the window start
     if (lane == 0) E = hist_identity();
     uint64_t r[K];
