@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
                 if (full) {
                     for (uint32_t i8 = i0; i8 < i0 + SEQ_WIN; i8 += 8) {
                         sr_check<7>(R, top - 32);
-#pragma unroll 2
+#pragma unroll 8
                         for (uint32_t i = i8; i < i8 + 8; i++) SEQ_STEP(i, false)
                     }
                 }
