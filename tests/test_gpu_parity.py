@@ -297,3 +297,31 @@ def test_c5_per_gpu_share(dec):
     out, sc, r = dec.decode(blob, Q | VER)
     assert first_status(sc, r) == 0 and sc.n_frames == 8192 and all(r.checksum_ok[i] for i in range(8192))
     assert hashlib.sha256(out).digest() == hashlib.sha256(exp).digest()
+
+
+def test_pipelined_host_path_falls_back_on_a_bad_frame(dec):
+    """>= 512 frames with content sizes take the sharded, pipelined host path; a frame that fails (or disagrees with its declared
+    size) makes the call fall back to the plain path, whose packing of the output (a failed frame contributes no bytes) is kept"""
+    blob, exp = corpora.c2_small(64)
+    sc1 = Z.Scan(blob, Q)
+    one = [blob[sc1.frames[i].src_off:sc1.frames[i].src_off + sc1.frames[i].src_len] for i in range(64)]
+    frames = [one[i % 64] for i in range(600)]
+    good = b"".join(frames)
+    out, sc, r = dec.decode(good, Q | VER)                       # pipelined, nothing wrong
+    assert first_status(sc, r) == 0 and sc.n_frames == 600 and all(r.checksum_ok[i] for i in range(600))
+    assert out == b"".join(exp[(i % 64) * 131072:(i % 64 + 1) * 131072] for i in range(600))
+    bad = bytearray(frames[300]); bad[len(bad) // 2] ^= 0x40
+    frames[300] = bytes(bad)
+    out, sc, r = dec.decode(b"".join(frames), Q | VER)
+    assert sc.status == 0 and sc.n_frames == 600
+    pos = 0
+    for i in range(600):
+        ok = r.status[i] == 0
+        if i != 300:
+            assert ok and r.checksum_ok[i] == 1
+        assert r.dst_off[i] == pos and r.dst_len[i] == (131072 if ok else 0)
+        if ok and i != 300:
+            assert out[pos:pos + 131072] == exp[(i % 64) * 131072:(i % 64 + 1) * 131072]
+        pos += r.dst_len[i]
+    assert r.status[300] != 0 or r.checksum_ok[300] == 0
+    assert r.total.value == pos
