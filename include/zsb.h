@@ -58,7 +58,8 @@ enum {
 #define ZSB_PRINT_SKIPPABLE   0x01u  /* src/main.rs:22-24,45-49 : skippable payloads become output      */
 #define ZSB_VERIFY_CHECKSUM   0x02u  /* compute XXH64 of every frame that stores one (frame.rs:239-259) */
 #define ZSB_REFERENCE_QUIRKS  0x04u  /* reject exactly what the reference rejects */
-#define ZSB_SRC_ON_DEVICE     0x08u  /* src is a device pointer (compressed bytes resident in HBM)      */
+#define ZSB_SRC_ON_DEVICE     0x08u  /* src is a device pointer (compressed bytes resident in HBM); no padding needed: the kernels never touch
+                                        an aligned 128-byte line that holds no byte of the buffer              */
 #define ZSB_DST_ON_DEVICE     0x10u  /* dst is a device pointer (output stays in HBM)                   */
 #define ZSB_STRICT_DICT       0x20u  /* fail frames carrying a dict id (the reference ignores it)       */
 
