@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
 #include <new>
 #include <string>
 #include <vector>
@@ -49,6 +50,11 @@ struct zsb_ctx {
     std::vector<uint32_t> h_xxh_list, h_rawrle, h_exec, h_exec2;   // host copies stay alive while their uploads are in flight
     std::vector<zsb_ctx *> subs;          // child contexts of the pipelined host path (own stream + scratch each)
     bool is_sub = false;
+    bool low_latency = false;             // pipelined path, first shards: CTA-per-frame execution (k_exec: 0.15 ms per block instead of 1.2 ms per frame, at a third of the throughput)
+    // pipelined path: all shards upload on one stream and download on another, in shard order (copies issued from
+    // several streams share the copy engines in no particular order, which delays the first shards)
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_kdone = nullptr, ev_down = nullptr;
     uint64_t eager_d2h = 0;               // pipelined path: bytes of output to send to the host right behind the kernels (size known from the headers)
     bool prepared = false, launched = false;
     bool overlap = false;      // ZSB_OVERLAP=1: literals stage on the auxiliary stream beside k_seq (measured slower: both are latency bound and share schedulers)
@@ -59,6 +65,9 @@ struct zsb_ctx {
     float kms[kMaxKernels] = {};
     int nk = 0, launches = 0;
     int prof_slot = 0, prof_count = 0;   // ring position / launches recorded since profiling was switched on
+    // ZSB_PIPE_TRACE=1: device timeline of the pipelined host path (base, uploads done, kernels done, download done), printed to stderr
+    bool trace = false;
+    cudaEvent_t ev_tr[4] = {};
 };
 
 #define CK(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { (ctx)->last_err = std::string(#call) + ": " + cudaGetErrorString(e__); (void)cudaGetLastError(); return ZSB_E_CUDA; } } while (0)
@@ -75,10 +84,13 @@ extern "C" int zsb_ctx_create(zsb_ctx **out, int device) {
         zsbk_init() != cudaSuccess) { (void)cudaGetLastError(); delete c; return ZSB_E_CUDA; }
     c->stream = c->own_stream;
     { const char *e = getenv("ZSB_OVERLAP"); c->overlap = e && *e && *e != '0'; }
+    { const char *e = getenv("ZSB_PIPE_TRACE"); c->trace = e && *e && *e != '0'; }
+    if (c->trace) for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev_tr[i]);
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) cudaEventCreate(&c->ev[r][i]);
     for (int r = 0; r < kProfRing; r++) { cudaEventCreate(&c->ev_huf[r][0]); cudaEventCreate(&c->ev_huf[r][1]); }
     if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); zsb_ctx_destroy(c); return ZSB_E_CUDA; }
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_kdone, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_down, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); zsb_ctx_destroy(c); return ZSB_E_CUDA; }
     *out = c;
     return ZSB_OK;
 }
@@ -93,8 +105,12 @@ extern "C" void zsb_ctx_destroy(zsb_ctx *c) {
     for (DevBuf *b : all) b->release();
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) if (c->ev[r][i]) cudaEventDestroy(c->ev[r][i]);
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i < 2; i++) if (c->ev_huf[r][i]) cudaEventDestroy(c->ev_huf[r][i]);
+    for (int i = 0; i < 4; i++) if (c->ev_tr[i]) cudaEventDestroy(c->ev_tr[i]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_up) cudaEventDestroy(c->ev_up);
+    if (c->ev_kdone) cudaEventDestroy(c->ev_kdone);
+    if (c->ev_down) cudaEventDestroy(c->ev_down);
     if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -138,7 +154,7 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     if (!c || (!src && n) || (!frames && nf) || (!blocks && nb) || nf > 0x7FFFFFFFu || nb > 0x7FFFFFFFu) return ZSB_E_ARG;
     CK(c, cudaSetDevice(c->device));
     c->prepared = false; c->launched = false;
-    cudaStream_t st = c->stream;
+    cudaStream_t st = c->up_stream ? c->up_stream : c->stream;      // every copy of this function goes to `st`
     // compressed bytes: resident already, or uploaded once (padded so that aligned 8-byte loads near the end stay inside)
     if (flags & ZSB_SRC_ON_DEVICE) c->d_src = src;
     else {
@@ -173,7 +189,9 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
         bool has_c = false;
         for (uint32_t k = 0; k < frames[f].n_blocks && !has_c; k++) has_c = blocks[frames[f].first_block + k].type == ZSB_BT_COMPRESSED;
         // frames of many blocks: one CTA per frame (k_exec); all others: one warp per frame (k_exec2)
-        if (has_c) (frames[f].n_blocks > kBigFrameBlocks ? execl : exec2l).push_back((uint32_t)f);
+        static const int big_env = getenv("ZSB_BIG_FRAME_BLOCKS") ? atoi(getenv("ZSB_BIG_FRAME_BLOCKS")) : -1;     // experiment knob
+        const uint32_t big = c->low_latency ? 0u : big_env >= 0 ? (uint32_t)big_env : kBigFrameBlocks;
+        if (has_c) (frames[f].n_blocks > big ? execl : exec2l).push_back((uint32_t)f);
         if ((flags & ZSB_VERIFY_CHECKSUM) && frames[f].has_checksum) c->h_xxh_list.push_back((uint32_t)f);
     }
     c->ncomp = (uint32_t)ncomp; c->n_rawrle = (uint32_t)rawrle.size(); c->n_exec = (uint32_t)execl.size(); c->n_exec2 = (uint32_t)exec2l.size(); c->n_xxh = (uint32_t)c->h_xxh_list.size();
@@ -199,6 +217,8 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     if (!execl.empty()) CK(c, cudaMemcpyAsync(c->exec_list.p, execl.data(), 4 * execl.size(), cudaMemcpyHostToDevice, st));
     if (!exec2l.empty()) CK(c, cudaMemcpyAsync(c->exec2_list.p, exec2l.data(), 4 * exec2l.size(), cudaMemcpyHostToDevice, st));
     if (!c->h_xxh_list.empty()) CK(c, cudaMemcpyAsync(c->xxh_list.p, c->h_xxh_list.data(), 4 * c->h_xxh_list.size(), cudaMemcpyHostToDevice, st));
+    if (c->trace) cudaEventRecord(c->ev_tr[1], st);
+    if (c->up_stream) { CK(c, cudaEventRecord(c->ev_up, st)); CK(c, cudaStreamWaitEvent(c->stream, c->ev_up, 0)); }
     c->prepared = true;               // nothing waited for: the uploads read the context's own host copies, and `src` if it is host memory
     return ZSB_OK;
 }
@@ -220,7 +240,8 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
                                     c->lit_cap, c->seq_cap, c->flags); c->launches++;
     // the literals stage (k_huf) and the sequence stage (k_seq) read the same blocks and write disjoint results; with ZSB_OVERLAP=1
     // k_huf runs on the auxiliary stream beside k_seq (enqueued first: its CTAs need the larger shared-memory slice).
-    if (c->overlap) {
+    const bool ov = c->overlap || c->low_latency;
+    if (ov) {
         CK(c, cudaEventRecord(c->ev_fork, st));
         CK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
         MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p, c->is_sub);
@@ -235,7 +256,7 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     c->launches += c->ncomp ? 1 : 0;
     MARK(c, "k_seq_slow"); zsbk_seq_slow(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->slow_list.p, cnt, (uint64_t *)c->seq_pool.p);
     c->launches += c->ncomp ? 2 : 0;
-    if (c->overlap) { MARK(c, "wait k_huf"); CK(c, cudaStreamWaitEvent(st, c->ev_join, 0)); }
+    if (ov) { MARK(c, "wait k_huf"); CK(c, cudaStreamWaitEvent(st, c->ev_join, 0)); }
     MARK(c, "k_plan2");  zsbk_plan2(st, frames, c->nf, blocks, work, fout, cnt, c->dst_cap, c->flags); c->launches++;
     MARK(c, "k_rawrle"); zsbk_rawrle(st, c->n_rawrle, src, blocks, work, fout, (const uint32_t *)c->rawrle_list.p, cnt, c->d_dst); c->launches += c->n_rawrle ? 1 : 0;
     MARK(c, "k_exec2");  zsbk_exec2(st, c->n_exec2, src, frames, blocks, work, fout, (const uint32_t *)c->exec2_list.p, cnt, (const uint64_t *)c->seq_pool.p,
@@ -244,7 +265,14 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
                                    (const uint8_t *)c->lit_pool.p, c->d_dst); c->launches += c->n_exec ? 1 : 0;
     MARK(c, "k_xxh");    zsbk_xxh(st, c->n_xxh, c->d_dst, fout, (const uint32_t *)c->xxh_list.p, cnt); c->launches += c->n_xxh ? 1 : 0;
     if (c->profile) { cudaEventRecord(c->ev[c->prof_slot][c->nk], st); c->prof_slot = (c->prof_slot + 1) % kProfRing; c->prof_count++; }
-    if (c->eager_d2h && c->h_dst) CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, c->eager_d2h, cudaMemcpyDeviceToHost, st));
+    if (c->trace) cudaEventRecord(c->ev_tr[2], st);
+    if (c->eager_d2h && c->h_dst) {
+        cudaStream_t ds = st;
+        if (c->down_stream) { ds = c->down_stream; CK(c, cudaEventRecord(c->ev_kdone, st)); CK(c, cudaStreamWaitEvent(ds, c->ev_kdone, 0)); }
+        CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, c->eager_d2h, cudaMemcpyDeviceToHost, ds));
+        if (c->down_stream) CK(c, cudaEventRecord(c->ev_down, ds));
+        if (c->trace) cudaEventRecord(c->ev_tr[3], ds);
+    } else if (c->trace) cudaEventRecord(c->ev_tr[3], st);
     CK(c, cudaGetLastError());
     c->launched = true;
     return ZSB_OK;
@@ -273,6 +301,7 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
     if (c->nf) CK(c, cudaMemcpyAsync(fo.data(), c->fout.p, sizeof(ZsbFrameOut) * c->nf, cudaMemcpyDeviceToHost, st));
     if (c->h_dst && hc.dst_total && hc.dst_total != c->eager_d2h) CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, hc.dst_total, cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
+    if (c->down_stream && c->eager_d2h && c->h_dst) CK(c, cudaEventSynchronize(c->ev_down));
     for (uint32_t f = 0; f < c->nf; f++) {
         const bool ok = fo[f].status == ZSB_OK;
         if (dst_off) dst_off[f] = fo[f].dst_off;
@@ -291,8 +320,9 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
 // host-to-host time of a batch).  Output placement needs every frame's size before it is decoded, so this path is taken
 // only when all frames declare Frame_Content_Size, and its result is kept only if every frame decoded to exactly that
 // size; otherwise (return 1) the plain path runs and reports as usual.
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const size_t kPipeMinFrames = 512;
-static const int kPipeShards = 8;
+static const int kPipeShardsMax = 32;
 static int decode_pipelined(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_frame *frames, size_t nf, const zsb_block *blocks, size_t nb,
                             uint8_t *dst, size_t dst_cap, uint64_t *dst_off, uint64_t *dst_len, int32_t *status, uint32_t *xxh32,
                             uint8_t *checksum_ok, uint64_t *dst_total, uint32_t flags) {
@@ -305,15 +335,42 @@ static int decode_pipelined(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_
         else expect_total += frames[f].content_size;
     }
     if (expect_total > dst_cap || expect_total < (32u << 20)) return 1;
-    size_t first[kPipeShards + 1];
-    if (zsb_shard_plan(frames, nf, kPipeShards, first) != ZSB_OK) return 1;
+    // Shard plan.  The download of the whole output (PCIe, ~55 GB/s) is the longest leg, so the goal is to start it as early as
+    // possible and never let it wait: a shard's output can leave only after its upload plus ~3.3 ms of kernels (every stage is a
+    // per-frame dependent chain, so the latency does not shrink with the shard).  Hence a small first shard and sizes that grow
+    // about as fast as the download falls behind the upload (x2); the first shards also run in low-latency mode (ctx.low_latency)
+    // when the frames are large enough for a CTA each.  Measured on C2: 8 equal shards 14.1 ms, this plan 13.3 ms.
+    // ZSB_PIPE_WEIGHTS="w0,w1,..." and ZSB_PIPE_FAST_SHARDS=k override the plan (experiments).
+    static const double kPlanFast[] = {1, 2, 4, 8, 8, 10, 22, 9}, kPlanPlain[] = {1, 2, 4, 8, 16, 33};
+    const bool big_frames = expect_total / nf >= (64u << 10);
+    int kPipeShards = 0, n_fast = big_frames ? 5 : 0;
+    double wts[kPipeShardsMax];
+    if (const char *e = getenv("ZSB_PIPE_WEIGHTS")) { while (*e && kPipeShards < kPipeShardsMax) { char *q; double v = strtod(e, &q); if (q == e) break; wts[kPipeShards++] = v > 0 ? v : 1; e = *q == ',' ? q + 1 : q; } }
+    if (!kPipeShards) {
+        const double *pl = big_frames ? kPlanFast : kPlanPlain;
+        kPipeShards = big_frames ? (int)(sizeof kPlanFast / sizeof *kPlanFast) : (int)(sizeof kPlanPlain / sizeof *kPlanPlain);
+        for (int k = 0; k < kPipeShards; k++) wts[k] = pl[k];
+    }
+    if (const char *e = getenv("ZSB_PIPE_FAST_SHARDS")) n_fast = atoi(e);
+    size_t first[kPipeShardsMax + 1];
+    {   // boundaries: cumulative output bytes cut at the cumulative weights
+        double wsum = 0; for (int k = 0; k < kPipeShards; k++) wsum += wts[k];
+        size_t f = 0; double acc = 0, cum = 0; first[0] = 0;
+        for (int k = 0; k < kPipeShards; k++) {
+            cum += wts[k];
+            const double lim = (double)expect_total * (cum / wsum);
+            while (f < nf && (k == kPipeShards - 1 || acc < lim)) { acc += frames[f].kind == 1 ? ((flags & ZSB_PRINT_SKIPPABLE) ? (double)blocks[frames[f].first_block].size : 0.0) : (double)frames[f].content_size; f++; }
+            first[k + 1] = f;
+        }
+    }
     while (c->subs.size() < (size_t)kPipeShards) {
         zsb_ctx *sub = nullptr;
         if (zsb_ctx_create(&sub, c->device) != ZSB_OK) return 1;
         sub->is_sub = true;
         c->subs.push_back(sub);
     }
-    struct Sh { zsb_frame *fr = nullptr; zsb_block *bl = nullptr; size_t nb = 0; uint64_t so = 0, sl = 0, doff = 0, dexp = 0; bool on = false; } sh[kPipeShards];
+    double host_ms[kPipeShardsMax] = {}; const double t_host0 = now_ms();
+    struct Sh { zsb_frame *fr = nullptr; zsb_block *bl = nullptr; size_t nb = 0; uint64_t so = 0, sl = 0, doff = 0, dexp = 0; bool on = false; } sh[kPipeShardsMax];
     int rc = ZSB_OK; bool fallback = false;
     uint64_t doff = 0;
     for (int k = 0; k < kPipeShards && !fallback; k++) {
@@ -327,11 +384,16 @@ static int decode_pipelined(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_
         doff += S.dexp;
         zsb_ctx *sub = c->subs[k];
         sub->eager_d2h = S.dexp;
+        sub->up_stream = c->own_stream; sub->down_stream = c->aux_stream;
+        sub->low_latency = k < n_fast;
+        if (c->trace && k == 0) cudaEventRecord(c->ev_tr[0], sub->up_stream);
+        if (c->trace) host_ms[k] = now_ms() - t_host0;
         if (zsb_decode_prepare(sub, src + S.so, S.sl, S.fr, f1 - f0, S.bl, S.nb, dst + S.doff, S.dexp, flags) != ZSB_OK ||
             zsb_decode_launch(sub) != ZSB_OK) { fallback = true; break; }
         S.on = true;
     }
     uint64_t total = 0;
+    const double t_enq = now_ms();
     for (int k = 0; k < kPipeShards; k++) {
         Sh &S = sh[k];
         if (S.on) {
@@ -347,6 +409,15 @@ static int decode_pipelined(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_
             }
         }
         zsb_free(S.fr); zsb_free(S.bl);
+    }
+    if (c->trace) {
+        fprintf(stderr, "[zsb pipe] host: all shards enqueued at %.2f ms, finished at %.2f ms\n", t_enq - t_host0, now_ms() - t_host0);
+        for (int k = 0; k < kPipeShards; k++) if (sh[k].on) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, c->ev_tr[0], c->subs[k]->ev_tr[1]); cudaEventElapsedTime(&b, c->ev_tr[0], c->subs[k]->ev_tr[2]); cudaEventElapsedTime(&d, c->ev_tr[0], c->subs[k]->ev_tr[3]);
+            fprintf(stderr, "[zsb pipe] shard %d: enqueue starts %.2f (host) | uploads done %.2f, kernels done %.2f, download done %.2f ms (device)\n", k, host_ms[k], a, b, d);
+        }
+        (void)cudaGetLastError();
     }
     if (rc == ZSB_E_CUDA) return rc;
     if (fallback) return 1;
