@@ -317,14 +317,16 @@ __device__ __forceinline__ Hist hist_bcast(const Hist &h, int l) {
 struct Seq2Carry { int64_t top; uint32_t lit_acc, out_acc; Hist H; int bad; };
 // codes -> (ll, ml, offset_value, bits consumed) of one sequence whose first bit lies just below absolute bit `top`
 struct Seq2One { uint32_t ll, ml, ov; };
-__device__ __forceinline__ void seq2_codes(const uint32_t *tab, uint32_t word, bool valid, uint32_t &eL, uint32_t &eM, uint32_t &cO, uint32_t &px,
+__device__ __forceinline__ void seq2_codes(uint32_t tab_sa, uint32_t word, bool valid, uint32_t &eL, uint32_t &eM, uint32_t &cO, uint32_t &px,
                                            uint32_t &tot, int &bad) {
     uint32_t cL = ZSB_W_CL(word), cM = ZSB_W_CM(word);
     cO = ZSB_W_CO(word);
     if (cL > ZSB_MAX_LL_CODE || cO > ZSB_MAX_OF_CODE || cM > ZSB_MAX_ML_CODE) { bad = 1; cL = cO = cM = 0; }    // sequence.rs:46-48
     // small codes carry no extra bits (sequence.rs:98-191: LL codes 0..15 are the length itself, ML codes 0..31 the length - 3):
     // the table is only consulted for the rare larger ones, which keeps these loads off the SM's shared-memory path
-    eL = cL < 16 ? cL : tab[cL]; eM = cM < 32 ? cM + 3u : tab[36 + cM];
+    eL = cL; eM = cM + 3u;
+    if (cL >= 16) eL = zsb_lds32(tab_sa + 4u * cL);
+    if (cM >= 32) eM = zsb_lds32(tab_sa + 4u * (36u + cM));
     px = valid ? (eL >> 24) + (eM >> 24) + cO : 0u;
     tot = valid ? px + ZSB_W_NB(word) : 0u;
 }
@@ -346,14 +348,14 @@ __device__ __forceinline__ Seq2One seq2_values(const uint8_t *base8, int64_t top
 // fraction of the shuffles and compositions of a one-per-lane layout, which matters because the shuffles share the SM's
 // load/store path with the producer's table loads.
 #define SEQ_PER_LANE 4
-__device__ __forceinline__ void seq2_window(const uint8_t *base8, const uint32_t *tab, const uint32_t *wd, uint32_t i0, uint32_t nseq, uint32_t regen,
+__device__ __forceinline__ void seq2_window(const uint8_t *base8, uint32_t tab_sa, const uint32_t *wd, uint32_t i0, uint32_t nseq, uint32_t regen,
                                             uint64_t *rec, Seq2Carry &C, uint32_t lane) {
     constexpr int K = SEQ_PER_LANE;
     const uint32_t ia = i0 + K * lane;
     bool v[K]; uint32_t eL[K], eM[K], cO[K], px[K], tot[K];
     uint32_t lane_tot = 0;
 #pragma unroll
-    for (int j = 0; j < K; j++) { v[j] = ia + j < nseq; seq2_codes(tab, wd[j], v[j], eL[j], eM[j], cO[j], px[j], tot[j], C.bad); lane_tot += tot[j]; }
+    for (int j = 0; j < K; j++) { v[j] = ia + j < nseq; seq2_codes(tab_sa, wd[j], v[j], eL[j], eM[j], cO[j], px[j], tot[j], C.bad); lane_tot += tot[j]; }
     // bit positions: exclusive prefix of the bits consumed
     uint32_t inc = lane_tot;
 #pragma unroll
@@ -518,18 +520,19 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
         {                                                                                                                                   \
             const uint32_t eL = zsb_lds32(aL), eO = zsb_lds32(aO), eM = zsb_lds32(aM);                                                      \
             const uint32_t sum = eL + eO + eM;                 /* byte 0: state bits, byte 1: extra bits (no carries: <= 27, <= 63) */     \
-            const uint32_t px = zsb_prmt(sum, 0, 0x4441);                                                                                   \
-            const uint32_t nbs = (LAST) ? 0u : sum & 0xFFu;                                                                                 \
-            const uint32_t e = (uint32_t)(top - 32) - px;      /* lowest bit of the 32 wanted; below the stream only after an over-read */ \
+            /* lowest bit of the 32 wanted = top - 32 - extra bits (one dot product with the byte weights 0,-1,0,0); below the stream only  \
+               after an over-read */                                                                                                         \
+            const uint32_t e = (uint32_t)__dp4a((int)sum, 0x0000FF00, top - 32);                                                             \
             const uint32_t e3 = e >> 3;                                                                                                     \
             const uint32_t w0 = zsb_lds32v((e3 & 0x1FCu) | ring_sa), w1 = zsb_lds32v(((e3 + 4u) & 0x1FCu) | ring_sa);                         \
+            const uint32_t sLM = eL + eM;                      /* low 5 bits: LL + ML state bits (<= 18) */                                 \
             const uint32_t t = __funnelshift_r(w0, w1, e);     /* the state bits, top-aligned */                                            \
             /* the funnel shifts take their 5-bit amounts straight from the cells (nb in bits 0..4) */                                      \
-            const uint32_t bL = zsb_fsl(t, 0, eL), t2 = zsb_fsl(0, t, eL), bM = zsb_fsl(t2, 0, eM), bO = zsb_fsl(zsb_fsl(0, t2, eM), 0, eO); \
-            top -= (int32_t)(px + nbs);                                                                                                     \
+            const uint32_t bL = zsb_fsl(t, 0, eL), bM = zsb_fsl(zsb_fsl(0, t, eL), 0, eM), bO = zsb_fsl(zsb_fsl(0, t, sLM), 0, eO);        \
+            top = __dp4a((int)sum, (LAST) ? 0x0000FF00 : 0x0000FFFF, top);     /* top -= extra bits + state bits */                        \
             aL = tbL + (ZSB_CELL_BASE(eL) + bL) * (SEQ_CHAINS * 4); aM = tbM + (ZSB_CELL_BASE(eM) + bM) * (SEQ_CHAINS * 4);                 \
             aO = tbO + (ZSB_CELL_BASE(eO) + bO) * (SEQ_CHAINS * 4);                                        /* sequence.rs:80-88 */          \
-            wrow[(i_) & (2 * SEQ_WIN - 1)] = seq_fast_word(eL, eO, eM, nbs);                                                                              \
+            wrow[(i_) & (2 * SEQ_WIN - 1)] = seq_fast_word(eL, eO, eM, (LAST) ? 0u : sum);                                                                              \
         }
         for (uint32_t i0 = 0; i0 < maxn; i0 += SEQ_WIN) {
             const uint32_t B = i0 / SEQ_WIN;
@@ -557,6 +560,7 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
     } else {
         // ---- phase 2: this warp's chains, batch by batch as the producer delivers them
         const uint32_t h = warp - 1, c0 = h * SEQ_CPH;     // this warp's chains: c0 .. c0 + SEQ_CPH - 1
+        const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(S.tab);
         Seq2Carry C[SEQ_CPH];
         uint32_t nsq[SEQ_CPH];
 #pragma unroll
@@ -574,7 +578,7 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
                 if (b * SEQ_WIN < nsq[k]) {
                     const uint4 ww = *reinterpret_cast<const uint4 *>(&S.words[c0 + k][(b & 1u) * SEQ_WIN + SEQ_PER_LANE * lane]);
                     const uint32_t wd[4] = {ww.x, ww.y, ww.z, ww.w};
-                    seq2_window(base8, S.tab, wd, b * SEQ_WIN, nsq[k], S.regen[c0 + k], reinterpret_cast<uint64_t *>((uintptr_t)S.rec[c0 + k]), C[k], lane);
+                    seq2_window(base8, tab_sa, wd, b * SEQ_WIN, nsq[k], S.regen[c0 + k], reinterpret_cast<uint64_t *>((uintptr_t)S.rec[c0 + k]), C[k], lane);
                 }
             }
             if (b + 2 < nbat) seq_bar_arrive(SEQ_BAR_FREE + (b & 1u));
