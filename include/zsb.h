@@ -137,14 +137,20 @@ const char *zsb_last_cuda_error(const zsb_ctx *ctx);
  * and the frame stores a checksum; checksum_ok = 1 if equal to the stored value (a mismatch is
  * reported, not an error -- the reference only prints a warning, frame.rs:251-254).
  * *dst_total = bytes produced.  Returns ZSB_OK if the batch ran (inspect status[]), else an error.
- * With host buffers and >= 512 frames that all declare Frame_Content_Size the batch is cut into 8 shards by frame, each on its
- * own stream: upload, kernels and download of different shards overlap (same results; pinned host memory makes the copies
- * asynchronous). */
+ * With host buffers and >= 512 frames that all declare Frame_Content_Size the batch is cut into shards by frame (a small first
+ * shard, then growing), each with its own stream and scratch: upload, kernels and download of different shards overlap (same
+ * results; page-locked host memory -- zsb_host_alloc -- makes the copies asynchronous). */
 int zsb_decode(zsb_ctx *ctx, const uint8_t *src, size_t n,
                const zsb_frame *frames, size_t n_frames, const zsb_block *blocks, size_t n_blocks,
                uint8_t *dst, size_t dst_cap, uint64_t *dst_off, uint64_t *dst_len,
                int32_t *status, uint32_t *xxh32, uint8_t *checksum_ok,
                uint64_t *dst_total, uint32_t flags);
+
+/* Page-locked host buffers for src/dst of zsb_decode: copies from and to pageable memory are staged by the driver and
+ * block the calling thread, which serialises the shards of the pipelined path (a binding would back its input and
+ * output Vec<u8> with these).  NULL on failure.  Not for zsb_free. */
+void *zsb_host_alloc(size_t n);
+void  zsb_host_free(void *p);
 
 /* Split zsb_decode for callers that keep data resident and time the GPU work only:
  * prepare enqueues the upload of the descriptors (and of src unless ZSB_SRC_ON_DEVICE: src must stay unchanged until finish)

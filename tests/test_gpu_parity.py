@@ -325,3 +325,27 @@ def test_pipelined_host_path_falls_back_on_a_bad_frame(dec):
         pos += r.dst_len[i]
     assert r.status[300] != 0 or r.checksum_ok[300] == 0
     assert r.total.value == pos
+
+
+def test_pipelined_host_path_page_locked_buffers_small_frames(dec):
+    """The pipelined host path on zsb_host_alloc buffers, with frames small enough (16 KiB) that the plan without the low-latency
+    first shards is taken, and a batch of 128 KiB frames through the plan with them; both against the plaintext."""
+    import ctypes as C
+    import gen_corpus as G
+    L = Z.lib()
+    for frame_size, n in ((16384, 2400), (131072, 640)):
+        blob, exp = G.make_c2(n, seed=11, frame_size=frame_size)
+        src = L.zsb_host_alloc(len(blob)); dst = L.zsb_host_alloc(len(exp))
+        assert src and dst
+        try:
+            C.memmove(src, blob, len(blob))
+            sc = Z.Scan((src, len(blob)), Q)
+            assert sc.status == 0 and sc.n_frames == n
+            r = Z.BatchResult(n)
+            rc = L.zsb_decode(dec.ctx.h, C.c_void_p(src), len(blob), sc.frames, n, sc.blocks, sc.n_blocks, C.c_void_p(dst), len(exp),
+                              r.dst_off, r.dst_len, r.status, r.xxh32, r.checksum_ok, C.byref(r.total), Q | VER)
+            assert rc == 0 and r.first_error() is None and r.total.value == len(exp)
+            assert all(r.checksum_ok[i] for i in range(n)) and all(r.dst_off[i] == i * frame_size for i in range(n))
+            assert C.string_at(dst, len(exp)) == exp
+        finally:
+            L.zsb_host_free(src); L.zsb_host_free(dst)

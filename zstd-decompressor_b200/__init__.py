@@ -88,6 +88,8 @@ def lib():
     L.zsb_scan.argtypes = [vp, sz, C.c_uint32, C.c_uint64, C.POINTER(C.POINTER(ZsbFrame)), C.POINTER(sz),
                            C.POINTER(C.POINTER(ZsbBlock)), C.POINTER(sz), u64p, u64p]
     L.zsb_free.argtypes = [vp]
+    L.zsb_host_alloc.argtypes = [C.c_size_t]; L.zsb_host_alloc.restype = vp
+    L.zsb_host_free.argtypes = [vp]; L.zsb_host_free.restype = None
     L.zsb_ctx_create.argtypes = [C.POINTER(vp), C.c_int]
     L.zsb_ctx_destroy.argtypes = [vp]
     L.zsb_ctx_set_stream.argtypes = [vp, vp]
@@ -119,7 +121,7 @@ EXPORTED_SYMBOLS = [
     "zsb_scan", "zsb_free", "zsb_ctx_create", "zsb_ctx_destroy", "zsb_ctx_set_stream", "zsb_last_cuda_error", "zsb_ctx_set_profile",
     "zsb_last_launch_count", "zsb_last_kernel_times", "zsb_kernel_times_avg", "zsb_decode", "zsb_decode_prepare", "zsb_decode_launch", "zsb_decode_finish",
     "zsb_decompress", "zsb_fse_table_parse", "zsb_fse_table_from_distribution", "zsb_huffman_parse", "zsb_execute_sequences",
-    "zsb_xxh64", "zsb_strerror", "zsb_version", "zsb_shard_plan", "zsb_shard_extract"]
+    "zsb_xxh64", "zsb_strerror", "zsb_version", "zsb_shard_plan", "zsb_shard_extract", "zsb_host_alloc", "zsb_host_free"]
 
 
 # ------------------------------------------------------------------------------------------ scan

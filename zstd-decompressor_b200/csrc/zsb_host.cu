@@ -148,6 +148,13 @@ extern "C" int zsb_kernel_times_avg(zsb_ctx *c, const char **names, float *ms, i
     return n;
 }
 
+extern "C" void *zsb_host_alloc(size_t n) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void zsb_host_free(void *p) { if (p && cudaFreeHost(p) != cudaSuccess) (void)cudaGetLastError(); }
+
 // ======================================================================================= batch decode
 extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_frame *frames, size_t nf,
                                   const zsb_block *blocks, size_t nb, uint8_t *dst, size_t dst_cap, uint32_t flags) {
