@@ -55,6 +55,9 @@ struct zsb_ctx {
     // several streams share the copy engines in no particular order, which delays the first shards)
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
     cudaEvent_t ev_up = nullptr, ev_kdone = nullptr, ev_down = nullptr;
+    // pipelined path: counters and per-frame results are read back right behind the kernels, ahead of the shard's big download
+    // (page-locked staging: pin = ZsbCounters, then nf x ZsbFrameOut)
+    uint8_t *pin = nullptr; size_t pin_cap = 0; bool pin_valid = false;
     uint64_t eager_d2h = 0;               // pipelined path: bytes of output to send to the host right behind the kernels (size known from the headers)
     bool prepared = false, launched = false;
     bool overlap = false;      // ZSB_OVERLAP=1: literals stage on the auxiliary stream beside k_seq (measured slower: both are latency bound and share schedulers)
@@ -106,6 +109,7 @@ extern "C" void zsb_ctx_destroy(zsb_ctx *c) {
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) if (c->ev[r][i]) cudaEventDestroy(c->ev[r][i]);
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i < 2; i++) if (c->ev_huf[r][i]) cudaEventDestroy(c->ev_huf[r][i]);
     for (int i = 0; i < 4; i++) if (c->ev_tr[i]) cudaEventDestroy(c->ev_tr[i]);
+    if (c->pin) cudaFreeHost(c->pin);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_up) cudaEventDestroy(c->ev_up);
@@ -273,6 +277,20 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     MARK(c, "k_xxh");    zsbk_xxh(st, c->n_xxh, c->d_dst, fout, (const uint32_t *)c->xxh_list.p, cnt); c->launches += c->n_xxh ? 1 : 0;
     if (c->profile) { cudaEventRecord(c->ev[c->prof_slot][c->nk], st); c->prof_slot = (c->prof_slot + 1) % kProfRing; c->prof_count++; }
     if (c->trace) cudaEventRecord(c->ev_tr[2], st);
+    c->pin_valid = false;
+    if (c->down_stream && c->eager_d2h && c->h_dst) {
+        const size_t need = 64 + sizeof(ZsbFrameOut) * (size_t)c->nf;
+        if (need > c->pin_cap) {
+            if (c->pin) cudaFreeHost(c->pin);
+            c->pin = nullptr; c->pin_cap = 0;
+            if (cudaHostAlloc((void **)&c->pin, need + need / 4, cudaHostAllocDefault) == cudaSuccess) c->pin_cap = need + need / 4; else (void)cudaGetLastError();
+        }
+        if (c->pin) {
+            CK(c, cudaMemcpyAsync(c->pin, cnt, sizeof(ZsbCounters), cudaMemcpyDeviceToHost, st));
+            if (c->nf) CK(c, cudaMemcpyAsync(c->pin + 64, fout, sizeof(ZsbFrameOut) * (size_t)c->nf, cudaMemcpyDeviceToHost, st));
+            c->pin_valid = true;
+        }
+    }
     if (c->eager_d2h && c->h_dst) {
         cudaStream_t ds = st;
         if (c->down_stream) { ds = c->down_stream; CK(c, cudaEventRecord(c->ev_kdone, st)); CK(c, cudaStreamWaitEvent(ds, c->ev_kdone, 0)); }
@@ -291,9 +309,13 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
     CK(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     ZsbCounters hc;
+    bool from_pin = false;
     for (int attempt = 0;; attempt++) {
-        CK(c, cudaMemcpyAsync(&hc, c->counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
-        CK(c, cudaStreamSynchronize(st));
+        if (c->pin_valid) { CK(c, cudaStreamSynchronize(st)); memcpy(&hc, c->pin, sizeof hc); from_pin = !hc.overflow; }
+        else {
+            CK(c, cudaMemcpyAsync(&hc, c->counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
+            CK(c, cudaStreamSynchronize(st));
+        }
         if (!hc.overflow) break;
         if (attempt >= 2) { c->last_err = "scratch overflow persists"; return ZSB_E_NOMEM; }
         // the entropy scratch was too small for this input: size it exactly and run the batch again
@@ -305,7 +327,8 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
     }
     if (c->profile) { const int r = (c->prof_slot + kProfRing - 1) % kProfRing; for (int i = 0; i < c->nk; i++) cudaEventElapsedTime(&c->kms[i], c->ev[r][i], c->ev[r][i + 1]); }
     std::vector<ZsbFrameOut> fo(c->nf);
-    if (c->nf) CK(c, cudaMemcpyAsync(fo.data(), c->fout.p, sizeof(ZsbFrameOut) * c->nf, cudaMemcpyDeviceToHost, st));
+    if (from_pin) { if (c->nf) memcpy(fo.data(), c->pin + 64, sizeof(ZsbFrameOut) * (size_t)c->nf); }
+    else if (c->nf) CK(c, cudaMemcpyAsync(fo.data(), c->fout.p, sizeof(ZsbFrameOut) * c->nf, cudaMemcpyDeviceToHost, st));
     if (c->h_dst && hc.dst_total && hc.dst_total != c->eager_d2h) CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, hc.dst_total, cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     if (c->down_stream && c->eager_d2h && c->h_dst) CK(c, cudaEventSynchronize(c->ev_down));
