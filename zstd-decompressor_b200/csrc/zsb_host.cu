@@ -274,9 +274,19 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
                                     (const uint8_t *)c->lit_pool.p, c->d_dst); c->launches += c->n_exec2 ? 1 : 0;
     MARK(c, "k_exec");   zsbk_exec(st, c->n_exec, src, frames, blocks, work, fout, (const uint32_t *)c->exec_list.p, cnt, (const uint64_t *)c->seq_pool.p,
                                    (const uint8_t *)c->lit_pool.p, c->d_dst); c->launches += c->n_exec ? 1 : 0;
+    // pipelined path: the shard's output may leave as soon as it is written -- the checksums are computed from HBM while the
+    // download runs (both only read the output)
+    const bool early_down = c->down_stream && c->eager_d2h && c->h_dst;
+    if (early_down) {
+        if (c->trace) cudaEventRecord(c->ev_tr[2], st);
+        CK(c, cudaEventRecord(c->ev_kdone, st)); CK(c, cudaStreamWaitEvent(c->down_stream, c->ev_kdone, 0));
+        CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, c->eager_d2h, cudaMemcpyDeviceToHost, c->down_stream));
+        CK(c, cudaEventRecord(c->ev_down, c->down_stream));
+        if (c->trace) cudaEventRecord(c->ev_tr[3], c->down_stream);
+    }
     MARK(c, "k_xxh");    zsbk_xxh(st, c->n_xxh, c->d_dst, fout, (const uint32_t *)c->xxh_list.p, cnt); c->launches += c->n_xxh ? 1 : 0;
     if (c->profile) { cudaEventRecord(c->ev[c->prof_slot][c->nk], st); c->prof_slot = (c->prof_slot + 1) % kProfRing; c->prof_count++; }
-    if (c->trace) cudaEventRecord(c->ev_tr[2], st);
+    if (c->trace && !early_down) cudaEventRecord(c->ev_tr[2], st);
     c->pin_valid = false;
     if (c->down_stream && c->eager_d2h && c->h_dst) {
         const size_t need = 64 + sizeof(ZsbFrameOut) * (size_t)c->nf;
@@ -291,13 +301,10 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
             c->pin_valid = true;
         }
     }
-    if (c->eager_d2h && c->h_dst) {
-        cudaStream_t ds = st;
-        if (c->down_stream) { ds = c->down_stream; CK(c, cudaEventRecord(c->ev_kdone, st)); CK(c, cudaStreamWaitEvent(ds, c->ev_kdone, 0)); }
-        CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, c->eager_d2h, cudaMemcpyDeviceToHost, ds));
-        if (c->down_stream) CK(c, cudaEventRecord(c->ev_down, ds));
-        if (c->trace) cudaEventRecord(c->ev_tr[3], ds);
-    } else if (c->trace) cudaEventRecord(c->ev_tr[3], st);
+    if (!early_down) {
+        if (c->eager_d2h && c->h_dst) CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, c->eager_d2h, cudaMemcpyDeviceToHost, st));
+        if (c->trace) cudaEventRecord(c->ev_tr[3], st);
+    }
     CK(c, cudaGetLastError());
     c->launched = true;
     return ZSB_OK;
@@ -369,9 +376,9 @@ static int decode_pipelined(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_
     // possible and never let it wait: a shard's output can leave only after its upload plus ~3.3 ms of kernels (every stage is a
     // per-frame dependent chain, so the latency does not shrink with the shard).  Hence a small first shard and sizes that grow
     // about as fast as the download falls behind the upload (x2); the first shards also run in low-latency mode (ctx.low_latency)
-    // when the frames are large enough for a CTA each.  Measured on C2: 8 equal shards 14.1 ms, this plan 13.3 ms.
+    // when the frames are large enough for a CTA each.  Measured on C2: 8 equal shards 14.1 ms, this plan 12.3 ms.
     // ZSB_PIPE_WEIGHTS="w0,w1,..." and ZSB_PIPE_FAST_SHARDS=k override the plan (experiments).
-    static const double kPlanFast[] = {1, 2, 4, 8, 8, 10, 22, 9}, kPlanPlain[] = {1, 2, 4, 8, 16, 33};
+    static const double kPlanFast[] = {1, 2, 4, 8, 8, 10, 14, 17}, kPlanPlain[] = {1, 2, 4, 8, 16, 33};
     const bool big_frames = expect_total / nf >= (64u << 10);
     int kPipeShards = 0, n_fast = big_frames ? 5 : 0;
     double wts[kPipeShardsMax];
