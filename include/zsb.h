@@ -146,6 +146,20 @@ int zsb_decode(zsb_ctx *ctx, const uint8_t *src, size_t n,
                int32_t *status, uint32_t *xxh32, uint8_t *checksum_ok,
                uint64_t *dst_total, uint32_t flags);
 
+/* zsb_scan + zsb_decode on host buffers in one call, the host walk overlapped with the GPU work: the walk stops at shard
+ * boundaries and the frames found so far are already uploading and decoding while the rest of the buffer is walked (== the
+ * reference's FrameIterator feeding Frame::decode, frame.rs:94-99 / main.rs:42-53).  Returns what zsb_scan returns; frames /
+ * blocks as from zsb_scan, results[f] as the per-frame arrays of zsb_decode (all three malloc'd: zsb_free). */
+typedef struct zsb_result {
+    uint64_t dst_off, dst_len;
+    int32_t  status;
+    uint32_t xxh32;
+    uint8_t  checksum_ok, pad[7];
+} zsb_result;
+int zsb_scan_decode(zsb_ctx *ctx, const uint8_t *src, size_t n, uint8_t *dst, size_t dst_cap, uint32_t flags, uint64_t max_window,
+                    zsb_frame **frames, size_t *n_frames, zsb_block **blocks, size_t *n_blocks,
+                    zsb_result **results, uint64_t *dst_total, uint64_t *err_a, uint64_t *err_b);
+
 /* Page-locked host buffers for src/dst of zsb_decode: copies from and to pageable memory are staged by the driver and
  * block the calling thread, which serialises the shards of the pipelined path (a binding would back its input and
  * output Vec<u8> with these).  NULL on failure.  Not for zsb_free. */

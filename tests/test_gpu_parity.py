@@ -349,3 +349,51 @@ def test_pipelined_host_path_page_locked_buffers_small_frames(dec):
             assert C.string_at(dst, len(exp)) == exp
         finally:
             L.zsb_host_free(src); L.zsb_host_free(dst)
+
+
+def _scan_decode_equals_scan_then_decode(dec, blob, flags, cap=None):
+    """zsb_scan_decode against zsb_scan + zsb_decode on the same buffer: same scan verdict, descriptors, per-frame results, bytes."""
+    import ctypes as C
+    L = Z.lib()
+    sc = Z.Scan(blob, flags)
+    cap = cap if cap is not None else max(Z.capacity_bound(sc, flags), 1)
+    out, _, r = dec.decode(blob, flags, dst_cap=cap, scan=sc)
+    src = L.zsb_host_alloc(max(len(blob), 1)); dst = L.zsb_host_alloc(cap)
+    try:
+        C.memmove(src, blob, len(blob))
+        sd = Z.ScanDecode(dec.ctx, (src, len(blob)), (dst, cap), flags)
+        assert sd.status == sc.status and (sd.err_a, sd.err_b) == (sc.err_a, sc.err_b)
+        assert sd.n_frames == sc.n_frames and sd.n_blocks == sc.n_blocks and sd.total == r.total.value
+        fsz, bsz = C.sizeof(Z.ZsbFrame), C.sizeof(Z.ZsbBlock)
+        assert C.string_at(sd.frames, fsz * sc.n_frames) == C.string_at(sc.frames, fsz * sc.n_frames)
+        assert C.string_at(sd.blocks, bsz * sc.n_blocks) == C.string_at(sc.blocks, bsz * sc.n_blocks)
+        for i in range(sc.n_frames):
+            q = sd.results[i]
+            assert (q.dst_off, q.dst_len, q.status, q.xxh32, q.checksum_ok) == (r.dst_off[i], r.dst_len[i], r.status[i], r.xxh32[i], r.checksum_ok[i]), i
+        assert C.string_at(dst, sd.total) == out
+        assert (sd.first_error() is None) == (r.first_error() is None)
+    finally:
+        L.zsb_host_free(src); L.zsb_host_free(dst)
+    return sd
+
+
+def test_scan_decode_streams_the_walk(dec):
+    """zsb_scan_decode (walk overlapped with upload and decode) on: a batch large enough to stream; the same with a corrupted frame
+    (the pipeline is given up, results as the plain path); with trailing garbage (scan error after good frames); frames without
+    content size; a small input; an empty input."""
+    import gen_corpus as G
+    blob, exp = G.make_c2(640, seed=13)
+    sd = _scan_decode_equals_scan_then_decode(dec, blob, Q | VER)
+    assert sd.status == 0 and sd.total == len(exp) and sd.first_error() is None
+    sc = Z.Scan(blob, Q)
+    bad = bytearray(blob); f = sc.frames[333]; bad[f.src_off + f.src_len // 2] ^= 0x10
+    _scan_decode_equals_scan_then_decode(dec, bytes(bad), Q | VER, cap=len(exp))
+    sd = _scan_decode_equals_scan_then_decode(dec, blob + b"\x01\x02\x03\x04\x05", Q | VER, cap=len(exp))
+    assert sd.status != 0 and sd.n_frames == 641
+    nofcs = blob[:sc.frames[100].src_off] + b"".join(G.compress(exp[i * 131072:(i + 1) * 131072], content_size=False) for i in range(100, 400))
+    assert len(nofcs) > (16 << 20)
+    sd = _scan_decode_equals_scan_then_decode(dec, nofcs, Q | VER)
+    assert sd.total == 400 * 131072
+    _scan_decode_equals_scan_then_decode(dec, corpora.fixture("moby-dick.txt.zst"), Q | VER)
+    _scan_decode_equals_scan_then_decode(dec, b"", Q | VER)
+    _scan_decode_equals_scan_then_decode(dec, blob, Q | VER, cap=len(exp) // 2)          # output does not fit

@@ -43,6 +43,11 @@ class ZsbBlock(C.Structure):
                 ("pad", C.c_uint8 * 6)]
 
 
+class ZsbResult(C.Structure):
+    _fields_ = [("dst_off", C.c_uint64), ("dst_len", C.c_uint64), ("status", C.c_int32), ("xxh32", C.c_uint32), ("checksum_ok", C.c_uint8),
+                ("pad", C.c_uint8 * 7)]
+
+
 class ZsbError(Exception):
     """Carries the zsb status code; codes 1..62 are the reference's error variants (include/zsb.h)."""
     def __init__(self, code, a=0, b=0, what=""):
@@ -102,6 +107,8 @@ def lib():
     L.zsb_decode_prepare.argtypes = [vp, vp, sz, C.POINTER(ZsbFrame), sz, C.POINTER(ZsbBlock), sz, vp, sz, C.c_uint32]
     L.zsb_decode_launch.argtypes = [vp]
     L.zsb_decode_finish.argtypes = [vp, u64p, u64p, i32p, u32p, u8p, u64p]
+    L.zsb_scan_decode.argtypes = [vp, vp, sz, vp, sz, C.c_uint32, C.c_uint64, C.POINTER(C.POINTER(ZsbFrame)), C.POINTER(sz),
+                                  C.POINTER(C.POINTER(ZsbBlock)), C.POINTER(sz), C.POINTER(C.POINTER(ZsbResult)), u64p, u64p, u64p]
     L.zsb_decompress.argtypes = [vp, vp, sz, C.c_uint32, C.POINTER(vp), C.POINTER(sz), u64p, u64p]
     L.zsb_fse_table_parse.argtypes = [vp, C.c_char_p, sz, C.c_int, u8p, C.POINTER(C.c_uint16), C.POINTER(sz), C.POINTER(C.c_int16), C.POINTER(sz)]
     L.zsb_fse_table_from_distribution.argtypes = [vp, C.c_uint8, C.POINTER(C.c_int16), sz, C.POINTER(C.c_uint16)]
@@ -121,7 +128,7 @@ EXPORTED_SYMBOLS = [
     "zsb_scan", "zsb_free", "zsb_ctx_create", "zsb_ctx_destroy", "zsb_ctx_set_stream", "zsb_last_cuda_error", "zsb_ctx_set_profile",
     "zsb_last_launch_count", "zsb_last_kernel_times", "zsb_kernel_times_avg", "zsb_decode", "zsb_decode_prepare", "zsb_decode_launch", "zsb_decode_finish",
     "zsb_decompress", "zsb_fse_table_parse", "zsb_fse_table_from_distribution", "zsb_huffman_parse", "zsb_execute_sequences",
-    "zsb_xxh64", "zsb_strerror", "zsb_version", "zsb_shard_plan", "zsb_shard_extract", "zsb_host_alloc", "zsb_host_free"]
+    "zsb_xxh64", "zsb_strerror", "zsb_version", "zsb_shard_plan", "zsb_shard_extract", "zsb_host_alloc", "zsb_host_free", "zsb_scan_decode"]
 
 
 # ------------------------------------------------------------------------------------------ scan
@@ -229,6 +236,39 @@ class BatchResult:
             if self.status[i]:
                 return i, self.status[i]
         return None
+
+
+class ScanDecode:
+    """zsb_scan_decode: walk + decode of a host buffer into a host buffer in one call (the walk overlaps the GPU work).
+    src / dst are (pointer, length) pairs; page-locked memory (zsb_host_alloc, torch pinned tensors) keeps the copies asynchronous.
+    Attributes as Scan (frames, blocks, n_frames, n_blocks, status = what zsb_scan would return) plus results[f] (ZsbResult) and total."""
+    def __init__(self, ctx, src, dst, flags=VERIFY_CHECKSUM, max_window=0):
+        fp, bp, rp = C.POINTER(ZsbFrame)(), C.POINTER(ZsbBlock)(), C.POINTER(ZsbResult)()
+        nf, nb, tot, ea, eb = C.c_size_t(), C.c_size_t(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.status = lib().zsb_scan_decode(ctx.h, C.c_void_p(src[0]), src[1], C.c_void_p(dst[0]), dst[1], flags, max_window,
+                                            C.byref(fp), C.byref(nf), C.byref(bp), C.byref(nb), C.byref(rp), C.byref(tot), C.byref(ea), C.byref(eb))
+        self.frames, self.blocks, self.results = fp, bp, rp
+        self.n_frames, self.n_blocks, self.total = nf.value, nb.value, tot.value
+        self.err_a, self.err_b = ea.value, eb.value
+        if not rp and self.status:                      # the call itself failed (arguments, CUDA, memory): nothing was produced
+            raise ZsbError(self.status, what="zsb_scan_decode" + (": " + ctx.cuda_error() if self.status == E_CUDA else ""))
+
+    def first_error(self):
+        n = self.n_frames
+        raw = C.string_at(self.results, C.sizeof(ZsbResult) * n) if n else b""
+        if all(raw[16 + k::32].count(0) == n for k in range(4)):      # every status zero: the common case at C speed
+            return None
+        for i in range(n):
+            if self.results[i].status:
+                return i, self.results[i].status
+        return None
+
+    def __del__(self):
+        try:
+            for p in ("frames", "blocks", "results"):
+                if getattr(self, p, None): lib().zsb_free(getattr(self, p))
+        except Exception:
+            pass
 
 
 class Decoder:

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include "zsb_kernels.h"
+#include "zsb_scan.h"
 
 // ======================================================================================= context
 namespace {
@@ -360,6 +361,104 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const size_t kPipeMinFrames = 512;
 static const int kPipeShardsMax = 32;
+// bytes frame f contributes to the output
+static inline uint64_t frame_out_bytes(const zsb_frame &f, const zsb_block *blocks, uint32_t flags) {
+    return f.kind == 1 ? ((flags & ZSB_PRINT_SKIPPABLE) ? blocks[f.first_block].size : 0) : f.content_size;
+}
+// Shard plan.  The download of the whole output (PCIe, ~55 GB/s) is the longest leg, so the goal is to start it as early as
+// possible and never let it wait: a shard's output can leave only after its upload plus ~2-3 ms of kernels (every stage is a
+// per-frame dependent chain, so the latency does not shrink with the shard).  Hence a small first shard and sizes that grow
+// about as fast as the download falls behind the upload (x2); the first shards also run in low-latency mode (ctx.low_latency)
+// when the frames are large enough for a CTA each.  Measured on C2: 8 equal shards 14.1 ms, this plan 12.3 ms.
+// ZSB_PIPE_WEIGHTS="w0,w1,..." and ZSB_PIPE_FAST_SHARDS=k override the plan (experiments).
+static const double kPlanFast[] = {1, 2, 4, 8, 8, 10, 14, 17}, kPlanPlain[] = {1, 2, 4, 8, 16, 33};
+static const int kPlanFastShards = 5;
+static int pipe_plan(bool big_frames, double *wts, int &n_fast) {
+    int ns = 0;
+    n_fast = big_frames ? kPlanFastShards : 0;
+    if (const char *e = getenv("ZSB_PIPE_WEIGHTS")) { while (*e && ns < kPipeShardsMax) { char *q; double v = strtod(e, &q); if (q == e) break; wts[ns++] = v > 0 ? v : 1; e = *q == ',' ? q + 1 : q; } }
+    if (!ns) {
+        const double *pl = big_frames ? kPlanFast : kPlanPlain;
+        ns = big_frames ? (int)(sizeof kPlanFast / sizeof *kPlanFast) : (int)(sizeof kPlanPlain / sizeof *kPlanPlain);
+        for (int k = 0; k < ns; k++) wts[k] = pl[k];
+    }
+    if (const char *e = getenv("ZSB_PIPE_FAST_SHARDS")) n_fast = atoi(e);
+    return ns;
+}
+
+// The shards of one pipelined call: dispatch() enqueues upload + kernels + download of a frame range on the next child context,
+// collect() waits for all of them in order and merges the per-frame results.
+struct Pipe {
+    zsb_ctx *c; const uint8_t *src; uint8_t *dst; size_t dst_cap; uint32_t flags;
+    struct Sh { size_t f0 = 0, f1 = 0; zsb_frame *fr = nullptr; zsb_block *bl = nullptr; size_t nb = 0; uint64_t so = 0, sl = 0, doff = 0, dexp = 0; bool on = false; double host_ms = 0; } sh[kPipeShardsMax];
+    int n = 0;
+    uint64_t doff = 0;
+    double t0 = 0, t_enq = 0;
+    Pipe(zsb_ctx *ctx, const uint8_t *s, uint8_t *d, size_t cap, uint32_t fl) : c(ctx), src(s), dst(d), dst_cap(cap), flags(fl) { t0 = now_ms(); }
+    ~Pipe() { for (int k = 0; k < n; k++) { zsb_free(sh[k].fr); zsb_free(sh[k].bl); } }
+    // frames [f0, f1) of the (possibly still growing) descriptor arrays become the next shard; false = give the pipeline up
+    bool dispatch(const zsb_frame *frames, size_t nf, const zsb_block *blocks, size_t nb, size_t f0, size_t f1, bool low_latency) {
+        if (n >= kPipeShardsMax) return false;
+        const int k = n++;
+        Sh &S = sh[k];
+        S.f0 = f0; S.f1 = f1; S.doff = doff;
+        if (f0 == f1) return true;
+        while (c->subs.size() <= (size_t)k) {
+            zsb_ctx *sub = nullptr;
+            if (zsb_ctx_create(&sub, c->device) != ZSB_OK) return false;
+            sub->is_sub = true;
+            c->subs.push_back(sub);
+        }
+        if (zsb_shard_extract(frames, nf, blocks, nb, f0, f1, &S.fr, &S.bl, &S.nb, &S.so, &S.sl) != ZSB_OK) return false;
+        for (size_t f = f0; f < f1; f++) S.dexp += frame_out_bytes(frames[f], blocks, flags);
+        if (S.doff + S.dexp > dst_cap) return false;
+        doff += S.dexp;
+        zsb_ctx *sub = c->subs[k];
+        sub->eager_d2h = S.dexp;
+        sub->up_stream = c->own_stream; sub->down_stream = c->aux_stream;
+        sub->low_latency = low_latency;
+        bool first_on = true; for (int j = 0; j < k; j++) first_on = first_on && !sh[j].on;
+        if (c->trace && first_on) cudaEventRecord(c->ev_tr[0], sub->up_stream);
+        if (c->trace) S.host_ms = now_ms() - t0;
+        if (zsb_decode_prepare(sub, src + S.so, S.sl, S.fr, f1 - f0, S.bl, S.nb, dst + S.doff, S.dexp, flags) != ZSB_OK ||
+            zsb_decode_launch(sub) != ZSB_OK) return false;
+        S.on = true;
+        return true;
+    }
+    // returns ZSB_OK, ZSB_E_CUDA, or 1 when the result must not be used (a frame failed or disagreed with its declared size)
+    int collect(uint64_t *dst_off, uint64_t *dst_len, int32_t *status, uint32_t *xxh32, uint8_t *checksum_ok, uint64_t *dst_total) {
+        int rc = ZSB_OK; bool bad = false;
+        uint64_t total = 0;
+        t_enq = now_ms();
+        for (int k = 0; k < n; k++) {
+            Sh &S = sh[k];
+            if (!S.on) continue;
+            uint64_t t = 0;
+            const int r = zsb_decode_finish(c->subs[k], dst_off ? dst_off + S.f0 : nullptr, dst_len ? dst_len + S.f0 : nullptr, status ? status + S.f0 : nullptr,
+                                            xxh32 ? xxh32 + S.f0 : nullptr, checksum_ok ? checksum_ok + S.f0 : nullptr, &t);
+            if (r != ZSB_OK) { rc = r; c->last_err = c->subs[k]->last_err; bad = true; }
+            else {
+                if (t != S.dexp) bad = true;
+                if (dst_off) for (size_t f = S.f0; f < S.f1; f++) dst_off[f] += S.doff;
+                total += t;
+            }
+        }
+        if (c->trace) {
+            fprintf(stderr, "[zsb pipe] host: all shards enqueued at %.2f ms, finished at %.2f ms\n", t_enq - t0, now_ms() - t0);
+            for (int k = 0; k < n; k++) if (sh[k].on) {
+                float a = 0, b = 0, d = 0;
+                cudaEventElapsedTime(&a, c->ev_tr[0], c->subs[k]->ev_tr[1]); cudaEventElapsedTime(&b, c->ev_tr[0], c->subs[k]->ev_tr[2]); cudaEventElapsedTime(&d, c->ev_tr[0], c->subs[k]->ev_tr[3]);
+                fprintf(stderr, "[zsb pipe] shard %d: enqueue starts %.2f (host) | uploads done %.2f, output written %.2f, download done %.2f ms (device)\n", k, sh[k].host_ms, a, b, d);
+            }
+            (void)cudaGetLastError();
+        }
+        if (rc == ZSB_E_CUDA) return rc;
+        if (bad) return 1;
+        if (dst_total) *dst_total = total;
+        return ZSB_OK;
+    }
+};
+
 static int decode_pipelined(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_frame *frames, size_t nf, const zsb_block *blocks, size_t nb,
                             uint8_t *dst, size_t dst_cap, uint64_t *dst_off, uint64_t *dst_len, int32_t *status, uint32_t *xxh32,
                             uint8_t *checksum_ok, uint64_t *dst_total, uint32_t flags) {
@@ -367,99 +466,27 @@ static int decode_pipelined(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_
     uint64_t expect_total = 0;
     for (size_t f = 0; f < nf; f++) {
         if (frames[f].status != ZSB_OK) return 1;
-        if (frames[f].kind == 1) { if (flags & ZSB_PRINT_SKIPPABLE) expect_total += blocks[frames[f].first_block].size; }
-        else if (!frames[f].has_content_size) return 1;
-        else expect_total += frames[f].content_size;
+        if (frames[f].kind == 0 && !frames[f].has_content_size) return 1;
+        expect_total += frame_out_bytes(frames[f], blocks, flags);
     }
     if (expect_total > dst_cap || expect_total < (32u << 20)) return 1;
-    // Shard plan.  The download of the whole output (PCIe, ~55 GB/s) is the longest leg, so the goal is to start it as early as
-    // possible and never let it wait: a shard's output can leave only after its upload plus ~3.3 ms of kernels (every stage is a
-    // per-frame dependent chain, so the latency does not shrink with the shard).  Hence a small first shard and sizes that grow
-    // about as fast as the download falls behind the upload (x2); the first shards also run in low-latency mode (ctx.low_latency)
-    // when the frames are large enough for a CTA each.  Measured on C2: 8 equal shards 14.1 ms, this plan 12.3 ms.
-    // ZSB_PIPE_WEIGHTS="w0,w1,..." and ZSB_PIPE_FAST_SHARDS=k override the plan (experiments).
-    static const double kPlanFast[] = {1, 2, 4, 8, 8, 10, 14, 17}, kPlanPlain[] = {1, 2, 4, 8, 16, 33};
-    const bool big_frames = expect_total / nf >= (64u << 10);
-    int kPipeShards = 0, n_fast = big_frames ? 5 : 0;
-    double wts[kPipeShardsMax];
-    if (const char *e = getenv("ZSB_PIPE_WEIGHTS")) { while (*e && kPipeShards < kPipeShardsMax) { char *q; double v = strtod(e, &q); if (q == e) break; wts[kPipeShards++] = v > 0 ? v : 1; e = *q == ',' ? q + 1 : q; } }
-    if (!kPipeShards) {
-        const double *pl = big_frames ? kPlanFast : kPlanPlain;
-        kPipeShards = big_frames ? (int)(sizeof kPlanFast / sizeof *kPlanFast) : (int)(sizeof kPlanPlain / sizeof *kPlanPlain);
-        for (int k = 0; k < kPipeShards; k++) wts[k] = pl[k];
+    double wts[kPipeShardsMax]; int n_fast = 0;
+    const int ns = pipe_plan(expect_total / nf >= (64u << 10), wts, n_fast);
+    double wsum = 0; for (int k = 0; k < ns; k++) wsum += wts[k];
+    Pipe P(c, src, dst, dst_cap, flags);
+    // boundaries: cumulative output bytes cut at the cumulative weights
+    size_t f = 0; double acc = 0, cum = 0;
+    bool ok = true;
+    for (int k = 0; k < ns && ok; k++) {
+        cum += wts[k];
+        const double lim = (double)expect_total * (cum / wsum);
+        const size_t f0 = f;
+        while (f < nf && (k == ns - 1 || acc < lim)) { acc += (double)frame_out_bytes(frames[f], blocks, flags); f++; }
+        ok = P.dispatch(frames, nf, blocks, nb, f0, f, k < n_fast);
     }
-    if (const char *e = getenv("ZSB_PIPE_FAST_SHARDS")) n_fast = atoi(e);
-    size_t first[kPipeShardsMax + 1];
-    {   // boundaries: cumulative output bytes cut at the cumulative weights
-        double wsum = 0; for (int k = 0; k < kPipeShards; k++) wsum += wts[k];
-        size_t f = 0; double acc = 0, cum = 0; first[0] = 0;
-        for (int k = 0; k < kPipeShards; k++) {
-            cum += wts[k];
-            const double lim = (double)expect_total * (cum / wsum);
-            while (f < nf && (k == kPipeShards - 1 || acc < lim)) { acc += frames[f].kind == 1 ? ((flags & ZSB_PRINT_SKIPPABLE) ? (double)blocks[frames[f].first_block].size : 0.0) : (double)frames[f].content_size; f++; }
-            first[k + 1] = f;
-        }
-    }
-    while (c->subs.size() < (size_t)kPipeShards) {
-        zsb_ctx *sub = nullptr;
-        if (zsb_ctx_create(&sub, c->device) != ZSB_OK) return 1;
-        sub->is_sub = true;
-        c->subs.push_back(sub);
-    }
-    double host_ms[kPipeShardsMax] = {}; const double t_host0 = now_ms();
-    struct Sh { zsb_frame *fr = nullptr; zsb_block *bl = nullptr; size_t nb = 0; uint64_t so = 0, sl = 0, doff = 0, dexp = 0; bool on = false; } sh[kPipeShardsMax];
-    int rc = ZSB_OK; bool fallback = false;
-    uint64_t doff = 0;
-    for (int k = 0; k < kPipeShards && !fallback; k++) {
-        Sh &S = sh[k];
-        const size_t f0 = first[k], f1 = first[k + 1];
-        S.doff = doff;
-        if (f0 == f1) continue;
-        if (zsb_shard_extract(frames, nf, blocks, nb, f0, f1, &S.fr, &S.bl, &S.nb, &S.so, &S.sl) != ZSB_OK) { fallback = true; break; }
-        for (size_t f = f0; f < f1; f++)
-            S.dexp += frames[f].kind == 1 ? ((flags & ZSB_PRINT_SKIPPABLE) ? blocks[frames[f].first_block].size : 0) : frames[f].content_size;
-        doff += S.dexp;
-        zsb_ctx *sub = c->subs[k];
-        sub->eager_d2h = S.dexp;
-        sub->up_stream = c->own_stream; sub->down_stream = c->aux_stream;
-        sub->low_latency = k < n_fast;
-        if (c->trace && k == 0) cudaEventRecord(c->ev_tr[0], sub->up_stream);
-        if (c->trace) host_ms[k] = now_ms() - t_host0;
-        if (zsb_decode_prepare(sub, src + S.so, S.sl, S.fr, f1 - f0, S.bl, S.nb, dst + S.doff, S.dexp, flags) != ZSB_OK ||
-            zsb_decode_launch(sub) != ZSB_OK) { fallback = true; break; }
-        S.on = true;
-    }
-    uint64_t total = 0;
-    const double t_enq = now_ms();
-    for (int k = 0; k < kPipeShards; k++) {
-        Sh &S = sh[k];
-        if (S.on) {
-            const size_t f0 = first[k], f1 = first[k + 1];
-            uint64_t t = 0;
-            const int r = zsb_decode_finish(c->subs[k], dst_off ? dst_off + f0 : nullptr, dst_len ? dst_len + f0 : nullptr, status ? status + f0 : nullptr,
-                                            xxh32 ? xxh32 + f0 : nullptr, checksum_ok ? checksum_ok + f0 : nullptr, &t);
-            if (r != ZSB_OK) { rc = r; c->last_err = c->subs[k]->last_err; fallback = true; }
-            else {
-                if (t != S.dexp) fallback = true;                                   // a frame failed or disagreed with its declared size
-                if (dst_off) for (size_t f = f0; f < f1; f++) dst_off[f] += S.doff;
-                total += t;
-            }
-        }
-        zsb_free(S.fr); zsb_free(S.bl);
-    }
-    if (c->trace) {
-        fprintf(stderr, "[zsb pipe] host: all shards enqueued at %.2f ms, finished at %.2f ms\n", t_enq - t_host0, now_ms() - t_host0);
-        for (int k = 0; k < kPipeShards; k++) if (sh[k].on) {
-            float a = 0, b = 0, d = 0;
-            cudaEventElapsedTime(&a, c->ev_tr[0], c->subs[k]->ev_tr[1]); cudaEventElapsedTime(&b, c->ev_tr[0], c->subs[k]->ev_tr[2]); cudaEventElapsedTime(&d, c->ev_tr[0], c->subs[k]->ev_tr[3]);
-            fprintf(stderr, "[zsb pipe] shard %d: enqueue starts %.2f (host) | uploads done %.2f, kernels done %.2f, download done %.2f ms (device)\n", k, host_ms[k], a, b, d);
-        }
-        (void)cudaGetLastError();
-    }
+    const int rc = P.collect(dst_off, dst_len, status, xxh32, checksum_ok, dst_total);
     if (rc == ZSB_E_CUDA) return rc;
-    if (fallback) return 1;
-    if (dst_total) *dst_total = total;
-    return ZSB_OK;
+    return (ok && rc == ZSB_OK) ? ZSB_OK : 1;
 }
 
 extern "C" int zsb_decode(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_frame *frames, size_t nf, const zsb_block *blocks, size_t nb,
@@ -474,6 +501,63 @@ extern "C" int zsb_decode(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_fr
     rc = zsb_decode_launch(c);
     if (rc) return rc;
     return zsb_decode_finish(c, dst_off, dst_len, status, xxh32, checksum_ok, dst_total);
+}
+
+// zsb_scan + zsb_decode in one call on host buffers, with the host walk overlapped: the walk stops at every shard boundary
+// (a fraction of the compressed bytes) and the frames found so far start uploading and decoding while the rest of the buffer
+// is still being walked.  Results are those of zsb_scan followed by zsb_decode.  Anything that keeps the pipelined path from
+// applying (a frame without Frame_Content_Size, a malformed frame, an output that does not fit, a frame that fails or
+// disagrees with its declared size) ends in the plain zsb_decode over the completed scan.
+extern "C" int zsb_scan_decode(zsb_ctx *c, const uint8_t *src, size_t n, uint8_t *dst, size_t dst_cap, uint32_t flags, uint64_t max_window,
+                               zsb_frame **frames_out, size_t *n_frames, zsb_block **blocks_out, size_t *n_blocks,
+                               zsb_result **results_out, uint64_t *dst_total, uint64_t *err_a, uint64_t *err_b) {
+    if (!c || c->is_sub || (!src && n) || !dst || !frames_out || !n_frames || !blocks_out || !n_blocks || !results_out) return ZSB_E_ARG;
+    *frames_out = nullptr; *blocks_out = nullptr; *results_out = nullptr; *n_frames = 0; *n_blocks = 0;
+    flags &= ~(ZSB_SRC_ON_DEVICE | ZSB_DST_ON_DEVICE);
+    ZsbScanner sc(src, n, flags, max_window);
+    Pipe P(c, src, dst, dst_cap, flags);
+    bool streamed = n >= (16u << 20);                                   // worth cutting up at all
+    if (streamed) {
+        double wts[kPipeShardsMax]; int n_fast = 0;
+        const int ns = pipe_plan(true, wts, n_fast);
+        double wsum = 0, cum = 0; for (int k = 0; k < ns; k++) wsum += wts[k];
+        for (int k = 0; k < ns && streamed && !sc.done; k++) {
+            cum += wts[k];
+            const size_t lim = k == ns - 1 ? n : (size_t)((double)n * (cum / wsum));
+            const size_t f0 = sc.frames.size();
+            while (!sc.done && sc.pos < lim) if (!sc.next()) break;
+            if (sc.code != ZSB_OK) { streamed = false; break; }          // the walk ended on a malformed frame
+            const size_t f1 = sc.frames.size();
+            uint64_t out = 0;
+            for (size_t f = f0; f < f1 && streamed; f++) {
+                if (sc.frames[f].kind == 0 && !sc.frames[f].has_content_size) streamed = false;
+                out += frame_out_bytes(sc.frames[f], sc.blocks.data(), flags);
+            }
+            if (!streamed) break;
+            const bool big = f1 > f0 && out / (f1 - f0) >= (64u << 10);
+            if (!P.dispatch(sc.frames.data(), f1, sc.blocks.data(), sc.blocks.size(), f0, f1, big && k < n_fast)) streamed = false;
+        }
+    }
+    while (sc.next()) {}                                                 // whatever is left (nothing, unless the pipeline was given up)
+    const size_t nf = sc.frames.size();
+    std::vector<uint64_t> off(nf + 1), len(nf + 1); std::vector<int32_t> st(nf + 1); std::vector<uint32_t> xh(nf + 1); std::vector<uint8_t> ck(nf + 1);
+    uint64_t total = 0;
+    int rc = P.collect(off.data(), len.data(), st.data(), xh.data(), ck.data(), &total);     // also drains shards of a pipeline given up
+    if (rc == ZSB_E_CUDA) return rc;
+    if (!streamed || rc != ZSB_OK) {
+        rc = zsb_decode(c, src, n, sc.frames.data(), nf, sc.blocks.data(), sc.blocks.size(), dst, dst_cap, off.data(), len.data(), st.data(), xh.data(), ck.data(), &total, flags);
+        if (rc) return rc;
+    }
+    zsb_result *res = (zsb_result *)malloc(sizeof(zsb_result) * (nf + 1));
+    if (!res) return ZSB_E_NOMEM;
+    for (size_t f = 0; f < nf; f++) { res[f].dst_off = off[f]; res[f].dst_len = len[f]; res[f].status = st[f]; res[f].xxh32 = xh[f]; res[f].checksum_ok = ck[f]; memset(res[f].pad, 0, sizeof res[f].pad); }
+    rc = sc.release(frames_out, n_frames, blocks_out, n_blocks);
+    if (rc) { free(res); return rc; }
+    *results_out = res;
+    if (dst_total) *dst_total = total;
+    if (err_a) *err_a = sc.err_a;
+    if (err_b) *err_b = sc.err_b;
+    return sc.code;
 }
 
 // src/main.rs:42-58 : all-or-nothing whole-buffer decode

@@ -7,6 +7,7 @@
 #include <string.h>
 #include <vector>
 #include "zsb_common.h"
+#include "zsb_scan.h"
 
 #define MAGIC_ZSTD 0xFD2FB528u
 #define MAGIC_SKIP 0x184D2A50u
@@ -55,83 +56,98 @@ bool parse_header(Cursor &c, zsb_frame &f, ScanErr &e) {
 }
 }  // namespace
 
-extern "C" int zsb_scan(const uint8_t *src, size_t n, uint32_t flags, uint64_t max_window,
-                        zsb_frame **frames_out, size_t *n_frames, zsb_block **blocks_out, size_t *n_blocks,
-                        uint64_t *err_a, uint64_t *err_b) {
-    if (!frames_out || !n_frames || !blocks_out || !n_blocks || (!src && n)) return ZSB_E_ARG;
+// One frame (FrameIterator::next frame.rs:94-99): appends its descriptor (and its blocks) and returns true, or appends the
+// failed frame (no blocks, status = the error) and returns false; false with nothing appended when the input is exhausted.
+bool ZsbScanner::next() {
+    if (done) return false;
+    Cursor c{src, n, pos};
+    if (c.left() == 0) { done = true; return false; }
     const bool quirks = (flags & ZSB_REFERENCE_QUIRKS) != 0;
-    if (max_window == 0) max_window = ZSB_MAX_WINDOW_DEFAULT;
-    std::vector<zsb_frame> frames; std::vector<zsb_block> blocks;
-    Cursor c{src, n, 0};
     ScanErr e{ZSB_OK, 0, 0};
-    while (c.left() != 0) {                                          // FrameIterator::next frame.rs:94-99
-        zsb_frame f; memset(&f, 0, sizeof f);
-        f.src_off = c.pos; f.first_block = (uint32_t)blocks.size();
-        bool ok = false;
-        do {
-            if (!need(c, 4, e)) break;                               // Frame::parse frame.rs:61-77
-            const uint32_t magic = (uint32_t)rd_le(c.p + c.pos, 4); c.pos += 4;
-            f.magic = magic;
-            if (magic == MAGIC_ZSTD) {
-                f.kind = 0;
-                if (!parse_header(c, f, e)) break;                   // ZStandard::parse frame.rs:198-230
-                if (f.window_size > max_window) { e.code = ZSB_E_WINDOW_TOO_BIG; e.a = max_window; e.b = f.window_size; break; }
-                if ((flags & ZSB_STRICT_DICT) && f.has_dict_id && f.dict_id != 0) { e.code = ZSB_E_DICTIONARY; e.a = f.dict_id; e.b = 0; break; }
-                bool bad = false;
-                for (;;) {                                           // Block::parse block.rs:43-72
-                    if (c.left() < 3) { e.code = ZSB_E_NOT_ENOUGH_BYTES; e.a = 3; e.b = c.left(); bad = true; break; }
-                    const uint32_t v = (uint32_t)rd_le(c.p + c.pos, 3); c.pos += 3;
-                    zsb_block b; memset(&b, 0, sizeof b);
-                    b.last = v & 1; b.type = (v >> 1) & 3; b.size = v >> 3; b.frame = (uint32_t)frames.size(); b.src_off = c.pos;
-                    if (b.type == 3) { e.code = ZSB_E_RESERVED_BLOCK; e.a = e.b = 0; bad = true; break; }
-                    if (b.type == ZSB_BT_RLE) {
-                        if (c.left() < 1) { e.code = ZSB_E_NOT_ENOUGH_BYTES; e.a = 1; e.b = 0; bad = true; break; }
-                        c.pos += 1;
-                    } else {
-                        if (b.size == 0 && quirks) { e.code = ZSB_E_EMPTY_SLICE; e.a = e.b = 0; bad = true; break; }   // slice(0), SURVEY Q2
-                        if (c.left() < b.size) { e.code = ZSB_E_NOT_ENOUGH_BYTES; e.a = b.size; e.b = c.left(); bad = true; break; }
-                        c.pos += b.size;
-                    }
-                    blocks.push_back(b);
-                    if (b.last) break;
-                }
-                if (bad) break;
-                if (f.has_checksum) {
-                    if (c.left() < 4) { e.code = ZSB_E_MISSING_CHECKSUM; e.a = 4; e.b = c.left(); break; }
-                    f.stored_checksum = (uint32_t)rd_le(c.p + c.pos, 4); c.pos += 4;
-                }
-                ok = true;
-            } else if ((magic ^ MAGIC_SKIP) <= 0x0F) {
-                f.kind = 1;
-                if (!need(c, 4, e)) break;
-                const uint32_t len = (uint32_t)rd_le(c.p + c.pos, 4); c.pos += 4;
-                if (len == 0 && quirks) { e.code = ZSB_E_EMPTY_SLICE; e.a = e.b = 0; break; }
-                if (!need(c, len, e)) break;
+    zsb_frame f; memset(&f, 0, sizeof f);
+    f.src_off = c.pos; f.first_block = (uint32_t)blocks.size();
+    bool ok = false;
+    do {
+        if (!need(c, 4, e)) break;                               // Frame::parse frame.rs:61-77
+        const uint32_t magic = (uint32_t)rd_le(c.p + c.pos, 4); c.pos += 4;
+        f.magic = magic;
+        if (magic == MAGIC_ZSTD) {
+            f.kind = 0;
+            if (!parse_header(c, f, e)) break;                   // ZStandard::parse frame.rs:198-230
+            if (f.window_size > max_window) { e.code = ZSB_E_WINDOW_TOO_BIG; e.a = max_window; e.b = f.window_size; break; }
+            if ((flags & ZSB_STRICT_DICT) && f.has_dict_id && f.dict_id != 0) { e.code = ZSB_E_DICTIONARY; e.a = f.dict_id; e.b = 0; break; }
+            bool bad = false;
+            for (;;) {                                           // Block::parse block.rs:43-72
+                if (c.left() < 3) { e.code = ZSB_E_NOT_ENOUGH_BYTES; e.a = 3; e.b = c.left(); bad = true; break; }
+                const uint32_t v = (uint32_t)rd_le(c.p + c.pos, 3); c.pos += 3;
                 zsb_block b; memset(&b, 0, sizeof b);
-                b.type = ZSB_BT_SKIPPABLE; b.last = 1; b.size = len; b.frame = (uint32_t)frames.size(); b.src_off = c.pos;
+                b.last = v & 1; b.type = (v >> 1) & 3; b.size = v >> 3; b.frame = (uint32_t)frames.size(); b.src_off = c.pos;
+                if (b.type == 3) { e.code = ZSB_E_RESERVED_BLOCK; e.a = e.b = 0; bad = true; break; }
+                if (b.type == ZSB_BT_RLE) {
+                    if (c.left() < 1) { e.code = ZSB_E_NOT_ENOUGH_BYTES; e.a = 1; e.b = 0; bad = true; break; }
+                    c.pos += 1;
+                } else {
+                    if (b.size == 0 && quirks) { e.code = ZSB_E_EMPTY_SLICE; e.a = e.b = 0; bad = true; break; }   // slice(0), SURVEY Q2
+                    if (c.left() < b.size) { e.code = ZSB_E_NOT_ENOUGH_BYTES; e.a = b.size; e.b = c.left(); bad = true; break; }
+                    c.pos += b.size;
+                }
                 blocks.push_back(b);
-                c.pos += len;
-                ok = true;
-            } else { e.code = ZSB_E_UNRECOGNIZED_MAGIC; e.a = magic; e.b = 0; }
-        } while (0);
-        if (!ok) {
-            blocks.resize(f.first_block);                            // a failed frame contributes no blocks
-            f.n_blocks = 0; f.status = e.code; f.src_len = n - f.src_off;
-            frames.push_back(f);
-            break;
-        }
-        f.n_blocks = (uint32_t)blocks.size() - f.first_block; f.src_len = c.pos - f.src_off; f.status = ZSB_OK;
+                if (b.last) break;
+            }
+            if (bad) break;
+            if (f.has_checksum) {
+                if (c.left() < 4) { e.code = ZSB_E_MISSING_CHECKSUM; e.a = 4; e.b = c.left(); break; }
+                f.stored_checksum = (uint32_t)rd_le(c.p + c.pos, 4); c.pos += 4;
+            }
+            ok = true;
+        } else if ((magic ^ MAGIC_SKIP) <= 0x0F) {
+            f.kind = 1;
+            if (!need(c, 4, e)) break;
+            const uint32_t len = (uint32_t)rd_le(c.p + c.pos, 4); c.pos += 4;
+            if (len == 0 && quirks) { e.code = ZSB_E_EMPTY_SLICE; e.a = e.b = 0; break; }
+            if (!need(c, len, e)) break;
+            zsb_block b; memset(&b, 0, sizeof b);
+            b.type = ZSB_BT_SKIPPABLE; b.last = 1; b.size = len; b.frame = (uint32_t)frames.size(); b.src_off = c.pos;
+            blocks.push_back(b);
+            c.pos += len;
+            ok = true;
+        } else { e.code = ZSB_E_UNRECOGNIZED_MAGIC; e.a = magic; e.b = 0; }
+    } while (0);
+    if (!ok) {
+        blocks.resize(f.first_block);                            // a failed frame contributes no blocks
+        f.n_blocks = 0; f.status = e.code; f.src_len = n - f.src_off;
         frames.push_back(f);
+        code = e.code; err_a = e.a; err_b = e.b; done = true;
+        return false;
     }
+    f.n_blocks = (uint32_t)blocks.size() - f.first_block; f.src_len = c.pos - f.src_off; f.status = ZSB_OK;
+    frames.push_back(f);
+    pos = c.pos;
+    return true;
+}
+
+// the scanner's arrays as malloc'd copies (zsb_free)
+int ZsbScanner::release(zsb_frame **frames_out, size_t *n_frames, zsb_block **blocks_out, size_t *n_blocks) const {
     zsb_frame *fo = (zsb_frame *)malloc(sizeof(zsb_frame) * (frames.size() + 1));
     zsb_block *bo = (zsb_block *)malloc(sizeof(zsb_block) * (blocks.size() + 1));
     if (!fo || !bo) { free(fo); free(bo); return ZSB_E_NOMEM; }
     if (!frames.empty()) memcpy(fo, frames.data(), sizeof(zsb_frame) * frames.size());
     if (!blocks.empty()) memcpy(bo, blocks.data(), sizeof(zsb_block) * blocks.size());
     *frames_out = fo; *n_frames = frames.size(); *blocks_out = bo; *n_blocks = blocks.size();
-    if (err_a) *err_a = e.a;
-    if (err_b) *err_b = e.b;
-    return e.code;
+    return ZSB_OK;
+}
+
+extern "C" int zsb_scan(const uint8_t *src, size_t n, uint32_t flags, uint64_t max_window,
+                        zsb_frame **frames_out, size_t *n_frames, zsb_block **blocks_out, size_t *n_blocks,
+                        uint64_t *err_a, uint64_t *err_b) {
+    if (!frames_out || !n_frames || !blocks_out || !n_blocks || (!src && n)) return ZSB_E_ARG;
+    ZsbScanner sc(src, n, flags, max_window);
+    while (sc.next()) {}
+    const int rc = sc.release(frames_out, n_frames, blocks_out, n_blocks);
+    if (rc) return rc;
+    if (err_a) *err_a = sc.err_a;
+    if (err_b) *err_b = sc.err_b;
+    return sc.code;
 }
 extern "C" void zsb_free(void *p) { free(p); }
 
