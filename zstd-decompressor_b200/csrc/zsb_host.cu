@@ -252,18 +252,22 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
                                     c->lit_cap, c->seq_cap, c->flags); c->launches++;
     // the literals stage (k_huf) and the sequence stage (k_seq) read the same blocks and write disjoint results; with ZSB_OVERLAP=1
     // k_huf runs on the auxiliary stream beside k_seq (enqueued first: its CTAs need the larger shared-memory slice).
+    // tiny low-latency shards: 8 chains per k_seq CTA instead of 32 (fewer ring bank conflicts, less phase-2 work beside the
+    // producer: the first shard's output is ready 0.25 ms earlier); ZSB_LL_CHAINS overrides
+    static const uint32_t ll_env = getenv("ZSB_LL_CHAINS") ? (uint32_t)atoi(getenv("ZSB_LL_CHAINS")) : 8u;
+    const uint32_t ll_chains = (c->low_latency && c->ncomp <= 320) ? ll_env : 0u;
     const bool ov = c->overlap || c->low_latency;
     if (ov) {
         CK(c, cudaEventRecord(c->ev_fork, st));
         CK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-        MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p, c->is_sub);
+        MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p, c->is_sub, ll_chains);
         if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][0], c->aux_stream);
         zsbk_huf(c->aux_stream, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags);
         if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][1], c->aux_stream);
         CK(c, cudaEventRecord(c->ev_join, c->aux_stream));
     } else {
         MARK(c, "k_huf");  zsbk_huf(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags);
-        MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p, c->is_sub);
+        MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p, c->is_sub, ll_chains);
     }
     c->launches += c->ncomp ? 1 : 0;
     MARK(c, "k_seq_slow"); zsbk_seq_slow(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->slow_list.p, cnt, (uint64_t *)c->seq_pool.p);

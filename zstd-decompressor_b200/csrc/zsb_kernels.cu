@@ -1372,7 +1372,7 @@ void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_
     if (ncomp) k_huf<<<(ncomp + HUF_SLOTS - 1) / HUF_SLOTS, HUF_THREADS, 0, st>>>(src, src_len, work, huf_list, cnt, lit_pool, flags);
 }
 void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
-              uint64_t *seq_pool, uint32_t *slow_list, bool shared_device) {
+              uint64_t *seq_pool, uint32_t *slow_list, bool shared_device, uint32_t chains_hint) {
     if (!ncomp) return;
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148; }
@@ -1380,6 +1380,7 @@ void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork 
     const uint32_t waves = (ncomp + (uint32_t)n_sm * SEQ_CHAINS - 1) / ((uint32_t)n_sm * SEQ_CHAINS);
     uint32_t used = (ncomp + waves * (uint32_t)n_sm - 1) / (waves * (uint32_t)n_sm);
     if (used > SEQ_CHAINS || shared_device) used = SEQ_CHAINS;     // (batches of other streams run beside this one: as few SMs as possible)
+    if (chains_hint && chains_hint <= SEQ_CHAINS) used = chains_hint;      // low-latency shards of the pipelined host path
     if (used < 1) used = 1;
     k_seq<<<(ncomp + used - 1) / used, 32 * (1 + SEQ_HELPERS), SEQ_SMEM_FUSED, st>>>(src, work, seq_list, cnt, seq_pool, slow_list, used);
 }

@@ -20,7 +20,7 @@ void zsbk_plan1(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb
 void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *huf_list,
               const ZsbCounters *cnt, uint8_t *lit_pool, uint32_t flags);
 void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
-              uint64_t *seq_pool, uint32_t *slow_list, bool shared_device);
+              uint64_t *seq_pool, uint32_t *slow_list, bool shared_device, uint32_t chains_hint);
 void zsbk_seq_slow(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *slow_list,
                    const ZsbCounters *cnt, uint64_t *seq_pool);
 void zsbk_plan2(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb_block *blocks, ZsbBlockWork *work, ZsbFrameOut *fout,
