@@ -19,6 +19,7 @@
 // the execution stage runs a warp per frame and writes HBM with 16-byte stores.  DESIGN.md section 4 has the measurements
 // behind each of these choices.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include "zsb_kernels.h"
 #include "zsb_parse.h"
 #include "zsb_huf.h"
@@ -1379,7 +1380,9 @@ void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork 
     // one CTA per SM (shared memory): as few waves as possible, and the blocks spread evenly over the CTAs of those waves
     const uint32_t waves = (ncomp + (uint32_t)n_sm * SEQ_CHAINS - 1) / ((uint32_t)n_sm * SEQ_CHAINS);
     uint32_t used = (ncomp + waves * (uint32_t)n_sm - 1) / (waves * (uint32_t)n_sm);
-    if (used > SEQ_CHAINS || shared_device) used = SEQ_CHAINS;     // (batches of other streams run beside this one: as few SMs as possible)
+    static const uint32_t sub_chains = getenv("ZSB_SUB_CHAINS") ? (uint32_t)atoi(getenv("ZSB_SUB_CHAINS")) : SEQ_CHAINS;     // experiment knob
+    if (used > SEQ_CHAINS) used = SEQ_CHAINS;
+    if (shared_device) used = sub_chains;                          // (batches of other streams run beside this one: few SMs each)
     if (chains_hint && chains_hint <= SEQ_CHAINS) used = chains_hint;      // low-latency shards of the pipelined host path
     if (used < 1) used = 1;
     k_seq<<<(ncomp + used - 1) / used, 32 * (1 + SEQ_HELPERS), SEQ_SMEM_FUSED, st>>>(src, work, seq_list, cnt, seq_pool, slow_list, used);
