@@ -61,35 +61,54 @@ __device__ __forceinline__ uint64_t cta_scan_excl(uint64_t v, uint64_t *s_warp, 
 }
 
 // ======================================================================================= k_plan1
+// Several CTAs do the per-frame part side by side; the last one to finish (ticket) runs the scans, four blocks per thread.
 __global__ void __launch_bounds__(1024) k_plan1(const zsb_frame *__restrict__ frames, uint32_t nf, const zsb_block *__restrict__ blocks,
                                                 uint32_t nb, ZsbBlockWork *work, ZsbFrameOut *fout, uint32_t *huf_list, uint32_t *seq_list,
                                                 ZsbCounters *cnt, uint64_t lit_cap, uint64_t seq_cap, uint32_t flags) {
     __shared__ uint64_t s_warp[33];
     __shared__ uint64_t s_base[4];
+    __shared__ uint32_t s_last;
     const uint32_t tid = threadIdx.x;
     // (a) per-frame chaining of Huffman tables and table modes
-    for (uint32_t f = tid; f < nf; f += blockDim.x) {
+    for (uint32_t f = blockIdx.x * blockDim.x + tid; f < nf; f += gridDim.x * blockDim.x) {
         ZsbFrameOut o; o.dst_off = 0; o.dst_len = 0; o.xxh64 = 0; o.err_a = 0; o.err_b = 0; o.pad = 0;
         o.status = frames[f].status;
         if (o.status == ZSB_OK && frames[f].kind == 0) o.status = chain_frame(frames[f], blocks, work, flags, o.err_a, o.err_b);
         fout[f] = o;
     }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&cnt->ticket1, 1u) == gridDim.x - 1 ? 1u : 0u;
     if (tid < 4) s_base[tid] = 0;
     __syncthreads();
-    // (b) scratch placement and work lists: four scans over the blocks
-    for (uint32_t i0 = 0; i0 < nb; i0 += blockDim.x) {
-        const uint32_t i = i0 + tid;
-        uint64_t lit_need = 0, seq_need = 0, hf = 0, sf = 0;
-        if (i < nb && blocks[i].type == ZSB_BT_COMPRESSED && work[i].status == ZSB_OK) {
-            if (work[i].lit_type >= ZSB_LT_COMPRESSED) { lit_need = ((uint64_t)work[i].lit_regen + 15) & ~15ull; hf = 1; }
-            if (work[i].nseq) { seq_need = ((uint64_t)work[i].nseq + 1) & ~1ull; sf = 1; }     // even: the records of a block start 16-byte aligned
+    if (!s_last) return;
+    __threadfence();
+    // (b) scratch placement and work lists: four scans over the blocks, four consecutive blocks per thread and pass
+    for (uint32_t i0 = 0; i0 < nb; i0 += 4 * blockDim.x) {
+        uint64_t lit_need[4], seq_need[4]; uint32_t hf[4], sf[4];
+        uint64_t sl = 0, ss = 0, sh = 0, sq = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t i = i0 + 4 * tid + j;
+            lit_need[j] = 0; seq_need[j] = 0; hf[j] = 0; sf[j] = 0;
+            if (i < nb && blocks[i].type == ZSB_BT_COMPRESSED && __ldcg(&work[i].status) == ZSB_OK) {
+                if (__ldcg(&work[i].lit_type) >= ZSB_LT_COMPRESSED) { lit_need[j] = ((uint64_t)__ldcg(&work[i].lit_regen) + 15) & ~15ull; hf[j] = 1; }
+                const uint32_t ns = __ldcg(&work[i].nseq);
+                if (ns) { seq_need[j] = ((uint64_t)ns + 1) & ~1ull; sf[j] = 1; }     // even: the records of a block start 16-byte aligned
+            }
+            sl += lit_need[j]; ss += seq_need[j]; sh += hf[j]; sq += sf[j];
         }
         uint64_t t0, t1, t2, t3;
-        uint64_t a = cta_scan_excl(lit_need, s_warp, t0), b = cta_scan_excl(seq_need, s_warp, t1);
-        uint64_t c = cta_scan_excl(hf, s_warp, t2), d = cta_scan_excl(sf, s_warp, t3);
-        if (i < nb) {
-            if (hf) { work[i].lit_buf = s_base[0] + a; huf_list[s_base[2] + c] = i; }
-            if (sf) { work[i].seq_buf = s_base[1] + b; seq_list[s_base[3] + d] = i; }
+        uint64_t a = cta_scan_excl(sl, s_warp, t0) + s_base[0], b2 = cta_scan_excl(ss, s_warp, t1) + s_base[1];
+        uint64_t c = cta_scan_excl(sh, s_warp, t2) + s_base[2], d = cta_scan_excl(sq, s_warp, t3) + s_base[3];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t i = i0 + 4 * tid + j;
+            if (i < nb) {
+                if (hf[j]) { work[i].lit_buf = a; huf_list[c] = i; }
+                if (sf[j]) { work[i].seq_buf = b2; seq_list[d] = i; }
+            }
+            a += lit_need[j]; b2 += seq_need[j]; c += hf[j]; d += sf[j];
         }
         __syncthreads();
         if (tid == 0) { s_base[0] += t0; s_base[1] += t1; s_base[2] += t2; s_base[3] += t3; }
@@ -639,30 +658,50 @@ __global__ void __launch_bounds__(1024) k_plan2(const zsb_frame *__restrict__ fr
                                                 ZsbBlockWork *work, ZsbFrameOut *fout, ZsbCounters *cnt, uint64_t dst_cap, uint32_t flags) {
     __shared__ uint64_t s_warp[33];
     __shared__ uint64_t s_base, s_max;
+    __shared__ uint32_t s_last;
     const uint32_t tid = threadIdx.x;
     if (cnt->overflow) return;
-    if (tid == 0) { s_base = 0; s_max = 0; }
-    __syncthreads();
-    for (uint32_t f0 = 0; f0 < nf; f0 += blockDim.x) {
-        const uint32_t f = f0 + tid;
-        uint64_t len = 0; int st = ZSB_OK;
-        if (f < nf) {
-            st = fout[f].status;
-            if (st == ZSB_OK) {
-                if (frames[f].kind == 1) len = (flags & ZSB_PRINT_SKIPPABLE) ? blocks[frames[f].first_block].size : 0;   // main.rs:45-49
-                else {
-                    st = plan_frame(frames[f], blocks, work, len);
-                    if (st == ZSB_OK && frames[f].has_content_size && len != frames[f].content_size && !(flags & ZSB_REFERENCE_QUIRKS)) st = ZSB_E_CONTENT_SIZE;
-                    if (st != ZSB_OK) len = 0;
-                }
+    // (a) per frame, all CTAs side by side: size and status
+    for (uint32_t f = blockIdx.x * blockDim.x + tid; f < nf; f += gridDim.x * blockDim.x) {
+        uint64_t len = 0;
+        int st = fout[f].status;
+        if (st == ZSB_OK) {
+            if (frames[f].kind == 1) len = (flags & ZSB_PRINT_SKIPPABLE) ? blocks[frames[f].first_block].size : 0;   // main.rs:45-49
+            else {
+                st = plan_frame(frames[f], blocks, work, len);
+                if (st == ZSB_OK && frames[f].has_content_size && len != frames[f].content_size && !(flags & ZSB_REFERENCE_QUIRKS)) st = ZSB_E_CONTENT_SIZE;
+                if (st != ZSB_OK) len = 0;
             }
         }
+        fout[f].dst_len = len; fout[f].status = st;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) { s_last = atomicAdd(&cnt->ticket2, 1u) == gridDim.x - 1 ? 1u : 0u; s_base = 0; s_max = 0; }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // (b) the last CTA: output offsets by an exclusive scan, four consecutive frames per thread and pass
+    for (uint32_t f0 = 0; f0 < nf; f0 += 4 * blockDim.x) {
+        uint64_t len[4]; int st[4]; uint64_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t f = f0 + 4 * tid + j;
+            len[j] = 0; st[j] = ZSB_OK;
+            if (f < nf) { st[j] = __ldcg(&fout[f].status); len[j] = __ldcg(&fout[f].dst_len); }
+            sum += len[j];
+        }
         uint64_t tot;
-        uint64_t off = cta_scan_excl(len, s_warp, tot) + s_base;
-        if (f < nf) {
-            if (st == ZSB_OK && off + len > dst_cap) { st = ZSB_E_DST_TOO_SMALL; }
-            fout[f].dst_off = off; fout[f].dst_len = (st == ZSB_OK) ? len : 0; fout[f].status = st;
-            if (st == ZSB_OK && len) atomicMax((unsigned long long *)&s_max, (unsigned long long)(off + len));
+        uint64_t off = cta_scan_excl(sum, s_warp, tot) + s_base;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t f = f0 + 4 * tid + j;
+            if (f < nf) {
+                if (st[j] == ZSB_OK && off + len[j] > dst_cap) st[j] = ZSB_E_DST_TOO_SMALL;
+                fout[f].dst_off = off; fout[f].dst_len = (st[j] == ZSB_OK) ? len[j] : 0; fout[f].status = st[j];
+                if (st[j] == ZSB_OK && len[j]) atomicMax((unsigned long long *)&s_max, (unsigned long long)(off + len[j]));
+            }
+            off += len[j];
         }
         __syncthreads();
         if (tid == 0) s_base += tot;
@@ -1366,7 +1405,7 @@ void zsbk_parse(cudaStream_t st, const uint8_t *src, const zsb_block *blocks, Zs
 }
 void zsbk_plan1(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb_block *blocks, uint32_t nb, ZsbBlockWork *work,
                 ZsbFrameOut *fout, uint32_t *huf_list, uint32_t *seq_list, ZsbCounters *cnt, uint64_t lit_cap, uint64_t seq_cap, uint32_t flags) {
-    k_plan1<<<1, 1024, 0, st>>>(frames, nf, blocks, nb, work, fout, huf_list, seq_list, cnt, lit_cap, seq_cap, flags);
+    k_plan1<<<nf > 1024 ? (nf + 1023) / 1024 : 1, 1024, 0, st>>>(frames, nf, blocks, nb, work, fout, huf_list, seq_list, cnt, lit_cap, seq_cap, flags);
 }
 void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *huf_list,
               const ZsbCounters *cnt, uint8_t *lit_pool, uint32_t flags) {
@@ -1393,7 +1432,7 @@ void zsbk_seq_slow(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t
 }
 void zsbk_plan2(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb_block *blocks, ZsbBlockWork *work, ZsbFrameOut *fout,
                 ZsbCounters *cnt, uint64_t dst_cap, uint32_t flags) {
-    k_plan2<<<1, 1024, 0, st>>>(frames, nf, blocks, work, fout, cnt, dst_cap, flags);
+    k_plan2<<<nf > 1024 ? (nf + 1023) / 1024 : 1, 1024, 0, st>>>(frames, nf, blocks, work, fout, cnt, dst_cap, flags);
 }
 void zsbk_rawrle(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_block *blocks, const ZsbBlockWork *work, const ZsbFrameOut *fout,
                  const uint32_t *list, const ZsbCounters *cnt, uint8_t *dst) {

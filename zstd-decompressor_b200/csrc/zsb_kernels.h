@@ -11,6 +11,7 @@ struct ZsbCounters {
     uint32_t n_seq;       // blocks with at least one sequence
     uint32_t overflow;    // scratch too small: every later kernel exits, the host grows it and relaunches
     uint32_t n_slow;      // blocks the fast sequence path handed to the careful decoder
+    uint32_t ticket1, ticket2;   // k_plan1 / k_plan2: CTAs done with the per-frame part (the last one runs the scans)
 };
 
 cudaError_t zsbk_init();
