@@ -54,48 +54,87 @@ def workload_name(frames):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons during the timed region: NVML polled every ~5 ms from a thread (the device is found by
+    its UUID, so CUDA_VISIBLE_DEVICES does not matter); `nvidia-smi -lms 100` if NVML cannot be used."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nv, self.stop_flag, self.source = index, [], None, None, False, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            u = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("" if u.startswith("GPU-") else "GPU-") + u)
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
+            self.nv, self.h = self._nvml_handle()
+            self.max_sm = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                c = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                m = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append((time.time(), c, [n for n, bit in names if m & bit]))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ts, line in self.rows:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                c, m = float(f[1]), float(f[2])
+                c, self.max_sm = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            mx.append(m)
-            if t0 - 0.05 <= ts <= t1 + 0.15:
-                sm.append(c)
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        if not sm:
-            sm = [float(x.split(",")[1]) for _, x in self.rows[-3:] if len(x.split(",")) > 2] or [0.0]
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+            self.rows.append((time.time(), c, [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9])
+                                               if v.lower().startswith("active")]))
+
+    def stop(self, t0, t1):
+        if not self.source:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source (NVML and nvidia-smi unavailable)"], "samples": 0}
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        self.stop_flag = True
+        pad = 0.0 if self.source == "nvml" else 0.15
+        inside = [(c, r) for ts, c, r in self.rows if t0 - pad <= ts <= t1 + pad]
+        if not inside:                               # a timed region shorter than the sampling period: the nearest samples
+            inside = [(c, r) for ts, c, r in sorted(self.rows, key=lambda x: min(abs(x[0] - t0), abs(x[0] - t1)))[:3]]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_sm", None), "reasons": ["no clock sample"], "samples": 0, "source": self.source}
+        reasons = sorted({n for _, r in inside for n in r})
+        return {"sm_mhz": statistics.median(c for c, _ in inside), "sm_max_mhz": getattr(self, "max_sm", None), "reasons": reasons,
+                "samples": len(inside), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
