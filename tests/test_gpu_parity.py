@@ -397,3 +397,15 @@ def test_scan_decode_streams_the_walk(dec):
     _scan_decode_equals_scan_then_decode(dec, corpora.fixture("moby-dick.txt.zst"), Q | VER)
     _scan_decode_equals_scan_then_decode(dec, b"", Q | VER)
     _scan_decode_equals_scan_then_decode(dec, blob, Q | VER, cap=len(exp) // 2)          # output does not fit
+
+
+def test_decoder_scan_decode_on_ordinary_buffers(dec):
+    """Decoder.scan_decode on pageable memory (bytes in, bytes out), capacity grown on demand; equal to Decoder.decode."""
+    for blob in (corpora.fixture("moby-dick.txt.zst"), corpora.c4()[0], corpora.c2_small(64)[0]):
+        out, sc, r = dec.decode(blob, Q | VER)
+        out2, sd = dec.scan_decode(blob, Q | VER)
+        assert out2 == out and sd.status == sc.status and sd.n_frames == sc.n_frames
+        assert [sd.results[i].status for i in range(sd.n_frames)] == [r.status[i] for i in range(sc.n_frames)]
+    blob, exp = corpora.c2_small(64)
+    out3, sd = dec.scan_decode(blob, Q | VER, dst_cap=len(exp))
+    assert out3 == exp

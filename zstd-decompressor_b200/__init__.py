@@ -27,6 +27,7 @@ MAX_WIN_SIZE = 8 << 20          # frame.rs:44
 # flags (include/zsb.h)
 PRINT_SKIPPABLE, VERIFY_CHECKSUM, REFERENCE_QUIRKS, SRC_ON_DEVICE, DST_ON_DEVICE, STRICT_DICT = 1, 2, 4, 8, 16, 32
 OK = 0
+E_DST_TOO_SMALL = 103
 E_CUDA = 200
 
 
@@ -290,6 +291,21 @@ class Decoder:
                               r.dst_off, r.dst_len, r.status, r.xxh32, r.checksum_ok, C.byref(r.total), flags)
         self._check(rc, "zsb_decode")
         return out.raw[:r.total.value], sc, r
+
+    def scan_decode(self, data, flags=VERIFY_CHECKSUM, dst_cap=None):
+        """decode() with the walk overlapped (zsb_scan_decode).  dst_cap: output capacity; default 4 x the input + 1 MiB, grown and
+        retried when a frame reports that the output did not fit.  Returns (output bytes, ScanDecode)."""
+        buf, n = _as_buffer(data)
+        cap = dst_cap if dst_cap is not None else 4 * n + (1 << 20)
+        while True:
+            out = C.create_string_buffer(max(cap, 1))
+            sd = ScanDecode(self.ctx, (C.cast(buf, C.c_void_p).value or 0, n), (C.addressof(out), cap), flags)
+            sd._keep = (data, buf)
+            err = sd.first_error()
+            if dst_cap is None and err is not None and err[1] == E_DST_TOO_SMALL and cap < (1 << 40):
+                cap *= 4
+                continue
+            return out.raw[:sd.total], sd
 
     # ---- resident path: device pointers, explicit prepare / launch / finish (used by bench.py)
     def prepare(self, src_ptr, n, scan, dst_ptr, dst_cap, flags):
