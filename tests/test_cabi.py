@@ -104,3 +104,13 @@ def test_reference_api_mirror_without_gpu():
     assert h.content_checksum_flag and h.content_size == 126 and h.window_size == 126 and h.dictionnary_id is None
     assert frames[1].checksum() == 0x9f5d2e9e and len(frames[1].blocks()) == 4
     assert Z.MAX_WIN_SIZE == 8 << 20
+
+
+def test_result_struct_layout_matches_header():
+    """zsb_result (include/zsb.h) as the Python mirror sees it: 32 bytes, fields at the offsets ScanDecode.first_error relies on."""
+    import ctypes as C
+    assert C.sizeof(Z.ZsbResult) == 32
+    assert (Z.ZsbResult.dst_off.offset, Z.ZsbResult.dst_len.offset, Z.ZsbResult.status.offset, Z.ZsbResult.xxh32.offset,
+            Z.ZsbResult.checksum_ok.offset) == (0, 8, 16, 20, 24)
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "zsb.h")).read()
+    assert "typedef struct zsb_result" in hdr and "zsb_scan_decode" in hdr and "zsb_host_alloc" in hdr
