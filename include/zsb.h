@@ -139,7 +139,8 @@ const char *zsb_last_cuda_error(const zsb_ctx *ctx);
  * *dst_total = bytes produced.  Returns ZSB_OK if the batch ran (inspect status[]), else an error.
  * With host buffers and >= 512 frames that all declare Frame_Content_Size the batch is cut into shards by frame (a small first
  * shard, then growing), each with its own stream and scratch: upload, kernels and download of different shards overlap (same
- * results; page-locked host memory -- zsb_host_alloc -- makes the copies asynchronous). */
+ * results).  Only for page-locked src and dst (zsb_host_alloc, cudaHostAlloc, cudaHostRegister): copies from and to pageable
+ * memory block the caller, so pageable buffers are decoded as one batch. */
 int zsb_decode(zsb_ctx *ctx, const uint8_t *src, size_t n,
                const zsb_frame *frames, size_t n_frames, const zsb_block *blocks, size_t n_blocks,
                uint8_t *dst, size_t dst_cap, uint64_t *dst_off, uint64_t *dst_len,

@@ -24,6 +24,26 @@ def first_status(sc, r):
     return sc.status or next((r.status[i] for i in range(sc.n_frames) if r.status[i]), 0)
 
 
+def decode_pinned(dec, blob, flags, cap=None):
+    """Decoder.decode on page-locked buffers (zsb_host_alloc): what the pipelined host path requires.  -> (bytes, Scan, BatchResult)"""
+    import ctypes as C
+    L = Z.lib()
+    sc = Z.Scan(blob, flags)
+    cap = cap if cap is not None else max(Z.capacity_bound(sc, flags), 1)
+    src = L.zsb_host_alloc(max(len(blob), 1)); dst = L.zsb_host_alloc(cap)
+    assert src and dst
+    try:
+        C.memmove(src, blob, len(blob))
+        sp = Z.Scan((src, len(blob)), flags)
+        r = Z.BatchResult(sp.n_frames)
+        rc = L.zsb_decode(dec.ctx.h, C.c_void_p(src), len(blob), sp.frames, sp.n_frames, sp.blocks, sp.n_blocks, C.c_void_p(dst), cap,
+                          r.dst_off, r.dst_len, r.status, r.xxh32, r.checksum_ok, C.byref(r.total), flags)
+        assert rc == 0
+        return C.string_at(dst, r.total.value), sc, r
+    finally:
+        L.zsb_host_free(src); L.zsb_host_free(dst)
+
+
 # ---------------------------------------------------------------- stage level (mirrors the reference's tests)
 def test_fse_reference_vectors():                       # tests/decoders/fse.rs
     al, dist, table, consumed = Z.fse_table_parse([0x30, 0x6f, 0x9b, 0x03])
@@ -242,7 +262,7 @@ def test_gpu_matches_cpu_build_of_device_code(dec):
 def test_c2_full_size_round_trip(dec):
     import gen_corpus as G
     blob, exp = G.make_c2(4096, seed=2)
-    out, sc, r = dec.decode(blob, Q | VER)
+    out, sc, r = decode_pinned(dec, blob, Q | VER)             # page-locked buffers: the pipelined host path at full size
     assert first_status(sc, r) == 0 and sc.n_frames == 4096 and len(out) == 4096 * 131072
     assert hashlib.sha256(out).digest() == hashlib.sha256(exp).digest()
     assert all(r.checksum_ok[i] for i in range(4096))          # a checksum of checksums: every stored XXH64 verified on the GPU
@@ -307,12 +327,12 @@ def test_pipelined_host_path_falls_back_on_a_bad_frame(dec):
     one = [blob[sc1.frames[i].src_off:sc1.frames[i].src_off + sc1.frames[i].src_len] for i in range(64)]
     frames = [one[i % 64] for i in range(600)]
     good = b"".join(frames)
-    out, sc, r = dec.decode(good, Q | VER)                       # pipelined, nothing wrong
+    out, sc, r = decode_pinned(dec, good, Q | VER)               # pipelined, nothing wrong
     assert first_status(sc, r) == 0 and sc.n_frames == 600 and all(r.checksum_ok[i] for i in range(600))
     assert out == b"".join(exp[(i % 64) * 131072:(i % 64 + 1) * 131072] for i in range(600))
     bad = bytearray(frames[300]); bad[len(bad) // 2] ^= 0x40
     frames[300] = bytes(bad)
-    out, sc, r = dec.decode(b"".join(frames), Q | VER)
+    out, sc, r = decode_pinned(dec, b"".join(frames), Q | VER)
     assert sc.status == 0 and sc.n_frames == 600
     pos = 0
     for i in range(600):
@@ -409,3 +429,30 @@ def test_decoder_scan_decode_on_ordinary_buffers(dec):
     blob, exp = corpora.c2_small(64)
     out3, sd = dec.scan_decode(blob, Q | VER, dst_cap=len(exp))
     assert out3 == exp
+
+
+def test_pipelined_host_path_on_mixed_frames(dec):
+    """The pipelined host path (zsb_decode and zsb_scan_decode) over a batch that mixes every kind of frame of C4 that declares its
+    content size (raw / RLE / treeless / repeat-mode blocks, multi-block frames, skippable frames) with C2 text frames: >= 512
+    frames and > 32 MiB, so the shards -- the first ones in low-latency mode -- see all of them.  Expected output: the parts."""
+    _, _, _, parts = corpora.c4()
+    blob2, exp2 = corpora.c2_small(64)
+    sc2 = Z.Scan(blob2, Q)
+    text = [(blob2[sc2.frames[i].src_off:sc2.frames[i].src_off + sc2.frames[i].src_len], exp2[i * 131072:(i + 1) * 131072], False) for i in range(64)]
+    usable = []
+    for frame, plain, is_skip in parts:
+        s1 = Z.Scan(frame, Q)
+        if s1.status == 0 and all(s1.frames[i].kind == 1 or s1.frames[i].has_content_size for i in range(s1.n_frames)):
+            usable.append((frame, plain, is_skip))
+    assert len(usable) >= 8
+    rnd = random.Random(77)
+    seq = []
+    while sum(len(p) for _, p, _ in seq) < (40 << 20) or len(seq) < 600:
+        seq.append(rnd.choice(usable) if rnd.random() < 0.4 else rnd.choice(text))
+    blob = b"".join(f for f, _, _ in seq)
+    for flags, want in ((Q | VER | SKIP, b"".join(p for _, p, _ in seq)), (Q | VER, b"".join(p for _, p, s in seq if not s))):
+        out, sc, r = decode_pinned(dec, blob, flags, cap=len(want))
+        assert first_status(sc, r) == 0 and out == want
+        _scan_decode_equals_scan_then_decode(dec, blob, flags, cap=len(want))        # zsb_scan_decode on page-locked buffers
+        out3, sc3, r3 = dec.decode(blob, flags)                                      # pageable buffers: one batch
+        assert first_status(sc3, r3) == 0 and out3 == want
