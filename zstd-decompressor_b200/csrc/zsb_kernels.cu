@@ -3,12 +3,12 @@
 // Pipeline of one batch (all frames of the batch move through each stage together):
 //
 //   k_parse   1 lane / block      section headers                       (literals.rs:135-206, sequences.rs:52-143)
-//   k_plan1   1 CTA               per-frame table/tree chaining + scratch placement (scan) + work lists
+//   k_plan1   nf/1024 CTAs        per-frame table/tree chaining; the last CTA: scratch placement (scans) + work lists
 //   k_huf     1 lane / stream     Huffman weights -> LUT (smem) -> 4-stream literal decode   (huffman.rs, literals.rs:49-86)
 //   k_seq     1 lane / block      FSE tables (interleaved smem) + the serial 3-state chain      (fse.rs, sequence.rs, sequences.rs:191-237)
 //           + 1 lane / sequence   extra bits, positions, repeat-offset history -> packed records (sequence.rs:41-55, decoding_context.rs:50-75)
 //   k_seq_slow 1 lane / block     careful decoder for blocks the fast path handed over (exact error order)
-//   k_plan2   1 CTA               block/frame output offsets (scan), repeat-offset history, size checks
+//   k_plan2   nf/1024 CTAs        repeat-offset history, frame sizes, size checks; the last CTA: output offsets (scan)
 //   k_rawrle  1 CTA / block       raw / RLE block expansion, skippable payloads              (block.rs:76-79)
 //   k_exec2   1 warp / frame      sequence execution through a 2 KiB shared-memory ring      (decoding_context.rs:78-106)
 //   k_exec    1 CTA / frame       the same for frames of many blocks: a 128 KiB block image in shared memory
@@ -122,10 +122,10 @@ __global__ void __launch_bounds__(1024) k_plan1(const zsb_frame *__restrict__ fr
 }
 
 // ======================================================================================= k_huf
-// One warp per CTA, 8 blocks per warp: lane = 4 * slot + stream.  Per slot: LUT (4 KiB, aliased with the
+// Half a warp per CTA, 4 blocks per CTA: lane = 4 * slot + stream.  Per slot: LUT (4 KiB, aliased with the
 // weight FSE table while the weights are being decoded), weights, counts, ranks.  Per lane: a 256-byte ring
 // through which cp.async feeds its stream (zsb_stream.h).  The decode is one dependent chain per stream (LUT cell ->
-// code length -> next LUT index), so like k_seq1 the kernel is latency bound and shares the SMs with k_seq1.
+// code length -> next LUT index), so like k_seq the kernel is bound by the latency of that chain.
 #define HUF_SLOTS 4
 #define HUF_THREADS (4 * HUF_SLOTS)
 #define HUF_MASK (HUF_THREADS == 32 ? 0xFFFFFFFFu : ((1u << HUF_THREADS) - 1u))
