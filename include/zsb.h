@@ -137,9 +137,10 @@ const char *zsb_last_cuda_error(const zsb_ctx *ctx);
  * and the frame stores a checksum; checksum_ok = 1 if equal to the stored value (a mismatch is
  * reported, not an error -- the reference only prints a warning, frame.rs:251-254).
  * *dst_total = bytes produced.  Returns ZSB_OK if the batch ran (inspect status[]), else an error.
- * With host buffers and >= 512 frames that all declare Frame_Content_Size the batch is cut into shards by frame (a small first
- * shard, then growing), each with its own stream and scratch: upload, kernels and download of different shards overlap (same
- * results).  Only for page-locked src and dst (zsb_host_alloc, cudaHostAlloc, cudaHostRegister): copies from and to pageable
+ * With host buffers and >= 512 frames the batch is cut into shards by frame (a small first shard, then growing), each with its
+ * own stream and scratch: upload, kernels and download of different shards overlap (same results).  Frames that declare
+ * Frame_Content_Size are placed at once and leave right behind their kernels; from the first frame without one on, a shard
+ * decodes into a device buffer of its own and is sent to the host once the sizes before it are known.  Only for page-locked src and dst (zsb_host_alloc, cudaHostAlloc, cudaHostRegister): copies from and to pageable
  * memory block the caller, so pageable buffers are decoded as one batch. */
 int zsb_decode(zsb_ctx *ctx, const uint8_t *src, size_t n,
                const zsb_frame *frames, size_t n_frames, const zsb_block *blocks, size_t n_blocks,

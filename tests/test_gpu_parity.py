@@ -414,6 +414,13 @@ def test_scan_decode_streams_the_walk(dec):
     assert len(nofcs) > (16 << 20)
     sd = _scan_decode_equals_scan_then_decode(dec, nofcs, Q | VER)
     assert sd.total == 400 * 131072
+    # frames without content size are placed late (each shard into its own device buffer, sent to the host once the sizes before
+    # it are known); a frame that fails inside such a shard contributes no bytes, like on the plain path
+    sc_n = Z.Scan(nofcs, Q)
+    badn = bytearray(nofcs); f = sc_n.frames[250]; badn[f.src_off + f.src_len // 2] ^= 0x10
+    _scan_decode_equals_scan_then_decode(dec, bytes(badn), Q | VER, cap=400 * 131072)
+    out, _, r = decode_pinned(dec, nofcs * 2, Q | VER, cap=800 * 131072)          # zsb_decode, 800 frames, late placement from shard 0 on
+    assert r.first_error() is None and out == exp[:400 * 131072] * 2
     _scan_decode_equals_scan_then_decode(dec, corpora.fixture("moby-dick.txt.zst"), Q | VER)
     _scan_decode_equals_scan_then_decode(dec, b"", Q | VER)
     _scan_decode_equals_scan_then_decode(dec, blob, Q | VER, cap=len(exp) // 2)          # output does not fit

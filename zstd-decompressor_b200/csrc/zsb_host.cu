@@ -293,7 +293,7 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     if (c->profile) { cudaEventRecord(c->ev[c->prof_slot][c->nk], st); c->prof_slot = (c->prof_slot + 1) % kProfRing; c->prof_count++; }
     if (c->trace && !early_down) cudaEventRecord(c->ev_tr[2], st);
     c->pin_valid = false;
-    if (c->down_stream && c->eager_d2h && c->h_dst) {
+    if (c->down_stream) {
         const size_t need = 64 + sizeof(ZsbFrameOut) * (size_t)c->nf;
         if (need > c->pin_cap) {
             if (c->pin) cudaFreeHost(c->pin);
@@ -357,11 +357,11 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
     return ZSB_OK;
 }
 
-// Host buffers, many frames: the batch is cut into shards by frame (zsb_shard_plan) and every shard runs on its own
-// stream and scratch -- upload of shard k+1, kernels of shard k and download of shard k-1 overlap (PCIe is ~3/4 of the
-// host-to-host time of a batch).  Output placement needs every frame's size before it is decoded, so this path is taken
-// only when all frames declare Frame_Content_Size, and its result is kept only if every frame decoded to exactly that
-// size; otherwise (return 1) the plain path runs and reports as usual.
+// Host buffers, many frames: the batch is cut into shards by frame and every shard runs on its own stream and scratch --
+// upload of shard k+1, kernels of shard k and download of shard k-1 overlap (PCIe is ~3/4 of the host-to-host time of a
+// batch).  Early output placement needs every frame's size before it is decoded: shards whose frames all declare
+// Frame_Content_Size are placed at dispatch and kept only if every frame decoded to exactly that size (otherwise: return 1,
+// the plain path runs and reports as usual); shards from the first undeclared size on are placed late (struct Pipe).
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const size_t kPipeMinFrames = 512;
 static const int kPipeShardsMax = 32;
@@ -403,9 +403,13 @@ static int pipe_plan(bool big_frames, double *wts, int &n_fast) {
 // collect() waits for all of them in order and merges the per-frame results.
 struct Pipe {
     zsb_ctx *c; const uint8_t *src; uint8_t *dst; size_t dst_cap; uint32_t flags;
-    struct Sh { size_t f0 = 0, f1 = 0; zsb_frame *fr = nullptr; zsb_block *bl = nullptr; size_t nb = 0; uint64_t so = 0, sl = 0, doff = 0, dexp = 0; bool on = false; double host_ms = 0; } sh[kPipeShardsMax];
+    struct Sh { size_t f0 = 0, f1 = 0; zsb_frame *fr = nullptr; zsb_block *bl = nullptr; size_t nb = 0; uint64_t so = 0, sl = 0, doff = 0, dexp = 0; bool on = false, late = false; double host_ms = 0; } sh[kPipeShardsMax];
     int n = 0;
     uint64_t doff = 0;
+    // Shards whose frames all declare their size are placed when they are dispatched and downloaded right behind their kernels.
+    // From the first shard with a frame of unknown size on, placement is late: the shard decodes into its own device buffer
+    // (capacity: 128 KiB per compressed block) and collect() sends it to the host once the sizes before it are known.
+    bool late = false;
     double t0 = 0, t_enq = 0;
     Pipe(zsb_ctx *ctx, const uint8_t *s, uint8_t *d, size_t cap, uint32_t fl) : c(ctx), src(s), dst(d), dst_cap(cap), flags(fl) { t0 = now_ms(); }
     ~Pipe() { for (int k = 0; k < n; k++) { zsb_free(sh[k].fr); zsb_free(sh[k].bl); } }
@@ -416,6 +420,8 @@ struct Pipe {
         Sh &S = sh[k];
         S.f0 = f0; S.f1 = f1; S.doff = doff;
         if (f0 == f1) return true;
+        for (size_t f = f0; f < f1 && !late; f++) late = frames[f].kind == 0 && !frames[f].has_content_size;
+        S.late = late;
         while (c->subs.size() <= (size_t)k) {
             zsb_ctx *sub = nullptr;
             if (zsb_ctx_create(&sub, c->device) != ZSB_OK) return false;
@@ -423,25 +429,41 @@ struct Pipe {
             c->subs.push_back(sub);
         }
         if (zsb_shard_extract(frames, nf, blocks, nb, f0, f1, &S.fr, &S.bl, &S.nb, &S.so, &S.sl) != ZSB_OK) return false;
-        for (size_t f = f0; f < f1; f++) S.dexp += frame_out_bytes(frames[f], blocks, flags);
-        if (S.doff + S.dexp > dst_cap) return false;
-        doff += S.dexp;
         zsb_ctx *sub = c->subs[k];
-        sub->eager_d2h = S.dexp;
+        uint8_t *target = nullptr; uint32_t fl = flags;
+        if (!S.late) {
+            for (size_t f = f0; f < f1; f++) S.dexp += frame_out_bytes(frames[f], blocks, flags);
+            if (S.doff + S.dexp > dst_cap) return false;
+            doff += S.dexp;
+            sub->eager_d2h = S.dexp;
+            target = dst + S.doff;
+        } else {
+            for (size_t f = f0; f < f1; f++) {                      // capacity, not a promise: what the blocks can regenerate at most
+                if (frames[f].kind == 1) { S.dexp += frame_out_bytes(frames[f], blocks, flags); continue; }
+                for (uint32_t b = 0; b < frames[f].n_blocks; b++) {
+                    const zsb_block &B = blocks[frames[f].first_block + b];
+                    S.dexp += B.type == ZSB_BT_COMPRESSED ? ZSB_BLOCK_MAX : B.size;
+                }
+            }
+            cudaSetDevice(c->device);
+            if (sub->dst.ensure(S.dexp + 64) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+            sub->eager_d2h = 0;
+            target = (uint8_t *)sub->dst.p; fl |= ZSB_DST_ON_DEVICE;
+        }
         sub->up_stream = c->own_stream; sub->down_stream = c->aux_stream;
         sub->low_latency = low_latency;
         bool first_on = true; for (int j = 0; j < k; j++) first_on = first_on && !sh[j].on;
         if (c->trace && first_on) cudaEventRecord(c->ev_tr[0], sub->up_stream);
         if (c->trace) S.host_ms = now_ms() - t0;
-        if (zsb_decode_prepare(sub, src + S.so, S.sl, S.fr, f1 - f0, S.bl, S.nb, dst + S.doff, S.dexp, flags) != ZSB_OK ||
+        if (zsb_decode_prepare(sub, src + S.so, S.sl, S.fr, f1 - f0, S.bl, S.nb, target, S.dexp, fl) != ZSB_OK ||
             zsb_decode_launch(sub) != ZSB_OK) return false;
         S.on = true;
         return true;
     }
     // returns ZSB_OK, ZSB_E_CUDA, or 1 when the result must not be used (a frame failed or disagreed with its declared size)
     int collect(uint64_t *dst_off, uint64_t *dst_len, int32_t *status, uint32_t *xxh32, uint8_t *checksum_ok, uint64_t *dst_total) {
-        int rc = ZSB_OK; bool bad = false;
-        uint64_t total = 0;
+        int rc = ZSB_OK; bool bad = false, any_late = false;
+        uint64_t total = 0;                                  // == where the next late shard goes
         t_enq = now_ms();
         for (int k = 0; k < n; k++) {
             Sh &S = sh[k];
@@ -449,13 +471,22 @@ struct Pipe {
             uint64_t t = 0;
             const int r = zsb_decode_finish(c->subs[k], dst_off ? dst_off + S.f0 : nullptr, dst_len ? dst_len + S.f0 : nullptr, status ? status + S.f0 : nullptr,
                                             xxh32 ? xxh32 + S.f0 : nullptr, checksum_ok ? checksum_ok + S.f0 : nullptr, &t);
-            if (r != ZSB_OK) { rc = r; c->last_err = c->subs[k]->last_err; bad = true; }
-            else {
+            if (r != ZSB_OK) { rc = r; c->last_err = c->subs[k]->last_err; bad = true; continue; }
+            if (!S.late) {
                 if (t != S.dexp) bad = true;
                 if (dst_off) for (size_t f = S.f0; f < S.f1; f++) dst_off[f] += S.doff;
+                total = S.doff + t;
+            } else if (!bad) {
+                if (total + t > dst_cap) { bad = true; continue; }         // the plain path reports which frames do not fit
+                if (t && cudaMemcpyAsync(dst + total, c->subs[k]->d_dst, t, cudaMemcpyDeviceToHost, c->aux_stream) != cudaSuccess) {
+                    c->last_err = "cudaMemcpyAsync (late shard)"; (void)cudaGetLastError(); rc = ZSB_E_CUDA; bad = true; continue;
+                }
+                any_late = true;
+                if (dst_off) for (size_t f = S.f0; f < S.f1; f++) dst_off[f] += total;
                 total += t;
             }
         }
+        if (any_late && cudaStreamSynchronize(c->aux_stream) != cudaSuccess) { c->last_err = "cudaStreamSynchronize (late shards)"; (void)cudaGetLastError(); rc = ZSB_E_CUDA; }
         if (c->trace) {
             fprintf(stderr, "[zsb pipe] host: all shards enqueued at %.2f ms, finished at %.2f ms\n", t_enq - t0, now_ms() - t0);
             for (int k = 0; k < n; k++) if (sh[k].on) {
@@ -476,13 +507,15 @@ static int decode_pipelined(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_
                             uint8_t *dst, size_t dst_cap, uint64_t *dst_off, uint64_t *dst_len, int32_t *status, uint32_t *xxh32,
                             uint8_t *checksum_ok, uint64_t *dst_total, uint32_t flags) {
     (void)n;
-    uint64_t expect_total = 0;
+    // expected output: declared sizes, 2.4 x the compressed size where a frame does not declare one (text at level 3)
+    auto est = [&](const zsb_frame &fr) { return fr.kind == 0 && !fr.has_content_size ? (uint64_t)(2.4 * (double)fr.src_len) : frame_out_bytes(fr, blocks, flags); };
+    uint64_t expect_total = 0; bool all_sized = true;
     for (size_t f = 0; f < nf; f++) {
         if (frames[f].status != ZSB_OK) return 1;
-        if (frames[f].kind == 0 && !frames[f].has_content_size) return 1;
-        expect_total += frame_out_bytes(frames[f], blocks, flags);
+        if (frames[f].kind == 0 && !frames[f].has_content_size) all_sized = false;
+        expect_total += est(frames[f]);
     }
-    if (expect_total > dst_cap || expect_total < (32u << 20)) return 1;
+    if ((all_sized && expect_total > dst_cap) || expect_total < (32u << 20)) return 1;
     double wts[kPipeShardsMax]; int n_fast = 0;
     const int ns = pipe_plan(expect_total / nf >= (64u << 10), wts, n_fast);
     double wsum = 0; for (int k = 0; k < ns; k++) wsum += wts[k];
@@ -494,7 +527,7 @@ static int decode_pipelined(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_
         cum += wts[k];
         const double lim = (double)expect_total * (cum / wsum);
         const size_t f0 = f;
-        while (f < nf && (k == ns - 1 || acc < lim)) { acc += (double)frame_out_bytes(frames[f], blocks, flags); f++; }
+        while (f < nf && (k == ns - 1 || acc < lim)) { acc += (double)est(frames[f]); f++; }
         ok = P.dispatch(frames, nf, blocks, nb, f0, f, k < n_fast);
     }
     const int rc = P.collect(dst_off, dst_len, status, xxh32, checksum_ok, dst_total);
@@ -520,8 +553,8 @@ extern "C" int zsb_decode(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_fr
 // zsb_scan + zsb_decode in one call on host buffers, with the host walk overlapped: the walk stops at every shard boundary
 // (a fraction of the compressed bytes) and the frames found so far start uploading and decoding while the rest of the buffer
 // is still being walked.  Results are those of zsb_scan followed by zsb_decode.  Anything that keeps the pipelined path from
-// applying (a frame without Frame_Content_Size, a malformed frame, an output that does not fit, a frame that fails or
-// disagrees with its declared size) ends in the plain zsb_decode over the completed scan.
+// applying (a malformed frame, an output that does not fit, a frame that fails or disagrees with its declared size in a
+// shard that was placed early) ends in one plain batch over the completed scan.
 extern "C" int zsb_scan_decode(zsb_ctx *c, const uint8_t *src, size_t n, uint8_t *dst, size_t dst_cap, uint32_t flags, uint64_t max_window,
                                zsb_frame **frames_out, size_t *n_frames, zsb_block **blocks_out, size_t *n_blocks,
                                zsb_result **results_out, uint64_t *dst_total, uint64_t *err_a, uint64_t *err_b) {
@@ -531,6 +564,7 @@ extern "C" int zsb_scan_decode(zsb_ctx *c, const uint8_t *src, size_t n, uint8_t
     ZsbScanner sc(src, n, flags, max_window);
     Pipe P(c, src, dst, dst_cap, flags);
     bool streamed = n >= (16u << 20) && host_pinned(src) && host_pinned(dst);     // worth cutting up at all, and the copies asynchronous
+    const bool tried = streamed;
     if (streamed) {
         double wts[kPipeShardsMax]; int n_fast = 0;
         const int ns = pipe_plan(true, wts, n_fast);
@@ -543,11 +577,8 @@ extern "C" int zsb_scan_decode(zsb_ctx *c, const uint8_t *src, size_t n, uint8_t
             if (sc.code != ZSB_OK) { streamed = false; break; }          // the walk ended on a malformed frame
             const size_t f1 = sc.frames.size();
             uint64_t out = 0;
-            for (size_t f = f0; f < f1 && streamed; f++) {
-                if (sc.frames[f].kind == 0 && !sc.frames[f].has_content_size) streamed = false;
-                out += frame_out_bytes(sc.frames[f], sc.blocks.data(), flags);
-            }
-            if (!streamed) break;
+            for (size_t f = f0; f < f1; f++)
+                out += sc.frames[f].kind == 0 && !sc.frames[f].has_content_size ? (uint64_t)(2.4 * (double)sc.frames[f].src_len) : frame_out_bytes(sc.frames[f], sc.blocks.data(), flags);
             const bool big = f1 > f0 && out / (f1 - f0) >= (64u << 10);
             if (!P.dispatch(sc.frames.data(), f1, sc.blocks.data(), sc.blocks.size(), f0, f1, big && k < n_fast)) streamed = false;
         }
@@ -559,7 +590,12 @@ extern "C" int zsb_scan_decode(zsb_ctx *c, const uint8_t *src, size_t n, uint8_t
     int rc = P.collect(off.data(), len.data(), st.data(), xh.data(), ck.data(), &total);     // also drains shards of a pipeline given up
     if (rc == ZSB_E_CUDA) return rc;
     if (!streamed || rc != ZSB_OK) {
-        rc = zsb_decode(c, src, n, sc.frames.data(), nf, sc.blocks.data(), sc.blocks.size(), dst, dst_cap, off.data(), len.data(), st.data(), xh.data(), ck.data(), &total, flags);
+        if (!tried) rc = zsb_decode(c, src, n, sc.frames.data(), nf, sc.blocks.data(), sc.blocks.size(), dst, dst_cap, off.data(), len.data(), st.data(), xh.data(), ck.data(), &total, flags);
+        else {      // the pipeline was tried and given up: one plain batch (zsb_decode would try its own pipeline first)
+            rc = zsb_decode_prepare(c, src, n, sc.frames.data(), nf, sc.blocks.data(), sc.blocks.size(), dst, dst_cap, flags);
+            if (!rc) rc = zsb_decode_launch(c);
+            if (!rc) rc = zsb_decode_finish(c, off.data(), len.data(), st.data(), xh.data(), ck.data(), &total);
+        }
         if (rc) return rc;
     }
     zsb_result *res = (zsb_result *)malloc(sizeof(zsb_result) * (nf + 1));
