@@ -300,11 +300,11 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
             c->pin = nullptr; c->pin_cap = 0;
             if (cudaHostAlloc((void **)&c->pin, need + need / 4, cudaHostAllocDefault) == cudaSuccess) c->pin_cap = need + need / 4; else (void)cudaGetLastError();
         }
-        if (c->pin) {
-            CK(c, cudaMemcpyAsync(c->pin, cnt, sizeof(ZsbCounters), cudaMemcpyDeviceToHost, st));
-            if (c->nf) CK(c, cudaMemcpyAsync(c->pin + 64, fout, sizeof(ZsbFrameOut) * (size_t)c->nf, cudaMemcpyDeviceToHost, st));
+        void *pin_dev = nullptr;
+        if (c->pin && cudaHostGetDevicePointer(&pin_dev, c->pin, 0) == cudaSuccess && pin_dev) {
+            zsbk_publish(st, pin_dev, cnt, fout, c->nf);        // written by the kernel itself, not by a copy engine (see k_publish)
             c->pin_valid = true;
-        }
+        } else (void)cudaGetLastError();
     }
     if (!early_down) {
         if (c->eager_d2h && c->h_dst) CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, c->eager_d2h, cudaMemcpyDeviceToHost, st));
@@ -482,6 +482,7 @@ struct Pipe {
                     c->last_err = "cudaMemcpyAsync (late shard)"; (void)cudaGetLastError(); rc = ZSB_E_CUDA; bad = true; continue;
                 }
                 any_late = true;
+                if (c->trace) cudaEventRecord(c->subs[k]->ev_tr[3], c->aux_stream);
                 if (dst_off) for (size_t f = S.f0; f < S.f1; f++) dst_off[f] += total;
                 total += t;
             }

@@ -1432,6 +1432,20 @@ __global__ void k_stage_records(const uint32_t *tri, uint32_t nseq, uint32_t nli
 static cudaError_t set_smem(const void *fn, size_t bytes) {
     return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
+// Small results straight into page-locked host memory (the kernel writes over the bus itself): a cudaMemcpyAsync of a few KB would
+// queue behind the megabytes the copy engines are moving for other shards, and the host would learn a shard's sizes only then.
+__global__ void __launch_bounds__(256) k_publish(unsigned long long *host, const unsigned long long *a, uint32_t na, const unsigned long long *b, uint32_t nb, uint32_t b_at) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += gridDim.x * blockDim.x) {
+        if (i < na) host[i] = a[i]; else host[b_at + (i - na)] = b[i - na];
+    }
+}
+void zsbk_publish(cudaStream_t st, void *host_dev_ptr, const ZsbCounters *cnt, const ZsbFrameOut *fout, uint32_t nf) {
+    static_assert(sizeof(ZsbCounters) % 8 == 0 && sizeof(ZsbCounters) <= 64 && sizeof(ZsbFrameOut) % 8 == 0, "published as 8-byte words");
+    const uint32_t na = sizeof(ZsbCounters) / 8, nb = nf * (uint32_t)(sizeof(ZsbFrameOut) / 8);
+    k_publish<<<(na + nb + 255) / 256 < 64 ? (na + nb + 255) / 256 : 64, 256, 0, st>>>((unsigned long long *)host_dev_ptr, (const unsigned long long *)cnt, na,
+                                                                                   (const unsigned long long *)fout, nb, 8);
+}
+
 cudaError_t zsbk_init() {
     cudaError_t e = set_smem((const void *)k_seq_slow, SEQ_SLOW_SMEM_BYTES);
     if (e != cudaSuccess) return e;

@@ -32,6 +32,7 @@ void zsbk_exec(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame 
                ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst);
 void zsbk_exec2(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
                 ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst);
+void zsbk_publish(cudaStream_t st, void *host_dev_ptr, const ZsbCounters *cnt, const ZsbFrameOut *fout, uint32_t nf);
 void zsbk_xxh(cudaStream_t st, uint32_t n, const uint8_t *dst, ZsbFrameOut *fout, const uint32_t *list, const ZsbCounters *cnt);
 void zsbk_stage_fse(cudaStream_t st, const uint8_t *desc, uint32_t n, int max_sym, const int16_t *dist_in, int ndist_in, int al_in,
                     int *res, uint32_t *cells, int16_t *dist_out);
