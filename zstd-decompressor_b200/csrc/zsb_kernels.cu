@@ -13,6 +13,7 @@
 //   k_exec2   1 warp / frame      sequence execution through a 2 KiB shared-memory ring      (decoding_context.rs:78-106)
 //   k_exec    1 CTA / frame       the same for frames of many blocks: a 128 KiB block image in shared memory
 //   k_xxh     4 lanes / frame     XXH64 content checksum                                      (frame.rs:239-259)
+//   k_publish (pipelined host path only) counters and per-frame results into page-locked host memory
 //
 // Nothing here is a dense contraction: no tensor cores.  The entropy stages are serial per stream, so they run
 // lane-per-stream with all tables in shared memory and everything that is not on the serial chain moved to other warps;
