@@ -278,7 +278,7 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     MARK(c, "k_exec2");  zsbk_exec2(st, c->n_exec2, src, frames, blocks, work, fout, (const uint32_t *)c->exec2_list.p, cnt, (const uint64_t *)c->seq_pool.p,
                                     (const uint8_t *)c->lit_pool.p, c->d_dst); c->launches += c->n_exec2 ? 1 : 0;
     MARK(c, "k_exec");   zsbk_exec(st, c->n_exec, src, frames, blocks, work, fout, (const uint32_t *)c->exec_list.p, cnt, (const uint64_t *)c->seq_pool.p,
-                                   (const uint8_t *)c->lit_pool.p, c->d_dst); c->launches += c->n_exec ? 1 : 0;
+                                   (const uint8_t *)c->lit_pool.p, c->d_dst, c->is_sub); c->launches += c->n_exec ? 1 : 0;
     // pipelined path: the shard's output may leave as soon as it is written -- the checksums are computed from HBM while the
     // download runs (both only read the output)
     const bool early_down = c->down_stream && c->eager_d2h && c->h_dst;

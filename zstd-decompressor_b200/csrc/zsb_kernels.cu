@@ -752,8 +752,8 @@ __global__ void __launch_bounds__(256) k_rawrle(const uint8_t *__restrict__ src,
 }
 
 // ======================================================================================= k_exec
-#define EXEC_THREADS 512
-#define EXEC_WARPS (EXEC_THREADS / 32)
+// k_exec<512>: shards of the pipelined host path (it shares the SMs with other shards' k_seq: 1 024 threads of 60 registers would not fit
+// beside one); k_exec<1024>: frames of many blocks on their own (twice the batches in flight: 0.18 -> 0.11 ms per block)
 #define EXEC_LIT_STAGE 65536u
 #define EXEC_LONG 32u
 #define EXEC_OUT_BYTES (ZSB_BLOCK_MAX + 16)
@@ -871,6 +871,7 @@ __device__ __forceinline__ void exec_batch(uint32_t batch, uint32_t nseq, const 
     }
 }
 
+template <int EXEC_THREADS>
 __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restrict__ src, const zsb_frame *__restrict__ frames,
                                                           const zsb_block *__restrict__ blocks, const ZsbBlockWork *__restrict__ work,
                                                           ZsbFrameOut *fout, const uint32_t *__restrict__ exec_list,
@@ -924,7 +925,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
             const uint32_t oe = (uint32_t)lastrec & ZSB_REC_POS_MASK, le = (uint32_t)(lastrec >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK;
             for (uint32_t i = tid; i < regen - le; i += EXEC_THREADS) o[oe + i] = lit_at(L, le + i);   // decoding_context.rs:101-103
             const uint32_t nbatch = (nseq + 31) / 32;
-            for (uint32_t b = warp; b < nbatch; b += EXEC_WARPS)
+            for (uint32_t b = warp; b < nbatch; b += EXEC_THREADS / 32)
                 exec_batch(b, nseq, seqs, o, bm, L, W.rep_in, fr.kind == 0 ? W.out_off : 0, gblk, &s_err);
         }
         __syncthreads();
@@ -1452,7 +1453,9 @@ cudaError_t zsbk_init() {
     if (e != cudaSuccess) return e;
     e = set_smem((const void *)k_seq, SEQ_SMEM_FUSED);
     if (e != cudaSuccess) return e;
-    return set_smem((const void *)k_exec, EXEC_SMEM_BYTES);
+    e = set_smem((const void *)k_exec<512>, EXEC_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return set_smem((const void *)k_exec<1024>, EXEC_SMEM_BYTES);
 }
 void zsbk_parse(cudaStream_t st, const uint8_t *src, const zsb_block *blocks, ZsbBlockWork *work, uint32_t nb, uint32_t flags) {
     if (nb) k_parse<<<(nb + 127) / 128, 128, 0, st>>>(src, blocks, work, nb, flags);
@@ -1493,8 +1496,10 @@ void zsbk_rawrle(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_bloc
     if (n) k_rawrle<<<n, 256, 0, st>>>(src, blocks, work, fout, list, cnt, dst);
 }
 void zsbk_exec(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
-               ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst) {
-    if (n) k_exec<<<n, EXEC_THREADS, EXEC_SMEM_BYTES, st>>>(src, frames, blocks, work, fout, exec_list, cnt, seq_pool, lit_pool, dst);
+               ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst, bool shared_device) {
+    if (!n) return;
+    if (shared_device) k_exec<512><<<n, 512, EXEC_SMEM_BYTES, st>>>(src, frames, blocks, work, fout, exec_list, cnt, seq_pool, lit_pool, dst);
+    else k_exec<1024><<<n, 1024, EXEC_SMEM_BYTES, st>>>(src, frames, blocks, work, fout, exec_list, cnt, seq_pool, lit_pool, dst);
 }
 void zsbk_exec2(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
                 ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst) {
