@@ -32,7 +32,7 @@ def fse_build(type_, al, dist, stride=1):
 
 def cell_fields(c):
     """(code, base, nb, xb)"""
-    return ((c >> 16) & 0x3F, c >> 22, c & 0x1F, (c >> 8) & 0x3F)
+    return ((c >> 16) & 0x3F, c >> 22, (c >> 8) & 0x1F, c & 0x3F)
 
 
 def huf_parse(desc):

@@ -12,7 +12,7 @@ Q, SKIP = 4, 1   # ZSB_REFERENCE_QUIRKS, ZSB_PRINT_SKIPPABLE
 
 
 def as_states(cells):
-    return [((c >> 16) & 0x3F, c >> 22, c & 0x1F) for c in cells]   # (output, baseline, bits_to_read)
+    return [((c >> 16) & 0x3F, c >> 22, (c >> 8) & 0x1F) for c in cells]   # (output, baseline, bits_to_read)
 
 
 # ---------------------------------------------------------------- FSE tables (fse.rs)
@@ -61,7 +61,7 @@ def test_fse_predefined_tables_and_xbits():
     rc, cells = E.fse_build(0, 6, LL)
     assert rc == 0 and as_states(cells) == R.fse_from_distribution(6, LL)
     ll_bits = [0] * 16 + [1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
-    assert all(((c >> 8) & 0x3F) == ll_bits[(c >> 16) & 0x3F] for c in cells)
+    assert all((c & 0x3F) == ll_bits[(c >> 16) & 0x3F] for c in cells)
 
 
 def test_fse_errors():

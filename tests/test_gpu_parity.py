@@ -198,6 +198,13 @@ def test_c3_multi_block_frame_with_far_matches(dec):    # BASELINE config C3 at 
     assert out == sexp == R.main_decode(small)
 
 
+def test_sequences_with_many_extra_bits(dec):           # fields of > 32 extra bits per sequence (the sequence stage's window skips them)
+    blob, plain = corpora.wide_fields()
+    out, sc, r = dec.decode(blob, Q | VER)
+    assert first_status(sc, r) == 0 and r.checksum_ok[0] == 1
+    assert out == plain
+
+
 def test_rfc_only_inputs(dec):                          # classes the reference rejects
     for frame, plain in corpora.rfc_only():
         out, sc, r = dec.decode(frame, VER | SKIP)

@@ -61,14 +61,15 @@
 #define ZSB_OFF_MAX 0x7FFFFFFu   // largest real offset representable (128 MiB - 1)
 
 // FSE decoding-table cell, one 32-bit word (sequence tables and Huffman-weight table):
-//   bits 0..4 nb (state bits to read)   8..13 xb (extra bits of the symbol's code)
+//   bits 0..5 xb (extra bits of the symbol's code)   8..12 nb (state bits to read)
 //   bits 16..21 code (symbol, 63 = not a legal code)   22..31 base (next-state baseline)
-// The layout serves the fast sequence path (zsb_seqfast.h): the sum of three cells has the total state
-// bits in byte 0 and the total extra bits in byte 1 (no carries: <= 27 and <= 63); nb sits where a
-// funnel shift takes its 5-bit shift amount; base comes out with one shift.
-#define ZSB_CELL(nb, xb, base, code) ((uint32_t)(nb) | ((uint32_t)(xb) << 8) | ((uint32_t)(code) << 16) | ((uint32_t)(base) << 22))
-#define ZSB_CELL_NB(e) ((e) & 0x1Fu)
-#define ZSB_CELL_XB(e) (((e) >> 8) & 0x3Fu)
+// The layout serves the fast sequence path (zsb_seqfast.h, k_seq): the sum of three cells has the total extra bits in byte 0
+// and the total state bits in byte 1 (no carries: <= 63 and <= 27), so the sum itself is the funnel-shift amount that skips the
+// extra bits (the shift takes the low 5 bits, bit 5 selects the word pair), one dot product with the byte weights 1,1 gives
+// the bits a sequence consumes, and base comes out with one shift.
+#define ZSB_CELL(nb, xb, base, code) ((uint32_t)(xb) | ((uint32_t)(nb) << 8) | ((uint32_t)(code) << 16) | ((uint32_t)(base) << 22))
+#define ZSB_CELL_NB(e) (((e) >> 8) & 0x1Fu)
+#define ZSB_CELL_XB(e) ((e) & 0x3Fu)
 #define ZSB_CELL_CODE(e) (((e) >> 16) & 0x3Fu)
 #define ZSB_CELL_BASE(e) ((e) >> 22)
 

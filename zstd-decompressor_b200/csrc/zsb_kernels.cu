@@ -309,6 +309,7 @@ __device__ __forceinline__ int seq_build_table_warp(const uint8_t *src, const Zs
 #define SEQ_OF_CELLS 256      // offset tables have accuracy log <= 8 (RFC 8878); a log-9 one (the reference accepts it) takes the careful path
 #define SEQ_TBL_BYTES ((2 * SEQ_TBL_CELLS + SEQ_OF_CELLS) * SEQ_CHAINS * 4)
 #define SEQ_WIN 128           // sequences per hand-over and chain (SEQ_PER_LANE = 4 per phase-2 lane)
+#define SEQ_PF 8              // lines (of 128 bytes) the stream rings ask L2 for ahead of their own requests
 #define SEQ_WSTRIDE 260       // words per chain in the ring (two windows) + 4: rows stay 16-byte aligned, banks spread
 struct SeqShared {
     uint32_t words[SEQ_CHAINS][SEQ_WSTRIDE];
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
                 const uint32_t a0 = (uint32_t)T.al[0], a1 = (uint32_t)T.al[1], a2 = (uint32_t)T.al[2];
                 if (top - startbit < (int32_t)(a0 + a1 + a2)) rc = ZSB_E_NOT_ENOUGH_BITS;
                 else {
-                    sr_init<7>(R, top);
+                    sr_init<7, SEQ_PF>(R, top);
                     sr_load<7>(R, F, top);
                     const uint64_t W = fast_win_get(F);
                     const uint32_t sL = (uint32_t)zsb_shr64(W, 64 - a0), sO = (uint32_t)zsb_shr64(zsb_shl64(W, a0), 64 - a1),
@@ -533,48 +534,73 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
 #pragma unroll
         for (int d = 16; d; d >>= 1) maxn = max(maxn, __shfl_xor_sync(FULL, maxn, d));
         uint32_t *wrow = &S.words[lane < SEQ_CHAINS ? lane : 0][0];
-        // One step of the chain; LAST: no state update after the last sequence (sequence.rs:80).  The <= 27 state bits are
-        // fetched where they lie -- the 32 bits ending px bits below the cursor, two aligned ring words and one funnel
-        // shift -- so the step carries no window bookkeeping: ~35 instructions, of which two dependent shared-memory loads.
-        const uint32_t ring_sa = R.sa;                   // 512-byte aligned: ring byte address = ring_sa | (offset & 0x1FC)
+        // The bit window in registers.  The stream ring is never read on the chain: q2, q1, q0 are the ring words k, k-1, k-2
+        // (k = the word holding the next unread bit, `o` bits of it already consumed), n0 the word below them, n1..n3 three more
+        // that every step requests behind its cell loads, T2:T1:T0 the 96 bits from the cursor on, top-aligned ((q2:q1:q0:n0) << o).  A sequence consumes px <= 63
+        // extra bits and then <= 27 state bits, i.e. the state bits lie inside T whatever the codes are.
+        const uint32_t ring_sa = R.sa;                   // 512-byte aligned: ring byte address = ring_sa | (byte offset & 0x1FC)
+        const uint32_t zr = cnt->zero;                   // 0, but not to the compiler: see SEQ_STEP
+        uint32_t kb = 0, o = 0, q2 = 0, q1 = 0, q0 = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0, T2 = 0, T1 = 0, T0 = 0;
+        if (active) {
+            kb = (uint32_t)((top - 1) >> 5) * 4u; o = (32u - ((uint32_t)top & 31u)) & 31u;
+            q2 = zsb_lds32v((kb & 0x1FCu) | ring_sa); q1 = zsb_lds32v(((kb - 4u) & 0x1FCu) | ring_sa); q0 = zsb_lds32v(((kb - 8u) & 0x1FCu) | ring_sa);
+            n0 = zsb_lds32v(((kb - 12u) & 0x1FCu) | ring_sa);
+            T2 = zsb_fsl(q1, q2, o); T1 = zsb_fsl(q0, q1, o); T0 = zsb_fsl(n0, q0, o);
+        }
+        // One step of the chain; LAST: no state update after the last sequence (sequence.rs:80).  On the chain: the three cell
+        // loads, their sum, one funnel shift that skips the extra bits (the sum is its shift amount: byte 0 = extra bits, and bit 5
+        // picks the word pair), one per state that isolates its bits, the new cell address: one shared-memory load and ~6 ALU
+        // operations per sequence.  Off the chain: the window moves on by (extra + state bits) -- a dot product, two levels of
+        // selects over the carried words (0..3 whole words), three loads that refill the look-ahead, three shifts for the new T.
+#ifndef SEQ_DEP
+#define SEQ_DEP 0
+#endif
 #define SEQ_STEP(i_, LAST)                                                                                                                  \
         {                                                                                                                                   \
-            const uint32_t eL = zsb_lds32(aL), eO = zsb_lds32(aO), eM = zsb_lds32(aM);                                                      \
-            const uint32_t sum = eL + eO + eM;                 /* byte 0: state bits, byte 1: extra bits (no carries: <= 27, <= 63) */     \
-            /* lowest bit of the 32 wanted = top - 32 - extra bits (one dot product with the byte weights 0,-1,0,0); below the stream only  \
-               after an over-read */                                                                                                         \
-            const uint32_t e = (uint32_t)__dp4a((int)sum, 0x0000FF00, top - 32);                                                             \
-            const uint32_t e3 = e >> 3;                                                                                                     \
-            const uint32_t w0 = zsb_lds32v((e3 & 0x1FCu) | ring_sa), w1 = zsb_lds32v(((e3 + 4u) & 0x1FCu) | ring_sa);                         \
-            const uint32_t sLM = eL + eM;                      /* low 5 bits: LL + ML state bits (<= 18) */                                 \
-            const uint32_t t = __funnelshift_r(w0, w1, e);     /* the state bits, top-aligned */                                            \
-            /* the funnel shifts take their 5-bit amounts straight from the cells (nb in bits 0..4) */                                      \
-            const uint32_t bL = zsb_fsl(t, 0, eL), bM = zsb_fsl(zsb_fsl(0, t, eL), 0, eM), bO = zsb_fsl(zsb_fsl(0, t, sLM), 0, eO);        \
-            top = __dp4a((int)sum, (LAST) ? 0x0000FF00 : 0x0000FFFF, top);     /* top -= extra bits + state bits */                        \
+            const uint32_t eL = zsb_lds32(aL), eM = zsb_lds32(aM), eO = zsb_lds32(aO);                                                      \
+            /* (behind the cell loads, which are on the chain) the look-ahead words this step's window move may need */                     \
+            const uint32_t kd = SEQ_DEP ? kb + (eL & zr) : kb; /* == kb, but (SEQ_DEP) only known once the cell is there */                 \
+            n1 = zsb_lds32v(((kd - 16u) & 0x1FCu) | ring_sa); n2 = zsb_lds32v(((kd - 20u) & 0x1FCu) | ring_sa);                              \
+            n3 = zsb_lds32v(((kd - 24u) & 0x1FCu) | ring_sa);                                                                               \
+            const uint32_t sum = eL + eO + eM;                 /* byte 0: extra bits (<= 63), byte 1: state bits (<= 27) */                 \
+            const uint32_t tA = zsb_fsl(T1, T2, sum), tB = zsb_fsl(T0, T1, sum);                                                            \
+            const uint32_t t = (sum & 32u) ? tB : tA;          /* the state bits, top-aligned */                                            \
+            const uint32_t nL = eL >> 8, nM = eM >> 8, nO = eO >> 8, nLM = (eL + eM) >> 8;    /* shift amounts: nb in bits 0..4 */         \
+            const uint32_t bL = zsb_fsl(t, 0, nL), bM = zsb_fsl(zsb_fsl(0, t, nL), 0, nM), bO = zsb_fsl(zsb_fsl(0, t, nLM), 0, nO);         \
             aL = tbL + (ZSB_CELL_BASE(eL) + bL) * (SEQ_CHAINS * 4); aM = tbM + (ZSB_CELL_BASE(eM) + bM) * (SEQ_CHAINS * 4);                 \
             aO = tbO + (ZSB_CELL_BASE(eO) + bO) * (SEQ_CHAINS * 4);                                        /* sequence.rs:80-88 */          \
-            wrow[(i_) & (2 * SEQ_WIN - 1)] = seq_fast_word(eL, eO, eM, (LAST) ? 0u : sum);                                                                              \
+            wrow[(i_) & (2 * SEQ_WIN - 1)] = seq_fast_word(eL, eO, eM, (LAST) ? 0u : sum);                                                  \
+            /* the window moves on */                                                                                                       \
+            const uint32_t o2 = (uint32_t)__dp4a((int)sum, (LAST) ? 0x00000001 : 0x00000101, (int)o);     /* o + extra bits + state bits */ \
+            o = o2 & 31u;                                                                                                                   \
+            kb -= (o2 >> 5) * 4u;                                                                                                           \
+            if (o2 & 32u) { q2 = q1; q1 = q0; q0 = n0; n0 = n1; n1 = n2; n2 = n3; }                                                         \
+            if (o2 & 64u) { q2 = q0; q1 = n0; q0 = n1; n0 = n2; }                                                                           \
+            T2 = zsb_fsl(q1, q2, o); T1 = zsb_fsl(q0, q1, o); T0 = zsb_fsl(n0, q0, o);                                                      \
         }
+#define SEQ_TOP() ((int32_t)(kb * 8u + 32u - o))
         for (uint32_t i0 = 0; i0 < maxn; i0 += SEQ_WIN) {
             const uint32_t B = i0 / SEQ_WIN;
             if (B >= 2) seq_bar_sync(SEQ_BAR_FREE + (B & 1u));      // the phase-2 warps are done with window B-2, whose ring slots window B overwrites
             const bool full = i0 + SEQ_WIN < nseq;              // a whole window of sequences, none of them the last
-            // the stream rings are topped up every 8 steps (8 x 89 + 95 bits < one 128-byte line), by all lanes in the same pass
+            // the stream rings are topped up every 8 steps (8 x 90 bits + the 224 bits of look-ahead < one 128-byte line), by all lanes in the same pass
             if (!__any_sync(FULL, !full && i0 < nseq)) {
                 if (full) {
                     for (uint32_t i8 = i0; i8 < i0 + SEQ_WIN; i8 += 8) {
-                        sr_check<7>(R, top - 32);
+                        sr_check<7, SEQ_PF>(R, SEQ_TOP() - 160);
 #pragma unroll 8
                         for (uint32_t i = i8; i < i8 + 8; i++) SEQ_STEP(i, false)
                     }
                 }
             } else {
                 for (uint32_t i = i0; i < i0 + SEQ_WIN; i++)
-                    if (i < nseq) { if ((i & 7u) == 0) sr_check<7>(R, top - 32); SEQ_STEP(i, i + 1 == nseq) }
+                    if (i < nseq) { if ((i & 7u) == 0) sr_check<7, SEQ_PF>(R, SEQ_TOP() - 160); SEQ_STEP(i, i + 1 == nseq) }
             }
             __threadfence_block();
             seq_bar_arrive(SEQ_BAR_FULL + (B & 1u));                // window B is in the ring
         }
+        top = SEQ_TOP();
+#undef SEQ_TOP
 #undef SEQ_STEP
         // an over-read shows as a cursor below the stream start; illegal codes are caught by phase 2, which sees every code
         if (active && top < startbit) S.final_rc[lane] = ZSB_NEEDS_SLOW;
@@ -599,7 +625,11 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
                 if (b * SEQ_WIN < nsq[k]) {
                     const uint4 ww = *reinterpret_cast<const uint4 *>(&S.words[c0 + k][(b & 1u) * SEQ_WIN + SEQ_PER_LANE * lane]);
                     const uint32_t wd[4] = {ww.x, ww.y, ww.z, ww.w};
+#ifndef SEQ_NO_P2
                     seq2_window(base8, tab_sa, wd, b * SEQ_WIN, nsq[k], S.regen[c0 + k], reinterpret_cast<uint64_t *>((uintptr_t)S.rec[c0 + k]), C[k], lane);
+#else
+                    C[k].lit_acc += wd[0] & 1;
+#endif
                 }
             }
             if (b + 2 < nbat) seq_bar_arrive(SEQ_BAR_FREE + (b & 1u));

@@ -12,6 +12,7 @@ struct ZsbCounters {
     uint32_t overflow;    // scratch too small: every later kernel exits, the host grows it and relaunches
     uint32_t n_slow;      // blocks the fast sequence path handed to the careful decoder
     uint32_t ticket1, ticket2;   // k_plan1 / k_plan2: CTAs done with the per-frame part (the last one runs the scans)
+    uint32_t zero, pad;          // always 0: k_seq orders its look-ahead loads behind its cell loads with a data dependency on it
 };
 
 cudaError_t zsbk_init();

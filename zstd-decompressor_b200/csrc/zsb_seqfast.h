@@ -30,7 +30,7 @@
 #define ZSB_W_CM(w) (((w) >> 16) & 63u)
 #define ZSB_W_NB(w) (((w) >> 24) & 31u)
 ZSB_HD uint32_t seq_fast_word(uint32_t eL, uint32_t eO, uint32_t eM, uint32_t nbs) {
-    return zsb_prmt(zsb_prmt(eL, eO, 0x0062), zsb_prmt(eM, nbs, 0x0042), 0x5410);
+    return zsb_prmt(zsb_prmt(eL, eO, 0x0062), zsb_prmt(eM, nbs, 0x0052), 0x5410);      // nbs: a sum of cells, state bits in byte 1
 }
 
 // code -> baseline | extra bits << 24 (sequence.rs:98-191)
@@ -78,18 +78,19 @@ ZSB_HDN int seq_fast_phase1(const uint8_t *src, const ZsbBlockWork &w, const Seq
     for (uint32_t i = 0; i < nseq; i++) {
         const uint32_t eL = tL[sL * ts], eO = tO[sO * ts], eM = tM[sM * ts];
         W = fast_win_get(F);
-        const uint32_t sum = eL + eO + eM;                        // byte 0: state bits, byte 1: extra bits (no carries: <= 27, <= 63)
-        const uint32_t nbs = i + 1 == nseq ? 0u : sum & 0xFFu;    // no state update after the last sequence (sequence.rs:80)
-        const uint32_t px = zsb_prmt(sum, 0, 0x4441);
+        const uint32_t sum = eL + eO + eM;                        // byte 0: extra bits, byte 1: state bits (no carries: <= 63, <= 27)
+        const uint32_t nbs = i + 1 == nseq ? 0u : (sum >> 8) & 0xFFu;    // no state update after the last sequence (sequence.rs:80)
+        const uint32_t px = sum & 0xFFu;
         uint32_t skip = px;
         if (px + nbs > 64) { top -= (int32_t)px; fast_win_load(F, pw, top); W = fast_win_get(F); skip = 0; }   // state bits past the window: rare
         const uint32_t t = (uint32_t)(zsb_shl64(W, skip) >> 32);  // the <= 27 state bits, top-aligned
-        // the funnel shifts take their 5-bit amounts straight from the cells (nb in bits 0..4)
-        const uint32_t bL = zsb_fsl(t, 0, eL), t2 = zsb_fsl(0, t, eL), bM = zsb_fsl(t2, 0, eM), bO = zsb_fsl(zsb_fsl(0, t2, eM), 0, eO);
+        // the funnel shifts take their 5-bit amounts from the cells (nb in bits 8..12)
+        const uint32_t nL = eL >> 8, nM = eM >> 8, nO = eO >> 8;
+        const uint32_t bL = zsb_fsl(t, 0, nL), t2 = zsb_fsl(0, t, nL), bM = zsb_fsl(t2, 0, nM), bO = zsb_fsl(zsb_fsl(0, t2, nM), 0, nO);
         top -= (int32_t)(skip + nbs);
         fast_win_load(F, pw, top);
         sL = ZSB_CELL_BASE(eL) + bL; sM = ZSB_CELL_BASE(eM) + bM; sO = ZSB_CELL_BASE(eO) + bO;      // sequence.rs:80-88
-        words[i * ws] = seq_fast_word(eL, eO, eM, nbs);
+        words[i * ws] = seq_fast_word(eL, eO, eM, i + 1 == nseq ? 0u : sum);
     }
     // an over-read shows as a cursor below the stream start; illegal codes are caught by phase 2, which sees every code
     if (top < startbit) return ZSB_NEEDS_SLOW;

@@ -53,26 +53,37 @@ __device__ __forceinline__ uint64_t zsb_lds64v(uint32_t a) { uint64_t v; asm vol
 // a fixed latency instead of global loads whose misses would stall every chain of the warp.
 // Bit positions are relative to `pl`, a line-aligned address at least 16 bytes below the stream.
 struct StreamRing { uint32_t sa; const uint8_t *pl; int32_t low; };   // ring address, line base, lowest line requested
-template <int LB> __device__ __forceinline__ void sr_fetch(const StreamRing &r, int32_t line) {
+// PF > 0: also asks L2 for the line PF lines further down, so that by the time the ring requests it the bytes come from L2 and not from
+// HBM (the ring is only one line ahead of the cursor: an HBM round trip under load outlasts the ~8 chain steps between two top-ups,
+// and the warp-wide wait for the previous request then stalls all chains of the warp)
+template <int LB, int PF = 0> __device__ __forceinline__ void sr_fetch(const StreamRing &r, int32_t line) {
     const uint8_t *g = r.pl + ((size_t)(uint32_t)line << LB);
+    if (PF > 0 && line >= PF) {
+#pragma unroll
+        for (int k = 0; k < (1 << LB) / 32; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(g - ((size_t)PF << LB) + 32 * k));
+    }
     const uint32_t d = r.sa + (((uint32_t)line & 3u) << LB);
 #pragma unroll
     for (int k = 0; k < (1 << LB) / 16; k++) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 16 * k), "l"(g + 16 * k) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
-template <int LB> __device__ __forceinline__ void sr_init(StreamRing &r, int32_t top) {
+template <int LB, int PF = 0> __device__ __forceinline__ void sr_init(StreamRing &r, int32_t top) {
     const int32_t l0 = (top - 1) >> (LB + 3);
     r.low = l0 - 2 < 0 ? 0 : l0 - 2;
     for (int32_t l = l0; l >= r.low; l--) sr_fetch<LB>(r, l);
+    if (PF > 0) {       // the lines between the ring and the first line a top-up will ask L2 for
+        for (int32_t l = r.low - 1; l >= 0 && l >= r.low - PF; l--)
+            for (int k = 0; k < (1 << LB) / 32; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(r.pl + ((size_t)(uint32_t)l << LB) + 32 * k));
+    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 // Keeps the ring ahead of the cursor: when the window ending at `top` has entered line X (<= low+1), line X-2 is
 // requested and line X-1 awaited.  Must run at least once per line of progress: every step (sr_load), or every k steps
 // when k steps cannot consume a whole line (sr_check + sr_load_nocheck; all lanes of a warp then refill in the same
 // pass instead of diverging step by step).
-template <int LB> __device__ __forceinline__ void sr_check(StreamRing &r, int32_t top) {
+template <int LB, int PF = 0> __device__ __forceinline__ void sr_check(StreamRing &r, int32_t top) {
     int32_t a = top - 64; a = a < 0 ? 0 : a;
-    if ((a >> (LB + 3)) <= r.low + 1 && r.low > 0) { r.low--; sr_fetch<LB>(r, r.low); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    if ((a >> (LB + 3)) <= r.low + 1 && r.low > 0) { r.low--; sr_fetch<LB, PF>(r, r.low); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 }
 // window words for the 64 bits ending at `top`
 template <int LB> __device__ __forceinline__ void sr_load_nocheck(const StreamRing &r, FastWin &f, int32_t top) {
