@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
             n0 = zsb_lds32v(((kb - 12u) & 0x1FCu) | ring_sa);
             T2 = zsb_fsl(q1, q2, o); T1 = zsb_fsl(q0, q1, o); T0 = zsb_fsl(n0, q0, o);
         }
-        // One step of the chain; LAST: no state update after the last sequence (sequence.rs:80).  On the chain: the three cell
+        // One step of the chain.  On the chain: the three cell
         // loads, their sum, one funnel shift that skips the extra bits (the sum is its shift amount: byte 0 = extra bits, and bit 5
         // picks the word pair), one per state that isolates its bits, the new cell address: one shared-memory load and ~6 ALU
         // operations per sequence.  Off the chain: the window moves on by (extra + state bits) -- a dot product, two levels of
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
 #ifndef SEQ_DEP
 #define SEQ_DEP 0
 #endif
-#define SEQ_STEP(i_, LAST)                                                                                                                  \
+#define SEQ_STEP(i_)                                                                                                                        \
         {                                                                                                                                   \
             const uint32_t eL = zsb_lds32(aL), eM = zsb_lds32(aM), eO = zsb_lds32(aO);                                                      \
             /* (behind the cell loads, which are on the chain) the look-ahead words this step's window move may need */                     \
@@ -569,9 +569,11 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
             const uint32_t bL = zsb_fsl(t, 0, nL), bM = zsb_fsl(zsb_fsl(0, t, nL), 0, nM), bO = zsb_fsl(zsb_fsl(0, t, nLM), 0, nO);         \
             aL = tbL + (ZSB_CELL_BASE(eL) + bL) * (SEQ_CHAINS * 4); aM = tbM + (ZSB_CELL_BASE(eM) + bM) * (SEQ_CHAINS * 4);                 \
             aO = tbO + (ZSB_CELL_BASE(eO) + bO) * (SEQ_CHAINS * 4);                                        /* sequence.rs:80-88 */          \
-            wrow[(i_) & (2 * SEQ_WIN - 1)] = seq_fast_word(eL, eO, eM, (LAST) ? 0u : sum);                                                  \
+            wrow[(i_) & (2 * SEQ_WIN - 1)] = seq_fast_word(eL, eO, eM, sum);                                                                \
+            /* the cursor behind the extra bits of the last sequence (no state update follows it, sequence.rs:80): below the stream = over-read */ \
+            if ((i_) + 1 == nseq) top = SEQ_TOP() - (int32_t)(sum & 0xFFu);                                                                  \
             /* the window moves on */                                                                                                       \
-            const uint32_t o2 = (uint32_t)__dp4a((int)sum, (LAST) ? 0x00000001 : 0x00000101, (int)o);     /* o + extra bits + state bits */ \
+            const uint32_t o2 = (uint32_t)__dp4a((int)sum, 0x00000101, (int)o);                           /* o + extra bits + state bits */ \
             o = o2 & 31u;                                                                                                                   \
             kb -= (o2 >> 5) * 4u;                                                                                                           \
             if (o2 & 32u) { q2 = q1; q1 = q0; q0 = n0; n0 = n1; n1 = n2; n2 = n3; }                                                         \
@@ -582,24 +584,20 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
         for (uint32_t i0 = 0; i0 < maxn; i0 += SEQ_WIN) {
             const uint32_t B = i0 / SEQ_WIN;
             if (B >= 2) seq_bar_sync(SEQ_BAR_FREE + (B & 1u));      // the phase-2 warps are done with window B-2, whose ring slots window B overwrites
-            const bool full = i0 + SEQ_WIN < nseq;              // a whole window of sequences, none of them the last
-            // the stream rings are topped up every 8 steps (8 x 90 bits + the 224 bits of look-ahead < one 128-byte line), by all lanes in the same pass
-            if (!__any_sync(FULL, !full && i0 < nseq)) {
-                if (full) {
-                    for (uint32_t i8 = i0; i8 < i0 + SEQ_WIN; i8 += 8) {
-                        sr_check<7, SEQ_PF>(R, SEQ_TOP() - 160);
+            // A chain runs every step of every window it has a sequence in: past its last sequence it walks on from valid states over
+            // whatever the ring holds (nothing of that is used: phase 2 stops at nseq), so that no window needs a per-step test.  The
+            // stream rings are topped up every 8 steps (8 x 90 bits + the 224 bits of look-ahead < one 128-byte line), by all lanes in
+            // the same pass.
+            if (i0 < nseq) {
+                for (uint32_t i8 = i0; i8 < i0 + SEQ_WIN; i8 += 8) {
+                    sr_check<7, SEQ_PF>(R, SEQ_TOP() - 160);
 #pragma unroll 8
-                        for (uint32_t i = i8; i < i8 + 8; i++) SEQ_STEP(i, false)
-                    }
+                    for (uint32_t i = i8; i < i8 + 8; i++) SEQ_STEP(i)
                 }
-            } else {
-                for (uint32_t i = i0; i < i0 + SEQ_WIN; i++)
-                    if (i < nseq) { if ((i & 7u) == 0) sr_check<7, SEQ_PF>(R, SEQ_TOP() - 160); SEQ_STEP(i, i + 1 == nseq) }
             }
             __threadfence_block();
             seq_bar_arrive(SEQ_BAR_FULL + (B & 1u));                // window B is in the ring
         }
-        top = SEQ_TOP();
 #undef SEQ_TOP
 #undef SEQ_STEP
         // an over-read shows as a cursor below the stream start; illegal codes are caught by phase 2, which sees every code
