@@ -141,6 +141,24 @@ def make_c2(n_frames=4096, seed=2, frame_size=131072):
     return b"".join(frames), b"".join(text[o:o + frame_size] for o in offs)
 
 
+def make_c2_range(n_frames, seed, f0, f1, frame_size=131072):
+    """Frames [f0, f1) of the n_frames-frame corpus of that seed (the windows are drawn for all frames, only the range is compressed)."""
+    text = moby_text()
+    r = random.Random(seed)
+    offs = [r.randrange(len(text) - frame_size) for _ in range(n_frames)][f0:f1]
+    threads = min(32, (os.cpu_count() or 4))
+    out = [None] * len(offs)
+
+    def work(t):
+        c = Compressor(level=3)
+        for i in range(t, len(offs), threads):
+            out[i] = c.compress(text[offs[i]:offs[i] + frame_size])
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, range(threads)))
+    return b"".join(out), b"".join(text[o:o + frame_size] for o in offs)
+
+
 def make_c5(n_frames=65536, seed=5, frame_size=131072):
     return make_c2(n_frames, seed, frame_size)
 

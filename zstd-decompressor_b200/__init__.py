@@ -82,12 +82,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    try:
-        if _build_module().needs_build():
-            build()
-    except Exception:
-        if not os.path.exists(_SO):
-            raise
+    if not os.environ.get("ZSB_LIB_PATH") and _build_module().needs_build():
+        build()                                            # raises if nvcc is missing or the build fails: a stale library is never loaded silently
     L = C.CDLL(os.environ.get("ZSB_LIB_PATH") or _SO)      # ZSB_LIB_PATH: development knob, a differently tuned build of the same library
     u8p, sz, vp = C.POINTER(C.c_uint8), C.c_size_t, C.c_void_p
     u64p, i32p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)

@@ -32,6 +32,7 @@ struct DevBuf {
 const int kMaxKernels = 16;
 const int kProfRing = 32;     // launches whose per-kernel events are kept
 const uint32_t kBigFrameBlocks = 64;   // frames with more blocks than this are executed by a whole CTA (k_exec), not a warp (k_exec2)
+const size_t kSmallBatchFrames = 296;  // batches of at most this many frames (two per SM) give every multi-block frame a CTA
 }  // namespace
 
 struct zsb_ctx {
@@ -201,10 +202,14 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
         bool has_c = false;
         for (uint32_t k = 0; k < frames[f].n_blocks && !has_c; k++) has_c = blocks[frames[f].first_block + k].type == ZSB_BT_COMPRESSED;
         // frames of many blocks: one CTA per frame (k_exec); all others: one warp per frame (k_exec2)
+        // ... and, in a batch too small to fill the GPU with warps (a single file of a few frames, like BASELINE config C1), every frame of
+        // more than one block: a CTA takes 0.11 ms per block, a warp on its own 0.8 ms
         static const int big_env = getenv("ZSB_BIG_FRAME_BLOCKS") ? atoi(getenv("ZSB_BIG_FRAME_BLOCKS")) : -1;     // experiment knob
-        const uint32_t big = c->low_latency ? 0u : big_env >= 0 ? (uint32_t)big_env : kBigFrameBlocks;
-        if (has_c) (frames[f].n_blocks > big ? execl : exec2l).push_back((uint32_t)f);
-        if ((flags & ZSB_VERIFY_CHECKSUM) && frames[f].has_checksum) c->h_xxh_list.push_back((uint32_t)f);
+        const uint32_t big = c->low_latency ? 0u : big_env >= 0 ? (uint32_t)big_env : nf <= kSmallBatchFrames ? 1u : kBigFrameBlocks;
+        const bool cta = has_c && frames[f].n_blocks > big;
+        if (has_c) (cta ? execl : exec2l).push_back((uint32_t)f);
+        // frames executed by k_exec<1024> are hashed by its trailing warp, all others by k_xxh
+        if ((flags & ZSB_VERIFY_CHECKSUM) && frames[f].has_checksum && !(cta && !c->is_sub)) c->h_xxh_list.push_back((uint32_t)f);
     }
     c->ncomp = (uint32_t)ncomp; c->n_rawrle = (uint32_t)rawrle.size(); c->n_exec = (uint32_t)execl.size(); c->n_exec2 = (uint32_t)exec2l.size(); c->n_xxh = (uint32_t)c->h_xxh_list.size();
     if (lit_cap > c->lit_cap) c->lit_cap = lit_cap;
@@ -278,7 +283,7 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     MARK(c, "k_exec2");  zsbk_exec2(st, c->n_exec2, src, frames, blocks, work, fout, (const uint32_t *)c->exec2_list.p, cnt, (const uint64_t *)c->seq_pool.p,
                                     (const uint8_t *)c->lit_pool.p, c->d_dst); c->launches += c->n_exec2 ? 1 : 0;
     MARK(c, "k_exec");   zsbk_exec(st, c->n_exec, src, frames, blocks, work, fout, (const uint32_t *)c->exec_list.p, cnt, (const uint64_t *)c->seq_pool.p,
-                                   (const uint8_t *)c->lit_pool.p, c->d_dst, c->is_sub); c->launches += c->n_exec ? 1 : 0;
+                                   (const uint8_t *)c->lit_pool.p, c->d_dst, c->is_sub, c->flags); c->launches += c->n_exec ? 1 : 0;
     // pipelined path: the shard's output may leave as soon as it is written -- the checksums are computed from HBM while the
     // download runs (both only read the output)
     const bool early_down = c->down_stream && c->eager_d2h && c->h_dst;

@@ -779,6 +779,94 @@ __global__ void __launch_bounds__(256) k_rawrle(const uint8_t *__restrict__ src,
     else cta_copy_g2g(d, src + b.src_off, b.size);                         // block.rs:76 ; skippable payload frame.rs:81
 }
 
+// ======================================================================================= XXH64 primitives
+#define XP1 0x9E3779B185EBCA87ull
+#define XP2 0xC2B2AE3D27D4EB4Full
+#define XP3 0x165667B19E3779F9ull
+#define XP4 0x85EBCA77C2B2AE63ull
+#define XP5 0x27D4EB2F165667C5ull
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t xround(uint64_t acc, uint64_t in) { return rotl64(acc + in * XP2, 31) * XP1; }
+__device__ __forceinline__ uint64_t xmerge(uint64_t h, uint64_t v) { return (h ^ xround(0, v)) * XP1 + XP4; }
+// 8 bytes at any alignment from two aligned words
+__device__ __forceinline__ uint64_t ld64_any(const uint8_t *p) {
+    const uintptr_t a = (uintptr_t)p;
+    const unsigned long long *q = reinterpret_cast<const unsigned long long *>(a & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(a & 7) * 8;
+    uint64_t w0 = __ldcg(q);
+    if (sh == 0) return w0;
+    uint64_t w1 = __ldcg(q + 1);
+    return (w0 >> sh) | (w1 << (64 - sh));
+}
+
+// XXH64 of one frame by ONE warp that trails the executor of the same CTA (k_exec<.., true>): the frame's bytes are hashed from
+// HBM/L2 as soon as the executor has committed them (*done = committed bytes, ~0 = the frame failed), so that the checksum of a
+// frame of many blocks -- four dependent accumulator chains over all of its stripes, 33.5 M rounds for 1 GiB -- runs beside the
+// execution instead of behind it.  All 32 lanes load: one instruction fetches 8 stripes (256 consecutive bytes, lane l the word
+// l & 3 of stripe l >> 2) and 8 such loads are in flight (the chains are bound by their own latency only when ~64 stripes are on
+// their way: a lane that loaded its own word of every stripe, 8 at a time, took 115 cycles per round); lanes 0..3 hold the
+// accumulators and collect their words by shuffle.
+__device__ __forceinline__ void xxh_trail(const uint8_t *p, uint64_t len, volatile unsigned long long *done, uint64_t *result) {
+    const uint32_t lane = threadIdx.x & 31, q = lane & 3;
+    uint64_t v = q == 0 ? XP1 + XP2 : q == 1 ? XP2 : q == 2 ? 0ull : 0ull - XP1;
+    const uint64_t nstripes = len >> 5;
+    uint64_t cur = 0;
+    constexpr int NR = 8;            // loads in flight per lane; 8 stripes each
+    const uint8_t *g = p + 8 * lane;                                   // this lane's word of the first group of 8 stripes
+    const uint32_t sh = (uint32_t)((uintptr_t)g & 7) * 8;
+    const unsigned long long *ga = reinterpret_cast<const unsigned long long *>((uintptr_t)g & ~(uintptr_t)7);
+    while (cur < nstripes) {
+        const unsigned long long d = *done;
+        if (d == ~0ull) return;
+        uint64_t tgt = d >> 5; if (tgt > nstripes) tgt = nstripes;
+        if (tgt < nstripes && tgt - cur < 8 * NR) { __nanosleep(500); continue; }      // wait for a whole round of loads (or the end)
+        __threadfence();
+        // whole rounds of 8 * NR stripes
+        while (cur + 8 * NR <= tgt) {
+            uint64_t X[NR];
+            const unsigned long long *gs = ga + 4 * cur;
+            if (sh == 0) {
+#pragma unroll
+                for (int r = 0; r < NR; r++) X[r] = __ldcg(gs + 32 * r);
+            } else {
+#pragma unroll
+                for (int r = 0; r < NR; r++) X[r] = (__ldcg(gs + 32 * r) >> sh) | (__ldcg(gs + 32 * r + 1) << (64 - sh));
+            }
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) { const uint64_t x = __shfl_sync(FULL, X[r], 4 * j + q); v = rotl64(v + x * XP2, 31) * XP1; }
+            }
+            cur += 8 * NR;
+        }
+        // the rest of the stretch (only at the end of the frame), stripe by stripe
+        if (tgt == nstripes) {
+            for (; cur < tgt; cur++) { const uint64_t x = ld64_any(p + (cur << 5) + 8 * q); v = rotl64(v + x * XP2, 31) * XP1; }
+        }
+    }
+    // everything is committed only once *done == len (the tail bytes)
+    for (;;) { const unsigned long long d = *done; if (d == ~0ull) return; if (d >= len) break; __nanosleep(500); }
+    __threadfence();
+    const uint64_t v1 = __shfl_sync(FULL, v, 0), v2 = __shfl_sync(FULL, v, 1), v3 = __shfl_sync(FULL, v, 2), v4 = __shfl_sync(FULL, v, 3);
+    if (lane == 0) {
+        uint64_t h;
+        if (len >= 32) {
+            h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+            h = xmerge(h, v1); h = xmerge(h, v2); h = xmerge(h, v3); h = xmerge(h, v4);
+        } else h = XP5;
+        h += len;
+        const uint8_t *t = p + (nstripes << 5), *end = p + len;
+        while (t + 8 <= end) { h ^= xround(0, ld64_any(t)); h = rotl64(h, 27) * XP1 + XP4; t += 8; }
+        if (t + 4 <= end) {
+            uint32_t x = (uint32_t)__ldcg(t) | ((uint32_t)__ldcg(t + 1) << 8) | ((uint32_t)__ldcg(t + 2) << 16) | ((uint32_t)__ldcg(t + 3) << 24);
+            h ^= (uint64_t)x * XP1; h = rotl64(h, 23) * XP2 + XP3; t += 4;
+        }
+        while (t < end) { h ^= (uint64_t)__ldcg(t) * XP5; h = rotl64(h, 11) * XP1; t++; }
+        h ^= h >> 33; h *= XP2; h ^= h >> 29; h *= XP3; h ^= h >> 32;
+        *result = h;
+    }
+}
+
 // ======================================================================================= k_exec
 // k_exec<512>: shards of the pipelined host path (it shares the SMs with other shards' k_seq: 1 024 threads of 60 registers would not fit
 // beside one); k_exec<1024>: frames of many blocks on their own (twice the batches in flight: 0.18 -> 0.11 ms per block)
@@ -899,14 +987,18 @@ __device__ __forceinline__ void exec_batch(uint32_t batch, uint32_t nseq, const 
     }
 }
 
-template <int EXEC_THREADS>
+// XXH: the last warp of the CTA does not execute but hashes the frame behind the executor (xxh_trail); the others synchronise among
+// themselves with a named barrier.
+template <int EXEC_THREADS, bool XXH>
 __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restrict__ src, const zsb_frame *__restrict__ frames,
                                                           const zsb_block *__restrict__ blocks, const ZsbBlockWork *__restrict__ work,
                                                           ZsbFrameOut *fout, const uint32_t *__restrict__ exec_list,
                                                           const ZsbCounters *__restrict__ cnt, const uint64_t *__restrict__ seq_pool,
-                                                          const uint8_t *__restrict__ lit_pool, uint8_t *dst) {
+                                                          const uint8_t *__restrict__ lit_pool, uint8_t *dst, uint32_t flags) {
+    constexpr uint32_t ET = EXEC_THREADS - (XXH ? 32 : 0);            // executing threads
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ int s_err;
+    __shared__ unsigned long long s_done;                              // bytes of the frame committed to HBM, in order; ~0: the frame failed
     if (cnt->overflow) return;
     uint8_t *out_s = smem;
     uint32_t *bm = reinterpret_cast<uint32_t *>(smem + EXEC_OUT_BYTES);
@@ -917,12 +1009,21 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
     if (fo.status != ZSB_OK) return;
     const zsb_frame fr = frames[f];
     uint8_t *fdst = dst + fo.dst_off;
-    if (tid == 0) s_err = 0;
+    if (tid == 0) { s_err = 0; s_done = 0; }
     __syncthreads();
+    if (XXH && warp == ET / 32) {
+        if ((flags & ZSB_VERIFY_CHECKSUM) && fr.has_checksum) xxh_trail(fdst, fo.dst_len, &s_done, &fout[f].xxh64);
+        return;
+    }
+    auto sync_exec = [&]() { if (XXH) asm volatile("bar.sync 1, %0;" ::"r"(ET) : "memory"); else __syncthreads(); };
+    bool failed = false;
     for (uint32_t k = 0; k < fr.n_blocks; k++) {
         const uint32_t bi = fr.first_block + k;
-        if (blocks[bi].type != ZSB_BT_COMPRESSED) continue;
         const ZsbBlockWork &W = work[bi];
+        if (blocks[bi].type != ZSB_BT_COMPRESSED) {                    // written by k_rawrle
+            if (XXH && tid == 0) s_done = W.out_off + W.out_size;
+            continue;
+        }
         const uint32_t out_size = W.out_size, nseq = W.nseq, regen = W.lit_regen;
         uint8_t *gblk = fdst + W.out_off;
         const uint32_t shift = (uint32_t)((uintptr_t)gblk & 15);
@@ -937,38 +1038,41 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
             L.s = lit_s + ls;
             // stage the literals: aligned 16-byte loads once past the head
             uint32_t head = (16 - ls) & 15; if (head > regen) head = regen;
-            for (uint32_t i = tid; i < head; i += EXEC_THREADS) lit_s[ls + i] = __ldg(L.g + i);
+            for (uint32_t i = tid; i < head; i += ET) lit_s[ls + i] = __ldg(L.g + i);
             const uint32_t nv = (regen - head) >> 4;
             const uint4 *g4 = reinterpret_cast<const uint4 *>(L.g + head); uint4 *s4 = reinterpret_cast<uint4 *>(lit_s + ls + head);
-            for (uint32_t i = tid; i < nv; i += EXEC_THREADS) s4[i] = __ldg(g4 + i);
-            for (uint32_t i = head + (nv << 4) + tid; i < regen; i += EXEC_THREADS) lit_s[ls + i] = __ldg(L.g + i);
+            for (uint32_t i = tid; i < nv; i += ET) s4[i] = __ldg(g4 + i);
+            for (uint32_t i = head + (nv << 4) + tid; i < regen; i += ET) lit_s[ls + i] = __ldg(L.g + i);
         } else L.mode = 1;
-        if (nseq) for (uint32_t i = tid; i < (out_size + 31) / 32; i += EXEC_THREADS) bm[i] = 0;
-        __syncthreads();
+        if (nseq) for (uint32_t i = tid; i < (out_size + 31) / 32; i += ET) bm[i] = 0;
+        sync_exec();
         if (nseq == 0) {
-            for (uint32_t i = tid; i < regen; i += EXEC_THREADS) o[i] = lit_at(L, i);        // literals-only block (RFC; reference: Q1)
+            for (uint32_t i = tid; i < regen; i += ET) o[i] = lit_at(L, i);        // literals-only block (RFC; reference: Q1)
         } else {
             const uint64_t *seqs = seq_pool + W.seq_buf;
             const uint64_t lastrec = __ldg(seqs + nseq - 1);
             const uint32_t oe = (uint32_t)lastrec & ZSB_REC_POS_MASK, le = (uint32_t)(lastrec >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK;
-            for (uint32_t i = tid; i < regen - le; i += EXEC_THREADS) o[oe + i] = lit_at(L, le + i);   // decoding_context.rs:101-103
+            for (uint32_t i = tid; i < regen - le; i += ET) o[oe + i] = lit_at(L, le + i);   // decoding_context.rs:101-103
             const uint32_t nbatch = (nseq + 31) / 32;
-            for (uint32_t b = warp; b < nbatch; b += EXEC_THREADS / 32)
+            for (uint32_t b = warp; b < nbatch; b += ET / 32)
                 exec_batch(b, nseq, seqs, o, bm, L, W.rep_in, fr.kind == 0 ? W.out_off : 0, gblk, &s_err);
         }
-        __syncthreads();
+        sync_exec();
         // flush the block image to HBM: congruent alignment -> 16-byte stores
         {
             uint32_t head = (16 - shift) & 15; if (head > out_size) head = out_size;
-            for (uint32_t i = tid; i < head; i += EXEC_THREADS) gblk[i] = o[i];
+            for (uint32_t i = tid; i < head; i += ET) gblk[i] = o[i];
             const uint32_t nv = (out_size - head) >> 4;
             const uint4 *s4 = reinterpret_cast<const uint4 *>(o + head); uint4 *g4 = reinterpret_cast<uint4 *>(gblk + head);
-            for (uint32_t i = tid; i < nv; i += EXEC_THREADS) g4[i] = s4[i];
-            for (uint32_t i = head + (nv << 4) + tid; i < out_size; i += EXEC_THREADS) gblk[i] = o[i];
+            for (uint32_t i = tid; i < nv; i += ET) g4[i] = s4[i];
+            for (uint32_t i = head + (nv << 4) + tid; i < out_size; i += ET) gblk[i] = o[i];
         }
-        __syncthreads();
-        if (s_err) { if (tid == 0) { fout[f].status = s_err; fout[f].dst_len = 0; } break; }
+        if (XXH) __threadfence();                                      // the block is in HBM before the hashing warp is told so
+        sync_exec();
+        if (s_err) { if (tid == 0) { fout[f].status = s_err; fout[f].dst_len = 0; } failed = true; break; }
+        if (XXH && tid == 0) s_done = W.out_off + out_size;
     }
+    if (XXH && tid == 0) s_done = failed ? ~0ull : fo.dst_len;
 }
 
 // ======================================================================================= k_exec2
@@ -1250,24 +1354,6 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 7) k_exec2(const uint8_t *__re
 }
 
 // ======================================================================================= k_xxh
-#define XP1 0x9E3779B185EBCA87ull
-#define XP2 0xC2B2AE3D27D4EB4Full
-#define XP3 0x165667B19E3779F9ull
-#define XP4 0x85EBCA77C2B2AE63ull
-#define XP5 0x27D4EB2F165667C5ull
-__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
-__device__ __forceinline__ uint64_t xround(uint64_t acc, uint64_t in) { return rotl64(acc + in * XP2, 31) * XP1; }
-__device__ __forceinline__ uint64_t xmerge(uint64_t h, uint64_t v) { return (h ^ xround(0, v)) * XP1 + XP4; }
-// 8 bytes at any alignment from two aligned words
-__device__ __forceinline__ uint64_t ld64_any(const uint8_t *p) {
-    const uintptr_t a = (uintptr_t)p;
-    const unsigned long long *q = reinterpret_cast<const unsigned long long *>(a & ~(uintptr_t)7);
-    const uint32_t sh = (uint32_t)(a & 7) * 8;
-    uint64_t w0 = __ldcg(q);
-    if (sh == 0) return w0;
-    uint64_t w1 = __ldcg(q + 1);
-    return (w0 >> sh) | (w1 << (64 - sh));
-}
 // XXH64 has no combine step: a frame is four dependent accumulator chains over its 32-byte stripes
 // (round = rotl(acc + x*P2, 31) * P1, ~25 cycles), so a frame is four lanes and the kernel is bound by that
 // chain as long as the bytes arrive in time.  One warp hashes 8 frames (4 lanes each).  The frames' bytes are
@@ -1481,9 +1567,9 @@ cudaError_t zsbk_init() {
     if (e != cudaSuccess) return e;
     e = set_smem((const void *)k_seq, SEQ_SMEM_FUSED);
     if (e != cudaSuccess) return e;
-    e = set_smem((const void *)k_exec<512>, EXEC_SMEM_BYTES);
+    e = set_smem((const void *)k_exec<512, false>, EXEC_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    return set_smem((const void *)k_exec<1024>, EXEC_SMEM_BYTES);
+    return set_smem((const void *)k_exec<1024, true>, EXEC_SMEM_BYTES);
 }
 void zsbk_parse(cudaStream_t st, const uint8_t *src, const zsb_block *blocks, ZsbBlockWork *work, uint32_t nb, uint32_t flags) {
     if (nb) k_parse<<<(nb + 127) / 128, 128, 0, st>>>(src, blocks, work, nb, flags);
@@ -1524,10 +1610,12 @@ void zsbk_rawrle(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_bloc
     if (n) k_rawrle<<<n, 256, 0, st>>>(src, blocks, work, fout, list, cnt, dst);
 }
 void zsbk_exec(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
-               ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst, bool shared_device) {
+               ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst, bool shared_device,
+               uint32_t flags) {
     if (!n) return;
-    if (shared_device) k_exec<512><<<n, 512, EXEC_SMEM_BYTES, st>>>(src, frames, blocks, work, fout, exec_list, cnt, seq_pool, lit_pool, dst);
-    else k_exec<1024><<<n, 1024, EXEC_SMEM_BYTES, st>>>(src, frames, blocks, work, fout, exec_list, cnt, seq_pool, lit_pool, dst);
+    // (on its own: 31 executing warps and one that hashes the frame behind them, so a frame of many blocks is not hashed by k_xxh afterwards)
+    if (shared_device) k_exec<512, false><<<n, 512, EXEC_SMEM_BYTES, st>>>(src, frames, blocks, work, fout, exec_list, cnt, seq_pool, lit_pool, dst, flags);
+    else k_exec<1024, true><<<n, 1024, EXEC_SMEM_BYTES, st>>>(src, frames, blocks, work, fout, exec_list, cnt, seq_pool, lit_pool, dst, flags);
 }
 void zsbk_exec2(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
                 ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst) {
