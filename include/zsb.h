@@ -188,6 +188,31 @@ int zsb_last_kernel_times(const zsb_ctx *ctx, const char **names, float *ms, int
  * (at most the last 32). */
 int zsb_kernel_times_avg(zsb_ctx *ctx, const char **names, float *ms, int cap, int *n_launches);
 
+/* ---- several GPUs from one process (no reference counterpart: src/main.rs:27-60 is one thread on one CPU; frames are independent,
+ *      frame.rs:233).  zsb_multi owns one zsb_ctx per device and decodes ONE host buffer on all of them in one call: the container is
+ *      walked once, the frames are cut into one contiguous range per device, balanced on decompressed bytes and weighted by what each
+ *      device's host link delivers (zsb_multi_calibrate measures it with all devices copying at once; zsb_multi_set_weights sets it),
+ *      and every range runs through its device's context on a worker thread of its own (upload, kernels, download pipelined per
+ *      device as in zsb_decode).  No collective: every device writes its own slab of dst.  Results as zsb_scan_decode.  Frames without
+ *      Frame_Content_Size, a frame that fails or disagrees with its header, or a malformed container end in one plain decode on the
+ *      first device (same results).  src / dst: page-locked host memory (zsb_host_alloc) keeps the copies of all devices asynchronous. */
+typedef struct zsb_multi zsb_multi;
+int  zsb_multi_create(zsb_multi **m, const int *device_ids /* NULL: 0 .. n-1 */, int n_devices);
+void zsb_multi_destroy(zsb_multi *m);
+int  zsb_multi_device_count(const zsb_multi *m);
+zsb_ctx *zsb_multi_ctx(zsb_multi *m, int i);            /* the context of device i (owned by m), e.g. for resident decodes per device */
+int  zsb_multi_calibrate(zsb_multi *m, size_t bytes, int reps, double *gbs /* n_devices, may be NULL */);
+int  zsb_multi_set_weights(zsb_multi *m, const double *weights /* n_devices; NULL: equal */);
+int  zsb_multi_get_weights(const zsb_multi *m, double *weights);
+const char *zsb_multi_last_error(const zsb_multi *m);
+int  zsb_multi_scan_decode(zsb_multi *m, const uint8_t *src, size_t n, uint8_t *dst, size_t dst_cap, uint32_t flags, uint64_t max_window,
+                           zsb_frame **frames, size_t *n_frames, zsb_block **blocks, size_t *n_blocks,
+                           zsb_result **results, uint64_t *dst_total, uint64_t *err_a, uint64_t *err_b);
+/* NVLink gather for a single-stream consumer: device-resident slabs (slab i: sizes[i] bytes at src_ptrs[i] on src_devices[i]) ->
+ * dst_ptr on dst_device, back to back, one cudaMemcpyPeerAsync per slab; *ms = device time of the whole gather.  Timed and reported
+ * apart from any decode figure. */
+int  zsb_gather_peer(int n, const int *src_devices, const void *const *src_ptrs, const size_t *sizes, int dst_device, void *dst_ptr, float *ms);
+
 /* == whole-program behaviour of src/main.rs:42-58 : scan + decode + concatenate into a malloc'd
  *    buffer; all-or-nothing like the CLI (first error => no output).  Convenience for bindings. */
 int zsb_decompress(zsb_ctx *ctx, const uint8_t *src, size_t n, uint32_t flags,

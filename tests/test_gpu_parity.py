@@ -306,6 +306,44 @@ def test_two_gpus_two_ranks():
 
 
 # ---------------------------------------------------------------- BASELINE full sizes: C3 (one 1 GiB frame) and C5's per-GPU share
+def test_multi_gpu_one_call_one_buffer():               # zsb_multi_scan_decode: one pinned host buffer, every GPU of the box, weighted shards
+    import ctypes as C
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import gen_corpus as G
+    blob, plain = G.make_c2(1024 * n, seed=5)
+    L = Z.lib()
+    src, dst = L.zsb_host_alloc(len(blob)), L.zsb_host_alloc(len(plain) + 64)
+    try:
+        C.memmove(src, blob, len(blob))
+        m = Z.MultiContext(list(range(n)))
+        for w in (None, [1.0 + 0.5 * (i % 2) for i in range(n)]):
+            m.set_weights(w)
+            r = m.scan_decode((src, len(blob)), (dst, len(plain)), Q | VER)
+            assert r.status == 0 and r.total == len(plain) and r.first_error() is None and r.n_frames == 1024 * n
+            assert C.string_at(dst, len(plain)) == plain
+            assert all(r.results[i].checksum_ok == 1 and r.results[i].dst_off == i * 131072 for i in range(r.n_frames))
+        # a corrupted frame in the middle: the call falls back to one plain decode and reports exactly that frame
+        bad = bytearray(blob); sc = Z.Scan(blob, Q)
+        bad[sc.frames[700].src_off + 40] ^= 0xFF
+        C.memmove(src, bytes(bad), len(bad))
+        r = m.scan_decode((src, len(bad)), (dst, len(plain)), Q | VER)
+        ref_out, _, ref_r = Z.Decoder(Z.Context(0)).decode(bytes(bad), Q | VER)
+        assert [r.results[i].status for i in range(r.n_frames)] == [ref_r.status[i] for i in range(r.n_frames)]
+        assert C.string_at(dst, r.total) == ref_out
+        # NVLink gather of two device-resident slabs
+        a = torch.arange(1 << 20, dtype=torch.uint8, device="cuda:0"); b = torch.full((3 << 20,), 7, dtype=torch.uint8, device="cuda:1")
+        g = torch.empty((4 << 20) + 16, dtype=torch.uint8, device="cuda:0")
+        torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+        ms = Z.gather_peer([(0, a.data_ptr(), a.numel()), (1, b.data_ptr(), b.numel())], 0, g.data_ptr())
+        assert ms > 0 and torch.equal(g[:1 << 20].cpu(), a.cpu()) and bool((g[1 << 20:4 << 20] == 7).all())
+        m.close()
+    finally:
+        L.zsb_host_free(src); L.zsb_host_free(dst)
+
+
 def test_c3_full_size_single_frame(dec):
     """one multi-segment 1 GiB frame, 8 192 blocks, window 8 MiB: executed block after block by one CTA (k_exec);
     size-independent checks: SHA-256 against the plaintext and the stored XXH64 verified on the GPU"""

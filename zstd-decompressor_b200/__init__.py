@@ -115,6 +115,18 @@ def lib():
     L.zsb_shard_plan.argtypes = [C.POINTER(ZsbFrame), sz, C.c_int, C.POINTER(sz)]
     L.zsb_shard_extract.argtypes = [C.POINTER(ZsbFrame), sz, C.POINTER(ZsbBlock), sz, sz, sz, C.POINTER(C.POINTER(ZsbFrame)), C.POINTER(C.POINTER(ZsbBlock)),
                                     C.POINTER(sz), u64p, u64p]
+    dp = C.POINTER(C.c_double)
+    L.zsb_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    L.zsb_multi_destroy.argtypes = [vp]; L.zsb_multi_destroy.restype = None
+    L.zsb_multi_device_count.argtypes = [vp]
+    L.zsb_multi_ctx.argtypes = [vp, C.c_int]; L.zsb_multi_ctx.restype = vp
+    L.zsb_multi_calibrate.argtypes = [vp, sz, C.c_int, dp]
+    L.zsb_multi_set_weights.argtypes = [vp, dp]
+    L.zsb_multi_get_weights.argtypes = [vp, dp]
+    L.zsb_multi_last_error.argtypes = [vp]; L.zsb_multi_last_error.restype = C.c_char_p
+    L.zsb_multi_scan_decode.argtypes = [vp, vp, sz, vp, sz, C.c_uint32, C.c_uint64, C.POINTER(C.POINTER(ZsbFrame)), C.POINTER(sz),
+                                        C.POINTER(C.POINTER(ZsbBlock)), C.POINTER(sz), C.POINTER(C.POINTER(ZsbResult)), u64p, u64p, u64p]
+    L.zsb_gather_peer.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.POINTER(sz), C.c_int, vp, C.POINTER(C.c_float)]
     L.zsb_strerror.restype = C.c_char_p; L.zsb_strerror.argtypes = [C.c_int]
     L.zsb_version.restype = C.c_char_p
     _lib = L
@@ -125,7 +137,9 @@ EXPORTED_SYMBOLS = [
     "zsb_scan", "zsb_free", "zsb_ctx_create", "zsb_ctx_destroy", "zsb_ctx_set_stream", "zsb_last_cuda_error", "zsb_ctx_set_profile",
     "zsb_last_launch_count", "zsb_last_kernel_times", "zsb_kernel_times_avg", "zsb_decode", "zsb_decode_prepare", "zsb_decode_launch", "zsb_decode_finish",
     "zsb_decompress", "zsb_fse_table_parse", "zsb_fse_table_from_distribution", "zsb_huffman_parse", "zsb_execute_sequences",
-    "zsb_xxh64", "zsb_strerror", "zsb_version", "zsb_shard_plan", "zsb_shard_extract", "zsb_host_alloc", "zsb_host_free", "zsb_scan_decode"]
+    "zsb_xxh64", "zsb_strerror", "zsb_version", "zsb_shard_plan", "zsb_shard_extract", "zsb_host_alloc", "zsb_host_free", "zsb_scan_decode",
+    "zsb_multi_create", "zsb_multi_destroy", "zsb_multi_device_count", "zsb_multi_ctx", "zsb_multi_calibrate", "zsb_multi_set_weights", "zsb_multi_get_weights",
+    "zsb_multi_last_error", "zsb_multi_scan_decode", "zsb_gather_peer"]
 
 
 # ------------------------------------------------------------------------------------------ scan
@@ -266,6 +280,66 @@ class ScanDecode:
                 if getattr(self, p, None): lib().zsb_free(getattr(self, p))
         except Exception:
             pass
+
+
+class MultiContext:
+    """zsb_multi: one context per GPU of the box, one host buffer decoded on all of them in one call (frames sharded by contiguous ranges
+    weighted by each device's host link).  src / dst are (pointer, length) pairs of page-locked host memory."""
+    def __init__(self, devices):
+        h = C.c_void_p()
+        ids = (C.c_int * len(devices))(*devices)
+        rc = lib().zsb_multi_create(C.byref(h), ids, len(devices))
+        if rc:
+            raise ZsbError(rc, what="zsb_multi_create")
+        self.h, self.n = h, len(devices)
+
+    def calibrate(self, nbytes=64 << 20, reps=3):
+        g = (C.c_double * self.n)()
+        rc = lib().zsb_multi_calibrate(self.h, nbytes, reps, g)
+        if rc:
+            raise ZsbError(rc, what="zsb_multi_calibrate")
+        return list(g)
+
+    def weights(self):
+        w = (C.c_double * self.n)(); lib().zsb_multi_get_weights(self.h, w); return list(w)
+
+    def set_weights(self, w):
+        lib().zsb_multi_set_weights(self.h, (C.c_double * self.n)(*w) if w else None)
+
+    def scan_decode(self, src, dst, flags=VERIFY_CHECKSUM, max_window=0):
+        """-> ScanDecode-like object (frames, blocks, results, total, status)"""
+        r = ScanDecode.__new__(ScanDecode)
+        fp, bp, rp = C.POINTER(ZsbFrame)(), C.POINTER(ZsbBlock)(), C.POINTER(ZsbResult)()
+        nf, nb, tot, ea, eb = C.c_size_t(), C.c_size_t(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        r.status = lib().zsb_multi_scan_decode(self.h, C.c_void_p(src[0]), src[1], C.c_void_p(dst[0]), dst[1], flags, max_window,
+                                               C.byref(fp), C.byref(nf), C.byref(bp), C.byref(nb), C.byref(rp), C.byref(tot), C.byref(ea), C.byref(eb))
+        r.frames, r.blocks, r.results = fp, bp, rp
+        r.n_frames, r.n_blocks, r.total = nf.value, nb.value, tot.value
+        r.err_a, r.err_b = ea.value, eb.value
+        if not rp and r.status:
+            raise ZsbError(r.status, what="zsb_multi_scan_decode: " + lib().zsb_multi_last_error(self.h).decode())
+        return r
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().zsb_multi_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gather_peer(slabs, dst_device, dst_ptr):
+    """slabs: [(device, device pointer, bytes)] -> milliseconds of the NVLink gather into dst_ptr on dst_device (zsb_gather_peer)"""
+    n = len(slabs)
+    devs = (C.c_int * n)(*[s[0] for s in slabs]); ptrs = (C.c_void_p * n)(*[s[1] for s in slabs]); sizes = (C.c_size_t * n)(*[s[2] for s in slabs])
+    ms = C.c_float()
+    rc = lib().zsb_gather_peer(n, devs, ptrs, sizes, dst_device, C.c_void_p(dst_ptr), C.byref(ms))
+    if rc:
+        raise ZsbError(rc, what="zsb_gather_peer")
+    return ms.value
 
 
 class Decoder:
