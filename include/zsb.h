@@ -58,8 +58,9 @@ enum {
 #define ZSB_PRINT_SKIPPABLE   0x01u  /* src/main.rs:22-24,45-49 : skippable payloads become output      */
 #define ZSB_VERIFY_CHECKSUM   0x02u  /* compute XXH64 of every frame that stores one (frame.rs:239-259) */
 #define ZSB_REFERENCE_QUIRKS  0x04u  /* reject exactly what the reference rejects */
-#define ZSB_SRC_ON_DEVICE     0x08u  /* src is a device pointer (compressed bytes resident in HBM); no padding needed: the kernels never touch
-                                        an aligned 128-byte line that holds no byte of the buffer              */
+#define ZSB_SRC_ON_DEVICE     0x08u  /* src is a device pointer (compressed bytes resident in HBM).  The kernels read whole aligned 128-byte
+                                        lines: the allocation must be readable up to the next 128-byte boundary behind src + n (any
+                                        cudaMalloc'd buffer is; a sub-range of one is if 127 more bytes follow it)                   */
 #define ZSB_DST_ON_DEVICE     0x10u  /* dst is a device pointer (output stays in HBM)                   */
 #define ZSB_STRICT_DICT       0x20u  /* fail frames carrying a dict id (the reference ignores it)       */
 
@@ -156,6 +157,7 @@ typedef struct zsb_result {
     uint64_t dst_off, dst_len;
     int32_t  status;
     uint32_t xxh32;
+    uint32_t err_a, err_b;      /* payload of the frame's error variant where the reference's has one (NotEnoughBytes {requested, available} ...) */
     uint8_t  checksum_ok, pad[7];
 } zsb_result;
 int zsb_scan_decode(zsb_ctx *ctx, const uint8_t *src, size_t n, uint8_t *dst, size_t dst_cap, uint32_t flags, uint64_t max_window,
@@ -179,6 +181,9 @@ int zsb_decode_prepare(zsb_ctx *ctx, const uint8_t *src, size_t n,
 int zsb_decode_launch(zsb_ctx *ctx);
 int zsb_decode_finish(zsb_ctx *ctx, uint64_t *dst_off, uint64_t *dst_len, int32_t *status,
                       uint32_t *xxh32, uint8_t *checksum_ok, uint64_t *dst_total);
+/* Per-frame payloads of the errors the last zsb_decode / zsb_decode_finish reported in status[] (parsing::Error::NotEnoughBytes
+ * {requested, available} of a block's sections, tests/block.rs:72-78): err_a[f], err_b[f], 0 where the variant carries none. */
+int zsb_decode_errors(const zsb_ctx *ctx, uint32_t *err_a, uint32_t *err_b, size_t n_frames);
 /* Number of kernels enqueued by the last zsb_decode_launch, and per-kernel device times (ms) of the
  * last launch when profiling was enabled with zsb_ctx_set_profile(ctx, 1).  names[i] are static. */
 int zsb_ctx_set_profile(zsb_ctx *ctx, int enable);

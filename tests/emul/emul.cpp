@@ -112,10 +112,13 @@ int emul_decode(const uint8_t *src_in, size_t n, uint32_t flags, uint8_t *out, s
             int nw = 0, mb = 0; uint32_t dl = 0;
             int rc = huf_read_weights(src + w.huf_desc, w.huf_desc_end - w.huf_desc, weights, 1, nw, dl, ftbl, 1, cnt, 1, n - w.huf_desc,
                                       (flags & ZSB_REFERENCE_QUIRKS) != 0);
-            if (!rc) rc = huf_build_lut(weights, 1, nw, lut, rank, 1, mb, nullptr);
+            bool incomplete = false;
+            if (!rc) rc = huf_build_lut(weights, 1, nw, lut, rank, 1, mb, nullptr, (flags & ZSB_REFERENCE_QUIRKS) != 0, &incomplete);
             lits[i].assign(w.lit_regen + 16, 0);
+            const bool quirks = (flags & ZSB_REFERENCE_QUIRKS) != 0;
+            bool inexact = quirks && (w.lit_inexact || incomplete);
             uint64_t start = w.lit_src; uint32_t seg = (w.lit_regen + 3) / 4;
-            for (uint32_t s = 0; s < w.n_streams && !rc; s++) {
+            for (uint32_t s = 0; s < w.n_streams && !rc && !inexact; s++) {
                 uint32_t expect = w.n_streams == 1 ? w.lit_regen : (s < 3 ? seg : w.lit_regen - 3 * seg);
                 uint8_t *o = lits[i].data() + (w.n_streams == 1 ? 0 : s * seg);
                 rc = huf_decode_stream(src, start, start + w.stream_size[s], n, lut, mb, o, expect);
@@ -127,8 +130,16 @@ int emul_decode(const uint8_t *src_in, size_t n, uint32_t flags, uint8_t *out, s
                     if (frc == ZSB_OK) { if (rc == ZSB_OK && memcmp(fa, o, expect) == 0) g_huf_same++; else g_huf_diff++; }
                     else if (frc == ZSB_NEEDS_SLOW) { if (rc != ZSB_OK) g_huf_slow++; else g_huf_diff++; }
                     else g_huf_diff++;
+                    if (quirks && frc == ZSB_NEEDS_SLOW) { inexact = true; rc = 0; }      // k_huf: the block goes the reference's way
                 }
                 start += w.stream_size[s];
+            }
+            if (inexact && !rc) {                                                          // k_huf: huf_decode_block_ref, count then decode
+                uint32_t n1 = 0, n2 = 0;
+                rc = huf_decode_block_ref(src, n, w.lit_src, w.stream_size, lut, mb, nullptr, 0, n1);
+                if (!rc && n1 > ZSB_BLOCK_MAX) rc = ZSB_E_BLOCK_TOO_LARGE;
+                if (!rc) { lits[i].assign(n1 + 16, 0); rc = huf_decode_block_ref(src, n, w.lit_src, w.stream_size, lut, mb, lits[i].data(), n1, n2); }
+                if (!rc) w.lit_regen = n1;
             }
             if (rc) { w.status = rc; continue; }
         }
@@ -153,7 +164,8 @@ int emul_decode(const uint8_t *src_in, size_t n, uint32_t flags, uint8_t *out, s
         if (!st) {
             if (frames[f].kind == 1) len = (flags & ZSB_PRINT_SKIPPABLE) ? blocks[frames[f].first_block].size : 0;
             else {
-                st = plan_frame(frames[f], blocks, work.data(), len);
+                uint32_t pa = 0, pb = 0;
+                st = plan_frame(frames[f], blocks, work.data(), len, pa, pb);
                 if (!st && frames[f].has_content_size && len != frames[f].content_size && !(flags & ZSB_REFERENCE_QUIRKS)) st = ZSB_E_CONTENT_SIZE;
                 if (st) len = 0;
             }

@@ -107,10 +107,10 @@ def test_reference_api_mirror_without_gpu():
 
 
 def test_result_struct_layout_matches_header():
-    """zsb_result (include/zsb.h) as the Python mirror sees it: 32 bytes, fields at the offsets ScanDecode.first_error relies on."""
+    """zsb_result (include/zsb.h) as the Python mirror sees it: 40 bytes, fields at the offsets ScanDecode.first_error relies on."""
     import ctypes as C
-    assert C.sizeof(Z.ZsbResult) == 32
+    assert C.sizeof(Z.ZsbResult) == 40
     assert (Z.ZsbResult.dst_off.offset, Z.ZsbResult.dst_len.offset, Z.ZsbResult.status.offset, Z.ZsbResult.xxh32.offset,
-            Z.ZsbResult.checksum_ok.offset) == (0, 8, 16, 20, 24)
+            Z.ZsbResult.err_a.offset, Z.ZsbResult.err_b.offset, Z.ZsbResult.checksum_ok.offset) == (0, 8, 16, 20, 24, 28, 32)
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "zsb.h")).read()
     assert "typedef struct zsb_result" in hdr and "zsb_scan_decode" in hdr and "zsb_host_alloc" in hdr

@@ -45,8 +45,8 @@ class ZsbBlock(C.Structure):
 
 
 class ZsbResult(C.Structure):
-    _fields_ = [("dst_off", C.c_uint64), ("dst_len", C.c_uint64), ("status", C.c_int32), ("xxh32", C.c_uint32), ("checksum_ok", C.c_uint8),
-                ("pad", C.c_uint8 * 7)]
+    _fields_ = [("dst_off", C.c_uint64), ("dst_len", C.c_uint64), ("status", C.c_int32), ("xxh32", C.c_uint32), ("err_a", C.c_uint32), ("err_b", C.c_uint32),
+                ("checksum_ok", C.c_uint8), ("pad", C.c_uint8 * 7)]
 
 
 class ZsbError(Exception):
@@ -103,6 +103,7 @@ def lib():
     L.zsb_decode.argtypes = [vp, vp, sz, C.POINTER(ZsbFrame), sz, C.POINTER(ZsbBlock), sz, vp, sz, u64p, u64p, i32p, u32p, u8p, u64p, C.c_uint32]
     L.zsb_decode_prepare.argtypes = [vp, vp, sz, C.POINTER(ZsbFrame), sz, C.POINTER(ZsbBlock), sz, vp, sz, C.c_uint32]
     L.zsb_decode_launch.argtypes = [vp]
+    L.zsb_decode_errors.argtypes = [vp, u32p, u32p, sz]
     L.zsb_decode_finish.argtypes = [vp, u64p, u64p, i32p, u32p, u8p, u64p]
     L.zsb_scan_decode.argtypes = [vp, vp, sz, vp, sz, C.c_uint32, C.c_uint64, C.POINTER(C.POINTER(ZsbFrame)), C.POINTER(sz),
                                   C.POINTER(C.POINTER(ZsbBlock)), C.POINTER(sz), C.POINTER(C.POINTER(ZsbResult)), u64p, u64p, u64p]
@@ -139,7 +140,7 @@ EXPORTED_SYMBOLS = [
     "zsb_decompress", "zsb_fse_table_parse", "zsb_fse_table_from_distribution", "zsb_huffman_parse", "zsb_execute_sequences",
     "zsb_xxh64", "zsb_strerror", "zsb_version", "zsb_shard_plan", "zsb_shard_extract", "zsb_host_alloc", "zsb_host_free", "zsb_scan_decode",
     "zsb_multi_create", "zsb_multi_destroy", "zsb_multi_device_count", "zsb_multi_ctx", "zsb_multi_calibrate", "zsb_multi_set_weights", "zsb_multi_get_weights",
-    "zsb_multi_last_error", "zsb_multi_scan_decode", "zsb_gather_peer"]
+    "zsb_multi_last_error", "zsb_multi_scan_decode", "zsb_gather_peer", "zsb_decode_errors"]
 
 
 # ------------------------------------------------------------------------------------------ scan
@@ -239,6 +240,12 @@ class BatchResult:
         self.status = (C.c_int32 * max(nf, 1))(); self.xxh32 = (C.c_uint32 * max(nf, 1))(); self.checksum_ok = (C.c_uint8 * max(nf, 1))()
         self.total = C.c_uint64(); self.nf = nf
 
+    def errors(self, ctx):
+        """[(err_a, err_b)] per frame: the payloads of the reference's error variants (zsb_decode_errors)"""
+        a = (C.c_uint32 * max(self.nf, 1))(); b = (C.c_uint32 * max(self.nf, 1))()
+        lib().zsb_decode_errors(ctx.h, a, b, self.nf)
+        return [(a[i], b[i]) for i in range(self.nf)]
+
     def first_error(self):
         raw = bytes(self.status)[:4 * self.nf]
         if raw.count(0) == len(raw):            # the common case at C speed
@@ -267,7 +274,7 @@ class ScanDecode:
     def first_error(self):
         n = self.n_frames
         raw = C.string_at(self.results, C.sizeof(ZsbResult) * n) if n else b""
-        if all(raw[16 + k::32].count(0) == n for k in range(4)):      # every status zero: the common case at C speed
+        if all(raw[16 + k::C.sizeof(ZsbResult)].count(0) == n for k in range(4)):      # every status zero: the common case at C speed
             return None
         for i in range(n):
             if self.results[i].status:

@@ -88,10 +88,13 @@ struct ZsbBlockWork {
     uint64_t bs_off;         // sequence bitstream
     uint32_t bs_len;
     uint32_t nseq;
-    uint8_t  lit_type, n_streams, raw_modes, pad0;
+    uint8_t  lit_type, n_streams, raw_modes;
+    uint8_t  parse_stage;    // how far parse_block got: 0 in the literals section, 1 literals section read, 2 modes byte read, 3 / 4 / 5 LL / OF / ML table read
     uint8_t  mode[3];        // effective mode after repeat resolution (never ZSB_M_REPEAT once chained)
     uint8_t  rle_sym[3];
-    uint8_t  pad1[2];
+    uint8_t  lit_inexact;    // ZSB_REFERENCE_QUIRKS: the streams do not have the shape Regenerated_Size promises (a zero or truncated jump-table entry ...):
+                             // the literals are decoded the reference's way, every stream until its bits run out (huf_decode_block_ref)
+    uint8_t  pad1;
     // scratch placement
     uint64_t lit_buf;        // byte offset in the literal scratch (Huffman literals)
     uint64_t seq_buf;        // record index in the sequence scratch

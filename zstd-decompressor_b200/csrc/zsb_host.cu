@@ -32,6 +32,7 @@ struct DevBuf {
 const int kMaxKernels = 16;
 const int kProfRing = 32;     // launches whose per-kernel events are kept
 const uint32_t kBigFrameBlocks = 64;   // frames with more blocks than this are executed by a whole CTA (k_exec), not a warp (k_exec2)
+const uint64_t kLitOverflow = 4u << 20; // ZSB_REFERENCE_QUIRKS: room behind the literal scratch for blocks whose (corrupted) streams regenerate more than announced
 const size_t kSmallBatchFrames = 296;  // batches of at most this many frames (two per SM) give every multi-block frame a CTA
 }  // namespace
 
@@ -50,6 +51,7 @@ struct zsb_ctx {
     std::vector<zsb_frame> h_frames;
     std::vector<zsb_block> h_blocks;
     std::vector<uint32_t> h_xxh_list, h_rawrle, h_exec, h_exec2;   // host copies stay alive while their uploads are in flight
+    std::vector<uint32_t> h_err_a, h_err_b;                        // per-frame error payloads of the last finished batch (zsb_decode_errors)
     std::vector<zsb_ctx *> subs;          // child contexts of the pipelined host path (own stream + scratch each)
     bool is_sub = false;
     bool low_latency = false;             // pipelined path, first shards: CTA-per-frame execution (k_exec: 0.15 ms per block instead of 1.2 ms per frame, at a third of the throughput)
@@ -154,6 +156,15 @@ extern "C" int zsb_kernel_times_avg(zsb_ctx *c, const char **names, float *ms, i
     return n;
 }
 
+extern "C" int zsb_decode_errors(const zsb_ctx *c, uint32_t *err_a, uint32_t *err_b, size_t n_frames) {
+    if (!c) return ZSB_E_ARG;
+    for (size_t f = 0; f < n_frames; f++) {
+        if (err_a) err_a[f] = f < c->h_err_a.size() ? c->h_err_a[f] : 0;
+        if (err_b) err_b[f] = f < c->h_err_b.size() ? c->h_err_b[f] : 0;
+    }
+    return ZSB_OK;
+}
+
 extern "C" void *zsb_host_alloc(size_t n) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
@@ -171,9 +182,9 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     // compressed bytes: resident already, or uploaded once (padded so that aligned 8-byte loads near the end stay inside)
     if (flags & ZSB_SRC_ON_DEVICE) c->d_src = src;
     else {
-        CK(c, c->src.ensure(n + 64));
+        CK(c, c->src.ensure(n + 128));                // the stream rings of k_seq / k_huf read whole aligned 128-byte lines
         if (n) CK(c, cudaMemcpyAsync(c->src.p, src, n, cudaMemcpyHostToDevice, st));
-        CK(c, cudaMemsetAsync((uint8_t *)c->src.p + n, 0, 64, st));
+        CK(c, cudaMemsetAsync((uint8_t *)c->src.p + n, 0, 128, st));
         c->d_src = (const uint8_t *)c->src.p;
     }
     if (flags & ZSB_DST_ON_DEVICE) { c->d_dst = dst; c->h_dst = nullptr; }
@@ -226,7 +237,8 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     CK(c, c->exec2_list.ensure(4 * (exec2l.size() + 1)));
     CK(c, c->xxh_list.ensure(4 * (c->h_xxh_list.size() + 1)));
     CK(c, c->counters.ensure(sizeof(ZsbCounters)));
-    CK(c, c->lit_pool.ensure(c->lit_cap + 64));
+    c->lit_cap = (c->lit_cap + 15) & ~(uint64_t)15;
+    CK(c, c->lit_pool.ensure(c->lit_cap + kLitOverflow + 64));
     CK(c, c->seq_pool.ensure(8 * (c->seq_cap + 8)));
     if (nf) CK(c, cudaMemcpyAsync(c->frames.p, frames, sizeof(zsb_frame) * nf, cudaMemcpyHostToDevice, st));
     if (nb) CK(c, cudaMemcpyAsync(c->blocks.p, blocks, sizeof(zsb_block) * nb, cudaMemcpyHostToDevice, st));
@@ -267,11 +279,11 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
         CK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
         MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p, c->is_sub, ll_chains);
         if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][0], c->aux_stream);
-        zsbk_huf(c->aux_stream, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags);
+        zsbk_huf(c->aux_stream, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->lit_cap, 0, c->flags & ~ZSB_REFERENCE_QUIRKS);
         if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][1], c->aux_stream);
         CK(c, cudaEventRecord(c->ev_join, c->aux_stream));
     } else {
-        MARK(c, "k_huf");  zsbk_huf(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->flags);
+        MARK(c, "k_huf");  zsbk_huf(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->lit_cap, kLitOverflow, c->flags);
         MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p, c->is_sub, ll_chains);
     }
     c->launches += c->ncomp ? 1 : 0;
@@ -336,8 +348,8 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
         if (!hc.overflow) break;
         if (attempt >= 2) { c->last_err = "scratch overflow persists"; return ZSB_E_NOMEM; }
         // the entropy scratch was too small for this input: size it exactly and run the batch again
-        c->lit_cap = hc.lit_total + 64; c->seq_cap = hc.seq_total + 8;
-        CK(c, c->lit_pool.ensure(c->lit_cap + 64));
+        c->lit_cap = (hc.lit_total + 64 + 15) & ~(uint64_t)15; c->seq_cap = hc.seq_total + 8;
+        CK(c, c->lit_pool.ensure(c->lit_cap + kLitOverflow + 64));
         CK(c, c->seq_pool.ensure(8 * (c->seq_cap + 8)));
             int rc = zsb_decode_launch(c);
         if (rc) return rc;
@@ -349,8 +361,10 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
     if (c->h_dst && hc.dst_total && hc.dst_total != c->eager_d2h) CK(c, cudaMemcpyAsync(c->h_dst, c->d_dst, hc.dst_total, cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     if (c->down_stream && c->eager_d2h && c->h_dst) CK(c, cudaEventSynchronize(c->ev_down));
+    c->h_err_a.assign(c->nf, 0); c->h_err_b.assign(c->nf, 0);
     for (uint32_t f = 0; f < c->nf; f++) {
         const bool ok = fo[f].status == ZSB_OK;
+        if (!ok) { c->h_err_a[f] = fo[f].err_a; c->h_err_b[f] = fo[f].err_b; }
         if (dst_off) dst_off[f] = fo[f].dst_off;
         if (dst_len) dst_len[f] = ok ? fo[f].dst_len : 0;
         if (status) status[f] = fo[f].status;
@@ -469,6 +483,8 @@ struct Pipe {
     int collect(uint64_t *dst_off, uint64_t *dst_len, int32_t *status, uint32_t *xxh32, uint8_t *checksum_ok, uint64_t *dst_total) {
         int rc = ZSB_OK; bool bad = false, any_late = false;
         uint64_t total = 0;                                  // == where the next late shard goes
+        size_t nf_all = 0; for (int k = 0; k < n; k++) if (sh[k].f1 > nf_all) nf_all = sh[k].f1;
+        c->h_err_a.assign(nf_all, 0); c->h_err_b.assign(nf_all, 0);
         t_enq = now_ms();
         for (int k = 0; k < n; k++) {
             Sh &S = sh[k];
@@ -477,6 +493,7 @@ struct Pipe {
             const int r = zsb_decode_finish(c->subs[k], dst_off ? dst_off + S.f0 : nullptr, dst_len ? dst_len + S.f0 : nullptr, status ? status + S.f0 : nullptr,
                                             xxh32 ? xxh32 + S.f0 : nullptr, checksum_ok ? checksum_ok + S.f0 : nullptr, &t);
             if (r != ZSB_OK) { rc = r; c->last_err = c->subs[k]->last_err; bad = true; continue; }
+            if (c->h_err_a.size() >= S.f1) zsb_decode_errors(c->subs[k], c->h_err_a.data() + S.f0, c->h_err_b.data() + S.f0, S.f1 - S.f0);
             if (!S.late) {
                 if (t != S.dexp) bad = true;
                 if (dst_off) for (size_t f = S.f0; f < S.f1; f++) dst_off[f] += S.doff;
@@ -606,7 +623,10 @@ extern "C" int zsb_scan_decode(zsb_ctx *c, const uint8_t *src, size_t n, uint8_t
     }
     zsb_result *res = (zsb_result *)malloc(sizeof(zsb_result) * (nf + 1));
     if (!res) return ZSB_E_NOMEM;
-    for (size_t f = 0; f < nf; f++) { res[f].dst_off = off[f]; res[f].dst_len = len[f]; res[f].status = st[f]; res[f].xxh32 = xh[f]; res[f].checksum_ok = ck[f]; memset(res[f].pad, 0, sizeof res[f].pad); }
+    for (size_t f = 0; f < nf; f++) {
+        res[f].dst_off = off[f]; res[f].dst_len = len[f]; res[f].status = st[f]; res[f].xxh32 = xh[f]; res[f].checksum_ok = ck[f]; memset(res[f].pad, 0, sizeof res[f].pad);
+        res[f].err_a = f < c->h_err_a.size() ? c->h_err_a[f] : 0; res[f].err_b = f < c->h_err_b.size() ? c->h_err_b[f] : 0;
+    }
     rc = sc.release(frames_out, n_frames, blocks_out, n_blocks);
     if (rc) { free(res); return rc; }
     *results_out = res;
@@ -623,25 +643,34 @@ extern "C" int zsb_decompress(zsb_ctx *c, const uint8_t *src, size_t n, uint32_t
     *out = nullptr; *out_len = 0;
     flags &= ~(ZSB_SRC_ON_DEVICE | ZSB_DST_ON_DEVICE);
     zsb_frame *frames = nullptr; zsb_block *blocks = nullptr; size_t nf = 0, nb = 0;
-    int rc = zsb_scan(src, n, flags, 0, &frames, &nf, &blocks, &nb, err_a, err_b);
-    if (rc) { zsb_free(frames); zsb_free(blocks); return rc; }
-    // capacity: content sizes where declared; otherwise blocks regenerate at most 128 KiB each
+    const int scan_rc = zsb_scan(src, n, flags, 0, &frames, &nf, &blocks, &nb, err_a, err_b);
+    // src/main.rs:43-53 decodes every frame as the iterator yields it: an error in decoding frame j precedes the parse error of a later frame k,
+    // so the frames in front of a malformed one are decoded first and only then is the walk's error reported
+    const size_t nf_ok = scan_rc ? (nf ? nf - 1 : 0) : nf;
+    // capacity: content sizes where declared (never with ZSB_REFERENCE_QUIRKS: the reference does not compare the decoded length with
+    // Frame_Content_Size, a frame may be longer than it says); otherwise blocks regenerate at most 128 KiB each
     uint64_t cap = 0;
-    for (size_t f = 0; f < nf; f++) {
+    for (size_t f = 0; f < nf_ok; f++) {
         if (frames[f].kind == 1) { cap += blocks[frames[f].first_block].size; continue; }
-        if (frames[f].has_content_size) { cap += frames[f].content_size; continue; }
+        if (frames[f].has_content_size && !(flags & ZSB_REFERENCE_QUIRKS)) { cap += frames[f].content_size; continue; }
         for (uint32_t k = 0; k < frames[f].n_blocks; k++) {
             const zsb_block &b = blocks[frames[f].first_block + k];
             cap += b.type == ZSB_BT_COMPRESSED ? ZSB_BLOCK_MAX : b.size;
         }
     }
     uint8_t *dst = (uint8_t *)malloc(cap ? cap : 1);
-    std::vector<int32_t> status(nf);
-    std::vector<uint64_t> off(nf), len(nf);
+    std::vector<int32_t> status(nf_ok + 1);
+    std::vector<uint64_t> off(nf_ok + 1), len(nf_ok + 1);
     uint64_t total = 0;
     if (!dst) { zsb_free(frames); zsb_free(blocks); return ZSB_E_NOMEM; }
-    rc = zsb_decode(c, src, n, frames, nf, blocks, nb, dst, cap, off.data(), len.data(), status.data(), nullptr, nullptr, &total, flags);
-    if (!rc) for (size_t f = 0; f < nf && !rc; f++) rc = status[f];      // main.rs:51 first error aborts, no partial output
+    size_t nb_ok = nb;
+    if (scan_rc && nf) nb_ok = frames[nf - 1].first_block;              // (a failed frame has no blocks; its first_block is the count so far)
+    int rc = zsb_decode(c, src, n, frames, nf_ok, blocks, nb_ok, dst, cap, off.data(), len.data(), status.data(), nullptr, nullptr, &total, flags);
+    if (!rc) for (size_t f = 0; f < nf_ok && !rc; f++) {
+        rc = status[f];                                                  // main.rs:51 first error aborts, no partial output
+        if (rc) { uint32_t a = 0, b = 0; zsb_decode_errors(c, &a, &b, 0); if (f < c->h_err_a.size()) { a = c->h_err_a[f]; b = c->h_err_b[f]; } if (err_a) *err_a = a; if (err_b) *err_b = b; }
+    }
+    if (!rc) rc = scan_rc;
     zsb_free(frames); zsb_free(blocks);
     if (rc) { free(dst); return rc; }
     *out = dst; *out_len = total;

@@ -68,7 +68,15 @@ ZSB_HDN int huf_read_weights(const uint8_t *desc, uint64_t limit, uint8_t *weigh
 
 // weights -> LUT.  lut: 1<<maxbits uint16 entries: symbol | nbits << 8.  rank[16] scratch (strided).
 // lens_out (optional, 256 entries, stride 1): code length per symbol for the stage-level API.
-ZSB_HDN int huf_build_lut(uint8_t *weights, int ws, int nw, uint16_t *lut, uint32_t *rank, int rs, int &maxbits, uint8_t *lens_out) {
+// quirks (ZSB_REFERENCE_QUIRKS): where the reference's arithmetic (from_weights huffman.rs:177-203: the implied weight from
+// `(2^maxbits - sum) as u8`, no completeness check) builds a tree without panicking, that very tree is laid out -- it may be
+// incomplete (cells left ZSB_HUF_ABSENT: the reference panics when a stream reaches such a node) or drop symbols that find no room
+// (insert returns false, :161-175); where the reference panics, and always without quirks, RFC 8878 4.2.1.1 decides.
+#define ZSB_HUF_ABSENT 0xFFFFu
+// *incomplete (optional): the table has ZSB_HUF_ABSENT cells or dropped symbols: only huf_decode_block_ref may read it.
+ZSB_HDN int huf_build_lut(uint8_t *weights, int ws, int nw, uint16_t *lut, uint32_t *rank, int rs, int &maxbits, uint8_t *lens_out, bool quirks = false,
+                          bool *incomplete = nullptr) {
+    if (incomplete) *incomplete = false;
     uint32_t sum = 0;
     for (int i = 0; i < nw; i++) {
         uint32_t w = weights[i * ws];
@@ -76,12 +84,30 @@ ZSB_HDN int huf_build_lut(uint8_t *weights, int ws, int nw, uint16_t *lut, uint3
         if (w) sum += 1u << (w - 1);
     }
     if (sum == 0) return ZSB_E_CORRUPT;                                   // reference: discrete_log2(0) panics (huffman.rs:184)
-    int mb = zsb_flog2(sum) + 1;                                          // RFC 8878 4.2.1.1 (SURVEY Q5: reference is off by one when sum is 2^k)
-    if (mb > ZSB_HUF_MAX_BITS) return ZSB_E_CORRUPT;
-    uint32_t rest = (1u << mb) - sum;
-    if (rest & (rest - 1)) return ZSB_E_CORRUPT;                          // implied weight must be a power of two
-    uint32_t lastw = (uint32_t)zsb_flog2(rest) + 1;
     if (nw >= 256) return ZSB_E_CORRUPT;
+    int mb = zsb_flog2(sum) + 1;                                          // RFC 8878 4.2.1.1 (SURVEY Q5: reference is off by one when sum is 2^k)
+    uint32_t rest = (1u << mb) - sum;
+    uint32_t lastw = 0;
+    bool loose = false;                                                   // the reference's tree, not necessarily a complete code
+    if (quirks) {
+        const uint32_t p = (uint32_t)zsb_flog2(sum), pu = p + (((1u << p) < sum) ? 1u : 0u);
+        const uint32_t r8 = ((1u << pu) - sum) & 0xFFu;                  // `as u8` huffman.rs:190
+        bool panics = r8 == 0;                                            // discrete_log2(0)
+        const uint32_t lw = panics ? 0u : (uint32_t)zsb_flog2(r8) + 1u;
+        for (int i = 0; i < nw && !panics; i++) panics = weights[i * ws] > pu + 1;        // u8 underflow of the width
+        if (!panics && lw > pu + 1) panics = true;
+        if (!panics) {
+            if (pu > ZSB_HUF_MAX_BITS || pu == 0) return ZSB_E_CORRUPT;   // deeper than this library's table / a root that is a symbol (the reference never returns)
+            for (int i = 0; i < nw; i++) if (weights[i * ws] == pu + 1) return ZSB_E_CORRUPT;   // width 0: the same
+            if (lw == pu + 1) return ZSB_E_CORRUPT;
+            mb = (int)pu; lastw = lw; loose = true;
+        }
+    }
+    if (!loose) {
+        if (mb > ZSB_HUF_MAX_BITS) return ZSB_E_CORRUPT;
+        if (rest & (rest - 1)) return ZSB_E_CORRUPT;                      // implied weight must be a power of two
+        lastw = (uint32_t)zsb_flog2(rest) + 1;
+    }
     weights[nw * ws] = (uint8_t)lastw;
     int n = nw + 1;
     // rank[w] = first LUT cell of weight class w: lowest weights (longest codes) first (huffman.rs:161-175)
@@ -89,13 +115,16 @@ ZSB_HDN int huf_build_lut(uint8_t *weights, int ws, int nw, uint16_t *lut, uint3
     for (int i = 0; i < n; i++) rank[weights[i * ws] * rs] += 1;
     uint32_t start = 0;
     for (int w = 1; w <= mb; w++) { uint32_t c = rank[w * rs]; rank[w * rs] = start; start += c << (w - 1); }
-    if (start != (1u << mb)) return ZSB_E_CORRUPT;
+    if (!loose && start != (1u << mb)) return ZSB_E_CORRUPT;
+    if (incomplete) *incomplete = start != (1u << mb);
     if (lens_out) for (int i = 0; i < 256; i++) lens_out[i] = 0;
+    if (loose) for (uint32_t k = 0; k < (1u << mb); k++) lut[k] = ZSB_HUF_ABSENT;
     for (int i = 0; i < n; i++) {
         uint32_t w = weights[i * ws];
         if (!w) continue;
         uint32_t nbits = (uint32_t)mb + 1 - w, len = 1u << (w - 1), at = rank[w * rs];
         rank[w * rs] = at + len;
+        if (at + len > (1u << mb)) continue;                              // (quirks) no room left: the reference's insert returns false and the symbol is dropped
         uint16_t cell = (uint16_t)(i | (nbits << 8));
         for (uint32_t k = 0; k < len; k++) lut[at + k] = cell;
         if (lens_out) lens_out[i] = (uint8_t)nbits;
@@ -131,6 +160,43 @@ ZSB_HDN int huf_decode_stream(const uint8_t *src, uint64_t start, uint64_t end, 
         }
     }
     return n == expect ? ZSB_OK : ZSB_E_CORRUPT;
+}
+
+
+// ZSB_REFERENCE_QUIRKS: the literals of one block as the reference decodes them (LiteralsSection::decode literals.rs:70-81): stream
+// after stream in jump-table order, stopping at the first zero-sized entry, each decoded UNTIL ITS BITS RUN OUT (a symbol cut short is
+// NotEnoughBits, a stream whose last byte is 0 NullByte), the symbols of all streams concatenated; Regenerated_Size plays no part.
+// out == nullptr: count only.  n_out = symbols regenerated.  cap: room at out.
+ZSB_HDN int huf_decode_block_ref(const uint8_t *src, uint64_t src_end, uint64_t lit_src, const uint32_t *stream_size, const uint16_t *lut, int maxbits,
+                                 uint8_t *out, uint32_t cap, uint32_t &n_out) {
+    uint64_t start = lit_src;
+    uint32_t n = 0;
+    const uint32_t sh = 64u - (uint32_t)maxbits;
+    for (int s = 0; s < 4; s++) {
+        const uint32_t sz = stream_size[s];
+        if (sz == 0) break;
+        BackWin b;
+        const int rc = back_init(b, src, start, start + sz, src_end);
+        if (rc) return rc;
+        while (b.rem > 0) {
+            back_refill(b);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+            for (int k = 0; k < 5 && b.rem > 0; k++) {
+                const uint32_t cell = lut[(uint32_t)(b.hi >> sh)];
+                if (cell == ZSB_HUF_ABSENT) return ZSB_E_CORRUPT;         // an Absent node of an incomplete tree: the reference panics (huffman.rs:216)
+                const uint32_t nb = cell >> 8;
+                if ((int64_t)nb > b.rem) return ZSB_E_NOT_ENOUGH_BITS;
+                if (out) { if (n >= cap) return ZSB_E_BLOCK_TOO_LARGE; out[n] = (uint8_t)cell; }
+                n++;
+                back_consume(b, nb);
+            }
+        }
+        start += sz;
+    }
+    n_out = n;
+    return ZSB_OK;
 }
 
 

@@ -138,13 +138,15 @@ struct HufSlot {
     uint32_t rank[16];
     int maxbits;
     int status;
+    int incomplete;     // ZSB_REFERENCE_QUIRKS: the reference's tree for these weights is not a complete code (huf_build_lut)
 };
 __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__ src, uint64_t src_len, ZsbBlockWork *work,
-                                            const uint32_t *__restrict__ huf_list, const ZsbCounters *__restrict__ cnt,
-                                            uint8_t *lit_pool, uint32_t flags) {
+                                            const uint32_t *__restrict__ huf_list, ZsbCounters *cnt,
+                                            uint8_t *lit_pool, uint64_t lit_cap, uint64_t over_cap, uint32_t flags) {
     __shared__ HufSlot slots[HUF_SLOTS];
     __shared__ __align__(128) uint8_t rings[HUF_THREADS][256];
     if (cnt->overflow) return;
+    const bool quirks = (flags & ZSB_REFERENCE_QUIRKS) != 0;
     const uint32_t lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
     const uint32_t n = cnt->n_huf, idx = blockIdx.x * HUF_SLOTS + slot;
     if (blockIdx.x * HUF_SLOTS >= n) return;
@@ -155,17 +157,20 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__
         const ZsbBlockWork &w = work[bi];
         int nw = 0; uint32_t dl = 0;
         int rc = huf_read_weights(src + w.huf_desc, w.huf_desc_end - w.huf_desc, S.weights, 1, nw, dl, S.u.ftbl, 1, S.cnt, 1,
-                                  src_len - w.huf_desc, (flags & ZSB_REFERENCE_QUIRKS) != 0);
+                                  src_len - w.huf_desc, quirks);
         int mb = 0;
-        if (!rc) rc = huf_build_lut(S.weights, 1, nw, S.u.lut, S.rank, 1, mb, nullptr);
-        S.maxbits = mb; S.status = rc;
+        bool inc = false;
+        if (!rc) rc = huf_build_lut(S.weights, 1, nw, S.u.lut, S.rank, 1, mb, nullptr, quirks, &inc);
+        S.maxbits = mb; S.status = rc; S.incomplete = inc ? 1 : 0;
     }
     __syncwarp(HUF_MASK);
     int rc = 0;
+    bool inexact = false;                       // ZSB_REFERENCE_QUIRKS: this block's literals are decoded the reference's way
     if (active) {
         rc = S.status;
         const ZsbBlockWork &w = work[bi];
-        if (!rc && stream < w.n_streams) {
+        if (!rc && quirks && (w.lit_inexact || S.incomplete)) inexact = true;
+        else if (!rc && stream < w.n_streams) {
             const uint32_t regen = w.lit_regen;
             uint32_t seg, expect, ooff; uint64_t start = w.lit_src;
             if (w.n_streams == 1) { expect = regen; ooff = 0; }
@@ -175,12 +180,35 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__
             }
             rc = huf_fast_stream(src, start, start + w.stream_size[stream], S.u.lut, S.maxbits, lit_pool + w.lit_buf + ooff, expect,
                                  (uint32_t)__cvta_generic_to_shared(rings[lane]));
-            if (rc == ZSB_NEEDS_SLOW)    // the reference's verdict on this stream (literals.rs:70-81)
-                rc = huf_decode_stream(src, start, start + w.stream_size[stream], src_len, S.u.lut, S.maxbits, lit_pool + w.lit_buf + ooff, expect);
+            if (rc == ZSB_NEEDS_SLOW) {
+                if (quirks) { inexact = true; rc = ZSB_OK; }     // not the shape Regenerated_Size promises: the reference does not care (literals.rs:55)
+                else rc = huf_decode_stream(src, start, start + w.stream_size[stream], src_len, S.u.lut, S.maxbits, lit_pool + w.lit_buf + ooff, expect);
+            }
+        }
+    }
+    const uint32_t q0 = lane & ~3u;
+    const bool blk_inexact = __shfl_sync(HUF_MASK, (int)inexact, q0) || __shfl_sync(HUF_MASK, (int)inexact, q0 + 1) || __shfl_sync(HUF_MASK, (int)inexact, q0 + 2) ||
+                             __shfl_sync(HUF_MASK, (int)inexact, q0 + 3);
+    if (blk_inexact && active && stream == 0 && !S.status) {
+        // == LiteralsSection::decode (literals.rs:70-81): count, find room (the block's slot, else the overflow region), decode
+        ZsbBlockWork &w = work[bi];
+        uint32_t n1 = 0, n2 = 0;
+        rc = huf_decode_block_ref(src, src_len, w.lit_src, w.stream_size, S.u.lut, S.maxbits, nullptr, 0, n1);
+        if (!rc && n1 > ZSB_BLOCK_MAX) rc = ZSB_E_BLOCK_TOO_LARGE;
+        if (!rc) {
+            uint64_t at = w.lit_buf;
+            if (n1 > ((w.lit_regen + 15u) & ~15u)) {
+                const uint64_t need = ((uint64_t)n1 + 15) & ~15ull;
+                const uint64_t o = atomicAdd((unsigned long long *)&cnt->lit_over, (unsigned long long)need);
+                if (o + need > over_cap) rc = ZSB_E_CORRUPT;      // more corrupted blocks than the overflow region holds
+                else at = lit_cap + o;
+            }
+            if (!rc) rc = huf_decode_block_ref(src, src_len, w.lit_src, w.stream_size, S.u.lut, S.maxbits, lit_pool + at, n1, n2);
+            if (!rc) { w.lit_buf = at; w.lit_regen = n1; }
         }
     }
     // first failing stream of the block decides its status
-    const int r1 = __shfl_sync(HUF_MASK, rc, (lane & ~3u) + 1), r2 = __shfl_sync(HUF_MASK, rc, (lane & ~3u) + 2), r3 = __shfl_sync(HUF_MASK, rc, (lane & ~3u) + 3);
+    const int r1 = __shfl_sync(HUF_MASK, rc, q0 + 1), r2 = __shfl_sync(HUF_MASK, rc, q0 + 2), r3 = __shfl_sync(HUF_MASK, rc, q0 + 3);
     if (active && stream == 0) {
         int st = rc ? rc : r1 ? r1 : r2 ? r2 : r3;
         if (st) work[bi].lit_status = st;
@@ -697,7 +725,9 @@ __global__ void __launch_bounds__(1024) k_plan2(const zsb_frame *__restrict__ fr
         if (st == ZSB_OK) {
             if (frames[f].kind == 1) len = (flags & ZSB_PRINT_SKIPPABLE) ? blocks[frames[f].first_block].size : 0;   // main.rs:45-49
             else {
-                st = plan_frame(frames[f], blocks, work, len);
+                uint32_t ea = 0, eb = 0;
+                st = plan_frame(frames[f], blocks, work, len, ea, eb);
+                if (st != ZSB_OK) { fout[f].err_a = ea; fout[f].err_b = eb; }
                 if (st == ZSB_OK && frames[f].has_content_size && len != frames[f].content_size && !(flags & ZSB_REFERENCE_QUIRKS)) st = ZSB_E_CONTENT_SIZE;
                 if (st != ZSB_OK) len = 0;
             }
@@ -1341,6 +1371,7 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 7) k_exec2(const uint8_t *__re
                             *reinterpret_cast<uint4 *>(gblk + p) = *reinterpret_cast<const uint4 *>(ring + ((g0 + (uint32_t)p) & EX2_MASK));
                     } else ex2_flush(ring, gblk, g0, flushed, hi, lane);
                     flushed = hi;
+                    __syncwarp();               // the next batch may read these bytes back from HBM through other lanes
                 }
                 if (__any_sync(FULL, err != 0)) { err = ZSB_E_IMPOSSIBLE_VALUE; break; }
             }
@@ -1579,8 +1610,8 @@ void zsbk_plan1(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb
     k_plan1<<<nf > 1024 ? (nf + 1023) / 1024 : 1, 1024, 0, st>>>(frames, nf, blocks, nb, work, fout, huf_list, seq_list, cnt, lit_cap, seq_cap, flags);
 }
 void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *huf_list,
-              const ZsbCounters *cnt, uint8_t *lit_pool, uint32_t flags) {
-    if (ncomp) k_huf<<<(ncomp + HUF_SLOTS - 1) / HUF_SLOTS, HUF_THREADS, 0, st>>>(src, src_len, work, huf_list, cnt, lit_pool, flags);
+              ZsbCounters *cnt, uint8_t *lit_pool, uint64_t lit_cap, uint64_t over_cap, uint32_t flags) {
+    if (ncomp) k_huf<<<(ncomp + HUF_SLOTS - 1) / HUF_SLOTS, HUF_THREADS, 0, st>>>(src, src_len, work, huf_list, cnt, lit_pool, lit_cap, over_cap, flags);
 }
 void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
               uint64_t *seq_pool, uint32_t *slow_list, bool shared_device, uint32_t chains_hint) {

@@ -13,6 +13,8 @@ struct ZsbCounters {
     uint32_t n_slow;      // blocks the fast sequence path handed to the careful decoder
     uint32_t ticket1, ticket2;   // k_plan1 / k_plan2: CTAs done with the per-frame part (the last one runs the scans)
     uint32_t zero, pad;          // always 0: k_seq orders its look-ahead loads behind its cell loads with a data dependency on it
+    uint64_t lit_over;           // ZSB_REFERENCE_QUIRKS: bytes handed out of the overflow region behind the literal scratch (blocks whose streams
+                                 // regenerate more literals than Regenerated_Size announced)
 };
 
 cudaError_t zsbk_init();
@@ -20,7 +22,7 @@ void zsbk_parse(cudaStream_t st, const uint8_t *src, const zsb_block *blocks, Zs
 void zsbk_plan1(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb_block *blocks, uint32_t nb, ZsbBlockWork *work,
                 ZsbFrameOut *fout, uint32_t *huf_list, uint32_t *seq_list, ZsbCounters *cnt, uint64_t lit_cap, uint64_t seq_cap, uint32_t flags);
 void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *huf_list,
-              const ZsbCounters *cnt, uint8_t *lit_pool, uint32_t flags);
+              ZsbCounters *cnt, uint8_t *lit_pool, uint64_t lit_cap, uint64_t over_cap, uint32_t flags);
 void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
               uint64_t *seq_pool, uint32_t *slow_list, bool shared_device, uint32_t chains_hint);
 void zsbk_seq_slow(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *slow_list,

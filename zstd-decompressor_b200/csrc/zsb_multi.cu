@@ -177,6 +177,7 @@ extern "C" int zsb_multi_scan_decode(zsb_multi *m, const uint8_t *src, size_t n,
                     for (size_t i = 0; i < cnt; i++) {
                         zsb_result &R = res[f0 + i];
                         R.dst_off = off[f0] + o[i]; R.dst_len = l[i]; R.status = s[i]; R.xxh32 = x[i]; R.checksum_ok = k[i];
+
                         if (s[i] != ZSB_OK || R.dst_off != off[f0 + i]) J.exact = false;      // a frame failed or was not as long as declared: the slabs no longer abut
                     }
                     if (J.total != slab) J.exact = false;
@@ -199,7 +200,9 @@ extern "C" int zsb_multi_scan_decode(zsb_multi *m, const uint8_t *src, size_t n,
         std::vector<uint64_t> o(nf + 1), l(nf + 1); std::vector<int32_t> s(nf + 1); std::vector<uint32_t> x(nf + 1); std::vector<uint8_t> k(nf + 1);
         rc = zsb_decode(m->ctx[0], src, n, frames, nf, blocks, nb, dst, dst_cap, o.data(), l.data(), s.data(), x.data(), k.data(), &out_total, flags);
         if (rc != ZSB_OK) { m->last_err = zsb_last_cuda_error(m->ctx[0]); free(res); zsb_free(frames); zsb_free(blocks); return rc; }
-        for (size_t f = 0; f < nf; f++) { res[f].dst_off = o[f]; res[f].dst_len = l[f]; res[f].status = s[f]; res[f].xxh32 = x[f]; res[f].checksum_ok = k[f]; }
+        std::vector<uint32_t> ea(nf + 1, 0), eb(nf + 1, 0);
+        zsb_decode_errors(m->ctx[0], ea.data(), eb.data(), nf);
+        for (size_t f = 0; f < nf; f++) { res[f].dst_off = o[f]; res[f].dst_len = l[f]; res[f].status = s[f]; res[f].xxh32 = x[f]; res[f].checksum_ok = k[f]; res[f].err_a = ea[f]; res[f].err_b = eb[f]; }
     }
     *frames_out = frames; *n_frames = nf; *blocks_out = blocks; *n_blocks = nb; *results_out = res;
     if (dst_total) *dst_total = out_total;

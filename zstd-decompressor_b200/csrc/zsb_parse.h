@@ -19,7 +19,7 @@
 ZSB_HDN void parse_block(const uint8_t *src, const zsb_block &blk, ZsbBlockWork &w, uint32_t flags) {
     const bool quirks = (flags & ZSB_REFERENCE_QUIRKS) != 0;
     w.status = ZSB_OK; w.lit_status = ZSB_OK; w.err_a = w.err_b = 0; w.seq_rem0 = 0;
-    w.nseq = 0; w.lit_type = ZSB_LT_NONE; w.lit_regen = 0; w.n_streams = 0; w.raw_modes = 0;
+    w.nseq = 0; w.lit_type = ZSB_LT_NONE; w.lit_regen = 0; w.n_streams = 0; w.raw_modes = 0; w.parse_stage = 0; w.lit_inexact = 0;
     w.lit_used = 0; w.out_off = 0; w.lit_buf = 0; w.seq_buf = 0;
     w.mode[0] = w.mode[1] = w.mode[2] = ZSB_M_REPEAT;
     w.rep_out[0] = ZSB_OFF_SYM | (0u << 25); w.rep_out[1] = ZSB_OFF_SYM | (1u << 25); w.rep_out[2] = ZSB_OFF_SYM | (2u << 25);
@@ -78,18 +78,28 @@ ZSB_HDN void parse_block(const uint8_t *src, const zsb_block &blk, ZsbBlockWork 
             const uint32_t s1 = src[q] | (src[q + 1] << 8), s2 = src[q + 2] | (src[q + 3] << 8), s3 = src[q + 4] | (src[q + 5] << 8);
             if ((uint64_t)s1 + s2 + s3 > total - 6) ZSB_FAIL(w, ZSB_E_STREAMS_TOO_BIG, 0, 0);   // literals.rs:115-117
             const uint64_t s4 = total - 6 - s1 - s2 - s3;
-            w.stream_size[0] = s1; w.stream_size[1] = s2; w.stream_size[2] = s3; w.stream_size[3] = (uint32_t)s4;
-            if (s1 == 0 || s2 == 0 || s3 == 0 || s4 == 0) ZSB_FAIL(w, quirks && total == 6 ? ZSB_E_EMPTY_SLICE : ZSB_E_CORRUPT, 0, 0);
-            if (3 * ((regen + 3) / 4) > regen) ZSB_FAIL(w, ZSB_E_CORRUPT, 0, 0);   // streams 1-3 regenerate (regen+3)/4 symbols each
+            if (quirks) {
+                // the reference keeps `s4 as u16` (literals.rs:119-120), stops decoding at the first zero entry (:71-73) and never looks at
+                // Regenerated_Size (:55): anything but the regular shape is decoded its way (huf_decode_block_ref)
+                if (total == 6) ZSB_FAIL(w, ZSB_E_EMPTY_SLICE, 0, 0);                              // slice(0) literals.rs:130
+                w.stream_size[0] = s1; w.stream_size[1] = s2; w.stream_size[2] = s3; w.stream_size[3] = (uint32_t)(s4 & 0xFFFFu);
+                if (s1 == 0 || s2 == 0 || s3 == 0 || s4 == 0 || s4 > 0xFFFFu || 3 * ((regen + 3) / 4) > regen) w.lit_inexact = 1;
+            } else {
+                w.stream_size[0] = s1; w.stream_size[1] = s2; w.stream_size[2] = s3; w.stream_size[3] = (uint32_t)s4;
+                if (s1 == 0 || s2 == 0 || s3 == 0 || s4 == 0) ZSB_FAIL(w, ZSB_E_CORRUPT, 0, 0);
+                if (3 * ((regen + 3) / 4) > regen) ZSB_FAIL(w, ZSB_E_CORRUPT, 0, 0);   // streams 1-3 regenerate (regen+3)/4 symbols each
+            }
             w.lit_src = q + 6;
         } else {
             if (total == 0) ZSB_FAIL(w, quirks ? ZSB_E_EMPTY_SLICE : ZSB_E_CORRUPT, 0, 0);
-            w.stream_size[0] = (uint32_t)total; w.stream_size[1] = w.stream_size[2] = w.stream_size[3] = 0;
+            w.stream_size[0] = quirks ? (uint32_t)(total & 0xFFFFu) : (uint32_t)total; w.stream_size[1] = w.stream_size[2] = w.stream_size[3] = 0;   // `len as u16` literals.rs:122
+            if (quirks && total > 0xFFFFu) w.lit_inexact = 1;
             w.lit_src = q;
         }
         p = lend;
     }
     // ---- sequences section header (sequences.rs:52-143)
+    w.parse_stage = 1;
     if (p >= end) ZSB_FAIL(w, ZSB_E_NOT_ENOUGH_BYTES, 1, 0);
     uint32_t b0 = src[p++], nseq;
     if (b0 < 128) nseq = b0;
@@ -111,6 +121,7 @@ ZSB_HDN void parse_block(const uint8_t *src, const zsb_block &blk, ZsbBlockWork 
     const uint32_t mb = src[p++];
     if (mb & 3) ZSB_FAIL(w, ZSB_E_SEQ_RESERVED, 0, 0);
     w.raw_modes = (uint8_t)mb;
+    w.parse_stage = 2;
     for (int t = 0; t < 3; t++) {                                      // LL, OF, ML in this order (sequences.rs:116-141)
         const uint32_t m = (mb >> (6 - 2 * t)) & 3;
         w.mode[t] = (uint8_t)m;
@@ -126,10 +137,12 @@ ZSB_HDN void parse_block(const uint8_t *src, const zsb_block &blk, ZsbBlockWork 
             if (rc) ZSB_FAIL(w, rc, al, 0);
             w.tbl_desc[t] = p; p += fwd_bytes_read(f);
         }
+        w.parse_stage = (uint8_t)(3 + t);
     }
     if (p >= end) ZSB_FAIL(w, quirks ? ZSB_E_EMPTY_SLICE : ZSB_E_CORRUPT, 0, 0);   // empty bitstream: slice(0) sequences.rs:72
     w.bs_off = p; w.bs_len = (uint32_t)(end - p);
-    if (src[end - 1] == 0) ZSB_FAIL(w, ZSB_E_NULL_BYTE, 0, 0);        // BackwardBitParser::new parsing.rs:204
+    // (a bitstream whose last byte is 0 is NullByte, but only when the block is DECODED -- BackwardBitParser::new runs in
+    //  Sequences::decode, sequences.rs:211, behind the literals of the block: the sequence stage reports it, not this pass)
 }
 
 // Carries the Huffman table and the three table modes from block to block of one frame.
@@ -179,14 +192,14 @@ ZSB_HDN int chain_frame(const zsb_frame &fr, const zsb_block *blocks, ZsbBlockWo
 
 // Output placement and repeat-offset history of one frame, after the entropy stage.
 // Returns the frame status; total = regenerated size of the frame.
-ZSB_HDN int plan_frame(const zsb_frame &fr, const zsb_block *blocks, ZsbBlockWork *work, uint64_t &total) {
+ZSB_HDN int plan_frame(const zsb_frame &fr, const zsb_block *blocks, ZsbBlockWork *work, uint64_t &total, uint32_t &err_a, uint32_t &err_b) {
     uint32_t rep[3] = {1, 4, 8};                                       // decoding_context.rs:40
     uint64_t pos = 0;
     for (uint32_t k = 0; k < fr.n_blocks; k++) {
         const uint32_t bi = fr.first_block + k;
         ZsbBlockWork &w = work[bi];
         if (w.lit_status != ZSB_OK) { total = pos; return w.lit_status; }       // Block::decode: literals first (block.rs:83-85)
-        if (w.status != ZSB_OK) { total = pos; return w.status; }
+        if (w.status != ZSB_OK) { total = pos; err_a = w.err_a; err_b = w.err_b; return w.status; }
         w.out_off = pos;
         w.rep_in[0] = rep[0]; w.rep_in[1] = rep[1]; w.rep_in[2] = rep[2];
         if (blocks[bi].type == ZSB_BT_COMPRESSED && w.nseq) {

@@ -7,6 +7,8 @@
 #include <string.h>
 #include <vector>
 #include "zsb_common.h"
+#include "zsb_parse.h"
+#include "zsb_huf.h"
 #include "zsb_scan.h"
 
 #define MAGIC_ZSTD 0xFD2FB528u
@@ -55,6 +57,39 @@ bool parse_header(Cursor &c, zsb_frame &f, ScanErr &e) {
     return true;
 }
 }  // namespace
+
+// ZSB_REFERENCE_QUIRKS only.  The reference parses a block's sections -- literals header, Huffman tree, sequences header, FSE tables --
+// inside Block::parse, i.e. during the walk (ZStandard::parse is eager, frame.rs:210-223), while this library leaves them to the GPU.
+// The difference shows in ONE place: when the walk itself fails (a truncated block, a missing checksum ...), a section error of an
+// EARLIER block is what the reference has already returned.  So on a failed walk the blocks read so far are parsed here, on the host,
+// in the reference's order (LiteralsSection::parse literals.rs:88-133 incl. HuffmanDecoder::parse, then Sequences::parse
+// sequences.rs:52-143 incl. FseTable::parse per table); a well-formed container never pays for it.
+static int eager_sections(const uint8_t *src, size_t n, const zsb_block &blk, uint32_t flags, uint64_t &ea, uint64_t &eb) {
+    if (blk.type != ZSB_BT_COMPRESSED) return ZSB_OK;
+    ZsbBlockWork w;
+    parse_block(src, blk, w, flags);
+    ea = w.err_a; eb = w.err_b;
+    if (w.status != ZSB_OK && w.parse_stage == 0) return w.status >= ZSB_E_CORRUPT ? ZSB_OK : w.status;      // failed inside the literals section
+    if (w.lit_type == ZSB_LT_COMPRESSED) {                                           // HuffmanDecoder::parse huffman.rs:80-130, from_weights :177-203
+        static thread_local uint8_t weights[260]; static thread_local uint32_t ftbl[512]; static thread_local uint16_t lut[1 << ZSB_HUF_MAX_BITS];
+        int16_t cnt[ZSB_HUF_WEIGHT_SYMS]; uint32_t rank[16]; int nw = 0, mb = 0; uint32_t dl = 0;
+        int rc = huf_read_weights(src + w.huf_desc, w.huf_desc_end - w.huf_desc, weights, 1, nw, dl, ftbl, 1, cnt, 1, n - w.huf_desc, true);
+        if (!rc) rc = huf_build_lut(weights, 1, nw, lut, rank, 1, mb, nullptr, true);
+        if (rc && rc < ZSB_E_CORRUPT) { ea = eb = 0; return rc; }      // (codes >= 100 are this library's own limits, e.g. a tree deeper than 11: the reference parses on)
+    }
+    // FseTable::parse = parse_fse_table + from_distribution, table by table: a table read before the point of failure is also built
+    const int tables_read = w.parse_stage >= 3 ? w.parse_stage - 2 : 0;
+    for (int t = 0; t < tables_read; t++) {
+        if (w.mode[t] != ZSB_M_FSE) continue;
+        static thread_local int16_t cnt[256]; static thread_local uint32_t tbl[512];
+        FwdBits f; fwd_init(f, src + w.tbl_desc[t], w.tbl_end - w.tbl_desc[t]);
+        int al = 0, nsym = 0;
+        int rc = fse_read_ncount(f, cnt, 1, 256, al, nsym);
+        if (!rc) rc = fse_build_table(cnt, 1, nsym, al, tbl, 1, 3);
+        if (rc && rc < ZSB_E_CORRUPT) { ea = eb = 0; return rc; }
+    }
+    return (w.status == ZSB_E_NULL_BYTE || w.status >= ZSB_E_CORRUPT) ? ZSB_OK : w.status;      // (the end mark of the bitstream is looked at when the block is decoded, parsing.rs:204)
+}
 
 // One frame (FrameIterator::next frame.rs:94-99): appends its descriptor (and its blocks) and returns true, or appends the
 // failed frame (no blocks, status = the error) and returns false; false with nothing appended when the input is exhausted.
@@ -114,6 +149,13 @@ bool ZsbScanner::next() {
         } else { e.code = ZSB_E_UNRECOGNIZED_MAGIC; e.a = magic; e.b = 0; }
     } while (0);
     if (!ok) {
+        if (quirks && f.kind == 0 && blocks.size() > f.first_block) {
+            for (size_t i = f.first_block; i < blocks.size(); i++) {
+                uint64_t a = 0, b = 0;
+                const int rc = eager_sections(src, n, blocks[i], flags, a, b);
+                if (rc != ZSB_OK) { e.code = rc; e.a = a; e.b = b; break; }
+            }
+        }
         blocks.resize(f.first_block);                            // a failed frame contributes no blocks
         f.n_blocks = 0; f.status = e.code; f.src_len = n - f.src_off;
         frames.push_back(f);
