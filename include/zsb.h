@@ -105,6 +105,29 @@ int zsb_scan(const uint8_t *src, size_t n, uint32_t flags, uint64_t max_window,
              uint64_t *err_a, uint64_t *err_b);
 void zsb_free(void *p);
 
+/* == what Block::parse keeps of a compressed block besides its extent (block.rs:63-69): LiteralsSection (literals.rs:19-35: type, regenerated
+ *    size, jump table, Huffman tree, data) and Sequences (sequences.rs:41-48: number of sequences, the three SymbolCompressionModes with
+ *    their FSE tables, bitstream), parsed on the HOST from the block's bytes -- for `--info`, which prints the parsed frame and decodes
+ *    nothing (src/main.rs:35-40), and for callers that inspect a block.  The tables the decode uses are built on the GPU.
+ *    Returns the first parse error in the reference's order (status, err_a, err_b also in *out). */
+typedef struct zsb_fse_state { uint16_t output, baseline, bits_to_read; } zsb_fse_state;      /* fse.rs:72-76 */
+typedef struct zsb_sections {
+    int32_t  status; uint32_t err_a, err_b;
+    uint8_t  lit_type;                 /* 0 RawLiteralsBlock, 1 RLELiteralsBlock, 2 CompressedLiteralsBlock with a tree, 3 without (treeless) */
+    uint8_t  rle_byte, max_bits, pad0;
+    uint32_t regenerated_size;
+    uint16_t jump_table[4];
+    uint64_t lit_data_off, lit_data_len;      /* raw: the literals; compressed: `data`, the streams behind tree and jump table */
+    uint8_t  code_len[256];                   /* Huffman code length per symbol, 0 = not in the tree */
+    uint16_t code[256];                       /* its code, read MSB first (left = 0) */
+    uint32_t number_of_sequences;
+    uint8_t  mode[3], rle_symbol[3];          /* LL, OF, ML: 0 PredefinedMode, 1 RLEMode(symbol), 2 FseCompressedMode(table), 3 RepeatMode */
+    uint8_t  al[3], pad1[3];
+    zsb_fse_state table[3][512];              /* 1 << al[t] states when mode[t] == 2 */
+    uint64_t bitstream_off, bitstream_len;
+} zsb_sections;
+int zsb_block_sections(const uint8_t *src, size_t n, const zsb_block *block, uint32_t flags, zsb_sections *out);
+
 /* ---- sharding by frame over the GPUs of one box (no reference counterpart: the crate is single threaded; frames are
  *      independent because ZStandard::decode creates a fresh DecodingContext, frame.rs:233).  Host only.
  * zsb_shard_plan: first[0..n_shards] = contiguous frame ranges [first[s], first[s+1]) balanced on decompressed bytes

@@ -49,6 +49,42 @@ def test_info_zstandard_frame_header_blocks_checksum(cli):
     assert z.endswith("        ],\n        checksum: Some(\n            0x9f5d2e9e,\n        ),\n    },\n)\n")
 
 
+def test_info_compressed_blocks_huffman_tree_and_fse_tables(cli, tmp_path):
+    """main.rs:35-40 prints the PARSED frame: the Huffman tree through the reference's own Debug impl (huffman.rs:60-77) and the FSE
+    tables state by state (fse.rs:72-89).  Expected text: tests/rust_debug.py (container parsed in Python, tree and tables from the CPU
+    oracle), byte for byte; romeo.txt.zst also against the committed dump tests/golden/romeo_info.txt (written by the same module)."""
+    import rust_debug as D
+    import zasm
+    import gen_corpus as G
+    r = run(cli, "--info", os.path.join(FIX, "romeo.txt.zst"))
+    assert r.returncode == 0
+    assert r.stdout.decode() == open(os.path.join(corpora.ROOT, "tests", "golden", "romeo_info.txt")).read() == D.dump(corpora.fixture("romeo.txt.zst"))
+    cases = [zasm.frame_rle_modes(1)[0], zasm.frame_huffman_direct(2)[0], zasm.frame_huffman_direct(3, n=700, streams=1)[0], zasm.frame_treeless(3)[0],
+             G.compress(G.moby_text()[:200]), G.compress(G.moby_text()[200000:230000], level=19), corpora.fixture("welcome.zst") + corpora.fixture("romeo3.txt.zst")]
+    for i, d in enumerate(cases):
+        p = tmp_path / f"c{i}.zst"; p.write_bytes(d)
+        r = run(cli, "-i", str(p))
+        assert r.returncode == 0 and r.stdout.decode() == D.dump(d), i
+
+
+def test_info_section_error_prints_nothing_of_that_frame(cli, tmp_path):
+    """frame.rs:210-223: the sections are parsed with the frame; a bad modes byte (sequences::Error::ReservedSet) fails the second frame"""
+    d = bytearray(corpora.fixture("romeo.txt.zst"))
+    import zstd_inspect as I
+    blk = I.inspect(bytes(d))[0].blocks[0]
+    # the modes byte follows the literals section (header 5 bytes for size format 3? use the inspector's numbers) and the 1-byte sequence count
+    hdr = 3 if ((d[blk.src_off] >> 2) & 3) <= 1 else 4 if ((d[blk.src_off] >> 2) & 3) == 2 else 5
+    pos = blk.src_off + hdr + blk.lit_csize + 1
+    d[pos] |= 1
+    p = tmp_path / "two.zst"; p.write_bytes(corpora.fixture("welcome.zst") + bytes(d))
+    r = run(cli, "--info", str(p))
+    want, _, oerr = R.decode_frames(p.read_bytes(), quirks=True)
+    assert oerr is not None and oerr.code == 30
+    assert r.returncode == 1 and b"ReservedSet" in r.stderr
+    import rust_debug as D
+    assert r.stdout.decode() == D.dump(corpora.fixture("welcome.zst"))
+
+
 def test_info_reports_bad_magic_after_the_good_frames(cli, tmp_path):
     p = tmp_path / "bad.zst"
     p.write_bytes(corpora.fixture("skippables.zst") + b"\x01\x02\x03\x04\x05")

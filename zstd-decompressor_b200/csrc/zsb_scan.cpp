@@ -91,6 +91,85 @@ static int eager_sections(const uint8_t *src, size_t n, const zsb_block &blk, ui
     return (w.status == ZSB_E_NULL_BYTE || w.status >= ZSB_E_CORRUPT) ? ZSB_OK : w.status;      // (the end mark of the bitstream is looked at when the block is decoded, parsing.rs:204)
 }
 
+// FseTable::from_distribution (fse.rs:110-202) with full-width fields, for zsb_block_sections (the decode's cells keep 6 bits of the symbol)
+static int fse_states(const int16_t *cnt, int nsym, int al, zsb_fse_state *st) {
+    const int N = 1 << al;
+    std::vector<int> sym(N, -1), next(nsym > 0 ? nsym : 1, 0);
+    int high = N - 1;
+    for (int s = 0; s < nsym; s++) if (cnt[s] == -1) { if (high < 0) return ZSB_E_CORRUPTED_TABLE; sym[high--] = s; next[s] = 1; }
+    const int step = (N >> 1) + (N >> 3) + 3, mask = N - 1;
+    int pos = 0, placed = 0;
+    for (int s = 0; s < nsym; s++) {
+        if (cnt[s] <= 0) continue;
+        next[s] = cnt[s];
+        for (int k = 0; k < cnt[s]; k++) {
+            if (placed >= high + 1) return ZSB_E_CORRUPTED_TABLE;
+            sym[pos] = s; placed++;
+            pos = (pos + step) & mask;
+            while (pos > high) pos = (pos + step) & mask;
+        }
+    }
+    if (placed != high + 1) return ZSB_E_CORRUPTED_TABLE;
+    for (int i = 0; i < N; i++) {
+        const int s = sym[i];
+        const uint32_t nx = (uint32_t)next[s]++;
+        const uint32_t nb = (uint32_t)(al - zsb_flog2(nx));
+        st[i].output = (uint16_t)s; st[i].bits_to_read = (uint16_t)nb; st[i].baseline = (uint16_t)((nx << nb) - (uint32_t)N);
+    }
+    return ZSB_OK;
+}
+
+extern "C" int zsb_block_sections(const uint8_t *src, size_t n, const zsb_block *blk, uint32_t flags, zsb_sections *out) {
+    if (!src || !blk || !out || blk->type != ZSB_BT_COMPRESSED || blk->src_off + blk->size > n) return ZSB_E_ARG;
+    memset(out, 0, sizeof *out);
+    auto fail = [&](int rc, uint64_t a, uint64_t b) { out->status = rc; out->err_a = (uint32_t)a; out->err_b = (uint32_t)b; return rc; };
+    ZsbBlockWork w;
+    parse_block(src, *blk, w, flags);
+    if (w.status != ZSB_OK && w.parse_stage == 0) return fail(w.status, w.err_a, w.err_b);
+    out->lit_type = w.lit_type; out->regenerated_size = w.lit_regen;
+    if (w.lit_type == ZSB_LT_RAW) { out->lit_data_off = w.lit_src; out->lit_data_len = w.lit_regen; }
+    else if (w.lit_type == ZSB_LT_RLE) out->rle_byte = src[w.lit_src];
+    else {
+        for (int k = 0; k < 4; k++) out->jump_table[k] = (uint16_t)w.stream_size[k];
+        const uint64_t lend = w.lit_type == ZSB_LT_COMPRESSED ? w.huf_desc_end : 0;
+        if (w.lit_type == ZSB_LT_COMPRESSED) {
+            static thread_local uint8_t weights[260]; static thread_local uint32_t ftbl[512]; static thread_local uint16_t lut[1 << ZSB_HUF_MAX_BITS];
+            int16_t cnt[ZSB_HUF_WEIGHT_SYMS]; uint32_t rank[16]; int nw = 0, mb = 0; uint32_t dl = 0;
+            int rc = huf_read_weights(src + w.huf_desc, w.huf_desc_end - w.huf_desc, weights, 1, nw, dl, ftbl, 1, cnt, 1, n - w.huf_desc, (flags & ZSB_REFERENCE_QUIRKS) != 0);
+            if (!rc) rc = huf_build_lut(weights, 1, nw, lut, rank, 1, mb, nullptr, (flags & ZSB_REFERENCE_QUIRKS) != 0);
+            if (rc) return fail(rc, 0, 0);
+            out->max_bits = (uint8_t)mb;
+            for (uint32_t i = 0; i < (1u << mb); i++) {
+                if (lut[i] == ZSB_HUF_ABSENT) continue;
+                const uint32_t sy = lut[i] & 0xFFu, nb = lut[i] >> 8;
+                if (!out->code_len[sy]) { out->code_len[sy] = (uint8_t)nb; out->code[sy] = (uint16_t)(i >> (mb - nb)); }
+            }
+            out->lit_data_off = w.lit_src; out->lit_data_len = lend - w.lit_src;
+        } else {
+            // treeless: `data` runs to the end of the compressed literals (Compressed_Size bytes from the end of the section header)
+            uint64_t total = 0; for (int k = 0; k < 4; k++) total += w.stream_size[k];
+            out->lit_data_off = w.lit_src; out->lit_data_len = total;
+        }
+    }
+    if (w.status != ZSB_OK && w.parse_stage < 3) return fail(w.status, w.err_a, w.err_b);
+    out->number_of_sequences = w.nseq;
+    for (int t = 0; t < 3; t++) { out->mode[t] = w.nseq ? (uint8_t)((w.raw_modes >> (6 - 2 * t)) & 3) : (uint8_t)ZSB_M_REPEAT; out->rle_symbol[t] = w.rle_sym[t]; }
+    const int tables_read = w.nseq == 0 ? 0 : w.parse_stage >= 3 ? w.parse_stage - 2 : 0;
+    for (int t = 0; t < tables_read; t++) {
+        if (out->mode[t] != ZSB_M_FSE) continue;
+        static thread_local int16_t cnt[256];
+        FwdBits f; fwd_init(f, src + w.tbl_desc[t], w.tbl_end - w.tbl_desc[t]);
+        int al = 0, nsym = 0;
+        int rc = fse_read_ncount(f, cnt, 1, 256, al, nsym);
+        if (!rc) rc = fse_states(cnt, nsym, al, out->table[t]);
+        if (rc) return fail(rc, 0, 0);
+        out->al[t] = (uint8_t)al;
+    }
+    if (w.status != ZSB_OK) return fail(w.status, w.err_a, w.err_b);
+    if (w.nseq) { out->bitstream_off = w.bs_off; out->bitstream_len = w.bs_len; }
+    return ZSB_OK;
+}
+
 // One frame (FrameIterator::next frame.rs:94-99): appends its descriptor (and its blocks) and returns true, or appends the
 // failed frame (no blocks, status = the error) and returns false; false with nothing appended when the input is exhausted.
 bool ZsbScanner::next() {
