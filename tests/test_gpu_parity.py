@@ -277,11 +277,19 @@ def test_frame_longer_than_its_content_size_decodes_under_quirks(dec):
 def test_per_frame_error_payloads(dec):                 # tests/block.rs:72-78: NotEnoughBytes {requested, available} of a block's sections
     d = bytearray(corpora.fixture("romeo.txt.zst"))
     # literals section header of the only block: compressed size field made larger than the block
-    d[13] |= 0xF0; d[14] = 0xFF
+    d[12] |= 0xF0
     out, sc, r = dec.decode(bytes(d), Q | VER)
     want, _, oerr = R.decode_frames(bytes(d), quirks=True)
-    assert oerr is not None and r.status[0] == oerr.code == 1
+    assert oerr is not None and r.status[0] == oerr.code == 1 and (oerr.a, oerr.b) == (1017, 542)
     assert r.errors(dec.ctx)[0] == (oerr.a, oerr.b)
+    src, dst = Z.lib().zsb_host_alloc(len(d)), Z.lib().zsb_host_alloc(4096)
+    try:
+        import ctypes as C
+        C.memmove(src, bytes(d), len(d))
+        sd = Z.ScanDecode(dec.ctx, (src, len(d)), (dst, 4096), Q | VER)
+        assert sd.results[0].status == 1 and (sd.results[0].err_a, sd.results[0].err_b) == (1017, 542)
+    finally:
+        Z.lib().zsb_host_free(src); Z.lib().zsb_host_free(dst)
 
 
 def test_gpu_matches_cpu_build_of_device_code(dec):

@@ -77,11 +77,12 @@ ZSB_HDN int huf_read_weights(const uint8_t *desc, uint64_t limit, uint8_t *weigh
 ZSB_HDN int huf_build_lut(uint8_t *weights, int ws, int nw, uint16_t *lut, uint32_t *rank, int rs, int &maxbits, uint8_t *lens_out, bool quirks = false,
                           bool *incomplete = nullptr) {
     if (incomplete) *incomplete = false;
-    uint32_t sum = 0;
+    uint32_t sum = 0, wmax = 0;
     for (int i = 0; i < nw; i++) {
         uint32_t w = weights[i * ws];
         if (w > ZSB_HUF_MAX_BITS + 1) return ZSB_E_CORRUPT;
         if (w) sum += 1u << (w - 1);
+        wmax = w > wmax ? w : wmax;
     }
     if (sum == 0) return ZSB_E_CORRUPT;                                   // reference: discrete_log2(0) panics (huffman.rs:184)
     if (nw >= 256) return ZSB_E_CORRUPT;
@@ -94,12 +95,10 @@ ZSB_HDN int huf_build_lut(uint8_t *weights, int ws, int nw, uint16_t *lut, uint3
         const uint32_t r8 = ((1u << pu) - sum) & 0xFFu;                  // `as u8` huffman.rs:190
         bool panics = r8 == 0;                                            // discrete_log2(0)
         const uint32_t lw = panics ? 0u : (uint32_t)zsb_flog2(r8) + 1u;
-        for (int i = 0; i < nw && !panics; i++) panics = weights[i * ws] > pu + 1;        // u8 underflow of the width
-        if (!panics && lw > pu + 1) panics = true;
+        if (wmax > pu + 1 || lw > pu + 1) panics = true;                 // u8 underflow of a width
         if (!panics) {
             if (pu > ZSB_HUF_MAX_BITS || pu == 0) return ZSB_E_CORRUPT;   // deeper than this library's table / a root that is a symbol (the reference never returns)
-            for (int i = 0; i < nw; i++) if (weights[i * ws] == pu + 1) return ZSB_E_CORRUPT;   // width 0: the same
-            if (lw == pu + 1) return ZSB_E_CORRUPT;
+            if (wmax == pu + 1 || lw == pu + 1) return ZSB_E_CORRUPT;     // width 0: the same
             mb = (int)pu; lastw = lw; loose = true;
         }
     }

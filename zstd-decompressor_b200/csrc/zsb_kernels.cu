@@ -140,6 +140,26 @@ struct HufSlot {
     int status;
     int incomplete;     // ZSB_REFERENCE_QUIRKS: the reference's tree for these weights is not a complete code (huf_build_lut)
 };
+// (rare: out of line, so that the stream decode keeps its registers)
+__device__ __noinline__ int huf_block_ref_device(const uint8_t *src, uint64_t src_len, ZsbBlockWork &w, const uint16_t *lut, int maxbits, ZsbCounters *cnt, uint8_t *lit_pool,
+                                                 uint64_t lit_cap, uint64_t over_cap) {
+    // == LiteralsSection::decode (literals.rs:70-81): count, find room (the block's slot, else the overflow region), decode
+    uint32_t n1 = 0, n2 = 0;
+    int rc = huf_decode_block_ref(src, src_len, w.lit_src, w.stream_size, lut, maxbits, nullptr, 0, n1);
+    if (!rc && n1 > ZSB_BLOCK_MAX) rc = ZSB_E_BLOCK_TOO_LARGE;
+    if (rc) return rc;
+    uint64_t at = w.lit_buf;
+    if (n1 > ((w.lit_regen + 15u) & ~15u)) {
+        const uint64_t need = ((uint64_t)n1 + 15) & ~15ull;
+        const uint64_t o = atomicAdd((unsigned long long *)&cnt->lit_over, (unsigned long long)need);
+        if (o + need > over_cap) return ZSB_E_CORRUPT;      // more corrupted blocks than the overflow region holds
+        at = lit_cap + o;
+    }
+    rc = huf_decode_block_ref(src, src_len, w.lit_src, w.stream_size, lut, maxbits, lit_pool + at, n1, n2);
+    if (!rc) { w.lit_buf = at; w.lit_regen = n1; }
+    return rc;
+}
+
 __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__ src, uint64_t src_len, ZsbBlockWork *work,
                                             const uint32_t *__restrict__ huf_list, ZsbCounters *cnt,
                                             uint8_t *lit_pool, uint64_t lit_cap, uint64_t over_cap, uint32_t flags) {
@@ -190,22 +210,7 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__
     const bool blk_inexact = __shfl_sync(HUF_MASK, (int)inexact, q0) || __shfl_sync(HUF_MASK, (int)inexact, q0 + 1) || __shfl_sync(HUF_MASK, (int)inexact, q0 + 2) ||
                              __shfl_sync(HUF_MASK, (int)inexact, q0 + 3);
     if (blk_inexact && active && stream == 0 && !S.status) {
-        // == LiteralsSection::decode (literals.rs:70-81): count, find room (the block's slot, else the overflow region), decode
-        ZsbBlockWork &w = work[bi];
-        uint32_t n1 = 0, n2 = 0;
-        rc = huf_decode_block_ref(src, src_len, w.lit_src, w.stream_size, S.u.lut, S.maxbits, nullptr, 0, n1);
-        if (!rc && n1 > ZSB_BLOCK_MAX) rc = ZSB_E_BLOCK_TOO_LARGE;
-        if (!rc) {
-            uint64_t at = w.lit_buf;
-            if (n1 > ((w.lit_regen + 15u) & ~15u)) {
-                const uint64_t need = ((uint64_t)n1 + 15) & ~15ull;
-                const uint64_t o = atomicAdd((unsigned long long *)&cnt->lit_over, (unsigned long long)need);
-                if (o + need > over_cap) rc = ZSB_E_CORRUPT;      // more corrupted blocks than the overflow region holds
-                else at = lit_cap + o;
-            }
-            if (!rc) rc = huf_decode_block_ref(src, src_len, w.lit_src, w.stream_size, S.u.lut, S.maxbits, lit_pool + at, n1, n2);
-            if (!rc) { w.lit_buf = at; w.lit_regen = n1; }
-        }
+        rc = huf_block_ref_device(src, src_len, work[bi], S.u.lut, S.maxbits, cnt, lit_pool, lit_cap, over_cap);
     }
     // first failing stream of the block decides its status
     const int r1 = __shfl_sync(HUF_MASK, rc, q0 + 1), r2 = __shfl_sync(HUF_MASK, rc, q0 + 2), r3 = __shfl_sync(HUF_MASK, rc, q0 + 3);
