@@ -25,6 +25,7 @@
 #include "zsb_parse.h"
 #include "zsb_huf.h"
 #include "zsb_seqfast.h"
+#include "zsb_bulk.cuh"
 
 #define FULL 0xFFFFFFFFu
 
@@ -801,17 +802,67 @@ __device__ __forceinline__ void cta_fill_g(uint8_t *dst, uint8_t b, uint64_t n) 
 }
 
 // ======================================================================================= k_rawrle
+// Raw blocks and skippable payloads are copies, RLE blocks fills (block.rs:76-79, frame.rs:81).  One CTA per block; the 16-byte aligned
+// body moves by bulk copies (cp.async.bulk): an RLE block from one shared-memory tile of the byte, a raw block whose source and
+// destination share their alignment modulo 16 through two shared-memory tiles in alternation (HBM -> tile on an mbarrier, tile -> HBM
+// in a bulk group); threads only touch the unaligned head and tail.  A raw block whose alignments differ is copied by the threads.
+#define RR_TILE 16384u
 __global__ void __launch_bounds__(256) k_rawrle(const uint8_t *__restrict__ src, const zsb_block *__restrict__ blocks,
                                                 const ZsbBlockWork *__restrict__ work, const ZsbFrameOut *__restrict__ fout,
                                                 const uint32_t *__restrict__ list, const ZsbCounters *__restrict__ cnt, uint8_t *dst) {
+    __shared__ __align__(128) uint8_t tile[2][RR_TILE];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
     if (cnt->overflow) return;
     const uint32_t bi = list[blockIdx.x];
     const zsb_block b = blocks[bi];
     const ZsbFrameOut fo = fout[b.frame];
     if (fo.status != ZSB_OK || fo.dst_len == 0 || b.size == 0) return;
     uint8_t *d = dst + fo.dst_off + work[bi].out_off;
-    if (b.type == ZSB_BT_RLE) cta_fill_g(d, src[b.src_off], b.size);       // block.rs:77-79
-    else cta_copy_g2g(d, src + b.src_off, b.size);                         // block.rs:76 ; skippable payload frame.rs:81
+    const uint32_t tid = threadIdx.x, n = b.size;
+    uint32_t head = (16u - ((uint32_t)(uintptr_t)d & 15u)) & 15u; if (head > n) head = n;
+    const uint32_t body = (n - head) & ~15u;
+    if (b.type == ZSB_BT_RLE) {                                              // block.rs:77-79
+        const uint8_t v = src[b.src_off];
+        if (body >= 1024) {
+            const uint32_t w = v * 0x01010101u, fill = body < RR_TILE ? body : RR_TILE;
+            for (uint32_t i = tid; i < fill / 16; i += blockDim.x) reinterpret_cast<uint4 *>(tile[0])[i] = make_uint4(w, w, w, w);
+            zsb_fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t sa = (uint32_t)__cvta_generic_to_shared(tile[0]);
+                for (uint32_t at = 0; at < body; at += RR_TILE) zsb_bulk_s2g(d + head + at, sa, body - at < RR_TILE ? body - at : RR_TILE);
+                zsb_bulk_commit();
+            }
+            for (uint32_t i = tid; i < head; i += blockDim.x) d[i] = v;
+            for (uint32_t i = head + body + tid; i < n; i += blockDim.x) d[i] = v;
+            if (tid == 0) zsb_bulk_wait_read();                              // the tile is read before the CTA gives its shared memory back
+        } else cta_fill_g(d, v, n);
+        return;
+    }
+    const uint8_t *sp = src + b.src_off;                                     // block.rs:76 ; skippable payload frame.rs:81
+    if (body < 2048 || (((uintptr_t)d ^ (uintptr_t)sp) & 15) != 0) { cta_copy_g2g(d, sp, n); return; }
+    const uint32_t sa[2] = {(uint32_t)__cvta_generic_to_shared(tile[0]), (uint32_t)__cvta_generic_to_shared(tile[1])};
+    const uint32_t ma[2] = {(uint32_t)__cvta_generic_to_shared(&s_mbar[0]), (uint32_t)__cvta_generic_to_shared(&s_mbar[1])};
+    if (tid == 0) {
+        zsb_mbar_init(ma[0], 1); zsb_mbar_init(ma[1], 1);
+        const uint32_t nt = (body + RR_TILE - 1) / RR_TILE;
+        uint32_t ph[2] = {0, 0};
+        auto len_of = [&](uint32_t t) { return body - t * RR_TILE < RR_TILE ? body - t * RR_TILE : RR_TILE; };
+        zsb_mbar_expect(ma[0], len_of(0)); zsb_bulk_g2s(sa[0], sp + head, len_of(0), ma[0]);
+        for (uint32_t t = 0; t < nt; t++) {
+            const uint32_t k = t & 1;
+            if (t + 1 < nt) {
+                if (t >= 1) zsb_bulk_wait_read();                            // tile k^1 was handed to a store one round ago: read by now
+                zsb_mbar_expect(ma[k ^ 1], len_of(t + 1)); zsb_bulk_g2s(sa[k ^ 1], sp + head + (t + 1) * RR_TILE, len_of(t + 1), ma[k ^ 1]);
+            }
+            zsb_mbar_wait(ma[k], ph[k]); ph[k] ^= 1u;
+            zsb_bulk_s2g(d + head + t * RR_TILE, sa[k], len_of(t)); zsb_bulk_commit();
+        }
+        zsb_bulk_wait_read();
+    } else {
+        for (uint32_t i = tid - 1; i < head; i += blockDim.x - 1) d[i] = sp[i];
+        for (uint32_t i = head + body + tid - 1; i < n; i += blockDim.x - 1) d[i] = sp[i];
+    }
 }
 
 // ======================================================================================= XXH64 primitives
@@ -856,7 +907,8 @@ __device__ __forceinline__ void xxh_trail(const uint8_t *p, uint64_t len, volati
         uint64_t tgt = d >> 5; if (tgt > nstripes) tgt = nstripes;
         if (tgt < nstripes && tgt - cur < 8 * NR) { __nanosleep(500); continue; }      // wait for a whole round of loads (or the end)
         __threadfence();
-        // whole rounds of 8 * NR stripes
+        // whole rounds of 8 * NR stripes (requesting the next round before this one is hashed, with a second register set, changes nothing:
+        // the round is bound by the 64 dependent chain steps, ~65 cycles each beside 31 executing warps, not by its loads)
         while (cur + 8 * NR <= tgt) {
             uint64_t X[NR];
             const unsigned long long *gs = ga + 4 * cur;
@@ -973,9 +1025,22 @@ __device__ __forceinline__ void exec_batch(uint32_t batch, uint32_t nseq, const 
             const bool ready = (e <= (int)a0) || range_ready(bm, a0, (uint32_t)e);
             if (ready) {
                 __threadfence_block();
-                for (uint32_t k = 0; k < ml; k++) {
-                    const int sp = src + (int)k;
-                    o[dstm + k] = sp < 0 ? __ldcg(gblk + sp) : o[sp];
+                if (src + (int)ml <= 0) {
+                    // the whole source lies in earlier blocks of the frame (HBM/L2; in a frame with long-distance matches that is most
+                    // of them): eight bytes are requested before any is stored, so that their latencies overlap -- byte by byte, each
+                    // store would wait for its own load
+                    for (uint32_t k = 0; k < ml; k += 8) {
+                        uint8_t v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) v[j] = k + j < ml ? __ldcg(gblk + src + (int)(k + j)) : (uint8_t)0;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) if (k + j < ml) o[dstm + k + j] = v[j];
+                    }
+                } else {
+                    for (uint32_t k = 0; k < ml; k++) {
+                        const int sp = src + (int)k;
+                        o[dstm + k] = sp < 0 ? __ldcg(gblk + sp) : o[sp];
+                    }
                 }
                 pend = false; didm = true;
             }
@@ -1044,7 +1109,10 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
     if (fo.status != ZSB_OK) return;
     const zsb_frame fr = frames[f];
     uint8_t *fdst = dst + fo.dst_off;
-    if (tid == 0) { s_err = 0; s_done = 0; }
+    __shared__ __align__(8) unsigned long long s_mbar;                 // completion of the literal staging's bulk copy
+    const uint32_t mbar_sa = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    uint32_t mbar_phase = 0;
+    if (tid == 0) { s_err = 0; s_done = 0; zsb_mbar_init(mbar_sa, 1); }
     __syncthreads();
     if (XXH && warp == ET / 32) {
         if ((flags & ZSB_VERIFY_CHECKSUM) && fr.has_checksum) xxh_trail(fdst, fo.dst_len, &s_done, &fout[f].xxh64);
@@ -1066,20 +1134,25 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
         // literal source
         LitSrc L; L.rle = 0; L.s = nullptr;
         L.g = W.lit_type == ZSB_LT_RAW ? src + W.lit_src : lit_pool + W.lit_buf;
+        bool lit_wait = false;
         if (W.lit_type == ZSB_LT_RLE) { L.mode = 2; L.rle = src[W.lit_src]; }
         else if (regen <= EXEC_LIT_STAGE) {
             L.mode = 0;
             const uint32_t ls = (uint32_t)((uintptr_t)L.g & 15);
             L.s = lit_s + ls;
-            // stage the literals: aligned 16-byte loads once past the head
+            // stage the literals: the 16-byte aligned body by ONE bulk copy (cp.async.bulk, the copy engine moves up to 64 KiB while the
+            // threads clear the bitmap), head and tail bytes by the threads
             uint32_t head = (16 - ls) & 15; if (head > regen) head = regen;
             for (uint32_t i = tid; i < head; i += ET) lit_s[ls + i] = __ldg(L.g + i);
             const uint32_t nv = (regen - head) >> 4;
-            const uint4 *g4 = reinterpret_cast<const uint4 *>(L.g + head); uint4 *s4 = reinterpret_cast<uint4 *>(lit_s + ls + head);
-            for (uint32_t i = tid; i < nv; i += ET) s4[i] = __ldg(g4 + i);
+            if (nv) {
+                if (tid == 0) { zsb_mbar_expect(mbar_sa, nv << 4); zsb_bulk_g2s((uint32_t)__cvta_generic_to_shared(lit_s + ls + head), L.g + head, nv << 4, mbar_sa); }
+                lit_wait = true;
+            }
             for (uint32_t i = head + (nv << 4) + tid; i < regen; i += ET) lit_s[ls + i] = __ldg(L.g + i);
         } else L.mode = 1;
         if (nseq) for (uint32_t i = tid; i < (out_size + 31) / 32; i += ET) bm[i] = 0;
+        if (lit_wait) { zsb_mbar_wait(mbar_sa, mbar_phase); mbar_phase ^= 1u; }
         sync_exec();
         if (nseq == 0) {
             for (uint32_t i = tid; i < regen; i += ET) o[i] = lit_at(L, i);        // literals-only block (RFC; reference: Q1)
@@ -1092,15 +1165,17 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
             for (uint32_t b = warp; b < nbatch; b += ET / 32)
                 exec_batch(b, nseq, seqs, o, bm, L, W.rep_in, fr.kind == 0 ? W.out_off : 0, gblk, &s_err);
         }
+        zsb_fence_async_smem();                                        // the image was written with ordinary stores; the copy engine reads it
         sync_exec();
-        // flush the block image to HBM: congruent alignment -> 16-byte stores
+        // flush the block image to HBM: the image sits at the alignment of its destination, so its 16-byte aligned body leaves by ONE
+        // bulk copy (cp.async.bulk shared -> global, up to 128 KiB) issued by one thread; head and tail bytes by the threads
         {
             uint32_t head = (16 - shift) & 15; if (head > out_size) head = out_size;
-            for (uint32_t i = tid; i < head; i += ET) gblk[i] = o[i];
             const uint32_t nv = (out_size - head) >> 4;
-            const uint4 *s4 = reinterpret_cast<const uint4 *>(o + head); uint4 *g4 = reinterpret_cast<uint4 *>(gblk + head);
-            for (uint32_t i = tid; i < nv; i += ET) g4[i] = s4[i];
+            if (tid == 0 && nv) { zsb_bulk_s2g(gblk + head, (uint32_t)__cvta_generic_to_shared(o + head), nv << 4); zsb_bulk_commit(); }
+            for (uint32_t i = tid; i < head; i += ET) gblk[i] = o[i];
             for (uint32_t i = head + (nv << 4) + tid; i < out_size; i += ET) gblk[i] = o[i];
+            if (tid == 0 && nv) zsb_bulk_wait_all();                  // complete: the image may be overwritten, the bytes are in HBM
         }
         if (XXH) __threadfence();                                      // the block is in HBM before the hashing warp is told so
         sync_exec();
