@@ -211,6 +211,10 @@ int zsb_decode_errors(const zsb_ctx *ctx, uint32_t *err_a, uint32_t *err_b, size
  * last launch when profiling was enabled with zsb_ctx_set_profile(ctx, 1).  names[i] are static. */
 int zsb_ctx_set_profile(zsb_ctx *ctx, int enable);
 int zsb_last_launch_count(const zsb_ctx *ctx);
+/* How the sequence stage of the last batch ran: 0 = k_seq (records to HBM, executed afterwards), 1 = k_seqx (the first block of
+ * every frame with a known place executed by the sequence kernel itself), 2 = k_seqx, refused (a frame did not end up where its
+ * declared sizes put it) and the batch run again with k_seq.  The results are the same in all three. */
+int zsb_last_seqx_state(const zsb_ctx *ctx);
 int zsb_last_kernel_times(const zsb_ctx *ctx, const char **names, float *ms, int cap);
 /* Synchronises, then averages each kernel over the launches recorded since profiling was switched on
  * (at most the last 32). */

@@ -550,3 +550,76 @@ def test_pipelined_host_path_on_mixed_frames(dec):
         _scan_decode_equals_scan_then_decode(dec, blob, flags, cap=len(want))        # zsb_scan_decode on page-locked buffers
         out3, sc3, r3 = dec.decode(blob, flags)                                      # pageable buffers: one batch
         assert first_status(sc3, r3) == 0 and out3 == want
+
+
+# ---------------------------------------------------------------- k_seqx (ZSB_SEQX=1: sequence decoding + execution in one kernel)
+@pytest.fixture()
+def dec_seqx():
+    import os
+    os.environ["ZSB_SEQX"] = "1"                        # read when the context is created
+    try:
+        d = Z.Decoder(Z.Context(0))
+    finally:
+        del os.environ["ZSB_SEQX"]
+    return d
+
+
+def test_seqx_executes_placed_frames(dec, dec_seqx):
+    blob, exp = corpora.c2_small(256)
+    for fl in (VER, Q | VER):
+        out, sc, r = dec_seqx.decode(blob, fl)
+        assert dec_seqx.ctx.last_seqx_state() == 1       # every frame declares its size: all first blocks executed by k_seqx
+        assert first_status(sc, r) == 0 and all(r.checksum_ok[i] for i in range(256)) and out == exp
+    out, sc, r = dec.decode(blob, VER)
+    assert dec.ctx.last_seqx_state() == 0 and out == exp
+
+
+def test_seqx_frames_of_several_blocks_and_unknown_sizes(dec, dec_seqx):
+    """first block by k_seqx, the rest by k_exec2 from records; frames behind one without Frame_Content_Size are not placed"""
+    import gen_corpus as G
+    text = G.moby_text()
+    r0 = random.Random(11)
+    plains, frames = [], []
+    for i in range(320):                                # > 296 frames: frames of a few blocks stay with the warp-per-frame executor
+        n = r0.choice((1000, 70000, 140000, 300000))
+        o = r0.randrange(len(text) - n)
+        plains.append(text[o:o + n])
+        frames.append(G.compress(plains[-1], level=3, checksum=True, content_size=(i != 200)))
+    blob = b"".join(frames)
+    want = b"".join(plains)
+    out, sc, r = dec_seqx.decode(blob, Q | VER)
+    assert dec_seqx.ctx.last_seqx_state() == 1
+    assert first_status(sc, r) == 0 and sc.n_frames == 320 and all(r.checksum_ok[i] for i in range(320))
+    assert out == want
+    out2, sc2, r2 = dec.decode(blob, Q | VER)
+    assert out2 == want and list(r.dst_off[:320]) == list(r2.dst_off[:320])
+
+
+def test_seqx_refuses_when_a_frame_moves_the_others(dec, dec_seqx):
+    """a frame that fails (or does not regenerate what it declares) shifts every frame behind it: what k_seqx wrote is in the
+    wrong place, the batch runs again with k_seq, and the results are those of the plain path"""
+    blob, exp = corpora.c2_small(64)
+    sc0 = Z.Scan(blob, VER)
+    bad = bytearray(blob)
+    f5 = sc0.frames[5]
+    bad[f5.src_off + f5.src_len // 2] ^= 0x5A           # inside frame 5's only block
+    for fl in (VER, Q | VER):
+        out, sc, r = dec_seqx.decode(bytes(bad), fl)
+        assert dec_seqx.ctx.last_seqx_state() in (1, 2)
+        out2, sc2, r2 = dec.decode(bytes(bad), fl)
+        assert list(r.status[:64]) == list(r2.status[:64]) and list(r.dst_off[:64]) == list(r2.dst_off[:64])
+        assert list(r.dst_len[:64]) == list(r2.dst_len[:64]) and list(r.checksum_ok[:64]) == list(r2.checksum_ok[:64])
+        for i in range(64):
+            if r.status[i] == 0:
+                assert out[r.dst_off[i]:r.dst_off[i] + r.dst_len[i]] == out2[r2.dst_off[i]:r2.dst_off[i] + r2.dst_len[i]]
+    # a frame that declares 300 bytes and regenerates 50 000 (accepted under the quirks): k_seqx stops at the declared size
+    import gen_corpus as G
+    text = G.moby_text()[:50000]
+    liar = bytearray(G.compress(text, level=3, checksum=False))
+    assert liar[4] & 0x20 and (liar[4] >> 6) == 1
+    liar[5:7] = (300 - 256).to_bytes(2, "little")
+    f0, f1 = sc0.frames[0], sc0.frames[1]
+    mix = blob[f0.src_off:f0.src_off + f0.src_len] + bytes(liar) + blob[f1.src_off:f1.src_off + f1.src_len]
+    out, sc, r = dec_seqx.decode(mix, Q)
+    assert dec_seqx.ctx.last_seqx_state() == 2
+    assert first_status(sc, r) == 0 and out == R.main_decode(mix)

@@ -98,6 +98,7 @@ def lib():
     L.zsb_last_cuda_error.restype = C.c_char_p; L.zsb_last_cuda_error.argtypes = [vp]
     L.zsb_ctx_set_profile.argtypes = [vp, C.c_int]
     L.zsb_last_launch_count.argtypes = [vp]
+    L.zsb_last_seqx_state.argtypes = [vp]
     L.zsb_last_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     L.zsb_kernel_times_avg.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     L.zsb_decode.argtypes = [vp, vp, sz, C.POINTER(ZsbFrame), sz, C.POINTER(ZsbBlock), sz, vp, sz, u64p, u64p, i32p, u32p, u8p, u64p, C.c_uint32]
@@ -136,7 +137,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "zsb_scan", "zsb_free", "zsb_ctx_create", "zsb_ctx_destroy", "zsb_ctx_set_stream", "zsb_last_cuda_error", "zsb_ctx_set_profile",
-    "zsb_last_launch_count", "zsb_last_kernel_times", "zsb_kernel_times_avg", "zsb_decode", "zsb_decode_prepare", "zsb_decode_launch", "zsb_decode_finish",
+    "zsb_last_launch_count", "zsb_last_seqx_state", "zsb_last_kernel_times", "zsb_kernel_times_avg", "zsb_decode", "zsb_decode_prepare", "zsb_decode_launch", "zsb_decode_finish",
     "zsb_decompress", "zsb_fse_table_parse", "zsb_fse_table_from_distribution", "zsb_huffman_parse", "zsb_execute_sequences",
     "zsb_xxh64", "zsb_strerror", "zsb_version", "zsb_shard_plan", "zsb_shard_extract", "zsb_host_alloc", "zsb_host_free", "zsb_scan_decode",
     "zsb_multi_create", "zsb_multi_destroy", "zsb_multi_device_count", "zsb_multi_ctx", "zsb_multi_calibrate", "zsb_multi_set_weights", "zsb_multi_get_weights",
@@ -198,6 +199,10 @@ class Context:
 
     def last_launch_count(self):
         return lib().zsb_last_launch_count(self.h)
+
+    def last_seqx_state(self):
+        """0: k_seq, 1: k_seqx executed the placed blocks, 2: k_seqx refused and the batch ran again with k_seq."""
+        return lib().zsb_last_seqx_state(self.h)
 
     def kernel_times(self):
         names = (C.c_char_p * 16)(); ms = (C.c_float * 16)()

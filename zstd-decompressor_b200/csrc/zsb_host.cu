@@ -41,7 +41,7 @@ struct zsb_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr, aux_stream = nullptr;   // aux: the literals stage runs beside the sequence stage
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_huf[kProfRing][2] = {};
-    DevBuf src, frames, blocks, work, fout, huf_list, seq_list, rawrle_list, exec_list, exec2_list, xxh_list, lit_pool, seq_pool, slow_list, counters, dst, stage;
+    DevBuf src, frames, blocks, work, fout, huf_list, seq_list, rawrle_list, exec_list, exec2_list, xxh_list, lit_pool, seq_pool, slow_list, counters, dst, stage, pre_off;
     std::string last_err;
     // prepared batch
     const uint8_t *d_src = nullptr; uint8_t *d_dst = nullptr; uint8_t *h_dst = nullptr;
@@ -51,6 +51,9 @@ struct zsb_ctx {
     std::vector<zsb_frame> h_frames;
     std::vector<zsb_block> h_blocks;
     std::vector<uint32_t> h_xxh_list, h_rawrle, h_exec, h_exec2;   // host copies stay alive while their uploads are in flight
+    std::vector<uint64_t> h_pre_off;                               // where every frame is expected in dst (k_seqx), ~0: not known before decoding
+    int seqx_state = 0;                                            // zsb_last_seqx_state
+    bool use_seqx = false;                                         // this batch runs k_seqx
     std::vector<uint32_t> h_err_a, h_err_b;                        // per-frame error payloads of the last finished batch (zsb_decode_errors)
     std::vector<zsb_ctx *> subs;          // child contexts of the pipelined host path (own stream + scratch each)
     bool is_sub = false;
@@ -64,6 +67,8 @@ struct zsb_ctx {
     uint8_t *pin = nullptr; size_t pin_cap = 0; bool pin_valid = false;
     uint64_t eager_d2h = 0;               // pipelined path: bytes of output to send to the host right behind the kernels (size known from the headers)
     bool prepared = false, launched = false;
+    bool seqx = false;         // ZSB_SEQX=1: sequence decoding and execution in one kernel (k_seqx) where a frame's place is known beforehand; measured
+                               // slower than k_seq + k_exec2 (5.6 ms against 2.9 ms on C2: 64 registers per thread and 28 KiB of L1 for 29 warps), kept as an experiment
     bool overlap = false;      // ZSB_OVERLAP=1: literals stage on the auxiliary stream beside k_seq (measured slower: both are latency bound and share schedulers)
     // profiling
     bool profile = false;
@@ -91,6 +96,7 @@ extern "C" int zsb_ctx_create(zsb_ctx **out, int device) {
         zsbk_init() != cudaSuccess) { (void)cudaGetLastError(); delete c; return ZSB_E_CUDA; }
     c->stream = c->own_stream;
     { const char *e = getenv("ZSB_OVERLAP"); c->overlap = e && *e && *e != '0'; }
+    { const char *e = getenv("ZSB_SEQX"); c->seqx = e && *e && *e != '0'; }
     { const char *e = getenv("ZSB_PIPE_TRACE"); c->trace = e && *e && *e != '0'; }
     if (c->trace) for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev_tr[i]);
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) cudaEventCreate(&c->ev[r][i]);
@@ -107,7 +113,7 @@ extern "C" void zsb_ctx_destroy(zsb_ctx *c) {
     c->subs.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list, &c->exec2_list,
+    DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list, &c->exec2_list, &c->pre_off,
                      &c->xxh_list, &c->lit_pool, &c->seq_pool, &c->slow_list, &c->counters, &c->dst, &c->stage};
     for (DevBuf *b : all) b->release();
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) if (c->ev[r][i]) cudaEventDestroy(c->ev[r][i]);
@@ -127,6 +133,7 @@ extern "C" int zsb_ctx_set_stream(zsb_ctx *c, void *s) { if (!c) return ZSB_E_AR
 extern "C" const char *zsb_last_cuda_error(const zsb_ctx *c) { return c ? c->last_err.c_str() : "no context"; }
 extern "C" int zsb_ctx_set_profile(zsb_ctx *c, int en) { if (!c) return ZSB_E_ARG; c->profile = en != 0; c->prof_slot = 0; c->prof_count = 0; return ZSB_OK; }
 extern "C" int zsb_last_launch_count(const zsb_ctx *c) { return c ? c->launches : 0; }
+extern "C" int zsb_last_seqx_state(const zsb_ctx *c) { return c ? c->seqx_state : 0; }
 extern "C" int zsb_last_kernel_times(const zsb_ctx *c, const char **names, float *ms, int cap) {
     if (!c) return 0;
     int n = c->nk < cap ? c->nk : cap;
@@ -177,7 +184,7 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
                                   const zsb_block *blocks, size_t nb, uint8_t *dst, size_t dst_cap, uint32_t flags) {
     if (!c || (!src && n) || (!frames && nf) || (!blocks && nb) || nf > 0x7FFFFFFFu || nb > 0x7FFFFFFFu) return ZSB_E_ARG;
     CK(c, cudaSetDevice(c->device));
-    c->prepared = false; c->launched = false;
+    c->prepared = false; c->launched = false; c->seqx_state = 0;
     cudaStream_t st = c->up_stream ? c->up_stream : c->stream;      // every copy of this function goes to `st`
     // compressed bytes: resident already, or uploaded once (padded so that aligned 8-byte loads near the end stay inside)
     if (flags & ZSB_SRC_ON_DEVICE) c->d_src = src;
@@ -222,6 +229,31 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
         // frames executed by k_exec<1024> are hashed by its trailing warp, all others by k_xxh
         if ((flags & ZSB_VERIFY_CHECKSUM) && frames[f].has_checksum && !(cta && !c->is_sub)) c->h_xxh_list.push_back((uint32_t)f);
     }
+    // k_seqx: a frame whose predecessors all declare their size has a known place before anything is decoded, and its first block can
+    // be executed by the sequence kernel itself.  Only frames the warp-per-frame executor would take (k_exec2: it skips what is done),
+    // only when the literals are there before the sequence stage starts (no k_huf beside k_seq).  A frame that does not regenerate what
+    // it declares (an error, or accepted under ZSB_REFERENCE_QUIRKS) moves the frames behind it: k_plan2 notices, the batch runs again.
+    {
+        c->h_pre_off.assign(nf, ~0ull);
+        c->use_seqx = false;
+        if (c->seqx && !c->overlap && !c->low_latency && !exec2l.empty()) {
+            uint64_t off = 0; size_t e2 = 0; uint32_t placed = 0;
+            for (size_t f = 0; f < nf; f++) {
+                const zsb_frame &fr = frames[f];
+                uint64_t len = 0;
+                if (fr.status != ZSB_OK) len = 0;
+                else if (fr.kind == 1) len = (flags & ZSB_PRINT_SKIPPABLE) && fr.n_blocks ? blocks[fr.first_block].size : 0;
+                else if (!fr.has_content_size) break;                      // from here on nothing has a known place
+                else len = fr.content_size;
+                while (e2 < exec2l.size() && exec2l[e2] < f) e2++;
+                const bool warp_frame = e2 < exec2l.size() && exec2l[e2] == f;
+                if (warp_frame && fr.n_blocks && blocks[fr.first_block].type == ZSB_BT_COMPRESSED && len && off + len <= dst_cap) { c->h_pre_off[f] = off; placed++; }
+                off += len;
+            }
+            c->use_seqx = placed != 0;
+            if (getenv("ZSB_DEBUG")) fprintf(stderr, "zsb: k_seqx places %u of %zu frames\n", placed, nf);
+        }
+    }
     c->ncomp = (uint32_t)ncomp; c->n_rawrle = (uint32_t)rawrle.size(); c->n_exec = (uint32_t)execl.size(); c->n_exec2 = (uint32_t)exec2l.size(); c->n_xxh = (uint32_t)c->h_xxh_list.size();
     if (lit_cap > c->lit_cap) c->lit_cap = lit_cap;
     if (seq_cap > c->seq_cap) c->seq_cap = seq_cap;
@@ -235,6 +267,7 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     CK(c, c->rawrle_list.ensure(4 * (rawrle.size() + 1)));
     CK(c, c->exec_list.ensure(4 * (execl.size() + 1)));
     CK(c, c->exec2_list.ensure(4 * (exec2l.size() + 1)));
+    CK(c, c->pre_off.ensure(8 * (nf + 1)));
     CK(c, c->xxh_list.ensure(4 * (c->h_xxh_list.size() + 1)));
     CK(c, c->counters.ensure(sizeof(ZsbCounters)));
     c->lit_cap = (c->lit_cap + 15) & ~(uint64_t)15;
@@ -245,6 +278,7 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     if (!rawrle.empty()) CK(c, cudaMemcpyAsync(c->rawrle_list.p, rawrle.data(), 4 * rawrle.size(), cudaMemcpyHostToDevice, st));
     if (!execl.empty()) CK(c, cudaMemcpyAsync(c->exec_list.p, execl.data(), 4 * execl.size(), cudaMemcpyHostToDevice, st));
     if (!exec2l.empty()) CK(c, cudaMemcpyAsync(c->exec2_list.p, exec2l.data(), 4 * exec2l.size(), cudaMemcpyHostToDevice, st));
+    if (c->use_seqx) CK(c, cudaMemcpyAsync(c->pre_off.p, c->h_pre_off.data(), 8 * nf, cudaMemcpyHostToDevice, st));
     if (!c->h_xxh_list.empty()) CK(c, cudaMemcpyAsync(c->xxh_list.p, c->h_xxh_list.data(), 4 * c->h_xxh_list.size(), cudaMemcpyHostToDevice, st));
     if (c->trace) cudaEventRecord(c->ev_tr[1], st);
     if (c->up_stream) { CK(c, cudaEventRecord(c->ev_up, st)); CK(c, cudaStreamWaitEvent(c->stream, c->ev_up, 0)); }
@@ -263,6 +297,7 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     ZsbBlockWork *work = (ZsbBlockWork *)c->work.p; ZsbFrameOut *fout = (ZsbFrameOut *)c->fout.p;
     ZsbCounters *cnt = (ZsbCounters *)c->counters.p;
     c->nk = 0; c->launches = 0;
+    if (c->use_seqx) c->seqx_state = 1; else if (c->seqx_state != 2) c->seqx_state = 0;
     CK(c, cudaMemsetAsync(cnt, 0, sizeof(ZsbCounters), st));
     MARK(c, "k_parse");  zsbk_parse(st, src, blocks, work, c->nb, c->flags); c->launches += c->nb ? 1 : 0;
     MARK(c, "k_plan1");  zsbk_plan1(st, frames, c->nf, blocks, c->nb, work, fout, (uint32_t *)c->huf_list.p, (uint32_t *)c->seq_list.p, cnt,
@@ -274,23 +309,27 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     static const uint32_t ll_env = getenv("ZSB_LL_CHAINS") ? (uint32_t)atoi(getenv("ZSB_LL_CHAINS")) : 8u;
     const uint32_t ll_chains = (c->low_latency && c->ncomp <= 320) ? ll_env : 0u;
     const bool ov = c->overlap || c->low_latency;
+    const uint64_t *pre_off = c->use_seqx ? (const uint64_t *)c->pre_off.p : nullptr;
     if (ov) {
         CK(c, cudaEventRecord(c->ev_fork, st));
         CK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-        MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p, c->is_sub, ll_chains);
+        MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p, c->is_sub, ll_chains,
+                                    frames, blocks, nullptr, (const uint8_t *)c->lit_pool.p, c->d_dst);
         if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][0], c->aux_stream);
         zsbk_huf(c->aux_stream, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->lit_cap, 0, c->flags & ~ZSB_REFERENCE_QUIRKS);
         if (c->profile) cudaEventRecord(c->ev_huf[c->prof_slot][1], c->aux_stream);
         CK(c, cudaEventRecord(c->ev_join, c->aux_stream));
     } else {
         MARK(c, "k_huf");  zsbk_huf(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->huf_list.p, cnt, (uint8_t *)c->lit_pool.p, c->lit_cap, kLitOverflow, c->flags);
-        MARK(c, "k_seq");  zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p, c->is_sub, ll_chains);
+        MARK(c, pre_off ? "k_seqx" : "k_seq");
+        zsbk_seq(st, c->ncomp, src, work, (const uint32_t *)c->seq_list.p, cnt, (uint64_t *)c->seq_pool.p, (uint32_t *)c->slow_list.p, c->is_sub, ll_chains,
+                 frames, blocks, pre_off, (const uint8_t *)c->lit_pool.p, c->d_dst);
     }
     c->launches += c->ncomp ? 1 : 0;
     MARK(c, "k_seq_slow"); zsbk_seq_slow(st, c->ncomp, src, c->src_len, work, (const uint32_t *)c->slow_list.p, cnt, (uint64_t *)c->seq_pool.p);
     c->launches += c->ncomp ? 2 : 0;
     if (ov) { MARK(c, "wait k_huf"); CK(c, cudaStreamWaitEvent(st, c->ev_join, 0)); }
-    MARK(c, "k_plan2");  zsbk_plan2(st, frames, c->nf, blocks, work, fout, cnt, c->dst_cap, c->flags); c->launches++;
+    MARK(c, "k_plan2");  zsbk_plan2(st, frames, c->nf, blocks, work, fout, cnt, c->dst_cap, c->flags, pre_off); c->launches++;
     MARK(c, "k_rawrle"); zsbk_rawrle(st, c->n_rawrle, src, blocks, work, fout, (const uint32_t *)c->rawrle_list.p, cnt, c->d_dst); c->launches += c->n_rawrle ? 1 : 0;
     MARK(c, "k_exec2");  zsbk_exec2(st, c->n_exec2, src, frames, blocks, work, fout, (const uint32_t *)c->exec2_list.p, cnt, (const uint64_t *)c->seq_pool.p,
                                     (const uint8_t *)c->lit_pool.p, c->d_dst); c->launches += c->n_exec2 ? 1 : 0;
@@ -340,13 +379,22 @@ extern "C" int zsb_decode_finish(zsb_ctx *c, uint64_t *dst_off, uint64_t *dst_le
     ZsbCounters hc;
     bool from_pin = false;
     for (int attempt = 0;; attempt++) {
-        if (c->pin_valid) { CK(c, cudaStreamSynchronize(st)); memcpy(&hc, c->pin, sizeof hc); from_pin = !hc.overflow; }
+        if (c->pin_valid) { CK(c, cudaStreamSynchronize(st)); memcpy(&hc, c->pin, sizeof hc); from_pin = !hc.overflow && !hc.refuse; }
         else {
             CK(c, cudaMemcpyAsync(&hc, c->counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
             CK(c, cudaStreamSynchronize(st));
         }
-        if (!hc.overflow) break;
-        if (attempt >= 2) { c->last_err = "scratch overflow persists"; return ZSB_E_NOMEM; }
+        if (!hc.overflow && !hc.refuse) break;
+        if (attempt >= 3) { c->last_err = "scratch overflow persists"; return ZSB_E_NOMEM; }
+        if (!hc.overflow) {
+            // k_seqx executed a block where its frame did not end up (an earlier frame failed, or regenerates another size than it
+            // declares): the whole batch again, with the sequence stage writing records (k_seq)
+            c->use_seqx = false; c->seqx_state = 2;
+            if (getenv("ZSB_DEBUG")) fprintf(stderr, "zsb: k_seqx refused, batch runs again\n");
+            int rc = zsb_decode_launch(c);
+            if (rc) return rc;
+            continue;
+        }
         // the entropy scratch was too small for this input: size it exactly and run the batch again
         c->lit_cap = (hc.lit_total + 64 + 15) & ~(uint64_t)15; c->seq_cap = hc.seq_total + 8;
         CK(c, c->lit_pool.ensure(c->lit_cap + kLitOverflow + 64));

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__
 //       nb = AL - floor(log2(next)), base = (next << nb) - N  (fse.rs:169-189 in closed form, see zsb_fse.h).
 // Results are identical to fse_build_table cell for cell (tests: the reference's vectors and random distributions
 // through zsb_fse_table_from_distribution, which runs this code).
-struct FseWarpScratch { int16_t cnt[64]; uint16_t cum[66]; uint16_t next[64]; };
+struct FseWarpScratch { int16_t cnt[64]; uint16_t cum[66]; uint16_t next[64]; uint8_t desc[128]; };
 // tab: code -> baseline | extra bits << 24 for LL ([0..35]) and ML ([36..88]); type 3: plain table (xb = 0, code = symbol)
 __device__ __forceinline__ int fse_build_table_warp(FseWarpScratch &X, int nsym, int al, uint32_t *tbl, int ts, int type, const uint32_t *tab, uint32_t lane) {
     const int N = 1 << al, step = (N >> 1) + (N >> 3) + 3, mask = N - 1;
@@ -303,9 +303,17 @@ __device__ __forceinline__ int seq_build_table_warp(const uint8_t *src, const Zs
         nsym = zsb_predef_nsym(t); al = zsb_predef_al(t);
         for (int sy = (int)lane; sy < nsym; sy += 32) X.cnt[sy] = (int16_t)zsb_predef_count(t, sy);
     } else if (mode == ZSB_M_FSE) {
+        // the description is read by one lane, a few bits per symbol: from a shared-memory copy that the warp fetches in one go -- read
+        // where it lies, every symbol costs a dependent round trip to L2/HBM (measured: 31 k cycles per table, 95 us of set-up per CTA)
+        const uint8_t *dp = src + w.tbl_desc[t];
+        const uint64_t avail = w.tbl_end - w.tbl_desc[t];
+        const uint32_t nb = avail < sizeof X.desc ? (uint32_t)avail : (uint32_t)sizeof X.desc;
+        for (uint32_t i = lane; i < nb; i += 32) X.desc[i] = __ldg(dp + i);
+        __syncwarp();
         if (lane == 0) {
-            FwdBits f; fwd_init(f, src + w.tbl_desc[t], w.tbl_end - w.tbl_desc[t]);
+            FwdBits f; fwd_init(f, X.desc, nb);
             rc = fse_read_ncount(f, X.cnt, 1, 64, al, nsym);
+            if (rc == ZSB_E_NOT_ENOUGH_BITS && avail > nb) { fwd_init(f, dp, avail); rc = fse_read_ncount(f, X.cnt, 1, 64, al, nsym); }     // longer than the copy
             if (rc == ZSB_E_CORRUPT) rc = ZSB_TABLE_TOO_SMALL;            // more than 64 symbols described
         }
         rc = __shfl_sync(FULL, rc, 0); al = __shfl_sync(FULL, al, 0); nsym = __shfl_sync(FULL, nsym, 0);
@@ -338,30 +346,36 @@ __device__ __forceinline__ int seq_build_table_warp(const uint8_t *src, const Zs
 #define SEQ_CHAINS 32         // table columns / producer lanes of a CTA
 // (how many of them carry a block is chosen per launch so that the CTAs fill whole waves of one CTA per SM: 4 096 blocks on
 //  148 SMs run 28 chains per CTA in 147 CTAs; 32 would leave 20 SMs idle and load the others' phase-2 warps more)
-#define SEQ_HELPERS 16
-#define SEQ_CPH (SEQ_CHAINS / SEQ_HELPERS)       // chains per phase-2 warp
+#define SEQ_HELPERS 16        // k_seq: phase-2 warps, two chains each
 #define SEQ_OF_CELLS 256      // offset tables have accuracy log <= 8 (RFC 8878); a log-9 one (the reference accepts it) takes the careful path
 #define SEQ_TBL_BYTES ((2 * SEQ_TBL_CELLS + SEQ_OF_CELLS) * SEQ_CHAINS * 4)
-#define SEQ_WIN 128           // sequences per hand-over and chain (SEQ_PER_LANE = 4 per phase-2 lane)
+#define SEQ_WIN 128           // k_seq: sequences per hand-over and chain (SEQ_PER_LANE = 4 per phase-2 lane), two windows in the ring
 #define SEQ_PF 8              // lines (of 128 bytes) the stream rings ask L2 for ahead of their own requests
-#define SEQ_WSTRIDE 260       // words per chain in the ring (two windows) + 4: rows stay 16-byte aligned, banks spread
-struct SeqShared {
-    uint32_t words[SEQ_CHAINS][SEQ_WSTRIDE];
+// k_seqx (sequence decoding + execution in one kernel): one consumer warp per chain, windows of 32 sequences, four in the ring
+#define SEQX_WARPS 28
+#define SEQX_WIN 32
+#define SEQX_NBUF 4
+#define SEQX_RING 1024u       // bytes of recent output a consumer warp keeps in shared memory (k_exec2: 2 KiB)
+// WSTRIDE: words per chain in the ring (the windows) + 4: rows stay 16-byte aligned, banks spread
+template <int WSTRIDE>
+struct SeqSharedT {
+    uint32_t words[SEQ_CHAINS][WSTRIDE];
     uint32_t tab[36 + 53];                       // code -> baseline | extra bits << 24
     uint32_t nseq[SEQ_CHAINS];                   // 0: chain not running (no block, or it failed before the first sequence)
     uint32_t regen[SEQ_CHAINS], bi[SEQ_CHAINS];
     unsigned long long top0[SEQ_CHAINS], rec[SEQ_CHAINS];   // absolute bit position of sequence 0, record pointer
     int final_rc[SEQ_CHAINS];
     int tal[SEQ_CHAINS][3], trc[SEQ_CHAINS][3];  // accuracy log / build status of each table (built by the phase-2 warps during set-up)
+    unsigned long long gdst[SEQ_CHAINS];         // k_seqx: where the block's output goes (0: the chain only writes records)
+    uint32_t limit[SEQ_CHAINS];                  // k_seqx: bytes the block may produce there
 };
-// named barriers of the hand-over (0 is __syncthreads): FULL+parity: batch written, FREE+parity: batch consumed; every thread of the CTA takes part
-#define SEQ_BAR_FULL 1u
-#define SEQ_BAR_FREE 3u
-__device__ __forceinline__ void seq_bar_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(32u * (1 + SEQ_HELPERS)) : "memory"); }
-// the phase-2 warps among themselves (id 5)
-__device__ __forceinline__ void seq_bar_sync_helpers() { asm volatile("bar.sync 5, %0;" ::"r"(32u * SEQ_HELPERS) : "memory"); }
-__device__ __forceinline__ void seq_bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(32u * (1 + SEQ_HELPERS)) : "memory"); }
-#define SEQ_SMEM_FUSED (SEQ_TBL_BYTES + 256 * SEQ_CHAINS * 2 + sizeof(SeqShared))   // tables | counts, then stream rings | hand-over
+// named barriers of the hand-over (0 is __syncthreads): 1 + (window % NBUF): window written, 1 + NBUF + (window % NBUF): window
+// consumed; every thread of the CTA takes part.  1 + 2 * NBUF: the phase-2 warps among themselves.
+template <int NT> __device__ __forceinline__ void seq_bar_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(NT) : "memory"); }
+template <int NT> __device__ __forceinline__ void seq_bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(NT) : "memory"); }
+// tables | counts, then stream rings | hand-over (| the consumer warps' output rings)
+#define SEQ_SMEM_BYTES (SEQ_TBL_BYTES + 256 * SEQ_CHAINS * 2 + sizeof(SeqSharedT<SEQ_WIN * 2 + 4>))
+#define SEQX_SMEM_BYTES (SEQ_TBL_BYTES + 256 * SEQ_CHAINS * 2 + ((sizeof(SeqSharedT<SEQX_WIN * SEQX_NBUF + 4>) + 15) & ~15ull) + SEQX_WARPS * SEQX_RING)
 
 __device__ __forceinline__ Hist hist_shfl_up(const Hist &h, int d) {
     Hist r; r.h0 = __shfl_up_sync(FULL, h.h0, d); r.h1 = __shfl_up_sync(FULL, h.h1, d); r.h2 = __shfl_up_sync(FULL, h.h2, d); return r;
@@ -404,11 +418,11 @@ __device__ __forceinline__ Seq2One seq2_values(const uint8_t *base8, int64_t top
 // fraction of the shuffles and compositions of a one-per-lane layout, which matters because the shuffles share the SM's
 // load/store path with the producer's table loads.
 #define SEQ_PER_LANE 4
-__device__ __forceinline__ void seq2_window(const uint8_t *base8, uint32_t tab_sa, const uint32_t *wd, uint32_t i0, uint32_t nseq, uint32_t regen,
-                                            uint64_t *rec, Seq2Carry &C, uint32_t lane) {
-    constexpr int K = SEQ_PER_LANE;
+template <int K>
+__device__ __forceinline__ void seq2_records(const uint8_t *base8, uint32_t tab_sa, const uint32_t *wd, uint32_t i0, uint32_t nseq, uint32_t regen,
+                                             Seq2Carry &C, uint32_t lane, bool (&v)[K], uint64_t (&r)[K]) {
     const uint32_t ia = i0 + K * lane;
-    bool v[K]; uint32_t eL[K], eM[K], cO[K], px[K], tot[K];
+    uint32_t eL[K], eM[K], cO[K], px[K], tot[K];
     uint32_t lane_tot = 0;
 #pragma unroll
     for (int j = 0; j < K; j++) { v[j] = ia + j < nseq; seq2_codes(tab_sa, wd[j], v[j], eL[j], eM[j], cO[j], px[j], tot[j], C.bad); lane_tot += tot[j]; }
@@ -446,7 +460,6 @@ __device__ __forceinline__ void seq2_window(const uint8_t *base8, uint32_t tab_s
     }
     Hist E = hist_shfl_up(G, 1);                                   // history before this lane's first sequence, relative to the window start
     if (lane == 0) E = hist_identity();
-    uint64_t r[K];
 #pragma unroll
     for (int j = 0; j < K; j++) {
         lit += Q[j].ll; out += Q[j].ll + Q[j].ml;
@@ -455,6 +468,13 @@ __device__ __forceinline__ void seq2_window(const uint8_t *base8, uint32_t tab_s
         r[j] = (uint64_t)out | ((uint64_t)lit << ZSB_REC_POS_BITS) | ((uint64_t)off << (2 * ZSB_REC_POS_BITS));
     }
     C.H = hist_compose(hist_bcast(G, 31), C.H, C.bad);
+}
+__device__ __forceinline__ void seq2_window(const uint8_t *base8, uint32_t tab_sa, const uint32_t *wd, uint32_t i0, uint32_t nseq, uint32_t regen,
+                                            uint64_t *rec, Seq2Carry &C, uint32_t lane) {
+    constexpr int K = SEQ_PER_LANE;
+    const uint32_t ia = i0 + K * lane;
+    bool v[K]; uint64_t r[K];
+    seq2_records<K>(base8, tab_sa, wd, i0, nseq, regen, C, lane, v, r);
     // (records are 16-byte aligned: seq_buf is kept even and K is even)
 #pragma unroll
     for (int j = 0; j < K; j += 2) {
@@ -463,8 +483,29 @@ __device__ __forceinline__ void seq2_window(const uint8_t *base8, uint32_t tab_s
     }
 }
 
-__global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t *__restrict__ src, ZsbBlockWork *work, const uint32_t *__restrict__ seq_list,
-                                                                ZsbCounters *cnt, uint64_t *seq_pool, uint32_t *slow_list, uint32_t used) {
+// -DZSB_SEQ_TIMING (tools/probes/seq_timing.py): per-CTA cycle counts of the stages of k_seq
+#ifdef ZSB_SEQ_TIMING
+__device__ long long g_seq_timing[160][8];     // per CTA: start, tables built, states read, producer loop done, cycles the producer waited for free windows, helper 1: waited / worked / windows
+extern "C" int zsb_debug_seq_timing(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_seq_timing, sizeof g_seq_timing); }
+#define SEQ_T(i) do { if (lane == 0 && blockIdx.x < 160) g_seq_timing[blockIdx.x][i] = clock64(); } while (0)
+#else
+#define SEQ_T(i) do {} while (0)
+#endif
+// k_seq  = k_seq_t<16, 128, 2, false>: records to HBM, executed by k_exec2 / k_exec afterwards.
+// k_seqx = k_seq_t<28, 32, 4, true>:   one consumer warp per chain does phase 2 one sequence per lane and, where the place of the
+//          block's output is known beforehand (first block of a frame whose predecessors all declare their sizes), executes
+//          the sequences at once (seqx_consume, further down): no record round trip through HBM, and execution fills the issue slots the
+//          chain leaves empty.  Chains whose block cannot be placed write records as k_seq does.
+struct SeqxArgs { const zsb_frame *frames; const zsb_block *blocks; const uint64_t *pre_off; const uint8_t *lit_pool; uint8_t *dst; };
+template <int HELPERS, int WIN, int NBUF>
+__device__ __forceinline__ void seqx_consume(uint8_t *smem_rings, SeqSharedT<WIN * NBUF + 4> &S, const uint8_t *src, const uint8_t *base8, ZsbBlockWork *work,
+                                             ZsbCounters *cnt, uint32_t *slow_list, const SeqxArgs &A, uint32_t warp, uint32_t lane);
+template <int HELPERS, int WIN, int NBUF, bool FUSED>
+__global__ void __launch_bounds__(32 * (1 + HELPERS), 1) k_seq_t(const uint8_t *__restrict__ src, ZsbBlockWork *work, const uint32_t *__restrict__ seq_list,
+                                                                ZsbCounters *cnt, uint64_t *seq_pool, uint32_t *slow_list, uint32_t used, SeqxArgs A) {
+    constexpr int NT = 32 * (1 + HELPERS), CPH = SEQ_CHAINS / HELPERS;       // threads of the CTA; chains per phase-2 warp
+    constexpr uint32_t BAR_FULL = 1u, BAR_FREE = 1u + NBUF, BAR_HELPERS = 1u + 2u * NBUF;
+    typedef SeqSharedT<WIN * NBUF + 4> SeqShared;
     extern __shared__ __align__(1024) uint8_t smem[];      // the stream rings must be 512-byte aligned (SEQ_STEP)
     if (cnt->overflow) return;
     uint32_t *tbl = reinterpret_cast<uint32_t *>(smem);
@@ -475,6 +516,7 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
     const uint32_t mis = (uint32_t)((uintptr_t)src & 7);
     const uint8_t *base8 = src - mis;
 
+    if (warp == 0) SEQ_T(0);
     // ---- set-up: the phase-2 warps fill the code tables and build the 3 x 32 FSE tables, one warp per table (6 tables per
     // warp, fse_build_table_warp); then the producer lanes read their initial states
     SeqTables T;
@@ -491,13 +533,13 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
         bi = active ? seq_list[idx] : 0;
         if (active) { w = work[bi]; active = w.status == ZSB_OK; }
     } else {
-        for (uint32_t k = threadIdx.x - 32; k < 36 + 53; k += 32 * SEQ_HELPERS) S.tab[k] = k < 36 ? zsb_ll_entry(k) : zsb_ml_entry(k - 36);
+        for (uint32_t k = threadIdx.x - 32; k < 36 + 53; k += 32 * HELPERS) S.tab[k] = k < 36 ? zsb_ll_entry(k) : zsb_ml_entry(k - 36);
         __syncwarp();
         // the code tables are filled by all phase-2 warps together: wait for all of them
-        seq_bar_sync_helpers();
+        seq_bar_sync<32 * HELPERS>(BAR_HELPERS);
         FseWarpScratch &X = reinterpret_cast<FseWarpScratch *>(counts)[warp - 1];
-        for (uint32_t q = 0; q < 3 * SEQ_CPH; q++) {
-            const uint32_t c = (warp - 1) * SEQ_CPH + q / 3, t = q % 3, idx = blockIdx.x * used + c;
+        for (uint32_t q = 0; q < 3 * CPH; q++) {
+            const uint32_t c = (warp - 1) * CPH + q / 3, t = q % 3, idx = blockIdx.x * used + c;
             int rc = ZSB_OK, al = 0;
             if (c < used && idx < n) {
                 const ZsbBlockWork &wb = work[seq_list[idx]];
@@ -510,6 +552,7 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
         }
     }
     __syncthreads();                                   // tables built; the count area becomes the stream rings
+    if (warp == 0) SEQ_T(1);
     if (warp == 0) {
         T.ts = SEQ_CHAINS;
         T.tbl[0] = tbl + lane; T.tbl[1] = tbl + SEQ_TBL_CELLS * SEQ_CHAINS + lane; T.tbl[2] = tbl + (SEQ_TBL_CELLS + SEQ_OF_CELLS) * SEQ_CHAINS + lane;
@@ -558,9 +601,28 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
         S.top0[lane] = (unsigned long long)((int64_t)(R.pl - base8) * 8 + top);
         S.rec[lane] = (unsigned long long)(uintptr_t)(seq_pool + w.seq_buf);
         S.final_rc[lane] = ZSB_OK;
+        if (FUSED) {
+            // the block can be executed at once if its place in the output is known now: the first block of a frame the host could place
+            // (pre_off: every frame before it declares its size), literals there (k_huf ran before this kernel)
+            unsigned long long g = 0; uint32_t lim = 0;
+            if (active && A.pre_off && w.lit_status == ZSB_OK) {
+                const uint32_t f = A.blocks[bi].frame;
+                const uint64_t po = A.pre_off[f];
+                if (po != ~0ull && A.frames[f].first_block == bi) {
+                    g = (unsigned long long)(uintptr_t)(A.dst + po);
+                    const uint64_t cs = A.frames[f].content_size;
+                    lim = cs > ZSB_BLOCK_MAX ? (uint32_t)ZSB_BLOCK_MAX : (uint32_t)cs;
+                }
+            }
+            S.gdst[lane] = g; S.limit[lane] = lim;
+        }
     }
     __syncthreads();
 
+    if (warp == 0) SEQ_T(2);
+#ifdef ZSB_SEQ_TIMING
+    long long t_wait = 0, t_work = 0;
+#endif
     if (warp == 0) {
         // ---- producer: == the loop of seq_fast_phase1
         const uint32_t nseq = active ? w.nseq : 0u;
@@ -603,7 +665,7 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
             const uint32_t bL = zsb_fsl(t, 0, nL), bM = zsb_fsl(zsb_fsl(0, t, nL), 0, nM), bO = zsb_fsl(zsb_fsl(0, t, nLM), 0, nO);         \
             aL = tbL + (ZSB_CELL_BASE(eL) + bL) * (SEQ_CHAINS * 4); aM = tbM + (ZSB_CELL_BASE(eM) + bM) * (SEQ_CHAINS * 4);                 \
             aO = tbO + (ZSB_CELL_BASE(eO) + bO) * (SEQ_CHAINS * 4);                                        /* sequence.rs:80-88 */          \
-            wrow[(i_) & (2 * SEQ_WIN - 1)] = seq_fast_word(eL, eO, eM, sum);                                                                \
+            wrow[(i_) & (WIN * NBUF - 1)] = seq_fast_word(eL, eO, eM, sum);                                                                \
             /* the cursor behind the extra bits of the last sequence (no state update follows it, sequence.rs:80): below the stream = over-read */ \
             if ((i_) + 1 == nseq) top = SEQ_TOP() - (int32_t)(sum & 0xFFu);                                                                  \
             /* the window moves on */                                                                                                       \
@@ -615,60 +677,85 @@ __global__ void __launch_bounds__(32 * (1 + SEQ_HELPERS), 1) k_seq(const uint8_t
             T2 = zsb_fsl(q1, q2, o); T1 = zsb_fsl(q0, q1, o); T0 = zsb_fsl(n0, q0, o);                                                      \
         }
 #define SEQ_TOP() ((int32_t)(kb * 8u + 32u - o))
-        for (uint32_t i0 = 0; i0 < maxn; i0 += SEQ_WIN) {
-            const uint32_t B = i0 / SEQ_WIN;
-            if (B >= 2) seq_bar_sync(SEQ_BAR_FREE + (B & 1u));      // the phase-2 warps are done with window B-2, whose ring slots window B overwrites
+        for (uint32_t i0 = 0; i0 < maxn; i0 += WIN) {
+            const uint32_t B = i0 / WIN;
+#ifdef ZSB_SEQ_TIMING
+            const long long tw0 = clock64();
+#endif
+            if (B >= NBUF) seq_bar_sync<NT>(BAR_FREE + B % NBUF);   // the phase-2 warps are done with window B-NBUF, whose ring slots window B overwrites
+#ifdef ZSB_SEQ_TIMING
+            t_wait += clock64() - tw0;
+#endif
             // A chain runs every step of every window it has a sequence in: past its last sequence it walks on from valid states over
             // whatever the ring holds (nothing of that is used: phase 2 stops at nseq), so that no window needs a per-step test.  The
             // stream rings are topped up every 8 steps (8 x 90 bits + the 224 bits of look-ahead < one 128-byte line), by all lanes in
             // the same pass.
             if (i0 < nseq) {
-                for (uint32_t i8 = i0; i8 < i0 + SEQ_WIN; i8 += 8) {
+                for (uint32_t i8 = i0; i8 < i0 + WIN; i8 += 8) {
                     sr_check<7, SEQ_PF>(R, SEQ_TOP() - 160);
 #pragma unroll 8
                     for (uint32_t i = i8; i < i8 + 8; i++) SEQ_STEP(i)
                 }
             }
             __threadfence_block();
-            seq_bar_arrive(SEQ_BAR_FULL + (B & 1u));                // window B is in the ring
+            seq_bar_arrive<NT>(BAR_FULL + B % NBUF);                // window B is in the ring
         }
 #undef SEQ_TOP
 #undef SEQ_STEP
+        SEQ_T(3);
+#ifdef ZSB_SEQ_TIMING
+        if (lane == 0 && blockIdx.x < 160) g_seq_timing[blockIdx.x][4] = t_wait;
+#endif
         // an over-read shows as a cursor below the stream start; illegal codes are caught by phase 2, which sees every code
         if (active && top < startbit) S.final_rc[lane] = ZSB_NEEDS_SLOW;
+    } else if constexpr (FUSED) {
+        seqx_consume<HELPERS, WIN, NBUF>(smem + SEQ_TBL_BYTES + 256 * SEQ_CHAINS * 2 + ((sizeof(SeqShared) + 15) & ~15ull), S, src, base8, work, cnt, slow_list, A, warp, lane);
+        return;
     } else {
         // ---- phase 2: this warp's chains, batch by batch as the producer delivers them
-        const uint32_t h = warp - 1, c0 = h * SEQ_CPH;     // this warp's chains: c0 .. c0 + SEQ_CPH - 1
+        const uint32_t h = warp - 1, c0 = h * CPH;     // this warp's chains: c0 .. c0 + CPH - 1
         const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(S.tab);
-        Seq2Carry C[SEQ_CPH];
-        uint32_t nsq[SEQ_CPH];
+        Seq2Carry C[CPH];
+        uint32_t nsq[CPH];
 #pragma unroll
-        for (int k = 0; k < SEQ_CPH; k++) {
+        for (int k = 0; k < CPH; k++) {
             nsq[k] = S.nseq[c0 + k];
             C[k].top = (int64_t)S.top0[c0 + k]; C[k].lit_acc = 0; C[k].out_acc = 0; C[k].H = hist_identity(); C[k].bad = 0;
         }
         uint32_t nbat = 0;                                            // windows of the longest chain of the CTA: every warp takes part in every hand-over
 #pragma unroll
-        for (int c = 0; c < SEQ_CHAINS; c++) nbat = max(nbat, (S.nseq[c] + SEQ_WIN - 1) / SEQ_WIN);
+        for (int c = 0; c < SEQ_CHAINS; c++) nbat = max(nbat, (S.nseq[c] + WIN - 1) / WIN);
         for (uint32_t b = 0; b < nbat; b++) {
-            seq_bar_sync(SEQ_BAR_FULL + (b & 1u));
+#ifdef ZSB_SEQ_TIMING
+            const long long tw0 = clock64();
+#endif
+            seq_bar_sync<NT>(BAR_FULL + b % NBUF);
+#ifdef ZSB_SEQ_TIMING
+            const long long tw1 = clock64(); t_wait += tw1 - tw0;
+#endif
 #pragma unroll
-            for (int k = 0; k < SEQ_CPH; k++) {
-                if (b * SEQ_WIN < nsq[k]) {
-                    const uint4 ww = *reinterpret_cast<const uint4 *>(&S.words[c0 + k][(b & 1u) * SEQ_WIN + SEQ_PER_LANE * lane]);
+            for (int k = 0; k < CPH; k++) {
+                if (b * WIN < nsq[k]) {
+                    const uint4 ww = *reinterpret_cast<const uint4 *>(&S.words[c0 + k][(b % NBUF) * WIN + SEQ_PER_LANE * lane]);
                     const uint32_t wd[4] = {ww.x, ww.y, ww.z, ww.w};
 #ifndef SEQ_NO_P2
-                    seq2_window(base8, tab_sa, wd, b * SEQ_WIN, nsq[k], S.regen[c0 + k], reinterpret_cast<uint64_t *>((uintptr_t)S.rec[c0 + k]), C[k], lane);
+                    seq2_window(base8, tab_sa, wd, b * WIN, nsq[k], S.regen[c0 + k], reinterpret_cast<uint64_t *>((uintptr_t)S.rec[c0 + k]), C[k], lane);
 #else
                     C[k].lit_acc += wd[0] & 1;
 #endif
                 }
             }
-            if (b + 2 < nbat) seq_bar_arrive(SEQ_BAR_FREE + (b & 1u));
+            if (b + NBUF < nbat) seq_bar_arrive<NT>(BAR_FREE + b % NBUF);
+#ifdef ZSB_SEQ_TIMING
+            t_work += clock64() - tw1;
+#endif
         }
+#ifdef ZSB_SEQ_TIMING
+        if (warp == 1 && lane == 0 && blockIdx.x < 160) { g_seq_timing[blockIdx.x][5] = t_wait; g_seq_timing[blockIdx.x][6] = t_work; g_seq_timing[blockIdx.x][7] = nbat; }
+#endif
         __syncthreads();                           // the producer's final verdicts
 #pragma unroll
-        for (int k = 0; k < SEQ_CPH; k++) {
+        for (int k = 0; k < CPH; k++) {
             if (nsq[k] == 0) continue;
             const bool bad = __any_sync(FULL, C[k].bad) || S.final_rc[c0 + k] != ZSB_OK;
             if (lane == 0) {
@@ -718,7 +805,8 @@ __global__ void __launch_bounds__(32, 1) k_seq_slow(const uint8_t *__restrict__ 
 
 // ======================================================================================= k_plan2
 __global__ void __launch_bounds__(1024) k_plan2(const zsb_frame *__restrict__ frames, uint32_t nf, const zsb_block *__restrict__ blocks,
-                                                ZsbBlockWork *work, ZsbFrameOut *fout, ZsbCounters *cnt, uint64_t dst_cap, uint32_t flags) {
+                                                ZsbBlockWork *work, ZsbFrameOut *fout, ZsbCounters *cnt, uint64_t dst_cap, uint32_t flags,
+                                                const uint64_t *__restrict__ pre_off) {
     __shared__ uint64_t s_warp[33];
     __shared__ uint64_t s_base, s_max;
     __shared__ uint32_t s_last;
@@ -765,6 +853,8 @@ __global__ void __launch_bounds__(1024) k_plan2(const zsb_frame *__restrict__ fr
                 if (st[j] == ZSB_OK && off + len[j] > dst_cap) st[j] = ZSB_E_DST_TOO_SMALL;
                 fout[f].dst_off = off; fout[f].dst_len = (st[j] == ZSB_OK) ? len[j] : 0; fout[f].status = st[j];
                 if (st[j] == ZSB_OK && len[j]) atomicMax((unsigned long long *)&s_max, (unsigned long long)(off + len[j]));
+                // a block k_seqx has executed already lies where the host expected the frame to go
+                if (pre_off && st[j] == ZSB_OK && frames[f].kind == 0 && frames[f].n_blocks && __ldcg(&work[frames[f].first_block].fused) && off != pre_off[f]) cnt->refuse = 1u;
             }
             off += len[j];
         }
@@ -1200,7 +1290,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
 // Positions are 32-bit and relative to the start of the current block (negative = earlier blocks of the frame);
 // the ring index of a position is its global address modulo EX2_RING, so that frames and blocks continue
 // seamlessly and 16-byte units of the ring and of HBM coincide.
-#define EX2_RING 2048u
+#define EX2_RING 2048u           // k_exec2; the fused sequence kernel uses 1 KiB rings
 #define EX2_MASK (EX2_RING - 1u)
 #define EX2_WARPS 4
 #define EX2_LONG 16u
@@ -1210,25 +1300,29 @@ struct Ex2Lit { const uint8_t *p; uint32_t rle; bool is_rle; };
 __device__ __forceinline__ uint8_t ex2_lit(const Ex2Lit &L, uint32_t i) { return L.is_rle ? (uint8_t)L.rle : __ldg(L.p + i); }
 
 // ring -> HBM for positions [lo, hi): bytes up to the first 16-byte boundary of the global address, 16-byte units, tail bytes
+template <uint32_t RING = EX2_RING>
 __device__ __forceinline__ void ex2_flush(const uint8_t *ring, uint8_t *gblk, uint32_t g0, int32_t lo, int32_t hi, uint32_t lane) {
+    constexpr uint32_t EX2_MASK_ = RING - 1u;
     if (hi <= lo) return;
     int32_t a = lo + (int32_t)((16u - ((g0 + (uint32_t)lo) & 15u)) & 15u); if (a > hi) a = hi;
-    for (int32_t p = lo + (int32_t)lane; p < a; p += 32) gblk[p] = ring[(g0 + (uint32_t)p) & EX2_MASK];
+    for (int32_t p = lo + (int32_t)lane; p < a; p += 32) gblk[p] = ring[(g0 + (uint32_t)p) & EX2_MASK_];
     int32_t b = hi - (int32_t)((g0 + (uint32_t)hi) & 15u); if (b < a) b = a;
     for (int32_t p = a + 16 * (int32_t)lane; p < b; p += 512)
-        *reinterpret_cast<uint4 *>(gblk + p) = *reinterpret_cast<const uint4 *>(ring + ((g0 + (uint32_t)p) & EX2_MASK));
-    for (int32_t p = b + (int32_t)lane; p < hi; p += 32) gblk[p] = ring[(g0 + (uint32_t)p) & EX2_MASK];
+        *reinterpret_cast<uint4 *>(gblk + p) = *reinterpret_cast<const uint4 *>(ring + ((g0 + (uint32_t)p) & EX2_MASK_));
+    for (int32_t p = b + (int32_t)lane; p < hi; p += 32) gblk[p] = ring[(g0 + (uint32_t)p) & EX2_MASK_];
 }
 // one already produced byte of the frame: from the ring if it is still there, else from HBM
+template <uint32_t RING = EX2_RING>
 __device__ __forceinline__ uint8_t ex2_src(const uint8_t *ring, const uint8_t *gblk, uint32_t g0, int32_t ring_lo, int32_t p) {
-    return p >= ring_lo ? ring[(g0 + (uint32_t)p) & EX2_MASK] : __ldcg(gblk + p);
+    return p >= ring_lo ? ring[(g0 + (uint32_t)p) & (RING - 1u)] : __ldcg(gblk + p);
 }
 
 // ---- copies in units of up to 8 bytes: three aligned source words, two funnel shifts, predicated byte stores
 // store the low n (1..8) bytes of v1:v0 at ring position d (unmasked)
+template <uint32_t RING = EX2_RING>
 __device__ __forceinline__ void ex2_store8(uint8_t *ring, uint32_t d, uint32_t v0, uint32_t v1, uint32_t n) {
-    d &= EX2_MASK;
-    if (d + 8 <= EX2_RING) {
+    d &= RING - 1u;
+    if (d + 8 <= RING) {
         const uint32_t a = (uint32_t)__cvta_generic_to_shared(ring) + d;
         asm volatile(
             "{\n\t.reg .pred p1, p2, p3, p4, p5, p6, p7;\n\t.reg .b32 t;\n\t"
@@ -1245,15 +1339,16 @@ __device__ __forceinline__ void ex2_store8(uint8_t *ring, uint32_t d, uint32_t v
             ::"r"(a), "r"(v0), "r"(v1), "r"(n) : "memory");
     } else {
         const uint64_t v = ((uint64_t)v1 << 32) | v0;
-        for (uint32_t t = 0; t < n; t++) ring[(d + t) & EX2_MASK] = (uint8_t)(v >> (8 * t));
+        for (uint32_t t = 0; t < n; t++) ring[(d + t) & (RING - 1u)] = (uint8_t)(v >> (8 * t));
     }
 }
 // n (<= 8) bytes starting at ring position s (unmasked)
+template <uint32_t RING = EX2_RING>
 __device__ __forceinline__ void ex2_load8_ring(const uint8_t *ring, uint32_t s, uint32_t n, uint32_t &v0, uint32_t &v1) {
-    const uint32_t a = s & EX2_MASK & ~3u, sh = (s & 3u) * 8u;
+    const uint32_t a = s & (RING - 1u) & ~3u, sh = (s & 3u) * 8u;
     const uint32_t w0 = *reinterpret_cast<const uint32_t *>(ring + a);
-    const uint32_t w1 = *reinterpret_cast<const uint32_t *>(ring + ((a + 4) & EX2_MASK));
-    const uint32_t w2 = *reinterpret_cast<const uint32_t *>(ring + ((a + 8) & EX2_MASK));
+    const uint32_t w1 = *reinterpret_cast<const uint32_t *>(ring + ((a + 4) & (RING - 1u)));
+    const uint32_t w2 = *reinterpret_cast<const uint32_t *>(ring + ((a + 8) & (RING - 1u)));
     v0 = __funnelshift_r(w0, w1, sh); v1 = __funnelshift_r(w1, w2, sh);
 }
 // n (<= 16) bytes starting at global address g, in two steps so that the loads of several sources are in flight together:
@@ -1282,128 +1377,97 @@ __device__ __forceinline__ void ex2_unit(const ExRaw &r, int u, uint32_t &v0, ui
     else { v0 = __funnelshift_r(r.w2, r.w3, r.sh); v1 = __funnelshift_r(r.w3, r.w4, r.sh); }
 }
 
-__global__ void __launch_bounds__(32 * EX2_WARPS, 7) k_exec2(const uint8_t *__restrict__ src, const zsb_frame *__restrict__ frames,
-                                                             const zsb_block *__restrict__ blocks, const ZsbBlockWork *__restrict__ work,
-                                                             ZsbFrameOut *fout, const uint32_t *__restrict__ exec_list, uint32_t n,
-                                                             const ZsbCounters *__restrict__ cnt, const uint64_t *__restrict__ seq_pool,
-                                                             const uint8_t *__restrict__ lit_pool, uint8_t *dst) {
-    __shared__ __align__(128) uint8_t rings[EX2_WARPS][EX2_RING];
-    if (cnt->overflow) return;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t gw = blockIdx.x * EX2_WARPS + warp;
-    if (gw >= n) return;
-    uint8_t *ring = rings[warp];
-    const uint32_t f = exec_list[gw];
-    const ZsbFrameOut fo = fout[f];
-    if (fo.status != ZSB_OK) return;
-    const zsb_frame fr = frames[f];
-    uint8_t *fdst = dst + fo.dst_off;
-    int err = 0;
-    int32_t flushed = 0, ring_lo = 0;          // [ring_lo, ..) is in the ring, [.., flushed) is in HBM; ring_lo <= flushed always
-    for (uint32_t k = 0; k < fr.n_blocks && !err; k++) {
-        const uint32_t bi = fr.first_block + k;
-        const ZsbBlockWork &W = work[bi];
-        const uint32_t out_size = W.out_size;
-        uint8_t *gblk = fdst + W.out_off;
-        const uint32_t g0 = (uint32_t)(uintptr_t)gblk;
-        if (blocks[bi].type != ZSB_BT_COMPRESSED) {
-            ex2_flush(ring, gblk, g0, flushed, 0, lane);               // what earlier blocks left in the ring
-            flushed = ring_lo = (int32_t)out_size;                     // raw / RLE blocks were written by k_rawrle
-        } else {
-            const uint32_t nseq = W.nseq, regen = W.lit_regen;
-            Ex2Lit L;
-            L.is_rle = W.lit_type == ZSB_LT_RLE; L.rle = L.is_rle ? src[W.lit_src] : 0u;
-            L.p = W.lit_type == ZSB_LT_RAW ? src + W.lit_src : lit_pool + W.lit_buf;
-            const uint64_t *seqs = seq_pool + W.seq_buf;
-            const uint64_t P0 = W.out_off;
-            const uint32_t items = nseq + 1;   // the last item is the literal tail (decoding_context.rs:101-103); all there is when nseq == 0
-            uint32_t c_out = 0, c_lit = 0;
-            // records are requested two batches ahead: the batch after this one is looked at early (its literals are prefetched)
-            uint64_t rec_next = lane < nseq ? __ldg(seqs + lane) : 0ull, rec_next2 = lane + 32 < nseq ? __ldg(seqs + lane + 32) : 0ull;
-            ExRaw LR; bool lr_has = false;          // literal words of the current batch, requested during the previous one
-            for (uint32_t b0 = 0; b0 < items; b0 += 32) {
-                const uint32_t i = b0 + lane;
-                const uint64_t rec = rec_next;
-                rec_next = rec_next2;
-                if (i + 64 < nseq) rec_next2 = __ldg(seqs + i + 64);
-                const bool is_seq = i < nseq;
-                const uint32_t out_end = is_seq ? (uint32_t)rec & ZSB_REC_POS_MASK : out_size;
-                const uint32_t lit_end = is_seq ? (uint32_t)(rec >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK : regen;
+// per-frame state of a warp that executes sequences (k_exec2, and the consumer warps of the fused sequence kernel)
+struct Ex2State {
+    uint8_t *ring;              // RING bytes of shared memory, index = global address & (RING - 1)
+    uint8_t *gblk;              // global address of the current block's first byte; positions are relative to it
+    uint32_t g0;                // low 32 bits of gblk
+    int32_t flushed, ring_lo;   // [ring_lo, ..) is in the ring, [.., flushed) is in HBM; ring_lo <= flushed always
+    uint32_t c_out, c_lit;      // output / literal position behind the last item executed
+    ExRaw LR; bool lr_has;      // literal words of the next batch, requested during the current one
+    int err;
+};
+// One batch of (up to) 32 consecutive items of a block, one per lane: a sequence {out_end, lit_end: positions behind it, off: its resolved
+// offset}, or the literal tail of the block (is_seq false, out_end = the block's size, lit_end = its literal count); lanes without an item
+// repeat the ends of the last one.  has_next / next_lit_end: the lit_end of the same lane's item in the next batch (its literals are
+// requested now).  P0: frame-relative position of the block.  == DecodingContext::execute_sequences for these items (decoding_context.rs:78-106).
+// GIANT: the largest batch (bytes) that goes through the ring; <= RING - 16, so that everything below the ring's floor has been flushed
+template <uint32_t RING, uint32_t GIANT>
+__device__ __forceinline__ void ex2_batch(Ex2State &X, const Ex2Lit &L, uint64_t P0, bool is_seq, uint32_t out_end, uint32_t lit_end, uint32_t off,
+                                          bool has_next, uint32_t next_lit_end, uint32_t lane) {
                 uint32_t p_out = __shfl_up_sync(FULL, out_end, 1), p_lit = __shfl_up_sync(FULL, lit_end, 1);
-                if (lane == 0) { p_out = c_out; p_lit = c_lit; }
-                c_out = __shfl_sync(FULL, out_end, 31); c_lit = __shfl_sync(FULL, lit_end, 31);
+                if (lane == 0) { p_out = X.c_out; p_lit = X.c_lit; }
+                X.c_out = __shfl_sync(FULL, out_end, 31); X.c_lit = __shfl_sync(FULL, lit_end, 31);
                 const uint32_t ll = lit_end - p_lit;
                 uint32_t ml = out_end - p_out - ll;
-                const uint32_t off = is_seq ? seq_real_offset((uint32_t)(rec >> (2 * ZSB_REC_POS_BITS)), W.rep_in) : 1u;
-                const uint32_t dstm = p_out + ll;
-                if (is_seq && (off == 0 || (uint64_t)off > P0 + dstm)) { err = ZSB_E_IMPOSSIBLE_VALUE; ml = 0; }    // decoding_context.rs:86-90
+                                const uint32_t dstm = p_out + ll;
+                if (is_seq && (off == 0 || (uint64_t)off > P0 + dstm)) { X.err = ZSB_E_IMPOSSIBLE_VALUE; ml = 0; }    // decoding_context.rs:86-90
                 const int32_t srcp = (int32_t)dstm - (int32_t)off;
-                const uint32_t B0 = __shfl_sync(FULL, p_out, 0), B1 = c_out;
-                if (B1 - B0 > EX2_GIANT) {
+                const uint32_t B0 = __shfl_sync(FULL, p_out, 0), B1 = X.c_out;
+                if (B1 - B0 > GIANT) {
                     // a batch too large for the ring (a very long literal run or match): sequence by sequence, straight to HBM
-                    ex2_flush(ring, gblk, g0, flushed, (int32_t)B0, lane);
+                    ex2_flush<RING>(X.ring, X.gblk, X.g0, X.flushed, (int32_t)B0, lane);
                     __syncwarp();
                     for (int j = 0; j < 32; j++) {
                         const uint32_t jo = __shfl_sync(FULL, p_out, j), jll = __shfl_sync(FULL, ll, j), jml = __shfl_sync(FULL, ml, j);
                         const uint32_t jl = __shfl_sync(FULL, p_lit, j), joff = __shfl_sync(FULL, off, j);
                         const int32_t js = __shfl_sync(FULL, srcp, j);
                         const uint32_t jd = jo + jll;
-                        for (uint32_t q = lane; q < jll; q += 32) gblk[jo + q] = ex2_lit(L, jl + q);
+                        for (uint32_t q = lane; q < jll; q += 32) X.gblk[jo + q] = ex2_lit(L, jl + q);
                         __syncwarp();
                         if (joff >= 32) {
                             for (uint32_t k0 = 0; k0 < jml; k0 += 32) {           // 32 bytes at a time: a unit never reads what it writes
-                                if (k0 + lane < jml) gblk[jd + k0 + lane] = __ldcg(gblk + js + (int32_t)(k0 + lane));
+                                if (k0 + lane < jml) X.gblk[jd + k0 + lane] = __ldcg(X.gblk + js + (int32_t)(k0 + lane));
                                 __syncwarp();
                             }
                         } else {
-                            for (uint32_t q = lane; q < jml; q += 32) gblk[jd + q] = __ldcg(gblk + js + (int32_t)(q % joff));   // periodic with period off
+                            for (uint32_t q = lane; q < jml; q += 32) X.gblk[jd + q] = __ldcg(X.gblk + js + (int32_t)(q % joff));   // periodic with period off
                         }
                         __syncwarp();
                     }
-                    flushed = ring_lo = (int32_t)B1;
-                    lr_has = false;                 // nothing was requested for the next batch
-                    continue;
+                    X.flushed = X.ring_lo = (int32_t)B1;
+                    X.lr_has = false;                 // nothing was requested for the next batch
+                    return;
                 }
-                ring_lo = max(ring_lo, (int32_t)B1 - (int32_t)EX2_RING);
+                X.ring_lo = max(X.ring_lo, (int32_t)B1 - (int32_t)RING);
                 // ---- the HBM reads of the batch are requested first, so that their latencies overlap: the sources of short matches
                 // that lie entirely in HBM (<= 16 bytes: two units; they depend on nothing in this batch) ...
                 const int32_t send = srcp + (int32_t)ml;
-                const bool farm = ml && ml <= EX2_LONG && send <= ring_lo && !(off < 8 && off < ml);
+                const bool farm = ml && ml <= EX2_LONG && send <= X.ring_lo && !(off < 8 && off < ml);
                 ExRaw FR;
-                if (farm) ex2_issue(gblk + srcp, ml, FR, true);
+                if (farm) ex2_issue(X.gblk + srcp, ml, FR, true);
                 // ... and the literals of the NEXT batch (those of this batch were requested one batch ago)
                 ExRaw NR; bool n_has = false;
-                if (b0 + 32 < items && !L.is_rle) {
-                    const uint32_t n_end = (i + 32 < nseq) ? (uint32_t)(rec_next >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK : regen;
-                    uint32_t n_beg = __shfl_up_sync(FULL, n_end, 1);
-                    if (lane == 0) n_beg = c_lit;
-                    const uint32_t n_ll = n_end - n_beg;
+                if (has_next && !L.is_rle) {
+                    uint32_t n_beg = __shfl_up_sync(FULL, next_lit_end, 1);
+                    if (lane == 0) n_beg = X.c_lit;
+                    const uint32_t n_ll = next_lit_end - n_beg;
                     n_has = n_ll && n_ll <= EX2_LONG;
                     if (n_has) ex2_issue(L.p + n_beg, n_ll, NR, false);
                 }
                 // ---- literals (no dependency on earlier output, decoding_context.rs:92-93)
                 if (ll && ll <= EX2_LONG) {
-                    if (L.is_rle) { const uint32_t v = L.rle * 0x01010101u; for (uint32_t q = 0; q < ll; q += 8) ex2_store8(ring, g0 + p_out + q, v, v, min(ll - q, 8u)); }
+                    if (L.is_rle) { const uint32_t v = L.rle * 0x01010101u; for (uint32_t q = 0; q < ll; q += 8) ex2_store8<RING>(X.ring, X.g0 + p_out + q, v, v, min(ll - q, 8u)); }
                     else {
-                        if (!lr_has) ex2_issue(L.p + p_lit, ll, LR, false);           // first batch of a block
+                        if (!X.lr_has) ex2_issue(L.p + p_lit, ll, X.LR, false);           // first batch of a block
                         uint32_t v0, v1;
-                        ex2_unit(LR, 0, v0, v1); ex2_store8(ring, g0 + p_out, v0, v1, min(ll, 8u));
-                        if (ll > 8) { ex2_unit(LR, 1, v0, v1); ex2_store8(ring, g0 + p_out + 8, v0, v1, ll - 8); }
+                        ex2_unit(X.LR, 0, v0, v1); ex2_store8<RING>(X.ring, X.g0 + p_out, v0, v1, min(ll, 8u));
+                        if (ll > 8) { ex2_unit(X.LR, 1, v0, v1); ex2_store8<RING>(X.ring, X.g0 + p_out + 8, v0, v1, ll - 8); }
                     }
                 }
-                LR = NR; lr_has = n_has;
+                X.LR = NR; X.lr_has = n_has;
                 for (uint32_t m = __ballot_sync(FULL, ll > EX2_LONG); m; m &= m - 1) {
                     const int j = __ffs(m) - 1;
                     const uint32_t jo = __shfl_sync(FULL, p_out, j), jll = __shfl_sync(FULL, ll, j), jl = __shfl_sync(FULL, p_lit, j);
-                    for (uint32_t q = lane; q < jll; q += 32) ring[(g0 + jo + q) & EX2_MASK] = ex2_lit(L, jl + q);
+                    for (uint32_t q = lane; q < jll; q += 32) X.ring[(X.g0 + jo + q) & (RING - 1u)] = ex2_lit(L, jl + q);
                 }
                 __syncwarp();
                 // ---- matches (decoding_context.rs:95-98): a lane goes once everything it needs from other sequences is written,
                 // i.e. lies below the match start of the lowest sequence still pending
                 if (farm) {
                     uint32_t v0, v1;
-                    ex2_unit(FR, 0, v0, v1); ex2_store8(ring, g0 + dstm, v0, v1, min(ml, 8u));
-                    if (ml > 8) { ex2_unit(FR, 1, v0, v1); ex2_store8(ring, g0 + dstm + 8, v0, v1, ml - 8); }
+                    ex2_unit(FR, 0, v0, v1); ex2_store8<RING>(X.ring, X.g0 + dstm, v0, v1, min(ml, 8u));
+                    if (ml > 8) { ex2_unit(FR, 1, v0, v1); ex2_store8<RING>(X.ring, X.g0 + dstm + 8, v0, v1, ml - 8); }
                 }
                 __syncwarp();
                 bool pend = ml != 0 && !farm;
@@ -1415,15 +1479,15 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 7) k_exec2(const uint8_t *__re
                     const bool ready = pend && need <= done;
                     if (ready && ml <= EX2_LONG) {
                         if (off < 8 && off < ml) {                     // overlapping with a short period: byte by byte
-                            for (uint32_t q = 0; q < ml; q++) ring[(g0 + dstm + q) & EX2_MASK] = ex2_src(ring, gblk, g0, ring_lo, srcp + (int32_t)q);
-                        } else if (srcp >= ring_lo) {                  // source still in the ring; a unit never reads what it writes (off >= 8)
+                            for (uint32_t q = 0; q < ml; q++) X.ring[(X.g0 + dstm + q) & (RING - 1u)] = ex2_src<RING>(X.ring, X.gblk, X.g0, X.ring_lo, srcp + (int32_t)q);
+                        } else if (srcp >= X.ring_lo) {                  // source still in the X.ring; a unit never reads what it writes (off >= 8)
                             for (uint32_t q = 0; q < ml; q += 8) {
                                 const uint32_t c = min(ml - q, 8u); uint32_t v0, v1;
-                                ex2_load8_ring(ring, g0 + (uint32_t)srcp + q, c, v0, v1);
-                                ex2_store8(ring, g0 + dstm + q, v0, v1, c);
+                                ex2_load8_ring<RING>(X.ring, X.g0 + (uint32_t)srcp + q, c, v0, v1);
+                                ex2_store8<RING>(X.ring, X.g0 + dstm + q, v0, v1, c);
                             }
-                        } else {                                       // straddles the ring floor (sources entirely in HBM were done above)
-                            for (uint32_t q = 0; q < ml; q++) ring[(g0 + dstm + q) & EX2_MASK] = ex2_src(ring, gblk, g0, ring_lo, srcp + (int32_t)q);
+                        } else {                                       // straddles the X.ring floor (sources entirely in HBM were done above)
+                            for (uint32_t q = 0; q < ml; q++) X.ring[(X.g0 + dstm + q) & (RING - 1u)] = ex2_src<RING>(X.ring, X.gblk, X.g0, X.ring_lo, srcp + (int32_t)q);
                         }
                         pend = false;
                     }
@@ -1433,35 +1497,168 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 7) k_exec2(const uint8_t *__re
                         const int32_t js = __shfl_sync(FULL, srcp, j);
                         if (joff >= 32) {
                             for (uint32_t k0 = 0; k0 < jml; k0 += 32) {
-                                if (k0 + lane < jml) ring[(g0 + jd + k0 + lane) & EX2_MASK] = ex2_src(ring, gblk, g0, ring_lo, js + (int32_t)(k0 + lane));
+                                if (k0 + lane < jml) X.ring[(X.g0 + jd + k0 + lane) & (RING - 1u)] = ex2_src<RING>(X.ring, X.gblk, X.g0, X.ring_lo, js + (int32_t)(k0 + lane));
                                 __syncwarp();
                             }
                         } else {
-                            for (uint32_t q = lane; q < jml; q += 32) ring[(g0 + jd + q) & EX2_MASK] = ex2_src(ring, gblk, g0, ring_lo, js + (int32_t)(q % joff));
+                            for (uint32_t q = lane; q < jml; q += 32) X.ring[(X.g0 + jd + q) & (RING - 1u)] = ex2_src<RING>(X.ring, X.gblk, X.g0, X.ring_lo, js + (int32_t)(q % joff));
                         }
                         if ((int)lane == j) pend = false;
                     }
                     __syncwarp();
                 }
                 // ---- whole 16-byte units of the batch go to HBM
-                const int32_t hi = (int32_t)B1 - (int32_t)((g0 + B1) & 15u);
-                if (hi > flushed) {
-                    if (((g0 + (uint32_t)flushed) & 15u) == 0) {           // the usual case: whole 16-byte units only, at most a few per lane
-                        for (int32_t p = flushed + 16 * (int32_t)lane; p < hi; p += 512)
-                            *reinterpret_cast<uint4 *>(gblk + p) = *reinterpret_cast<const uint4 *>(ring + ((g0 + (uint32_t)p) & EX2_MASK));
-                    } else ex2_flush(ring, gblk, g0, flushed, hi, lane);
-                    flushed = hi;
+                const int32_t hi = (int32_t)B1 - (int32_t)((X.g0 + B1) & 15u);
+                if (hi > X.flushed) {
+                    if (((X.g0 + (uint32_t)X.flushed) & 15u) == 0) {           // the usual case: whole 16-byte units only, at most a few per lane
+                        for (int32_t p = X.flushed + 16 * (int32_t)lane; p < hi; p += 512)
+                            *reinterpret_cast<uint4 *>(X.gblk + p) = *reinterpret_cast<const uint4 *>(X.ring + ((X.g0 + (uint32_t)p) & (RING - 1u)));
+                    } else ex2_flush<RING>(X.ring, X.gblk, X.g0, X.flushed, hi, lane);
+                    X.flushed = hi;
                     __syncwarp();               // the next batch may read these bytes back from HBM through other lanes
                 }
-                if (__any_sync(FULL, err != 0)) { err = ZSB_E_IMPOSSIBLE_VALUE; break; }
+}
+
+// The consumer warps of k_seqx (k_seq_t<.., FUSED = true>): warp c + 1 takes chain c.  Per window of 32 sequences: phase 2 with one
+// sequence per lane (seq2_records<1>), then -- if the block's place is known -- the batch BEFORE it is executed (ex2_batch wants the
+// literal ends of the batch that follows, to request its literals early); else the records go to HBM as in k_seq.
+// Nothing is executed once phase 2 has seen anything illegal (the careful decoder redoes the block into records, k_exec2 executes them);
+// what was written until then lies inside the frame's own place.  An output that would leave that place (a frame that regenerates
+// more than its Frame_Content_Size) stops the execution and sets cnt->refuse: the host runs the batch again without k_seqx.
+template <int HELPERS, int WIN, int NBUF>
+__device__ __forceinline__ void seqx_consume(uint8_t *smem_rings, SeqSharedT<WIN * NBUF + 4> &S, const uint8_t *src, const uint8_t *base8, ZsbBlockWork *work,
+                                             ZsbCounters *cnt, uint32_t *slow_list, const SeqxArgs &A, uint32_t warp, uint32_t lane) {
+    static_assert(WIN == 32, "one sequence per lane and window");
+    constexpr int NT = 32 * (1 + HELPERS);
+    constexpr uint32_t BAR_FULL = 1u, BAR_FREE = 1u + NBUF;
+    const uint32_t c = warp - 1;
+    const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(S.tab);
+    const uint32_t nsq = S.nseq[c], regen = S.regen[c], bi = S.bi[c], limit = S.limit[c];
+    Seq2Carry C;
+    C.top = (int64_t)S.top0[c]; C.lit_acc = 0; C.out_acc = 0; C.H = hist_identity(); C.bad = 0;
+    uint32_t nbat = 0;                                                // windows of the longest chain of the CTA: every warp takes part in every hand-over
+#pragma unroll
+    for (int k = 0; k < SEQ_CHAINS; k++) nbat = max(nbat, (S.nseq[k] + WIN - 1) / WIN);
+    uint8_t *gdst = reinterpret_cast<uint8_t *>((uintptr_t)S.gdst[c]);
+    uint64_t *rec = reinterpret_cast<uint64_t *>((uintptr_t)S.rec[c]);
+    const bool placed = gdst != nullptr && nsq != 0;
+    bool exec = placed, refuse = false, xerr = false;
+    Ex2State X; Ex2Lit L;
+    X.ring = smem_rings + c * SEQX_RING; X.gblk = gdst; X.g0 = (uint32_t)(uintptr_t)gdst; X.flushed = 0; X.ring_lo = 0;
+    X.c_out = 0; X.c_lit = 0; X.lr_has = false; X.err = 0;
+    L.p = nullptr; L.rle = 0; L.is_rle = false;
+    if (placed) {
+        const ZsbBlockWork &W = work[bi];
+        L.is_rle = W.lit_type == ZSB_LT_RLE; L.rle = L.is_rle ? src[W.lit_src] : 0u;
+        L.p = W.lit_type == ZSB_LT_RAW ? src + W.lit_src : A.lit_pool + W.lit_buf;
+    }
+    const uint32_t rep0[3] = {1u, 4u, 8u};                            // the history a frame starts with (decoding_context.rs:40)
+    const uint32_t items = nsq + 1;                                   // the last item is the literal tail
+    const uint32_t nloop = placed ? max(nbat, (items + 31) / 32 + 1) : nbat;
+    uint32_t c_oe = 0, c_le = 0, c_off = 1; bool c_seq = false;       // the batch waiting to be executed: out_end, lit_end, offset, sequence?
+    for (uint32_t B = 0; B < nloop; B++) {
+        uint32_t n_oe = 0, n_le = 0, n_off = 1; bool n_seq = false;
+        if (B < nbat) {
+            seq_bar_sync<NT>(BAR_FULL + B % NBUF);
+            if (B * WIN < nsq) {
+                const uint32_t wd[1] = {S.words[c][(B % NBUF) * WIN + lane]};
+                bool v[1]; uint64_t r[1];
+                seq2_records<1>(base8, tab_sa, wd, B * WIN, nsq, regen, C, lane, v, r);
+                if (!placed) { if (v[0]) rec[B * WIN + lane] = r[0]; }
+                else if (v[0]) {
+                    n_seq = true; n_oe = (uint32_t)r[0] & ZSB_REC_POS_MASK; n_le = (uint32_t)(r[0] >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK;
+                    n_off = seq_real_offset((uint32_t)(r[0] >> (2 * ZSB_REC_POS_BITS)), rep0);
+                }
+            }
+            if (B + NBUF < nbat) seq_bar_arrive<NT>(BAR_FREE + B % NBUF);
+        }
+        if (!placed) continue;
+        if (!n_seq) { n_le = regen; n_oe = C.out_acc + (regen - C.lit_acc); }          // behind the last sequence: the literal tail, then nothing
+        if (exec && __any_sync(FULL, C.bad != 0)) exec = false;
+        if (exec && __any_sync(FULL, n_oe > limit)) { exec = false; refuse = true; }
+        if (exec && B >= 1 && (B - 1) * 32 < items) {
+            ex2_batch<SEQX_RING, SEQX_RING - 32>(X, L, 0, c_seq, c_oe, c_le, c_off, B * 32 < items, n_le, lane);
+            if (__any_sync(FULL, X.err != 0)) { exec = false; xerr = true; }
+        }
+        c_oe = n_oe; c_le = n_le; c_off = n_off; c_seq = n_seq;
+    }
+    __syncthreads();                           // the producer's final verdicts
+    if (nsq == 0) return;
+    const bool bad = __any_sync(FULL, C.bad != 0) || S.final_rc[c] != ZSB_OK;
+    const uint32_t out_size = C.out_acc + (regen - C.lit_acc);
+    if (exec && !bad) {                        // what is left in the ring
+        uint8_t *gend = gdst + out_size;
+        ex2_flush<SEQX_RING>(X.ring, gend, (uint32_t)(uintptr_t)gend, X.flushed - (int32_t)out_size, 0, lane);
+    }
+    if (lane == 0) {
+        ZsbBlockWork &g = work[bi];
+        if (bad) { g.status = ZSB_NEEDS_SLOW; slow_list[atomicAdd(&cnt->n_slow, 1u)] = bi; }
+        else {
+            g.lit_used = C.lit_acc; g.out_size = out_size;
+            g.rep_out[0] = C.H.h0; g.rep_out[1] = C.H.h1; g.rep_out[2] = C.H.h2;
+            if (xerr) g.fused = 2; else if (exec) g.fused = 1; else if (refuse) cnt->refuse = 1u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * EX2_WARPS, 7) k_exec2(const uint8_t *__restrict__ src, const zsb_frame *__restrict__ frames,
+                                                             const zsb_block *__restrict__ blocks, const ZsbBlockWork *__restrict__ work,
+                                                             ZsbFrameOut *fout, const uint32_t *__restrict__ exec_list, uint32_t n,
+                                                             const ZsbCounters *__restrict__ cnt, const uint64_t *__restrict__ seq_pool,
+                                                             const uint8_t *__restrict__ lit_pool, uint8_t *dst) {
+    __shared__ __align__(128) uint8_t rings[EX2_WARPS][EX2_RING];
+    if (cnt->overflow) return;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * EX2_WARPS + warp;
+    if (gw >= n) return;
+    Ex2State X;
+    X.ring = rings[warp]; X.err = 0; X.flushed = 0; X.ring_lo = 0;
+    const uint32_t f = exec_list[gw];
+    const ZsbFrameOut fo = fout[f];
+    if (fo.status != ZSB_OK) return;
+    const zsb_frame fr = frames[f];
+    uint8_t *fdst = dst + fo.dst_off;
+    for (uint32_t k = 0; k < fr.n_blocks && !X.err; k++) {
+        const uint32_t bi = fr.first_block + k;
+        const ZsbBlockWork &W = work[bi];
+        const uint32_t out_size = W.out_size;
+        X.gblk = fdst + W.out_off; X.g0 = (uint32_t)(uintptr_t)X.gblk;
+        if (blocks[bi].type != ZSB_BT_COMPRESSED || W.fused) {
+            if (W.fused == 2) { X.err = ZSB_E_IMPOSSIBLE_VALUE; break; }
+            ex2_flush(X.ring, X.gblk, X.g0, X.flushed, 0, lane);       // what earlier blocks left in the ring
+            X.flushed = X.ring_lo = (int32_t)out_size;                 // raw / RLE blocks were written by k_rawrle, blocks executed by k_seqx are there too
+        } else {
+            const uint32_t nseq = W.nseq, regen = W.lit_regen;
+            Ex2Lit L;
+            L.is_rle = W.lit_type == ZSB_LT_RLE; L.rle = L.is_rle ? src[W.lit_src] : 0u;
+            L.p = W.lit_type == ZSB_LT_RAW ? src + W.lit_src : lit_pool + W.lit_buf;
+            const uint64_t *seqs = seq_pool + W.seq_buf;
+            const uint64_t P0 = W.out_off;
+            const uint32_t items = nseq + 1;   // the last item is the literal tail (decoding_context.rs:101-103); all there is when nseq == 0
+            X.c_out = 0; X.c_lit = 0; X.lr_has = false;
+            // records are requested two batches ahead: the batch after this one is looked at early (its literals are prefetched)
+            uint64_t rec_next = lane < nseq ? __ldg(seqs + lane) : 0ull, rec_next2 = lane + 32 < nseq ? __ldg(seqs + lane + 32) : 0ull;
+            for (uint32_t b0 = 0; b0 < items; b0 += 32) {
+                const uint32_t i = b0 + lane;
+                const uint64_t rec = rec_next;
+                rec_next = rec_next2;
+                if (i + 64 < nseq) rec_next2 = __ldg(seqs + i + 64);
+                const bool is_seq = i < nseq;
+                const uint32_t out_end = is_seq ? (uint32_t)rec & ZSB_REC_POS_MASK : out_size;
+                const uint32_t lit_end = is_seq ? (uint32_t)(rec >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK : regen;
+                const uint32_t off = is_seq ? seq_real_offset((uint32_t)(rec >> (2 * ZSB_REC_POS_BITS)), W.rep_in) : 1u;
+                const bool has_next = b0 + 32 < items;
+                const uint32_t next_lit_end = (i + 32 < nseq) ? (uint32_t)(rec_next >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK : regen;
+                ex2_batch<EX2_RING, EX2_GIANT>(X, L, P0, is_seq, out_end, lit_end, off, has_next, next_lit_end, lane);
+                if (__any_sync(FULL, X.err != 0)) { X.err = ZSB_E_IMPOSSIBLE_VALUE; break; }
             }
         }
-        flushed -= (int32_t)out_size; ring_lo -= (int32_t)out_size;   // positions become relative to the next block
+        X.flushed -= (int32_t)out_size; X.ring_lo -= (int32_t)out_size;   // positions become relative to the next block
         __syncwarp();
     }
-    if (__any_sync(FULL, err != 0)) { if (lane == 0) { fout[f].status = ZSB_E_IMPOSSIBLE_VALUE; fout[f].dst_len = 0; } return; }
+    if (__any_sync(FULL, X.err != 0)) { if (lane == 0) { fout[f].status = ZSB_E_IMPOSSIBLE_VALUE; fout[f].dst_len = 0; } return; }
     uint8_t *gend = fdst + fo.dst_len;
-    ex2_flush(ring, gend, (uint32_t)(uintptr_t)gend, flushed, 0, lane);
+    ex2_flush(X.ring, gend, (uint32_t)(uintptr_t)gend, X.flushed, 0, lane);
 }
 
 // ======================================================================================= k_xxh
@@ -1676,7 +1873,9 @@ void zsbk_publish(cudaStream_t st, void *host_dev_ptr, const ZsbCounters *cnt, c
 cudaError_t zsbk_init() {
     cudaError_t e = set_smem((const void *)k_seq_slow, SEQ_SLOW_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    e = set_smem((const void *)k_seq, SEQ_SMEM_FUSED);
+    e = set_smem((const void *)k_seq_t<SEQ_HELPERS, SEQ_WIN, 2, false>, SEQ_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = set_smem((const void *)k_seq_t<SEQX_WARPS, SEQX_WIN, SEQX_NBUF, true>, SEQX_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     e = set_smem((const void *)k_exec<512, false>, EXEC_SMEM_BYTES);
     if (e != cudaSuccess) return e;
@@ -1694,7 +1893,8 @@ void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_
     if (ncomp) k_huf<<<(ncomp + HUF_SLOTS - 1) / HUF_SLOTS, HUF_THREADS, 0, st>>>(src, src_len, work, huf_list, cnt, lit_pool, lit_cap, over_cap, flags);
 }
 void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
-              uint64_t *seq_pool, uint32_t *slow_list, bool shared_device, uint32_t chains_hint) {
+              uint64_t *seq_pool, uint32_t *slow_list, bool shared_device, uint32_t chains_hint, const zsb_frame *frames, const zsb_block *blocks,
+              const uint64_t *pre_off, const uint8_t *lit_pool, uint8_t *dst) {
     if (!ncomp) return;
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148; }
@@ -1706,15 +1906,25 @@ void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork 
     if (shared_device) used = sub_chains;                          // (batches of other streams run beside this one: few SMs each)
     if (chains_hint && chains_hint <= SEQ_CHAINS) used = chains_hint;      // low-latency shards of the pipelined host path
     if (used < 1) used = 1;
-    k_seq<<<(ncomp + used - 1) / used, 32 * (1 + SEQ_HELPERS), SEQ_SMEM_FUSED, st>>>(src, work, seq_list, cnt, seq_pool, slow_list, used);
+    SeqxArgs A; A.frames = frames; A.blocks = blocks; A.pre_off = pre_off; A.lit_pool = lit_pool; A.dst = dst;
+    if (pre_off) {
+        // k_seqx: one consumer warp per chain, at most SEQX_WARPS chains per CTA
+        const uint32_t wx = (ncomp + (uint32_t)n_sm * SEQX_WARPS - 1) / ((uint32_t)n_sm * SEQX_WARPS);
+        uint32_t ux = (ncomp + wx * (uint32_t)n_sm - 1) / (wx * (uint32_t)n_sm);
+        if (ux > SEQX_WARPS) ux = SEQX_WARPS;
+        if (ux < 1) ux = 1;
+        k_seq_t<SEQX_WARPS, SEQX_WIN, SEQX_NBUF, true><<<(ncomp + ux - 1) / ux, 32 * (1 + SEQX_WARPS), SEQX_SMEM_BYTES, st>>>(src, work, seq_list, cnt, seq_pool, slow_list, ux, A);
+        return;
+    }
+    k_seq_t<SEQ_HELPERS, SEQ_WIN, 2, false><<<(ncomp + used - 1) / used, 32 * (1 + SEQ_HELPERS), SEQ_SMEM_BYTES, st>>>(src, work, seq_list, cnt, seq_pool, slow_list, used, A);
 }
 void zsbk_seq_slow(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *slow_list,
                    const ZsbCounters *cnt, uint64_t *seq_pool) {
     if (ncomp) k_seq_slow<<<(ncomp + 31) / 32, 32, SEQ_SLOW_SMEM_BYTES, st>>>(src, src_len, work, slow_list, cnt, seq_pool);
 }
 void zsbk_plan2(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb_block *blocks, ZsbBlockWork *work, ZsbFrameOut *fout,
-                ZsbCounters *cnt, uint64_t dst_cap, uint32_t flags) {
-    k_plan2<<<nf > 1024 ? (nf + 1023) / 1024 : 1, 1024, 0, st>>>(frames, nf, blocks, work, fout, cnt, dst_cap, flags);
+                ZsbCounters *cnt, uint64_t dst_cap, uint32_t flags, const uint64_t *pre_off) {
+    k_plan2<<<nf > 1024 ? (nf + 1023) / 1024 : 1, 1024, 0, st>>>(frames, nf, blocks, work, fout, cnt, dst_cap, flags, pre_off);
 }
 void zsbk_rawrle(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_block *blocks, const ZsbBlockWork *work, const ZsbFrameOut *fout,
                  const uint32_t *list, const ZsbCounters *cnt, uint8_t *dst) {

@@ -12,7 +12,8 @@ struct ZsbCounters {
     uint32_t overflow;    // scratch too small: every later kernel exits, the host grows it and relaunches
     uint32_t n_slow;      // blocks the fast sequence path handed to the careful decoder
     uint32_t ticket1, ticket2;   // k_plan1 / k_plan2: CTAs done with the per-frame part (the last one runs the scans)
-    uint32_t zero, pad;          // always 0: k_seq orders its look-ahead loads behind its cell loads with a data dependency on it
+    uint32_t zero;               // always 0: k_seq can order its look-ahead loads behind its cell loads with a data dependency on it
+    uint32_t refuse;             // k_seqx executed a block where its frame did not end up (a frame before it failed or lied about its size): the host runs the batch again without k_seqx
     uint64_t lit_over;           // ZSB_REFERENCE_QUIRKS: bytes handed out of the overflow region behind the literal scratch (blocks whose streams
                                  // regenerate more literals than Regenerated_Size announced)
 };
@@ -24,11 +25,13 @@ void zsbk_plan1(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb
 void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *huf_list,
               ZsbCounters *cnt, uint8_t *lit_pool, uint64_t lit_cap, uint64_t over_cap, uint32_t flags);
 void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
-              uint64_t *seq_pool, uint32_t *slow_list, bool shared_device, uint32_t chains_hint);
+              uint64_t *seq_pool, uint32_t *slow_list, bool shared_device, uint32_t chains_hint, const zsb_frame *frames, const zsb_block *blocks,
+              const uint64_t *pre_off /* per frame: where the host expects it in dst, ~0 = unknown; nullptr: k_seq, else k_seqx */,
+              const uint8_t *lit_pool, uint8_t *dst);
 void zsbk_seq_slow(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *slow_list,
                    const ZsbCounters *cnt, uint64_t *seq_pool);
 void zsbk_plan2(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb_block *blocks, ZsbBlockWork *work, ZsbFrameOut *fout,
-                ZsbCounters *cnt, uint64_t dst_cap, uint32_t flags);
+                ZsbCounters *cnt, uint64_t dst_cap, uint32_t flags, const uint64_t *pre_off);
 void zsbk_rawrle(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_block *blocks, const ZsbBlockWork *work, const ZsbFrameOut *fout,
                  const uint32_t *list, const ZsbCounters *cnt, uint8_t *dst);
 void zsbk_exec(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,

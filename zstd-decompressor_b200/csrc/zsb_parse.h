@@ -19,7 +19,7 @@
 ZSB_HDN void parse_block(const uint8_t *src, const zsb_block &blk, ZsbBlockWork &w, uint32_t flags) {
     const bool quirks = (flags & ZSB_REFERENCE_QUIRKS) != 0;
     w.status = ZSB_OK; w.lit_status = ZSB_OK; w.err_a = w.err_b = 0; w.seq_rem0 = 0;
-    w.nseq = 0; w.lit_type = ZSB_LT_NONE; w.lit_regen = 0; w.n_streams = 0; w.raw_modes = 0; w.parse_stage = 0; w.lit_inexact = 0;
+    w.nseq = 0; w.lit_type = ZSB_LT_NONE; w.lit_regen = 0; w.n_streams = 0; w.raw_modes = 0; w.parse_stage = 0; w.lit_inexact = 0; w.fused = 0;
     w.lit_used = 0; w.out_off = 0; w.lit_buf = 0; w.seq_buf = 0;
     w.mode[0] = w.mode[1] = w.mode[2] = ZSB_M_REPEAT;
     w.rep_out[0] = ZSB_OFF_SYM | (0u << 25); w.rep_out[1] = ZSB_OFF_SYM | (1u << 25); w.rep_out[2] = ZSB_OFF_SYM | (2u << 25);
