@@ -161,6 +161,13 @@ __device__ __noinline__ int huf_block_ref_device(const uint8_t *src, uint64_t sr
     return rc;
 }
 
+#ifdef ZSB_SEQ_TIMING
+__device__ long long g_huf_timing[1024][4];     // per CTA: start, tables built, streams decoded
+extern "C" int zsb_debug_huf_timing(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_huf_timing, sizeof g_huf_timing); }
+#define HUF_T(i) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_huf_timing[blockIdx.x][i] = clock64(); } while (0)
+#else
+#define HUF_T(i) do {} while (0)
+#endif
 __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__ src, uint64_t src_len, ZsbBlockWork *work,
                                             const uint32_t *__restrict__ huf_list, ZsbCounters *cnt,
                                             uint8_t *lit_pool, uint64_t lit_cap, uint64_t over_cap, uint32_t flags) {
@@ -174,17 +181,20 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__
     const bool active = idx < n;
     const uint32_t bi = active ? huf_list[idx] : 0;
     HufSlot &S = slots[slot];
+    HUF_T(0);
     if (active && stream == 0) {
         const ZsbBlockWork &w = work[bi];
         int nw = 0; uint32_t dl = 0;
         int rc = huf_read_weights(src + w.huf_desc, w.huf_desc_end - w.huf_desc, S.weights, 1, nw, dl, S.u.ftbl, 1, S.cnt, 1,
                                   src_len - w.huf_desc, quirks);
+        HUF_T(3);
         int mb = 0;
         bool inc = false;
         if (!rc) rc = huf_build_lut(S.weights, 1, nw, S.u.lut, S.rank, 1, mb, nullptr, quirks, &inc);
         S.maxbits = mb; S.status = rc; S.incomplete = inc ? 1 : 0;
     }
     __syncwarp(HUF_MASK);
+    HUF_T(1);
     int rc = 0;
     bool inexact = false;                       // ZSB_REFERENCE_QUIRKS: this block's literals are decoded the reference's way
     if (active) {
@@ -207,6 +217,8 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__
             }
         }
     }
+    __syncwarp(HUF_MASK);
+    HUF_T(2);
     const uint32_t q0 = lane & ~3u;
     const bool blk_inexact = __shfl_sync(HUF_MASK, (int)inexact, q0) || __shfl_sync(HUF_MASK, (int)inexact, q0 + 1) || __shfl_sync(HUF_MASK, (int)inexact, q0 + 2) ||
                              __shfl_sync(HUF_MASK, (int)inexact, q0 + 3);
@@ -235,7 +247,12 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__
 // through zsb_fse_table_from_distribution, which runs this code).
 struct FseWarpScratch { int16_t cnt[64]; uint16_t cum[66]; uint16_t next[64]; uint8_t desc[128]; };
 // tab: code -> baseline | extra bits << 24 for LL ([0..35]) and ML ([36..88]); type 3: plain table (xb = 0, code = symbol)
-__device__ __forceinline__ int fse_build_table_warp(FseWarpScratch &X, int nsym, int al, uint32_t *tbl, int ts, int type, const uint32_t *tab, uint32_t lane) {
+// stage (optional, N bytes of shared memory): the symbol of every cell is kept there until the cells are computed, and only the finished
+// cells go to tbl.  k_seq builds into columns of an interleaved table (ts = 32 words: every access of the warp hits ONE bank, 32 wavefronts
+// each) -- staged, a table costs 16 such stores instead of 16 stores, 16 loads and 16 more stores (tried and measured: one LANE per table,
+// 32 tables per warp, conflict free but serial and divergent: 1.2 M cycles of set-up per CTA instead of 0.19 M).
+__device__ __forceinline__ int fse_build_table_warp(FseWarpScratch &X, int nsym, int al, uint32_t *tbl, int ts, int type, const uint32_t *tab, uint32_t lane,
+                                                    uint8_t *stage = nullptr) {
     const int N = 1 << al, step = (N >> 1) + (N >> 3) + 3, mask = N - 1;
     const uint32_t lt = (1u << lane) - 1u;
     int nlow = 0, total = 0;
@@ -250,7 +267,10 @@ __device__ __forceinline__ int fse_build_table_warp(FseWarpScratch &X, int nsym,
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, inc, d); if ((int)lane >= d) inc += t; }
         if (sy < nsym) { X.cum[sy] = (uint16_t)(total + inc - p); X.next[sy] = (uint16_t)(low ? 1 : p); }
-        if (low) { const int cell = N - 1 - (nlow + __popc(lm & lt)); if (cell >= 0) tbl[cell * ts] = (uint32_t)sy; else overflow = true; }
+        if (low) {
+            const int cell = N - 1 - (nlow + __popc(lm & lt));
+            if (cell < 0) overflow = true; else if (stage) stage[cell] = (uint8_t)sy; else tbl[cell * ts] = (uint32_t)sy;
+        }
         nlow += __popc(lm); total += __shfl_sync(FULL, inc, 31);
     }
     const int high = N - 1 - nlow;
@@ -267,13 +287,13 @@ __device__ __forceinline__ int fse_build_table_warp(FseWarpScratch &X, int nsym,
         if (valid) {
             int lo = 0, hi = nsym;                      // cum[lo] <= j < cum[hi]
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int)X.cum[mid] <= j) lo = mid; else hi = mid; }
-            tbl[pos * ts] = (uint32_t)lo;
+            if (stage) stage[pos] = (uint8_t)lo; else tbl[pos * ts] = (uint32_t)lo;
         }
     }
     __syncwarp();
     for (int i0 = 0; i0 < N; i0 += 32) {
         const int i = i0 + (int)lane;
-        const uint32_t sy = tbl[i * ts];
+        const uint32_t sy = stage ? (uint32_t)stage[i] : tbl[i * ts];
         const uint32_t g = __match_any_sync(FULL, sy);
         const uint32_t r = __popc(g & lt);
         const uint32_t nx = (uint32_t)X.next[sy] + r;
@@ -294,7 +314,7 @@ __device__ __forceinline__ int fse_build_table_warp(FseWarpScratch &X, int nsym,
 }
 // Table t (0 LL, 1 OF, 2 ML) of block w by one warp: == seq_build_table (zsb_seq.h) with max_sym = 64.  All lanes return the same status.
 __device__ __forceinline__ int seq_build_table_warp(const uint8_t *src, const ZsbBlockWork &w, int t, uint32_t *tbl, int ts, FseWarpScratch &X,
-                                                    const uint32_t *tab, int max_al, int &al_out, uint32_t lane) {
+                                                    const uint32_t *tab, int max_al, int &al_out, uint32_t lane, uint8_t *stage = nullptr) {
     const int mode = w.mode[t];
     al_out = 0;
     if (mode == ZSB_M_RLE) { if (lane == 0) fse_build_rle(w.rle_sym[t], tbl, t); return ZSB_OK; }
@@ -321,7 +341,7 @@ __device__ __forceinline__ int seq_build_table_warp(const uint8_t *src, const Zs
     } else return ZSB_E_NO_PREVIOUS_DECODER;
     if (max_al && al > max_al) return ZSB_TABLE_TOO_SMALL;
     __syncwarp();
-    rc = fse_build_table_warp(X, nsym, al, tbl, ts, t, tab, lane);
+    rc = fse_build_table_warp(X, nsym, al, tbl, ts, t, tab, lane, stage);
     __syncwarp();
     if (!rc) al_out = al;
     return rc;
@@ -517,10 +537,10 @@ __global__ void __launch_bounds__(32 * (1 + HELPERS), 1) k_seq_t(const uint8_t *
     const uint8_t *base8 = src - mis;
 
     if (warp == 0) SEQ_T(0);
-    // ---- set-up: the phase-2 warps fill the code tables and build the 3 x 32 FSE tables, one warp per table (6 tables per
-    // warp, fse_build_table_warp); then the producer lanes read their initial states
+    // ---- set-up: the phase-2 warps fill the code tables and build the 3 x 32 FSE tables, one warp per table (fse_build_table_warp);
+    // then the producer lanes read their initial states
     SeqTables T;
-    ZsbBlockWork w;
+    struct { uint64_t bs_off, seq_buf; uint32_t bs_len, nseq, lit_regen; int32_t lit_status; } w = {0, 0, 0, 0, 0, 0};   // the fields of work[bi] the producer lane needs
     bool active = false;
     uint32_t bi = 0;
     FastWin F; StreamRing R;
@@ -531,13 +551,20 @@ __global__ void __launch_bounds__(32 * (1 + HELPERS), 1) k_seq_t(const uint8_t *
         const uint32_t idx = blockIdx.x * used + lane;
         active = lane < used && idx < n;
         bi = active ? seq_list[idx] : 0;
-        if (active) { w = work[bi]; active = w.status == ZSB_OK; }
+        if (active) {
+            const ZsbBlockWork &g = work[bi];
+            w.bs_off = g.bs_off; w.seq_buf = g.seq_buf; w.bs_len = g.bs_len; w.nseq = g.nseq; w.lit_regen = g.lit_regen; w.lit_status = g.lit_status;
+            active = g.status == ZSB_OK;
+        }
     } else {
         for (uint32_t k = threadIdx.x - 32; k < 36 + 53; k += 32 * HELPERS) S.tab[k] = k < 36 ? zsb_ll_entry(k) : zsb_ml_entry(k - 36);
         __syncwarp();
         // the code tables are filled by all phase-2 warps together: wait for all of them
         seq_bar_sync<32 * HELPERS>(BAR_HELPERS);
         FseWarpScratch &X = reinterpret_cast<FseWarpScratch *>(counts)[warp - 1];
+        // (the word ring is idle during set-up: every warp keeps the symbols of the table it is building there, see fse_build_table_warp)
+        uint8_t *stage = reinterpret_cast<uint8_t *>(&S.words[0][0]) + (warp - 1) * SEQ_TBL_CELLS;
+        static_assert(sizeof S.words >= HELPERS * SEQ_TBL_CELLS, "symbol staging does not fit the word ring");
         for (uint32_t q = 0; q < 3 * CPH; q++) {
             const uint32_t c = (warp - 1) * CPH + q / 3, t = q % 3, idx = blockIdx.x * used + c;
             int rc = ZSB_OK, al = 0;
@@ -545,7 +572,7 @@ __global__ void __launch_bounds__(32 * (1 + HELPERS), 1) k_seq_t(const uint8_t *
                 const ZsbBlockWork &wb = work[seq_list[idx]];
                 if (wb.status == ZSB_OK) {
                     uint32_t *tb = tbl + (t == 0 ? 0 : t == 1 ? SEQ_TBL_CELLS * SEQ_CHAINS : (SEQ_TBL_CELLS + SEQ_OF_CELLS) * SEQ_CHAINS) + c;
-                    rc = seq_build_table_warp(src, wb, (int)t, tb, SEQ_CHAINS, X, S.tab, t == 1 ? 8 : 9, al, lane);
+                    rc = seq_build_table_warp(src, wb, (int)t, tb, SEQ_CHAINS, X, S.tab, t == 1 ? 8 : 9, al, lane, stage);
                 }
             }
             if (lane == 0) { S.tal[c][t] = al; S.trc[c][t] = rc; }
