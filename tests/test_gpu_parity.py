@@ -623,3 +623,33 @@ def test_seqx_refuses_when_a_frame_moves_the_others(dec, dec_seqx):
     out, sc, r = dec_seqx.decode(mix, Q)
     assert dec_seqx.ctx.last_seqx_state() == 2
     assert first_status(sc, r) == 0 and out == R.main_decode(mix)
+
+
+# ---------------------------------------------------------------- k_exec in wavefront mode (ZSB_WAVE=n: several CTAs per frame)
+def test_wavefront_execution_of_multi_block_frames(dec):
+    import os
+    os.environ["ZSB_WAVE"] = "8"                        # read when the context is created
+    try:
+        dw = Z.Decoder(Z.Context(0))
+    finally:
+        del os.environ["ZSB_WAVE"]
+    small, sexp = corpora.c3_small(3 << 20)             # one frame of 24 blocks, matches reaching into the blocks before
+    out, sc, r = dw.decode(small, Q | VER)
+    assert first_status(sc, r) == 0 and r.checksum_ok[0] == 1 and out == sexp
+    for name in corpora.FIXTURE_NAMES:                  # the reference's fixtures (C1): a few frames of a few blocks
+        d = corpora.fixture(name)
+        out, sc, r = dw.decode(d, Q | VER | SKIP)
+        out2, sc2, r2 = dec.decode(d, Q | VER | SKIP)
+        assert out == out2 and list(r.status[:sc.n_frames]) == list(r2.status[:sc2.n_frames])
+        assert list(r.checksum_ok[:sc.n_frames]) == list(r2.checksum_ok[:sc2.n_frames])
+    blob, _, _, _ = corpora.c4()                        # every block kind, raw / RLE blocks between compressed ones, failing frames
+    out, sc, r = dw.decode(blob, Q | VER)
+    out2, sc2, r2 = dec.decode(blob, Q | VER)
+    assert out == out2 and list(r.status[:sc.n_frames]) == list(r2.status[:sc2.n_frames])
+    # an impossible offset in a late block of a frame of many blocks: every CTA of the frame stops, the status is the plain path's
+    import gen_corpus as G
+    blob3, exp3 = G.make_c3(total=2 << 20)
+    bad = bytearray(blob3); bad[len(bad) * 3 // 4] ^= 0x10
+    out, sc, r = dw.decode(bytes(bad), Q | VER)
+    out2, sc2, r2 = dec.decode(bytes(bad), Q | VER)
+    assert (r.status[0] != 0) == (r2.status[0] != 0) and (r.status[0] != 0 or r.checksum_ok[0] == r2.checksum_ok[0])

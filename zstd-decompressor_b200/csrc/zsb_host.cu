@@ -41,7 +41,7 @@ struct zsb_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr, aux_stream = nullptr;   // aux: the literals stage runs beside the sequence stage
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_huf[kProfRing][2] = {};
-    DevBuf src, frames, blocks, work, fout, huf_list, seq_list, rawrle_list, exec_list, exec2_list, xxh_list, lit_pool, seq_pool, slow_list, counters, dst, stage, pre_off;
+    DevBuf src, frames, blocks, work, fout, huf_list, seq_list, rawrle_list, exec_list, exec2_list, xxh_list, lit_pool, seq_pool, slow_list, counters, dst, stage, pre_off, wave;
     std::string last_err;
     // prepared batch
     const uint8_t *d_src = nullptr; uint8_t *d_dst = nullptr; uint8_t *h_dst = nullptr;
@@ -53,6 +53,8 @@ struct zsb_ctx {
     std::vector<uint32_t> h_xxh_list, h_rawrle, h_exec, h_exec2;   // host copies stay alive while their uploads are in flight
     std::vector<uint64_t> h_pre_off;                               // where every frame is expected in dst (k_seqx), ~0: not known before decoding
     int seqx_state = 0;                                            // zsb_last_seqx_state
+    uint32_t wave_max = 1;                                         // ZSB_WAVE: most CTAs per frame k_exec may use (1: one CTA per frame, block after block)
+    uint32_t wave_ctas = 1;                                        // CTAs per frame of k_exec (wavefront mode when > 1)
     bool use_seqx = false;                                         // this batch runs k_seqx
     std::vector<uint32_t> h_err_a, h_err_b;                        // per-frame error payloads of the last finished batch (zsb_decode_errors)
     std::vector<zsb_ctx *> subs;          // child contexts of the pipelined host path (own stream + scratch each)
@@ -97,6 +99,7 @@ extern "C" int zsb_ctx_create(zsb_ctx **out, int device) {
     c->stream = c->own_stream;
     { const char *e = getenv("ZSB_OVERLAP"); c->overlap = e && *e && *e != '0'; }
     { const char *e = getenv("ZSB_SEQX"); c->seqx = e && *e && *e != '0'; }
+    { const char *e = getenv("ZSB_WAVE"); const int v = e ? atoi(e) : 1; c->wave_max = v < 1 ? 1u : v > 64 ? 64u : (uint32_t)v; }
     { const char *e = getenv("ZSB_PIPE_TRACE"); c->trace = e && *e && *e != '0'; }
     if (c->trace) for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev_tr[i]);
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) cudaEventCreate(&c->ev[r][i]);
@@ -113,7 +116,7 @@ extern "C" void zsb_ctx_destroy(zsb_ctx *c) {
     c->subs.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list, &c->exec2_list, &c->pre_off,
+    DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list, &c->exec2_list, &c->pre_off, &c->wave,
                      &c->xxh_list, &c->lit_pool, &c->seq_pool, &c->slow_list, &c->counters, &c->dst, &c->stage};
     for (DevBuf *b : all) b->release();
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) if (c->ev[r][i]) cudaEventDestroy(c->ev[r][i]);
@@ -254,6 +257,18 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
             if (getenv("ZSB_DEBUG")) fprintf(stderr, "zsb: k_seqx places %u of %zu frames\n", placed, nf);
         }
     }
+    // k_exec in wavefront mode (ZSB_WAVE=n, n > 1): the CTA-per-frame list is short (a single large frame, a file of a few frames), so every
+    // frame gets up to n CTAs that take its blocks in order (ZsbWave).  All of them must fit the GPU at once only for speed, not for progress.
+    // Off by default: measured on C3 (text, zstd -3) it gains nothing -- half the sequences of a block wait, directly or through bytes that
+    // do, for the block before it (tools/probes/c3_dependencies.py), and a batch of 32 sequences proceeds only when all of its lanes can.
+    {
+        uint32_t maxb = 0;
+        for (uint32_t f : execl) maxb = std::max(maxb, frames[f].n_blocks);
+        uint32_t g = execl.empty() ? 1u : (uint32_t)(148 / execl.size());
+        if (g > c->wave_max) g = c->wave_max;
+        if (g > maxb) g = maxb;
+        c->wave_ctas = (c->is_sub || g < 2) ? 1u : g;
+    }
     c->ncomp = (uint32_t)ncomp; c->n_rawrle = (uint32_t)rawrle.size(); c->n_exec = (uint32_t)execl.size(); c->n_exec2 = (uint32_t)exec2l.size(); c->n_xxh = (uint32_t)c->h_xxh_list.size();
     if (lit_cap > c->lit_cap) c->lit_cap = lit_cap;
     if (seq_cap > c->seq_cap) c->seq_cap = seq_cap;
@@ -268,6 +283,7 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     CK(c, c->exec_list.ensure(4 * (execl.size() + 1)));
     CK(c, c->exec2_list.ensure(4 * (exec2l.size() + 1)));
     CK(c, c->pre_off.ensure(8 * (nf + 1)));
+    if (c->wave_ctas > 1) CK(c, c->wave.ensure(32 * execl.size() + 4 * (nb + 1)));
     CK(c, c->xxh_list.ensure(4 * (c->h_xxh_list.size() + 1)));
     CK(c, c->counters.ensure(sizeof(ZsbCounters)));
     c->lit_cap = (c->lit_cap + 15) & ~(uint64_t)15;
@@ -333,8 +349,10 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     MARK(c, "k_rawrle"); zsbk_rawrle(st, c->n_rawrle, src, blocks, work, fout, (const uint32_t *)c->rawrle_list.p, cnt, c->d_dst); c->launches += c->n_rawrle ? 1 : 0;
     MARK(c, "k_exec2");  zsbk_exec2(st, c->n_exec2, src, frames, blocks, work, fout, (const uint32_t *)c->exec2_list.p, cnt, (const uint64_t *)c->seq_pool.p,
                                     (const uint8_t *)c->lit_pool.p, c->d_dst); c->launches += c->n_exec2 ? 1 : 0;
+    if (c->n_exec && c->wave_ctas > 1) CK(c, cudaMemsetAsync(c->wave.p, 0, 32 * (size_t)c->n_exec + 4 * ((size_t)c->nb + 1), st));
     MARK(c, "k_exec");   zsbk_exec(st, c->n_exec, src, frames, blocks, work, fout, (const uint32_t *)c->exec_list.p, cnt, (const uint64_t *)c->seq_pool.p,
-                                   (const uint8_t *)c->lit_pool.p, c->d_dst, c->is_sub, c->flags); c->launches += c->n_exec ? 1 : 0;
+                                   (const uint8_t *)c->lit_pool.p, c->d_dst, c->is_sub, c->flags, c->wave_ctas > 1 ? c->wave.p : nullptr,
+                                   c->wave_ctas > 1 ? (uint32_t *)((uint8_t *)c->wave.p + 32 * (size_t)c->n_exec) : nullptr, c->wave_ctas); c->launches += c->n_exec ? 1 : 0;
     // pipelined path: the shard's output may leave as soon as it is written -- the checksums are computed from HBM while the
     // download runs (both only read the output)
     const bool early_down = c->down_stream && c->eager_d2h && c->h_dst;

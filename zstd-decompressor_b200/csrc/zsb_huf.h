@@ -74,15 +74,18 @@ ZSB_HDN int huf_read_weights(const uint8_t *desc, uint64_t limit, uint8_t *weigh
 // (insert returns false, :161-175); where the reference panics, and always without quirks, RFC 8878 4.2.1.1 decides.
 #define ZSB_HUF_ABSENT 0xFFFFu
 // *incomplete (optional): the table has ZSB_HUF_ABSENT cells or dropped symbols: only huf_decode_block_ref may read it.
-ZSB_HDN int huf_build_lut(uint8_t *weights, int ws, int nw, uint16_t *lut, uint32_t *rank, int rs, int &maxbits, uint8_t *lens_out, bool quirks = false,
-                          bool *incomplete = nullptr) {
+// The arithmetic of huf_build_lut up to the first LUT cell of every weight class (rank[w]); appends the implied weight (n = nw + 1).
+struct HufPlan { int mb, n; bool loose; };
+ZSB_HDN int huf_lut_plan(uint8_t *weights, int ws, int nw, uint32_t *rank, int rs, HufPlan &P, bool quirks, bool *incomplete) {
     if (incomplete) *incomplete = false;
     uint32_t sum = 0, wmax = 0;
+    for (int w = 0; w <= ZSB_HUF_MAX_BITS + 1; w++) rank[w * rs] = 0;     // (first: symbols per weight class, counted in the same pass)
     for (int i = 0; i < nw; i++) {
         uint32_t w = weights[i * ws];
         if (w > ZSB_HUF_MAX_BITS + 1) return ZSB_E_CORRUPT;
         if (w) sum += 1u << (w - 1);
         wmax = w > wmax ? w : wmax;
+        rank[w * rs] += 1;
     }
     if (sum == 0) return ZSB_E_CORRUPT;                                   // reference: discrete_log2(0) panics (huffman.rs:184)
     if (nw >= 256) return ZSB_E_CORRUPT;
@@ -110,12 +113,21 @@ ZSB_HDN int huf_build_lut(uint8_t *weights, int ws, int nw, uint16_t *lut, uint3
     weights[nw * ws] = (uint8_t)lastw;
     int n = nw + 1;
     // rank[w] = first LUT cell of weight class w: lowest weights (longest codes) first (huffman.rs:161-175)
-    for (int w = 0; w <= ZSB_HUF_MAX_BITS + 1; w++) rank[w * rs] = 0;
-    for (int i = 0; i < n; i++) rank[weights[i * ws] * rs] += 1;
+    rank[lastw * rs] += 1;
     uint32_t start = 0;
     for (int w = 1; w <= mb; w++) { uint32_t c = rank[w * rs]; rank[w * rs] = start; start += c << (w - 1); }
     if (!loose && start != (1u << mb)) return ZSB_E_CORRUPT;
     if (incomplete) *incomplete = start != (1u << mb);
+    P.mb = mb; P.n = n; P.loose = loose;
+    return ZSB_OK;
+}
+ZSB_HDN int huf_build_lut(uint8_t *weights, int ws, int nw, uint16_t *lut, uint32_t *rank, int rs, int &maxbits, uint8_t *lens_out, bool quirks = false,
+                          bool *incomplete = nullptr) {
+    HufPlan P;
+    const int rc = huf_lut_plan(weights, ws, nw, rank, rs, P, quirks, incomplete);
+    if (rc) return rc;
+    const int mb = P.mb, n = P.n;
+    const bool loose = P.loose;
     if (lens_out) for (int i = 0; i < 256; i++) lens_out[i] = 0;
     if (loose) for (uint32_t k = 0; k < (1u << mb); k++) lut[k] = ZSB_HUF_ABSENT;
     for (int i = 0; i < n; i++) {

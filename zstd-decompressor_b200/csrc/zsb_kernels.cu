@@ -132,15 +132,26 @@ __global__ void __launch_bounds__(1024) k_plan1(const zsb_frame *__restrict__ fr
 #define HUF_THREADS (4 * HUF_SLOTS)
 #define HUF_MASK (HUF_THREADS == 32 ? 0xFFFFFFFFu : ((1u << HUF_THREADS) - 1u))
 #define HUF_LUT_BYTES (2u << ZSB_HUF_MAX_BITS)   // 4096
-struct HufSlot {
+struct __align__(16) HufSlot {
     union { uint16_t lut[1 << ZSB_HUF_MAX_BITS]; uint32_t ftbl[512]; } u;
     uint8_t weights[260];
+    uint16_t at[256];   // first LUT cell of every symbol (HUF_NO_ROOM: none); the four lanes of the slot fill the LUT from it
     int16_t cnt[ZSB_HUF_WEIGHT_SYMS];
     uint32_t rank[16];
     int maxbits;
     int status;
+    int n, loose;       // symbols with the implied one; the LUT starts out as ZSB_HUF_ABSENT (huf_lut_plan)
     int incomplete;     // ZSB_REFERENCE_QUIRKS: the reference's tree for these weights is not a complete code (huf_build_lut)
 };
+#define HUF_NO_ROOM 0xFFFFu
+// `len` cells from lut[at] on: 16-byte stores where the alignment allows
+__device__ __forceinline__ void huf_fill(uint16_t *lut, uint32_t at, uint32_t len, uint32_t cell) {
+    uint32_t a = at; const uint32_t e = at + len;
+    while (a < e && (a & 7u)) lut[a++] = (uint16_t)cell;
+    const uint32_t c2 = cell | (cell << 16);
+    for (; a + 8 <= e; a += 8) *reinterpret_cast<uint4 *>(lut + a) = make_uint4(c2, c2, c2, c2);
+    while (a < e) lut[a++] = (uint16_t)cell;
+}
 // (rare: out of line, so that the stream decode keeps its registers)
 __device__ __noinline__ int huf_block_ref_device(const uint8_t *src, uint64_t src_len, ZsbBlockWork &w, const uint16_t *lut, int maxbits, ZsbCounters *cnt, uint8_t *lit_pool,
                                                  uint64_t lit_cap, uint64_t over_cap) {
@@ -188,10 +199,44 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__
         int rc = huf_read_weights(src + w.huf_desc, w.huf_desc_end - w.huf_desc, S.weights, 1, nw, dl, S.u.ftbl, 1, S.cnt, 1,
                                   src_len - w.huf_desc, quirks);
         HUF_T(3);
-        int mb = 0;
+        // == huf_build_lut (zsb_huf.h), the filling left to all four lanes of the slot: one lane on its own spends 159 k cycles there
+        // (2 048 cells a cell at a time, the four slots' loops diverging), against 44 k for the weights and 520 k for the streams
+        HufPlan P; P.mb = 0; P.n = 0; P.loose = false;
         bool inc = false;
-        if (!rc) rc = huf_build_lut(S.weights, 1, nw, S.u.lut, S.rank, 1, mb, nullptr, quirks, &inc);
-        S.maxbits = mb; S.status = rc; S.incomplete = inc ? 1 : 0;
+        if (!rc) rc = huf_lut_plan(S.weights, 1, nw, S.rank, 1, P, quirks, &inc);
+        if (!rc) {
+            for (int i = 0; i < P.n; i++) {                            // where every symbol's cells start: the classes fill up in symbol order
+                const uint32_t wt = S.weights[i];
+                uint32_t at = HUF_NO_ROOM;
+                if (wt) {
+                    const uint32_t len = 1u << (wt - 1);
+                    at = S.rank[wt]; S.rank[wt] = at + len;
+                    if (at + len > (1u << P.mb)) at = HUF_NO_ROOM;     // (quirks) no room left: the reference drops the symbol
+                }
+                S.at[i] = (uint16_t)at;
+            }
+        }
+        S.maxbits = P.mb; S.n = P.n; S.loose = P.loose ? 1 : 0; S.status = rc; S.incomplete = inc ? 1 : 0;
+    }
+    __syncwarp(HUF_MASK);
+    if (active && !S.status) {
+        const int mb = S.maxbits;
+        if (S.loose) {
+            for (uint32_t k = 8 * stream; k < (1u << mb); k += 32) {
+                if (k + 8 <= (1u << mb)) *reinterpret_cast<uint4 *>(S.u.lut + k) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                else for (uint32_t j = k; j < (1u << mb); j++) S.u.lut[j] = ZSB_HUF_ABSENT;
+            }
+        }
+    }
+    __syncwarp(HUF_MASK);
+    if (active && !S.status) {
+        const int mb = S.maxbits;
+        for (int i = (int)stream; i < S.n; i += 4) {
+            const uint32_t at = S.at[i];
+            if (at == HUF_NO_ROOM) continue;
+            const uint32_t wt = S.weights[i];
+            huf_fill(S.u.lut, at, 1u << (wt - 1), (uint32_t)i | (((uint32_t)mb + 1 - wt) << 8));
+        }
     }
     __syncwarp(HUF_MASK);
     HUF_T(1);
@@ -1009,7 +1054,9 @@ __device__ __forceinline__ uint64_t ld64_any(const uint8_t *p) {
 // l & 3 of stripe l >> 2) and 8 such loads are in flight (the chains are bound by their own latency only when ~64 stripes are on
 // their way: a lane that loaded its own word of every stripe, 8 at a time, took 115 cycles per round); lanes 0..3 hold the
 // accumulators and collect their words by shuffle.
-__device__ __forceinline__ void xxh_trail(const uint8_t *p, uint64_t len, volatile unsigned long long *done, uint64_t *result) {
+struct WaveCtx;
+__device__ void wave_advance(const WaveCtx &V);
+__device__ __forceinline__ void xxh_trail(const uint8_t *p, uint64_t len, volatile unsigned long long *done, uint64_t *result, const WaveCtx *V = nullptr) {
     const uint32_t lane = threadIdx.x & 31, q = lane & 3;
     uint64_t v = q == 0 ? XP1 + XP2 : q == 1 ? XP2 : q == 2 ? 0ull : 0ull - XP1;
     const uint64_t nstripes = len >> 5;
@@ -1019,10 +1066,11 @@ __device__ __forceinline__ void xxh_trail(const uint8_t *p, uint64_t len, volati
     const uint32_t sh = (uint32_t)((uintptr_t)g & 7) * 8;
     const unsigned long long *ga = reinterpret_cast<const unsigned long long *>((uintptr_t)g & ~(uintptr_t)7);
     while (cur < nstripes) {
-        const unsigned long long d = *done;
+        // (lane 0's view for all lanes: the loop must not diverge, it shuffles)
+        const unsigned long long d = __shfl_sync(FULL, *done, 0);
         if (d == ~0ull) return;
         uint64_t tgt = d >> 5; if (tgt > nstripes) tgt = nstripes;
-        if (tgt < nstripes && tgt - cur < 8 * NR) { __nanosleep(500); continue; }      // wait for a whole round of loads (or the end)
+        if (tgt < nstripes && tgt - cur < 8 * NR) { __nanosleep(500); if (V && lane == 0) wave_advance(*V); __syncwarp(); continue; }      // wait for a whole round of loads (or the end)
         __threadfence();
         // whole rounds of 8 * NR stripes (requesting the next round before this one is hashed, with a second register set, changes nothing:
         // the round is bound by the 64 dependent chain steps, ~65 cycles each beside 31 executing warps, not by its loads)
@@ -1049,7 +1097,14 @@ __device__ __forceinline__ void xxh_trail(const uint8_t *p, uint64_t len, volati
         }
     }
     // everything is committed only once *done == len (the tail bytes)
-    for (;;) { const unsigned long long d = *done; if (d == ~0ull) return; if (d >= len) break; __nanosleep(500); }
+    for (;;) {
+        const unsigned long long d = __shfl_sync(FULL, *done, 0);
+        if (d == ~0ull) return;
+        if (d >= len) break;
+        __nanosleep(500);
+        if (V && lane == 0) wave_advance(*V);
+        __syncwarp();
+    }
     __threadfence();
     const uint64_t v1 = __shfl_sync(FULL, v, 0), v2 = __shfl_sync(FULL, v, 1), v3 = __shfl_sync(FULL, v, 2), v4 = __shfl_sync(FULL, v, 3);
     if (lane == 0) {
@@ -1099,9 +1154,50 @@ __device__ __forceinline__ void range_publish(uint32_t *bm, uint32_t a, uint32_t
     for (uint32_t w = a >> 5; w <= ((e - 1) >> 5); w++) atomicOr(&bm[w], range_mask(w, a, e));
 }
 
-// One batch of 32 consecutive sequences, one lane per sequence.
+// ---- several CTAs per frame (k_exec in wavefront mode).  The blocks of a frame are handed out in order by a ticket, so the CTAs that run
+// always hold the lowest unfinished blocks (no CTA waits for a block nobody runs); a block's entropy stages are long done, its place and
+// its repeat offsets are known (k_plan2), and what it needs from the blocks before it is bytes: a match whose source reaches below the block
+// start waits until the frame is committed to HBM up to the end of that source (front_pos: bytes committed contiguously from the frame's
+// start; frame.rs:232-260 decodes block after block -- the result is the same bytes, the order of the work is not the reference's).
+struct ZsbWave {
+    unsigned long long front_pos;    // ~0: the frame failed, nobody waits any more
+    uint32_t front_blk;              // blocks 0 .. front_blk-1 of the frame are committed
+    uint32_t ticket;                 // next block to hand out
+    uint32_t pad[4];
+};
+struct WaveCtx { ZsbWave *wf; uint32_t *done; const ZsbBlockWork *work; unsigned long long *s_front; uint32_t first, n_blocks; uint64_t frame_len; };   // done, work: of the frame's first block
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v; asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+// moves the frontier over every block that is marked done; called by whoever finishes a block and by whoever waits
+__device__ __noinline__ void wave_advance(const WaveCtx &V) {
+    for (;;) {
+        const uint32_t fb = ld_acquire_u32(&V.wf->front_blk);
+        if (fb >= V.n_blocks || !ld_acquire_u32(V.done + fb)) return;
+        if (atomicCAS(&V.wf->front_blk, fb, fb + 1) == fb)
+            atomicMax(&V.wf->front_pos, fb + 1 < V.n_blocks ? (unsigned long long)V.work[fb + 1].out_off : (unsigned long long)V.frame_len);
+    }
+}
+// block k of the frame is in HBM
+__device__ __forceinline__ void wave_commit(const WaveCtx &V, uint32_t k) {
+    __threadfence();
+    atomicExch(V.done + k, 1u);
+    asm volatile("fence.sc.gpu;" ::: "memory");          // two CTAs that finish neighbouring blocks at once: at least one sees the other's mark
+    wave_advance(V);
+}
+// is the frame committed up to byte `need`?  (the CTA's copy of the frontier first: most sources lie far below it)
+__device__ __forceinline__ bool wave_ready(const WaveCtx &V, uint64_t need) {
+    if (need <= *(volatile unsigned long long *)V.s_front) return true;
+    unsigned long long fp = ld_acquire_u64(&V.wf->front_pos);
+    if (need > fp) { wave_advance(V); fp = ld_acquire_u64(&V.wf->front_pos); }
+    atomicMax(V.s_front, fp);
+    return need <= fp;
+}
+
+// One batch of 32 consecutive sequences, one lane per sequence.  V (wavefront mode, else nullptr): sources below the block start are awaited.
 __device__ __forceinline__ void exec_batch(uint32_t batch, uint32_t nseq, const uint64_t *__restrict__ seqs, uint8_t *o, uint32_t *bm,
-                                           const LitSrc &L, const uint32_t *rep_in, uint64_t P0, const uint8_t *gblk, int *s_err) {
+                                           const LitSrc &L, const uint32_t *rep_in, uint64_t P0, const uint8_t *gblk, int *s_err, const WaveCtx *V) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t s = batch * 32 + lane;
     const bool valid = s < nseq;
@@ -1135,11 +1231,14 @@ __device__ __forceinline__ void exec_batch(uint32_t batch, uint32_t nseq, const 
     // match output; only [a0, e) below out_start comes from earlier sequences and must be awaited.
     const int e = min(src + (int)ml, (int)out_start);
     const uint32_t a0 = src > 0 ? (uint32_t)src : 0u;
+    // wavefront mode: the frame position up to which earlier blocks must be committed for this match (0: none of its source lies there)
+    uint64_t need = (V && pend && src < 0) ? P0 - (uint64_t)(uint32_t)(-min(src + (int)ml, 0)) : 0ull;
     for (uint32_t spins = 0;; spins++) {
         if (spins > (1u << 20)) { *s_err = ZSB_E_CORRUPT; break; }   // watchdog: a dependency that never resolves is a bug, not a hang
         bool didm = false;
         if (pend && !longM) {
-            const bool ready = (e <= (int)a0) || range_ready(bm, a0, (uint32_t)e);
+            bool ready = (e <= (int)a0) || range_ready(bm, a0, (uint32_t)e);
+            if (ready && need) { ready = wave_ready(*V, need); if (ready) need = 0; }
             if (ready) {
                 __threadfence_block();
                 if (src + (int)ml <= 0) {
@@ -1175,6 +1274,10 @@ __device__ __forceinline__ void exec_batch(uint32_t batch, uint32_t nseq, const 
                 }
             ok = __all_sync(FULL, ok);
             if (ok) {
+                const uint64_t jneed = __shfl_sync(FULL, need, j);
+                if (jneed) { if (lane == 0) ok = wave_ready(*V, jneed); ok = __shfl_sync(FULL, (int)ok, 0) != 0; }
+            }
+            if (ok) {
                 __threadfence_block();
                 // the copy is periodic with period off when the match overlaps its own output
                 for (uint32_t k = lane; k < jml; k += 32) {
@@ -1201,6 +1304,7 @@ __device__ __forceinline__ void exec_batch(uint32_t batch, uint32_t nseq, const 
         }
         first = false;
         if (!__any_sync(FULL, pend)) break;
+        if (V && __all_sync(FULL, !pend || need != 0)) { __nanosleep(200); if (spins > (1u << 19)) spins = 1u << 19; }   // only the frontier is missing: no watchdog for that, other CTAs are at work
     }
 }
 
@@ -1211,7 +1315,9 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
                                                           const zsb_block *__restrict__ blocks, const ZsbBlockWork *__restrict__ work,
                                                           ZsbFrameOut *fout, const uint32_t *__restrict__ exec_list,
                                                           const ZsbCounters *__restrict__ cnt, const uint64_t *__restrict__ seq_pool,
-                                                          const uint8_t *__restrict__ lit_pool, uint8_t *dst, uint32_t flags) {
+                                                          const uint8_t *__restrict__ lit_pool, uint8_t *dst, uint32_t flags,
+                                                          ZsbWave *wave, uint32_t *blk_done, uint32_t G) {
+    // wave != nullptr: G CTAs per frame (wavefront mode, see ZsbWave); else one CTA per frame, block after block
     constexpr uint32_t ET = EXEC_THREADS - (XXH ? 32 : 0);            // executing threads
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ int s_err;
@@ -1221,27 +1327,44 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
     uint32_t *bm = reinterpret_cast<uint32_t *>(smem + EXEC_OUT_BYTES);
     uint8_t *lit_s = smem + EXEC_OUT_BYTES + EXEC_BM_WORDS * 4;
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t f = exec_list[blockIdx.x];
+    const uint32_t li = wave ? blockIdx.x / G : blockIdx.x;
+    const uint32_t f = exec_list[li];
     const ZsbFrameOut fo = fout[f];
     if (fo.status != ZSB_OK) return;
     const zsb_frame fr = frames[f];
     uint8_t *fdst = dst + fo.dst_off;
+    __shared__ unsigned long long s_front;                             // wavefront mode: this CTA's copy of the frame's frontier
+    __shared__ uint32_t s_k;                                           // the block the CTA works on
+    WaveCtx V;
+    V.wf = wave ? wave + li : nullptr; V.done = blk_done ? blk_done + fr.first_block : nullptr; V.work = work + fr.first_block; V.s_front = &s_front;
+    V.first = fr.first_block; V.n_blocks = fr.n_blocks; V.frame_len = fo.dst_len;
     __shared__ __align__(8) unsigned long long s_mbar;                 // completion of the literal staging's bulk copy
     const uint32_t mbar_sa = (uint32_t)__cvta_generic_to_shared(&s_mbar);
     uint32_t mbar_phase = 0;
-    if (tid == 0) { s_err = 0; s_done = 0; zsb_mbar_init(mbar_sa, 1); }
+    if (tid == 0) { s_err = 0; s_done = 0; s_front = 0; s_k = 0; zsb_mbar_init(mbar_sa, 1); }
     __syncthreads();
     if (XXH && warp == ET / 32) {
-        if ((flags & ZSB_VERIFY_CHECKSUM) && fr.has_checksum) xxh_trail(fdst, fo.dst_len, &s_done, &fout[f].xxh64);
+        // (wavefront mode: the first of the frame's CTAs hashes, behind the frame's frontier instead of its own CTA's progress)
+        if ((flags & ZSB_VERIFY_CHECKSUM) && fr.has_checksum && (!wave || blockIdx.x % G == 0))
+            xxh_trail(fdst, fo.dst_len, wave ? &V.wf->front_pos : &s_done, &fout[f].xxh64, wave ? &V : nullptr);
         return;
     }
     auto sync_exec = [&]() { if (XXH) asm volatile("bar.sync 1, %0;" ::"r"(ET) : "memory"); else __syncthreads(); };
     bool failed = false;
-    for (uint32_t k = 0; k < fr.n_blocks; k++) {
+    for (uint32_t kk = 0;; kk++) {
+        uint32_t k = kk;
+        if (wave) {                                                    // the next block of the frame nobody has taken yet
+            sync_exec();
+            if (tid == 0) s_k = ld_acquire_u64(&V.wf->front_pos) == ~0ull ? ~0u : atomicAdd(&V.wf->ticket, 1u);
+            sync_exec();
+            k = s_k;
+        }
+        if (k >= fr.n_blocks) break;
         const uint32_t bi = fr.first_block + k;
         const ZsbBlockWork &W = work[bi];
         if (blocks[bi].type != ZSB_BT_COMPRESSED) {                    // written by k_rawrle
-            if (XXH && tid == 0) s_done = W.out_off + W.out_size;
+            if (wave) { if (tid == 0) wave_commit(V, k); }
+            else if (XXH && tid == 0) s_done = W.out_off + W.out_size;
             continue;
         }
         const uint32_t out_size = W.out_size, nseq = W.nseq, regen = W.lit_regen;
@@ -1280,7 +1403,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
             for (uint32_t i = tid; i < regen - le; i += ET) o[oe + i] = lit_at(L, le + i);   // decoding_context.rs:101-103
             const uint32_t nbatch = (nseq + 31) / 32;
             for (uint32_t b = warp; b < nbatch; b += ET / 32)
-                exec_batch(b, nseq, seqs, o, bm, L, W.rep_in, fr.kind == 0 ? W.out_off : 0, gblk, &s_err);
+                exec_batch(b, nseq, seqs, o, bm, L, W.rep_in, fr.kind == 0 ? W.out_off : 0, gblk, &s_err, wave ? &V : nullptr);
         }
         zsb_fence_async_smem();                                        // the image was written with ordinary stores; the copy engine reads it
         sync_exec();
@@ -1294,12 +1417,16 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
             for (uint32_t i = head + (nv << 4) + tid; i < out_size; i += ET) gblk[i] = o[i];
             if (tid == 0 && nv) zsb_bulk_wait_all();                  // complete: the image may be overwritten, the bytes are in HBM
         }
-        if (XXH) __threadfence();                                      // the block is in HBM before the hashing warp is told so
+        if (XXH || wave) __threadfence();                              // the block is in HBM before the hashing warp (other CTAs) are told so
         sync_exec();
-        if (s_err) { if (tid == 0) { fout[f].status = s_err; fout[f].dst_len = 0; } failed = true; break; }
-        if (XXH && tid == 0) s_done = W.out_off + out_size;
+        if (s_err) {
+            if (tid == 0) { fout[f].status = s_err; fout[f].dst_len = 0; if (wave) atomicMax(&V.wf->front_pos, ~0ull); }   // (nobody waits for this frame any more)
+            failed = true; break;
+        }
+        if (wave) { if (tid == 0) wave_commit(V, k); }
+        else if (XXH && tid == 0) s_done = W.out_off + out_size;
     }
-    if (XXH && tid == 0) s_done = failed ? ~0ull : fo.dst_len;
+    if (!wave && XXH && tid == 0) s_done = failed ? ~0ull : fo.dst_len;
 }
 
 // ======================================================================================= k_exec2
@@ -1959,11 +2086,16 @@ void zsbk_rawrle(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_bloc
 }
 void zsbk_exec(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
                ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst, bool shared_device,
-               uint32_t flags) {
+               uint32_t flags, void *wave, uint32_t *blk_done, uint32_t ctas_per_frame) {
     if (!n) return;
+    if (wave && !shared_device && ctas_per_frame > 1) {
+        k_exec<1024, true><<<n * ctas_per_frame, 1024, EXEC_SMEM_BYTES, st>>>(src, frames, blocks, work, fout, exec_list, cnt, seq_pool, lit_pool, dst, flags,
+                                                                              (ZsbWave *)wave, blk_done, ctas_per_frame);
+        return;
+    }
     // (on its own: 31 executing warps and one that hashes the frame behind them, so a frame of many blocks is not hashed by k_xxh afterwards)
-    if (shared_device) k_exec<512, false><<<n, 512, EXEC_SMEM_BYTES, st>>>(src, frames, blocks, work, fout, exec_list, cnt, seq_pool, lit_pool, dst, flags);
-    else k_exec<1024, true><<<n, 1024, EXEC_SMEM_BYTES, st>>>(src, frames, blocks, work, fout, exec_list, cnt, seq_pool, lit_pool, dst, flags);
+    if (shared_device) k_exec<512, false><<<n, 512, EXEC_SMEM_BYTES, st>>>(src, frames, blocks, work, fout, exec_list, cnt, seq_pool, lit_pool, dst, flags, nullptr, nullptr, 1);
+    else k_exec<1024, true><<<n, 1024, EXEC_SMEM_BYTES, st>>>(src, frames, blocks, work, fout, exec_list, cnt, seq_pool, lit_pool, dst, flags, nullptr, nullptr, 1);
 }
 void zsbk_exec2(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
                 ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst) {

@@ -36,7 +36,8 @@ void zsbk_rawrle(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_bloc
                  const uint32_t *list, const ZsbCounters *cnt, uint8_t *dst);
 void zsbk_exec(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
                ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst, bool shared_device,
-               uint32_t flags);
+               uint32_t flags, void *wave /* 32 zeroed bytes per listed frame, or nullptr */, uint32_t *blk_done /* one zeroed word per block of the batch */,
+               uint32_t ctas_per_frame /* > 1 with wave: wavefront mode */);
 void zsbk_exec2(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
                 ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst);
 void zsbk_publish(cudaStream_t st, void *host_dev_ptr, const ZsbCounters *cnt, const ZsbFrameOut *fout, uint32_t nf);
