@@ -53,7 +53,8 @@ struct zsb_ctx {
     std::vector<uint32_t> h_xxh_list, h_rawrle, h_exec, h_exec2;   // host copies stay alive while their uploads are in flight
     std::vector<uint64_t> h_pre_off;                               // where every frame is expected in dst (k_seqx), ~0: not known before decoding
     int seqx_state = 0;                                            // zsb_last_seqx_state
-    uint32_t wave_max = 1;                                         // ZSB_WAVE: most CTAs per frame k_exec may use (1: one CTA per frame, block after block)
+    uint32_t wave_max = 3;                                         // ZSB_WAVE: most CTAs per frame k_exec may use (1: one CTA per frame, block after block, hashing beside them)
+    bool wave_forced = false;                                      // ... set by the environment: used even when there is nothing to hash
     uint32_t wave_ctas = 1;                                        // CTAs per frame of k_exec (wavefront mode when > 1)
     bool use_seqx = false;                                         // this batch runs k_seqx
     std::vector<uint32_t> h_err_a, h_err_b;                        // per-frame error payloads of the last finished batch (zsb_decode_errors)
@@ -99,7 +100,7 @@ extern "C" int zsb_ctx_create(zsb_ctx **out, int device) {
     c->stream = c->own_stream;
     { const char *e = getenv("ZSB_OVERLAP"); c->overlap = e && *e && *e != '0'; }
     { const char *e = getenv("ZSB_SEQX"); c->seqx = e && *e && *e != '0'; }
-    { const char *e = getenv("ZSB_WAVE"); const int v = e ? atoi(e) : 1; c->wave_max = v < 1 ? 1u : v > 64 ? 64u : (uint32_t)v; }
+    { const char *e = getenv("ZSB_WAVE"); const int v = e ? atoi(e) : 3; c->wave_forced = e != nullptr; c->wave_max = v < 1 ? 1u : v > 64 ? 64u : (uint32_t)v; }
     { const char *e = getenv("ZSB_PIPE_TRACE"); c->trace = e && *e && *e != '0'; }
     if (c->trace) for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev_tr[i]);
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) cudaEventCreate(&c->ev[r][i]);
@@ -257,16 +258,19 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
             if (getenv("ZSB_DEBUG")) fprintf(stderr, "zsb: k_seqx places %u of %zu frames\n", placed, nf);
         }
     }
-    // k_exec in wavefront mode (ZSB_WAVE=n, n > 1): the CTA-per-frame list is short (a single large frame, a file of a few frames), so every
-    // frame gets up to n CTAs that take its blocks in order (ZsbWave).  All of them must fit the GPU at once only for speed, not for progress.
-    // Off by default: measured on C3 (text, zstd -3) it gains nothing -- half the sequences of a block wait, directly or through bytes that
-    // do, for the block before it (tools/probes/c3_dependencies.py), and a batch of 32 sequences proceeds only when all of its lanes can.
+    // k_exec in wavefront mode (ZSB_WAVE=n CTAs per frame, default 3 when checksums are verified): the CTA-per-frame list is short (a single
+    // large frame, a file of a few frames), so every frame gets one CTA that only hashes behind the frame's frontier and n-1 that take its
+    // blocks in order (ZsbWave).  The hashing CTA pays: its warp has an SM to itself (C3, 256 MiB, verified: 314 -> 247 ms, what the frame
+    // takes without its checksum).  A second executing CTA hides the staging and flushing of one block behind the execution of the next;
+    // more gain nothing on text at zstd -3: half the sequences of a block wait, directly or through bytes that do, for the block before it
+    // (tools/probes/c3_dependencies.py), and a batch of 32 sequences proceeds only when all of its lanes can (4 / 6 CTAs: 246 / 245 ms).
     {
         uint32_t maxb = 0;
         for (uint32_t f : execl) maxb = std::max(maxb, frames[f].n_blocks);
         uint32_t g = execl.empty() ? 1u : (uint32_t)(148 / execl.size());
         if (g > c->wave_max) g = c->wave_max;
-        if (g > maxb) g = maxb;
+        if (g > maxb + 1) g = maxb + 1;
+        if (!c->wave_forced && !(flags & ZSB_VERIFY_CHECKSUM)) g = 1;   // nothing to hash: one CTA per frame, block after block, is 3 % faster than two that take turns
         c->wave_ctas = (c->is_sub || g < 2) ? 1u : g;
     }
     c->ncomp = (uint32_t)ncomp; c->n_rawrle = (uint32_t)rawrle.size(); c->n_exec = (uint32_t)execl.size(); c->n_exec2 = (uint32_t)exec2l.size(); c->n_xxh = (uint32_t)c->h_xxh_list.size();

@@ -1195,6 +1195,11 @@ __device__ __forceinline__ bool wave_ready(const WaveCtx &V, uint64_t need) {
     return need <= fp;
 }
 
+// (defined with k_exec2: copies in units of up to 8 bytes through aligned words; here the "ring" is the block image, which never wraps)
+template <uint32_t RING> __device__ __forceinline__ void ex2_store8(uint8_t *ring, uint32_t d, uint32_t v0, uint32_t v1, uint32_t n);
+template <uint32_t RING> __device__ __forceinline__ void ex2_load8_ring(const uint8_t *ring, uint32_t s, uint32_t n, uint32_t &v0, uint32_t &v1);
+#define EXEC_IMG 262144u         // power of two above the block image
+
 // One batch of 32 consecutive sequences, one lane per sequence.  V (wavefront mode, else nullptr): sources below the block start are awaited.
 __device__ __forceinline__ void exec_batch(uint32_t batch, uint32_t nseq, const uint64_t *__restrict__ seqs, uint8_t *o, uint32_t *bm,
                                            const LitSrc &L, const uint32_t *rep_in, uint64_t P0, const uint8_t *gblk, int *s_err, const WaveCtx *V) {
@@ -1214,6 +1219,8 @@ __device__ __forceinline__ void exec_batch(uint32_t batch, uint32_t nseq, const 
     if (bad) *s_err = ZSB_E_IMPOSSIBLE_VALUE;
     const int src = (int)dstm - (int)off;
     const bool longL = ll > EXEC_LONG, longM = ml > EXEC_LONG;
+    uint8_t *img = reinterpret_cast<uint8_t *>((uintptr_t)o & ~(uintptr_t)15);     // the image starts at the alignment of its destination: o = img + ish
+    const uint32_t ish = (uint32_t)((uintptr_t)o & 15);
 
     // ---- literals: no dependency on earlier output (decoding_context.rs:92-93)
     if (ll && !longL)
@@ -1251,6 +1258,14 @@ __device__ __forceinline__ void exec_batch(uint32_t batch, uint32_t nseq, const 
                         for (int j = 0; j < 8; j++) v[j] = k + j < ml ? __ldcg(gblk + src + (int)(k + j)) : (uint8_t)0;
 #pragma unroll
                         for (int j = 0; j < 8; j++) if (k + j < ml) o[dstm + k + j] = v[j];
+                    }
+                } else if (src >= 0 && off >= 8) {
+                    // inside the block, no unit reads what it writes: eight bytes at a time (three aligned words in, funnel shifts, predicated
+                    // byte stores) -- byte by byte every byte pays a shared-memory round trip, and the batches behind this one wait for it
+                    for (uint32_t k = 0; k < ml; k += 8) {
+                        const uint32_t c = min(ml - k, 8u); uint32_t v0, v1;
+                        ex2_load8_ring<EXEC_IMG>(img, ish + (uint32_t)src + k, c, v0, v1);
+                        ex2_store8<EXEC_IMG>(img, ish + dstm + k, v0, v1, c);
                     }
                 } else {
                     for (uint32_t k = 0; k < ml; k++) {
@@ -1349,6 +1364,9 @@ __global__ void __launch_bounds__(EXEC_THREADS, 1) k_exec(const uint8_t *__restr
             xxh_trail(fdst, fo.dst_len, wave ? &V.wf->front_pos : &s_done, &fout[f].xxh64, wave ? &V : nullptr);
         return;
     }
+    // wavefront mode: the frame's first CTA does nothing but hash -- its one warp then has an SM to itself (beside 31 executing warps a
+    // round of the four accumulator chains takes 73 cycles instead of ~35, and a frame of many blocks is bound by exactly that)
+    if (wave && blockIdx.x % G == 0) return;
     auto sync_exec = [&]() { if (XXH) asm volatile("bar.sync 1, %0;" ::"r"(ET) : "memory"); else __syncthreads(); };
     bool failed = false;
     for (uint32_t kk = 0;; kk++) {
@@ -1473,7 +1491,7 @@ __device__ __forceinline__ uint8_t ex2_src(const uint8_t *ring, const uint8_t *g
 
 // ---- copies in units of up to 8 bytes: three aligned source words, two funnel shifts, predicated byte stores
 // store the low n (1..8) bytes of v1:v0 at ring position d (unmasked)
-template <uint32_t RING = EX2_RING>
+template <uint32_t RING>
 __device__ __forceinline__ void ex2_store8(uint8_t *ring, uint32_t d, uint32_t v0, uint32_t v1, uint32_t n) {
     d &= RING - 1u;
     if (d + 8 <= RING) {
@@ -1497,7 +1515,7 @@ __device__ __forceinline__ void ex2_store8(uint8_t *ring, uint32_t d, uint32_t v
     }
 }
 // n (<= 8) bytes starting at ring position s (unmasked)
-template <uint32_t RING = EX2_RING>
+template <uint32_t RING>
 __device__ __forceinline__ void ex2_load8_ring(const uint8_t *ring, uint32_t s, uint32_t n, uint32_t &v0, uint32_t &v1) {
     const uint32_t a = s & (RING - 1u) & ~3u, sh = (s & 3u) * 8u;
     const uint32_t w0 = *reinterpret_cast<const uint32_t *>(ring + a);
