@@ -668,6 +668,9 @@ extern "C" int zsb_scan_decode(zsb_ctx *c, const uint8_t *src, size_t n, uint8_t
             const size_t f0 = sc.frames.size();
             while (!sc.done && sc.pos < lim) if (!sc.next()) break;
             if (sc.code != ZSB_OK) { streamed = false; break; }          // the walk ended on a malformed frame
+            // the first shard swallowed the whole buffer (a single large frame, C3): nothing to overlap, and the context's own path executes a
+            // frame of many blocks with 1 024-thread CTAs and hashes it beside the execution, which a shard's context does not
+            if (k == 0 && (sc.done || sc.pos >= n)) { streamed = false; break; }
             const size_t f1 = sc.frames.size();
             uint64_t out = 0;
             for (size_t f = f0; f < f1; f++)
