@@ -1,0 +1,40 @@
+"""A small tour of the decode path for compute-sanitizer (memcheck / synccheck): the fixtures, C4, 64 C2 frames, a 3 MiB C3 frame,
+the same with ZSB_SEQX=1 and ZSB_WAVE=4, a host-buffer call and a few mutated inputs.
+    compute-sanitizer --tool memcheck python tools/probes/sanitize_target.py"""
+import os, random, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tools"))
+import corpora
+import zstd_decompressor_b200 as Z
+Q, SKIP, VER = Z.REFERENCE_QUIRKS, Z.PRINT_SKIPPABLE, Z.VERIFY_CHECKSUM
+
+
+def tour(dec, tag):
+    n = 0
+    for name in corpora.FIXTURE_NAMES:
+        d = corpora.fixture(name)
+        for fl in (Q | VER, VER | SKIP):
+            out, sc, r = dec.decode(d, fl); n += 1
+    blob, exp, exp_skip, _ = corpora.c4()
+    out, sc, r = dec.decode(blob, Q | VER); assert out == exp; n += 1
+    blob, exp = corpora.c2_small(64)
+    out, sc, r = dec.decode(blob, Q | VER); assert out == exp; n += 1
+    blob, exp = corpora.c3_small(3 << 20)
+    out, sc, r = dec.decode(blob, Q | VER); assert out == exp; n += 1
+    rnd = random.Random(7)
+    for src in corpora.list(corpora.mutation_sources().values())[:3]:
+        for _ in range(6):
+            d = corpora.mutate(rnd, src)
+            dec.decode(d, Q | VER); n += 1
+    print(tag, n, "decodes")
+
+
+tour(Z.Decoder(Z.Context(0)), "default")
+for k, v in (("ZSB_SEQX", "1"), ("ZSB_WAVE", "4")):
+    os.environ[k] = v
+    try:
+        d = Z.Decoder(Z.Context(0))
+    finally:
+        del os.environ[k]
+    tour(d, f"{k}={v}")
+print("done")
