@@ -653,3 +653,13 @@ def test_wavefront_execution_of_multi_block_frames(dec):
     out, sc, r = dw.decode(bytes(bad), Q | VER)
     out2, sc2, r2 = dec.decode(bytes(bad), Q | VER)
     assert (r.status[0] != 0) == (r2.status[0] != 0) and (r.status[0] != 0 or r.checksum_ok[0] == r2.checksum_ok[0])
+
+
+def test_tour_of_every_mode_in_one_context_each():
+    """tools/probes/sanitize_target.py: fixtures, C4, C2, C3 and mutated inputs one after the other in ONE context per mode (default,
+    ZSB_SEQX=1, ZSB_WAVE=4) -- scratch left behind by one batch must never matter to the next (a refused k_seqx block once had its stale
+    records executed)"""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "probes", "sanitize_target.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("done"), r.stdout[-500:] + r.stderr[-1500:]

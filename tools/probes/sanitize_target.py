@@ -1,4 +1,4 @@
-"""A small tour of the decode path for compute-sanitizer (memcheck / synccheck): the fixtures, C4, 64 C2 frames, a 3 MiB C3 frame,
+"""A small tour of the decode path (asserts every output; also the target for compute-sanitizer where the pool allows it): the fixtures, C4, 64 C2 frames, a 3 MiB C3 frame,
 the same with ZSB_SEQX=1 and ZSB_WAVE=4, a host-buffer call and a few mutated inputs.
     compute-sanitizer --tool memcheck python tools/probes/sanitize_target.py"""
 import os, random, sys
@@ -22,7 +22,7 @@ def tour(dec, tag):
     blob, exp = corpora.c3_small(3 << 20)
     out, sc, r = dec.decode(blob, Q | VER); assert out == exp; n += 1
     rnd = random.Random(7)
-    for src in corpora.list(corpora.mutation_sources().values())[:3]:
+    for src in list(corpora.mutation_sources().values())[:3]:
         for _ in range(6):
             d = corpora.mutate(rnd, src)
             dec.decode(d, Q | VER); n += 1

@@ -94,7 +94,8 @@ struct ZsbBlockWork {
     uint8_t  rle_sym[3];
     uint8_t  lit_inexact;    // ZSB_REFERENCE_QUIRKS: the streams do not have the shape Regenerated_Size promises (a zero or truncated jump-table entry ...):
                              // the literals are decoded the reference's way, every stream until its bits run out (huf_decode_block_ref)
-    uint8_t  fused;          // 1: the fused sequence kernel (k_seqx) executed this block into its predicted place already; 2: it did, and a match offset was impossible
+    uint8_t  fused;          // 1: the fused sequence kernel (k_seqx) executed this block into its predicted place already; 2: it did, and a match offset was impossible; 3: it gave up (the block
+                             // outgrew the frame's declared size): no records exist, the batch is run again
     // scratch placement
     uint64_t lit_buf;        // byte offset in the literal scratch (Huffman literals)
     uint64_t seq_buf;        // record index in the sequence scratch

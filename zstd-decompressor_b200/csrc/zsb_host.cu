@@ -70,6 +70,8 @@ struct zsb_ctx {
     uint8_t *pin = nullptr; size_t pin_cap = 0; bool pin_valid = false;
     uint64_t eager_d2h = 0;               // pipelined path: bytes of output to send to the host right behind the kernels (size known from the headers)
     bool prepared = false, launched = false;
+    bool debug_sync = false;   // ZSB_DEBUG=1
+    const char *dbg_prev = "the uploads";
     bool seqx = false;         // ZSB_SEQX=1: sequence decoding and execution in one kernel (k_seqx) where a frame's place is known beforehand; measured
                                // slower than k_seq + k_exec2 (5.6 ms against 2.9 ms on C2: 64 registers per thread and 28 KiB of L1 for 29 warps), kept as an experiment
     bool overlap = false;      // ZSB_OVERLAP=1: literals stage on the auxiliary stream beside k_seq (measured slower: both are latency bound and share schedulers)
@@ -100,6 +102,7 @@ extern "C" int zsb_ctx_create(zsb_ctx **out, int device) {
     c->stream = c->own_stream;
     { const char *e = getenv("ZSB_OVERLAP"); c->overlap = e && *e && *e != '0'; }
     { const char *e = getenv("ZSB_SEQX"); c->seqx = e && *e && *e != '0'; }
+    { const char *e = getenv("ZSB_DEBUG"); c->debug_sync = e && *e && *e != '0'; }
     { const char *e = getenv("ZSB_WAVE"); const int v = e ? atoi(e) : 3; c->wave_forced = e != nullptr; c->wave_max = v < 1 ? 1u : v > 64 ? 64u : (uint32_t)v; }
     { const char *e = getenv("ZSB_PIPE_TRACE"); c->trace = e && *e && *e != '0'; }
     if (c->trace) for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev_tr[i]);
@@ -306,7 +309,14 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     return ZSB_OK;
 }
 
-#define MARK(ctx, name) do { if ((ctx)->profile && (ctx)->nk < kMaxKernels) { (ctx)->kname[(ctx)->nk] = name; cudaEventRecord((ctx)->ev[(ctx)->prof_slot][(ctx)->nk], st); (ctx)->nk++; } } while (0)
+// ZSB_DEBUG=1: every stage is waited for before the next one is enqueued, so that a fault is reported with the name of the kernel that caused it
+#define MARK(ctx, name) do { \
+    if ((ctx)->debug_sync) { \
+        cudaError_t e__ = cudaStreamSynchronize(st); \
+        if (e__ != cudaSuccess) { (ctx)->last_err = std::string("before ") + (name) + " (after " + (ctx)->dbg_prev + "): " + cudaGetErrorString(e__); fprintf(stderr, "zsb: %s\n", (ctx)->last_err.c_str()); return ZSB_E_CUDA; } \
+        (ctx)->dbg_prev = (name); \
+    } \
+    if ((ctx)->profile && (ctx)->nk < kMaxKernels) { (ctx)->kname[(ctx)->nk] = name; cudaEventRecord((ctx)->ev[(ctx)->prof_slot][(ctx)->nk], st); (ctx)->nk++; } } while (0)
 
 extern "C" int zsb_decode_launch(zsb_ctx *c) {
     if (!c || !c->prepared) return ZSB_E_ARG;
@@ -368,6 +378,7 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
         if (c->trace) cudaEventRecord(c->ev_tr[3], c->down_stream);
     }
     MARK(c, "k_xxh");    zsbk_xxh(st, c->n_xxh, c->d_dst, fout, (const uint32_t *)c->xxh_list.p, cnt); c->launches += c->n_xxh ? 1 : 0;
+    if (c->debug_sync) { const bool pr = c->profile; c->profile = false; MARK(c, "the end of the batch"); c->profile = pr; c->dbg_prev = "the uploads"; }
     if (c->profile) { cudaEventRecord(c->ev[c->prof_slot][c->nk], st); c->prof_slot = (c->prof_slot + 1) % kProfRing; c->prof_count++; }
     if (c->trace && !early_down) cudaEventRecord(c->ev_tr[2], st);
     c->pin_valid = false;

@@ -1768,7 +1768,8 @@ __device__ __forceinline__ void seqx_consume(uint8_t *smem_rings, SeqSharedT<WIN
         else {
             g.lit_used = C.lit_acc; g.out_size = out_size;
             g.rep_out[0] = C.H.h0; g.rep_out[1] = C.H.h1; g.rep_out[2] = C.H.h2;
-            if (xerr) g.fused = 2; else if (exec) g.fused = 1; else if (refuse) cnt->refuse = 1u;
+            // (refused: no records were written for this block and nothing valid lies in dst -- k_exec2 must not touch it; the host runs the batch again)
+            if (xerr) g.fused = 2; else if (exec) g.fused = 1; else if (refuse) { g.fused = 3; cnt->refuse = 1u; }
         }
     }
 }
