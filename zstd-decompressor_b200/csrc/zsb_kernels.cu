@@ -6,13 +6,15 @@
 //   k_plan1   nf/1024 CTAs        per-frame table/tree chaining; the last CTA: scratch placement (scans) + work lists
 //   k_huf     1 lane / stream     Huffman weights -> LUT (smem) -> 4-stream literal decode   (huffman.rs, literals.rs:49-86)
 //   k_seq     1 lane / block      FSE tables (interleaved smem) + the serial 3-state chain      (fse.rs, sequence.rs, sequences.rs:191-237)
-//           + 1 lane / sequence   extra bits, positions, repeat-offset history -> packed records (sequence.rs:41-55, decoding_context.rs:50-75)
+//           + 1 lane / 4 sequences extra bits, positions, repeat-offset history -> packed records (sequence.rs:41-55, decoding_context.rs:50-75)
+//   (k_seqx   opt-in: k_seq whose phase-2 warps also execute the blocks whose place is known beforehand)
 //   k_seq_slow 1 lane / block     careful decoder for blocks the fast path handed over (exact error order)
 //   k_plan2   nf/1024 CTAs        repeat-offset history, frame sizes, size checks; the last CTA: output offsets (scan)
 //   k_rawrle  1 CTA / block       raw / RLE block expansion, skippable payloads              (block.rs:76-79)
 //   k_exec2   1 warp / frame      sequence execution through a 2 KiB shared-memory ring      (decoding_context.rs:78-106)
-//   k_exec    1 CTA / frame       the same for frames of many blocks: a 128 KiB block image in shared memory
-//   k_xxh     4 lanes / frame     XXH64 content checksum                                      (frame.rs:239-259)
+//   k_exec    1-3 CTAs / frame    the same for frames of many blocks: a 128 KiB block image in shared memory; with checksums one CTA of the
+//                                 frame only hashes (XXH64) behind the bytes the others have committed
+//   k_xxh     4 lanes / frame     XXH64 content checksum of the frames k_exec2 executed      (frame.rs:239-259)
 //   k_publish (pipelined host path only) counters and per-frame results into page-locked host memory
 //
 // Nothing here is a dense contraction: no tensor cores.  The entropy stages are serial per stream, so they run
@@ -397,16 +399,18 @@ __device__ __forceinline__ int seq_build_table_warp(const uint8_t *src, const Zs
 //
 //   warp 0 (producer)  the serial three-state FSE chain, one lane per block, SEQ_CHAINS = 32 blocks per CTA (so that a SM
 //                      hosts one producer warp and the phase-2 warps mostly run on the other sub-cores).  The chain is
-//                      latency bound (table cell -> bit count -> bit position -> next state: one shared-memory load and
-//                      ~8 dependent ALU operations per sequence), so it carries as little else as possible: tables
-//                      interleaved across the lanes (cell i of lane l at word i*32 + l: bank = l, conflict free), the bit window fed from a cp.async stream ring, one 32-bit word per sequence
-//                      into a shared-memory ring.
-//   warps 1..H (phase 2) one lane per sequence, 32 sequences per step and block: bit positions, extra-bit values,
+//                      latency bound (table cells -> their sum -> the state bits out of a register window -> next cell
+//                      addresses: one shared-memory load and ~6 dependent ALU operations per sequence, SEQ_STEP), so it carries
+//                      as little else as possible: tables interleaved across the lanes (cell i of lane l at word i*32 + l:
+//                      bank = l, conflict free), the bit window in registers, refilled from a cp.async stream ring, one 32-bit
+//                      word per sequence into a shared-memory ring.
+//   warps 1..H (phase 2) k_seq: four sequences per lane, 128 per step and block: bit positions, extra-bit values,
 //                      literal/output positions and the repeat-offset history by warp prefix operations; packed
 //                      records to HBM.  They run in the issue slots the producers leave empty (~70 %).
 //
-// Hand-over: the chains advance in lockstep, 64 sequences (one window per chain) at a time; the word ring holds two
-// windows per chain; named barriers (full / free, two of each) pass the batches on, so a waiting warp costs no issue slot.
+// Hand-over: the chains advance in lockstep, one window per chain (k_seq: 128 sequences, two windows in the ring) at a time;
+// named barriers (window written / window consumed, one pair per ring slot) pass the batches on, so a waiting warp costs no
+// issue slot.
 #define SEQ_TBL_CELLS 512
 #define SEQ_CHAINS 32         // table columns / producer lanes of a CTA
 // (how many of them carry a block is chosen per launch so that the CTAs fill whole waves of one CTA per SM: 4 096 blocks on
