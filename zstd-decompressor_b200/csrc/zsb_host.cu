@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <chrono>
 #include <new>
 #include <string>
@@ -42,6 +43,11 @@ struct zsb_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_huf[kProfRing][2] = {};
     DevBuf src, frames, blocks, work, fout, huf_list, seq_list, rawrle_list, exec_list, exec2_list, xxh_list, lit_pool, seq_pool, slow_list, counters, dst, stage, pre_off, wave;
+    DevBuf link_ent, link_meta;                                    // k_link: one 32-bit entry per output byte of the listed frames; frame list, block list, tickets
+    std::vector<uint64_t> h_link_meta;                             // host image of link_meta (frames: 2 words each, then blocks: 1 word each, then tickets)
+    uint32_t n_link = 0, n_link_blocks = 0;                        // frames / blocks executed by k_link_init + k_link_resolve
+    int link_mode = 1;                                             // ZSB_LINK: 0 never (k_exec), 1 frames k_exec would take (default), 2 every frame
+    int n_sm = 148;
     std::string last_err;
     // prepared batch
     const uint8_t *d_src = nullptr; uint8_t *d_dst = nullptr; uint8_t *h_dst = nullptr;
@@ -105,6 +111,8 @@ extern "C" int zsb_ctx_create(zsb_ctx **out, int device) {
     { const char *e = getenv("ZSB_DEBUG"); c->debug_sync = e && *e && *e != '0'; }
     { const char *e = getenv("ZSB_WAVE"); const int v = e ? atoi(e) : 3; c->wave_forced = e != nullptr; c->wave_max = v < 1 ? 1u : v > 64 ? 64u : (uint32_t)v; }
     { const char *e = getenv("ZSB_PIPE_TRACE"); c->trace = e && *e && *e != '0'; }
+    { const char *e = getenv("ZSB_LINK"); c->link_mode = e ? atoi(e) : 1; }
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->n_sm = v; else (void)cudaGetLastError(); }
     if (c->trace) for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev_tr[i]);
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) cudaEventCreate(&c->ev[r][i]);
     for (int r = 0; r < kProfRing; r++) { cudaEventCreate(&c->ev_huf[r][0]); cudaEventCreate(&c->ev_huf[r][1]); }
@@ -120,7 +128,7 @@ extern "C" void zsb_ctx_destroy(zsb_ctx *c) {
     c->subs.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list, &c->exec2_list, &c->pre_off, &c->wave,
+    DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list, &c->exec2_list, &c->pre_off, &c->wave, &c->link_ent, &c->link_meta,
                      &c->xxh_list, &c->lit_pool, &c->seq_pool, &c->slow_list, &c->counters, &c->dst, &c->stage};
     for (DevBuf *b : all) b->release();
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) if (c->ev[r][i]) cudaEventDestroy(c->ev[r][i]);
@@ -261,6 +269,42 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
             if (getenv("ZSB_DEBUG")) fprintf(stderr, "zsb: k_seqx places %u of %zu frames\n", placed, nf);
         }
     }
+    // Frames of many blocks (and every multi-block frame of a small batch): k_link_init + k_link_resolve -- one entry per output byte, pointer
+    // jumping -- instead of a CTA that walks the frame block after block (k_exec), as long as the entries fit (4 bytes per output byte; positions
+    // are 31 bits).  ZSB_LINK=0 keeps k_exec, ZSB_LINK=2 sends every frame this way (experiment).
+    c->n_link = 0; c->n_link_blocks = 0; c->h_link_meta.clear();
+    if (c->link_mode && !c->is_sub && !c->low_latency) {
+        std::vector<uint32_t> cand, keep;
+        if (c->link_mode >= 2) { cand = execl; cand.insert(cand.end(), exec2l.begin(), exec2l.end()); std::sort(cand.begin(), cand.end()); }
+        else cand = execl;
+        std::vector<uint64_t> fmeta, bmeta;
+        std::vector<uint32_t> taken;
+        uint64_t e_total = 0;
+        for (uint32_t f : cand) {
+            const zsb_frame &fr = frames[f];
+            uint64_t bound = 0;
+            for (uint32_t k = 0; k < fr.n_blocks; k++) { const zsb_block &b = blocks[fr.first_block + k]; bound += b.type == ZSB_BT_COMPRESSED ? (uint64_t)ZSB_BLOCK_MAX : b.size; }
+            if (bound > dst_cap) bound = dst_cap;
+            if (bound + 64 >= (1ull << 31)) { keep.push_back(f); continue; }
+            const uint32_t li = (uint32_t)taken.size();
+            fmeta.push_back(e_total); fmeta.push_back((uint64_t)f);
+            for (uint32_t k = 0; k < fr.n_blocks; k++) bmeta.push_back((uint64_t)(fr.first_block + k) | (uint64_t)li << 32);
+            e_total += (bound + 16 + 63) & ~63ull;
+            taken.push_back(f);
+        }
+        if (!taken.empty() && c->link_ent.ensure(4 * e_total + 256) == cudaSuccess) {
+            c->n_link = (uint32_t)taken.size(); c->n_link_blocks = (uint32_t)bmeta.size();
+            c->h_link_meta = fmeta;
+            c->h_link_meta.insert(c->h_link_meta.end(), bmeta.begin(), bmeta.end());
+            c->h_link_meta.resize(c->h_link_meta.size() + (taken.size() + 1) / 2, 0ull);     // tickets
+            if (c->link_mode >= 2) {
+                auto drop = [&](std::vector<uint32_t> &v) { std::vector<uint32_t> r; for (uint32_t f : v) if (!std::binary_search(taken.begin(), taken.end(), f)) r.push_back(f); v.swap(r); };
+                drop(execl); drop(exec2l);
+                // (their checksums: k_xxh_one)
+                std::vector<uint32_t> r; for (uint32_t f : c->h_xxh_list) if (!std::binary_search(taken.begin(), taken.end(), f)) r.push_back(f); c->h_xxh_list.swap(r);
+            } else execl = keep;
+        } else (void)cudaGetLastError();
+    }
     // k_exec in wavefront mode (ZSB_WAVE=n CTAs per frame, default 3 when checksums are verified): the CTA-per-frame list is short (a single
     // large frame, a file of a few frames), so every frame gets one CTA that only hashes behind the frame's frontier and n-1 that take its
     // blocks in order (ZsbWave).  The hashing CTA pays: its warp has an SM to itself (C3, 256 MiB, verified: 314 -> 247 ms, what the frame
@@ -292,6 +336,7 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     CK(c, c->pre_off.ensure(8 * (nf + 1)));
     if (c->wave_ctas > 1) CK(c, c->wave.ensure(32 * execl.size() + 4 * (nb + 1)));
     CK(c, c->xxh_list.ensure(4 * (c->h_xxh_list.size() + 1)));
+    if (c->n_link) CK(c, c->link_meta.ensure(8 * c->h_link_meta.size()));
     CK(c, c->counters.ensure(sizeof(ZsbCounters)));
     c->lit_cap = (c->lit_cap + 15) & ~(uint64_t)15;
     CK(c, c->lit_pool.ensure(c->lit_cap + kLitOverflow + 64));
@@ -302,6 +347,7 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
     if (!execl.empty()) CK(c, cudaMemcpyAsync(c->exec_list.p, execl.data(), 4 * execl.size(), cudaMemcpyHostToDevice, st));
     if (!exec2l.empty()) CK(c, cudaMemcpyAsync(c->exec2_list.p, exec2l.data(), 4 * exec2l.size(), cudaMemcpyHostToDevice, st));
     if (c->use_seqx) CK(c, cudaMemcpyAsync(c->pre_off.p, c->h_pre_off.data(), 8 * nf, cudaMemcpyHostToDevice, st));
+    if (c->n_link) CK(c, cudaMemcpyAsync(c->link_meta.p, c->h_link_meta.data(), 8 * c->h_link_meta.size(), cudaMemcpyHostToDevice, st));
     if (!c->h_xxh_list.empty()) CK(c, cudaMemcpyAsync(c->xxh_list.p, c->h_xxh_list.data(), 4 * c->h_xxh_list.size(), cudaMemcpyHostToDevice, st));
     if (c->trace) cudaEventRecord(c->ev_tr[1], st);
     if (c->up_stream) { CK(c, cudaEventRecord(c->ev_up, st)); CK(c, cudaStreamWaitEvent(c->stream, c->ev_up, 0)); }
@@ -367,6 +413,14 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
     MARK(c, "k_exec");   zsbk_exec(st, c->n_exec, src, frames, blocks, work, fout, (const uint32_t *)c->exec_list.p, cnt, (const uint64_t *)c->seq_pool.p,
                                    (const uint8_t *)c->lit_pool.p, c->d_dst, c->is_sub, c->flags, c->wave_ctas > 1 ? c->wave.p : nullptr,
                                    c->wave_ctas > 1 ? (uint32_t *)((uint8_t *)c->wave.p + 32 * (size_t)c->n_exec) : nullptr, c->wave_ctas); c->launches += c->n_exec ? 1 : 0;
+    if (c->n_link) {
+        const uint8_t *lm = (const uint8_t *)c->link_meta.p;
+        const void *lfr = lm, *lbl = lm + 16 * (size_t)c->n_link;
+        uint32_t *tickets = (uint32_t *)(lm + 16 * (size_t)c->n_link + 8 * (size_t)c->n_link_blocks);
+        CK(c, cudaMemsetAsync(tickets, 0, 4 * (size_t)c->n_link, st));         // (a relaunch of the same prepared batch starts from zero again)
+        MARK(c, "k_link");   zsbk_link(st, c->n_link, c->n_link_blocks, src, blocks, work, fout, lbl, lfr, cnt, (const uint64_t *)c->seq_pool.p, (const uint8_t *)c->lit_pool.p,
+                                       (uint32_t *)c->link_ent.p, tickets, c->d_dst, c->n_sm); c->launches += 2;
+    }
     // pipelined path: the shard's output may leave as soon as it is written -- the checksums are computed from HBM while the
     // download runs (both only read the output)
     const bool early_down = c->down_stream && c->eager_d2h && c->h_dst;
@@ -378,6 +432,9 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
         if (c->trace) cudaEventRecord(c->ev_tr[3], c->down_stream);
     }
     MARK(c, "k_xxh");    zsbk_xxh(st, c->n_xxh, c->d_dst, fout, (const uint32_t *)c->xxh_list.p, cnt); c->launches += c->n_xxh ? 1 : 0;
+    if (c->n_link && (c->flags & ZSB_VERIFY_CHECKSUM)) {
+        MARK(c, "k_xxh_one"); zsbk_xxh_one(st, c->n_link, c->d_dst, fout, frames, c->link_meta.p, cnt); c->launches++;
+    }
     if (c->debug_sync) { const bool pr = c->profile; c->profile = false; MARK(c, "the end of the batch"); c->profile = pr; c->dbg_prev = "the uploads"; }
     if (c->profile) { cudaEventRecord(c->ev[c->prof_slot][c->nk], st); c->prof_slot = (c->prof_slot + 1) % kProfRing; c->prof_count++; }
     if (c->trace && !early_down) cudaEventRecord(c->ev_tr[2], st);

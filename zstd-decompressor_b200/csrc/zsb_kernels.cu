@@ -1838,6 +1838,201 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 7) k_exec2(const uint8_t *__re
     ex2_flush(X.ring, gend, (uint32_t)(uintptr_t)gend, X.flushed, 0, lane);
 }
 
+// ======================================================================================= k_link_init / k_link_resolve
+// Sequence execution of frames of many blocks (decoding_context.rs:78-106) WITHOUT walking the frame in order.  execute_sequences is one
+// dependent chain through the whole frame -- a match may copy bytes the sequence before it wrote -- and on text at zstd -3 half the
+// sequences of a block depend, directly or through bytes that do, on the block before it (tools/probes/c3_dependencies.py), so a CTA per
+// frame (k_exec) runs at 0.12 ms per block whatever the number of CTAs.  What IS parallel is the question "which literal does this output
+// byte come from": every byte of the frame gets one 32-bit ENTRY in a scratch array,
+//      resolved    LINK_RES | byte value          (a literal, a raw / RLE block byte, or a match byte whose source is known)
+//      unresolved  index of its source byte       (frame relative, always smaller than its own index)
+// k_link_init writes the entries of all blocks side by side (nothing depends on anything: the records say where every sequence starts),
+// and k_link_resolve replaces entry[i] by entry[entry[i]] until it is resolved -- pointer jumping, in place and without any barrier:
+// an entry only ever holds a valid ancestor or the final byte, 32-bit accesses are single copies, so a reader that sees an old value
+// merely walks one hop more.  Nobody waits for anybody (a lane follows its chain itself if nobody shortened it), so there is nothing to
+// deadlock on; chunks are handed out in frame order by ticket, so the sources of most matches were resolved and written back (one hop)
+// by the time a chunk is taken.  The bytes go to dst in 32-bit words, 128 bytes per warp instruction.
+// HBM: 4 bytes of entry written and read back per output byte plus the chain hops, instead of 0.12 ms per 128 KiB block in order.
+#define LINK_RES 0x80000000u
+#define LINK_THREADS 256
+#define LINK_CHUNK (LINK_THREADS * 16u)       // entries (output bytes) per ticket of k_link_resolve: every lane takes 16
+struct ZsbLinkFrame { uint64_t e_off; uint32_t frame, pad; };   // entries of listed frame li start at ent + e_off; entry j <-> dst byte (dst_off & ~15) + j
+
+__device__ __forceinline__ void link_fail(ZsbFrameOut *fo, int code) { atomicCAS(&fo->status, (int)ZSB_OK, code); }
+
+__global__ void __launch_bounds__(LINK_THREADS) k_link_init(const uint8_t *__restrict__ src, const zsb_block *__restrict__ blocks,
+                                                            const ZsbBlockWork *__restrict__ work, ZsbFrameOut *fout,
+                                                            const uint2 *__restrict__ link_blocks, const ZsbLinkFrame *__restrict__ link_frames,
+                                                            const ZsbCounters *__restrict__ cnt, const uint64_t *__restrict__ seq_pool,
+                                                            const uint8_t *__restrict__ lit_pool, uint32_t *ent) {
+    if (cnt->overflow) return;
+    const uint2 it = link_blocks[blockIdx.x];
+    const uint32_t bi = it.x;
+    const ZsbLinkFrame lf = link_frames[it.y];
+    ZsbFrameOut *fo = fout + lf.frame;
+    if (fo->status != ZSB_OK) return;
+    const ZsbBlockWork &W = work[bi];
+    const zsb_block b = blocks[bi];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t P0 = (uint32_t)(fo->dst_off & 15) + (uint32_t)W.out_off;     // entry index of the block's first byte
+    uint32_t *E = ent + lf.e_off + P0;
+    if (b.type == ZSB_BT_RAW) {                                                   // block.rs:76
+        const uint8_t *sp = src + b.src_off;
+        for (uint32_t i = tid; i < b.size; i += LINK_THREADS) E[i] = LINK_RES | __ldg(sp + i);
+        return;
+    }
+    if (b.type == ZSB_BT_RLE) {                                                   // block.rs:77-79
+        const uint32_t v = LINK_RES | src[b.src_off];
+        for (uint32_t i = tid; i < b.size; i += LINK_THREADS) E[i] = v;
+        return;
+    }
+    if (b.type != ZSB_BT_COMPRESSED) return;
+    const uint32_t nseq = W.nseq, regen = W.lit_regen;
+    const bool lit_rle = W.lit_type == ZSB_LT_RLE;
+    const uint32_t rle = lit_rle ? src[W.lit_src] : 0u;
+    const uint8_t *lp = W.lit_type == ZSB_LT_RAW ? src + W.lit_src : lit_pool + W.lit_buf;
+    auto lit = [&](uint32_t i) -> uint32_t { return lit_rle ? rle : (uint32_t)__ldg(lp + i); };
+    if (nseq == 0) {                                                              // literals only (RFC 8878; the reference rejects it: Q1)
+        for (uint32_t i = tid; i < regen; i += LINK_THREADS) E[i] = LINK_RES | lit(i);
+        return;
+    }
+    const uint64_t *seqs = seq_pool + W.seq_buf;
+    {   // the literals behind the last sequence (decoding_context.rs:101-103)
+        const uint64_t lastrec = __ldg(seqs + nseq - 1);
+        const uint32_t oe = (uint32_t)lastrec & ZSB_REC_POS_MASK, le = (uint32_t)(lastrec >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK;
+        for (uint32_t i = tid; i < regen - le; i += LINK_THREADS) E[oe + i] = LINK_RES | lit(le + i);
+    }
+    const uint32_t r0 = W.rep_in[0], r1 = W.rep_in[1], r2 = W.rep_in[2];
+    const uint32_t nbatch = (nseq + 31) / 32;
+    for (uint32_t bt = warp; bt < nbatch; bt += LINK_THREADS / 32) {
+        // lane = sequence: where it starts and what it copies
+        const uint32_t s = bt * 32 + lane;
+        const bool valid = s < nseq;
+        const uint64_t rec = valid ? __ldg(seqs + s) : 0ull;
+        uint64_t prev = __shfl_up_sync(FULL, rec, 1);
+        if (lane == 0) prev = bt ? __ldg(seqs + s - 1) : 0ull;
+        const uint32_t out_start = (uint32_t)prev & ZSB_REC_POS_MASK, lit_start = (uint32_t)(prev >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK;
+        const uint32_t out_end = valid ? (uint32_t)rec & ZSB_REC_POS_MASK : 0xFFFFFFFFu;
+        const uint32_t ll = valid ? ((uint32_t)(rec >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK) - lit_start : 0u;
+        const uint32_t rep[3] = {r0, r1, r2};
+        uint32_t off = valid ? seq_real_offset((uint32_t)(rec >> (2 * ZSB_REC_POS_BITS)), rep) : 1u;
+        const uint32_t dstm = out_start + ll;
+        if (valid && (off == 0 || (uint64_t)off > W.out_off + dstm)) { link_fail(fo, ZSB_E_IMPOSSIBLE_VALUE); off = 0; }   // decoding_context.rs:86-90
+        // lane = output byte: the batch regenerates [lo, hi); a byte finds its sequence by bisection over the lanes' end positions
+        const uint32_t lo = __shfl_sync(FULL, out_start, 0);
+        const uint32_t nval = min(32u, nseq - bt * 32);
+        const uint32_t hi = __shfl_sync(FULL, out_end, nval - 1);
+        for (uint32_t p0 = lo; p0 < hi; p0 += 32) {
+            const uint32_t p = p0 + lane;
+            uint32_t o = 0;
+#pragma unroll
+            for (uint32_t st = 16; st; st >>= 1) { const uint32_t t = __shfl_sync(FULL, out_end, o + st - 1); if (t <= p) o += st; }
+            o = min(o, 31u);
+            const uint32_t o_start = __shfl_sync(FULL, out_start, o), o_lit = __shfl_sync(FULL, lit_start, o);
+            const uint32_t o_dstm = __shfl_sync(FULL, dstm, o), o_off = __shfl_sync(FULL, off, o);
+            if (p < hi) {
+                uint32_t e;
+                if (p < o_dstm) e = LINK_RES | lit(o_lit + (p - o_start));                       // decoding_context.rs:92-93
+                else if (o_off == 0) e = LINK_RES;                                                // the frame has failed: nothing points anywhere
+                else { uint32_t k = p - o_dstm; if (k >= o_off) k %= o_off; e = P0 + o_dstm - o_off + k; }   // :95-98, periodic when the match overlaps itself
+                E[p] = e;
+            }
+        }
+    }
+}
+
+// tickets: one zeroed word per listed frame.  Grid: a few CTAs per SM, every CTA goes through the frames in order.
+__global__ void __launch_bounds__(LINK_THREADS) k_link_resolve(ZsbFrameOut *fout, const ZsbLinkFrame *__restrict__ link_frames, uint32_t n,
+                                                               const ZsbCounters *__restrict__ cnt, uint32_t *ent, uint32_t *tickets, uint8_t *dst) {
+    __shared__ uint32_t s_c;
+    if (cnt->overflow) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t li = 0; li < n; li++) {
+        const ZsbLinkFrame lf = link_frames[li];
+        ZsbFrameOut *fo = fout + lf.frame;
+        const int st0 = *(volatile int *)&fo->status;
+        const uint64_t dst_off = fo->dst_off, dst_len = *(volatile uint64_t *)&fo->dst_len;
+        if (st0 != ZSB_OK) {                                                      // failed before, or in k_link_init: it regenerates nothing
+            if (blockIdx.x == 0 && tid == 0) fo->dst_len = 0;
+            continue;
+        }
+        const uint32_t shift = (uint32_t)(dst_off & 15);
+        const uint32_t jlo = shift, jhi = shift + (uint32_t)dst_len;              // the frame's entries
+        uint32_t *E = ent + lf.e_off;
+        uint8_t *dbase = dst + (dst_off - shift);                                 // 16-byte aligned; entry j <-> dbase[j]
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) s_c = atomicAdd(&tickets[li], 1u);
+            __syncthreads();
+            const uint64_t c0 = (uint64_t)s_c * LINK_CHUNK;
+            if (c0 >= jhi) break;
+            // a warp takes 512 consecutive entries: lane l the four entries 128 r + 4 l .. + 3 of each quarter r (16-byte loads, one 32-bit
+            // word of output per quarter: 128 contiguous bytes per warp instruction both ways)
+            const uint32_t wbase = (uint32_t)c0 + warp * 512u;
+            if (wbase >= jhi) continue;
+            uint32_t e[16];
+            uint32_t um = 0;                                                      // entries still unresolved
+            bool corrupt = false;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint32_t j = wbase + 128u * r + 4u * lane;
+                uint4 v = make_uint4(LINK_RES, LINK_RES, LINK_RES, LINK_RES);
+                if (j < jhi && j + 4 > jlo) v = __ldcg(reinterpret_cast<const uint4 *>(E + j));
+                e[4 * r] = v.x; e[4 * r + 1] = v.y; e[4 * r + 2] = v.z; e[4 * r + 3] = v.w;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t jj = j + q;
+                    if (jj < jlo || jj >= jhi) e[4 * r + q] = LINK_RES;           // not this frame's bytes (never written, never stored)
+                    else if (!(e[4 * r + q] & LINK_RES)) {
+                        if (e[4 * r + q] >= jj || e[4 * r + q] < jlo) { e[4 * r + q] = LINK_RES; corrupt = true; }
+                        else um |= 1u << (4 * r + q);
+                    }
+                }
+            }
+            const uint32_t um0 = um;
+            while (um) {
+                uint32_t t[16];
+#pragma unroll
+                for (int q = 0; q < 16; q++) if (um >> q & 1u) t[q] = __ldcg(E + e[q]);
+#pragma unroll
+                for (int q = 0; q < 16; q++)
+                    if (um >> q & 1u) {
+                        if (t[q] & LINK_RES) um &= ~(1u << q);
+                        else if (t[q] >= e[q] || t[q] < jlo) { t[q] = LINK_RES; um &= ~(1u << q); corrupt = true; }   // a chain only ever goes back: anything else is a bug, not a hang
+                        e[q] = t[q];
+                    }
+            }
+            if (corrupt) link_fail(fo, ZSB_E_CORRUPT);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint32_t j = wbase + 128u * r + 4u * lane;
+                if (j >= jhi || j + 4 <= jlo) continue;
+                // what was resolved here shortens every chain that comes through it
+                if (um0 >> (4 * r) & 15u) __stcg(reinterpret_cast<uint4 *>(E + j), make_uint4(e[4 * r], e[4 * r + 1], e[4 * r + 2], e[4 * r + 3]));
+                const uint32_t w = (e[4 * r] & 255u) | (e[4 * r + 1] & 255u) << 8 | (e[4 * r + 2] & 255u) << 16 | (e[4 * r + 3] & 255u) << 24;
+                if (j >= jlo && j + 4 <= jhi) *reinterpret_cast<uint32_t *>(dbase + j) = w;
+                else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) if (j + q >= jlo && j + q < jhi) dbase[j + q] = (uint8_t)(w >> (8 * q));
+                }
+            }
+        }
+    }
+}
+
+// XXH64 of the frames k_link_resolve wrote: a warp per frame (xxh_trail with everything committed), an SM to itself
+__global__ void __launch_bounds__(32) k_xxh_one(const uint8_t *__restrict__ dst, ZsbFrameOut *fout, const zsb_frame *__restrict__ frames,
+                                                const ZsbLinkFrame *__restrict__ link_frames, const ZsbCounters *__restrict__ cnt) {
+    if (cnt->overflow) return;
+    const uint32_t f = link_frames[blockIdx.x].frame;
+    if (!frames[f].has_checksum || fout[f].status != ZSB_OK) return;
+    __shared__ unsigned long long s_done;
+    const uint64_t len = fout[f].dst_len;
+    if (threadIdx.x == 0) s_done = len;
+    __syncwarp();
+    xxh_trail(dst + fout[f].dst_off, len, &s_done, &fout[f].xxh64);
+}
+
 // ======================================================================================= k_xxh
 // XXH64 has no combine step: a frame is four dependent accumulator chains over its 32-byte stripes
 // (round = rotl(acc + x*P2, 31) * P1, ~25 cycles), so a frame is four lanes and the kernel is bound by that
@@ -2123,6 +2318,16 @@ void zsbk_exec(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame 
 void zsbk_exec2(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
                 ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst) {
     if (n) k_exec2<<<(n + EX2_WARPS - 1) / EX2_WARPS, 32 * EX2_WARPS, 0, st>>>(src, frames, blocks, work, fout, exec_list, n, cnt, seq_pool, lit_pool, dst);
+}
+void zsbk_link(cudaStream_t st, uint32_t n_frames, uint32_t n_blocks, const uint8_t *src, const zsb_block *blocks, const ZsbBlockWork *work, ZsbFrameOut *fout,
+               const void *link_blocks, const void *link_frames, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool,
+               uint32_t *ent, uint32_t *tickets, uint8_t *dst, int n_sm) {
+    if (!n_frames) return;
+    if (n_blocks) k_link_init<<<n_blocks, LINK_THREADS, 0, st>>>(src, blocks, work, fout, (const uint2 *)link_blocks, (const ZsbLinkFrame *)link_frames, cnt, seq_pool, lit_pool, ent);
+    k_link_resolve<<<(n_sm > 0 ? n_sm : 148) * 8, LINK_THREADS, 0, st>>>(fout, (const ZsbLinkFrame *)link_frames, n_frames, cnt, ent, tickets, dst);
+}
+void zsbk_xxh_one(cudaStream_t st, uint32_t n_frames, const uint8_t *dst, ZsbFrameOut *fout, const zsb_frame *frames, const void *link_frames, const ZsbCounters *cnt) {
+    if (n_frames) k_xxh_one<<<n_frames, 32, 0, st>>>(dst, fout, frames, (const ZsbLinkFrame *)link_frames, cnt);
 }
 void zsbk_xxh(cudaStream_t st, uint32_t n, const uint8_t *dst, ZsbFrameOut *fout, const uint32_t *list, const ZsbCounters *cnt) {
     if (n) k_xxh<<<(n + XXH_WARPS * XXH_FRAMES - 1) / (XXH_WARPS * XXH_FRAMES), 32 * XXH_WARPS, 0, st>>>(dst, fout, list, n, cnt);

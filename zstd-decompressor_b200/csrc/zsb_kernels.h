@@ -40,6 +40,12 @@ void zsbk_exec(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame 
                uint32_t ctas_per_frame /* > 1 with wave: wavefront mode */);
 void zsbk_exec2(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame *frames, const zsb_block *blocks, const ZsbBlockWork *work,
                 ZsbFrameOut *fout, const uint32_t *exec_list, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool, uint8_t *dst);
+// frames of many blocks: one entry per output byte (k_link_init) and pointer jumping (k_link_resolve).  link_frames: n_frames x {uint64 entry offset,
+// uint32 frame, uint32 0}; link_blocks: n_blocks x {uint32 block, uint32 index into link_frames}; tickets: n_frames zeroed words
+void zsbk_link(cudaStream_t st, uint32_t n_frames, uint32_t n_blocks, const uint8_t *src, const zsb_block *blocks, const ZsbBlockWork *work, ZsbFrameOut *fout,
+               const void *link_blocks, const void *link_frames, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool,
+               uint32_t *ent, uint32_t *tickets, uint8_t *dst, int n_sm);
+void zsbk_xxh_one(cudaStream_t st, uint32_t n_frames, const uint8_t *dst, ZsbFrameOut *fout, const zsb_frame *frames, const void *link_frames, const ZsbCounters *cnt);
 void zsbk_publish(cudaStream_t st, void *host_dev_ptr, const ZsbCounters *cnt, const ZsbFrameOut *fout, uint32_t nf);
 void zsbk_xxh(cudaStream_t st, uint32_t n, const uint8_t *dst, ZsbFrameOut *fout, const uint32_t *list, const ZsbCounters *cnt);
 void zsbk_stage_fse(cudaStream_t st, const uint8_t *desc, uint32_t n, int max_sym, const int16_t *dist_in, int ndist_in, int al_in,
