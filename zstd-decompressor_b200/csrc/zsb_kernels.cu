@@ -64,6 +64,104 @@ __device__ __forceinline__ uint64_t cta_scan_excl(uint64_t v, uint64_t *s_warp, 
     return r;
 }
 
+// ---- frames of many blocks in the two plan kernels.  chain_frame / plan_frame walk a frame block after block, one lane per frame: a DRAM round
+// trip per block (1.2 us), 10 ms each for the 8 192 blocks of a 1 GiB frame.  A frame of more than PLAN_WARP_BLOCKS blocks is walked by the whole
+// warp instead: 32 blocks are fetched at once, the state the reference carries from block to block (literals.rs:59-66, sequences.rs:147-187,
+// decoding_context.rs:40,50-75) goes through them in registers, every lane writes its own block.
+#define PLAN_WARP_BLOCKS 64u
+__device__ __forceinline__ int warp_scan_max(int v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, v, d); if ((int)lane >= d) v = max(v, t); }
+    return v;
+}
+__device__ __noinline__ int chain_frame_warp(const zsb_frame &fr, const zsb_block *blocks, ZsbBlockWork *work, uint32_t flags, uint32_t &err_a, uint32_t &err_b, uint32_t lane) {
+    const bool quirks = (flags & ZSB_REFERENCE_QUIRKS) != 0;
+    int huf_src = -1, ts[3] = {-1, -1, -1};        // last block with a Huffman description / with a table of its own per LL, OF, ML
+    for (uint32_t k0 = 0; k0 < fr.n_blocks; k0 += 32) {
+        const uint32_t k = k0 + lane, bi = fr.first_block + k;
+        bool comp = false; int st = ZSB_OK; uint32_t lt = ZSB_LT_NONE, nseq = 0, m[3] = {0, 0, 0};
+        if (k < fr.n_blocks && blocks[bi].type == ZSB_BT_COMPRESSED) {
+            const ZsbBlockWork &w = work[bi];
+            comp = true; st = w.status; lt = w.lit_type; nseq = w.nseq; m[0] = w.mode[0]; m[1] = w.mode[1]; m[2] = w.mode[2];
+        }
+        const int hinc = warp_scan_max((comp && lt == ZSB_LT_COMPRESSED) ? (int)bi : -1, lane);
+        const int hsrc = max(hinc, huf_src);
+        int tinc[3], tsrc[3];
+        bool odd = comp && (st != ZSB_OK || (lt == ZSB_LT_TREELESS && hsrc < 0) || (nseq == 0 && quirks));
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            tinc[t] = warp_scan_max((comp && nseq && m[t] != ZSB_M_REPEAT) ? (int)bi : -1, lane);
+            int ex = __shfl_up_sync(FULL, tinc[t], 1); if (lane == 0) ex = -1;
+            tsrc[t] = max(ex, ts[t]);
+            odd = odd || (comp && nseq && m[t] == ZSB_M_REPEAT && tsrc[t] < 0);
+        }
+        if (__any_sync(FULL, odd)) {
+            // something the reference would report (or a block that failed to parse) among these 32: the lane-serial walk takes over from here,
+            // with the same state, and gives the reference's first error
+            int rc = 0;
+            if (lane == 0) rc = chain_frame_from(fr, blocks, work, flags, err_a, err_b, k0, huf_src, ts[0], ts[1], ts[2]);
+            err_a = __shfl_sync(FULL, err_a, 0); err_b = __shfl_sync(FULL, err_b, 0);
+            return __shfl_sync(FULL, rc, 0);
+        }
+        if (comp) {
+            ZsbBlockWork &w = work[bi];
+            if (lt == ZSB_LT_TREELESS) { w.huf_desc = work[hsrc].huf_desc; w.huf_desc_end = work[hsrc].huf_desc_end; }
+            if (nseq) {
+#pragma unroll
+                for (int t = 0; t < 3; t++)
+                    if (m[t] == ZSB_M_REPEAT) { const ZsbBlockWork &sw = work[tsrc[t]]; w.mode[t] = sw.mode[t]; w.rle_sym[t] = sw.rle_sym[t]; w.tbl_desc[t] = sw.tbl_desc[t]; }
+            }
+        }
+        huf_src = max(huf_src, __shfl_sync(FULL, hinc, 31));
+#pragma unroll
+        for (int t = 0; t < 3; t++) ts[t] = max(ts[t], __shfl_sync(FULL, tinc[t], 31));
+    }
+    return ZSB_OK;
+}
+__device__ __noinline__ int plan_frame_warp(const zsb_frame &fr, const zsb_block *blocks, ZsbBlockWork *work, uint64_t &total, uint32_t &err_a, uint32_t &err_b, uint32_t lane) {
+    uint32_t rep[3] = {1, 4, 8};                                       // decoding_context.rs:40
+    uint64_t pos = 0;
+    for (uint32_t k0 = 0; k0 < fr.n_blocks; k0 += 32) {
+        const uint32_t k = k0 + lane, bi = fr.first_block + k;
+        const bool in = k < fr.n_blocks;
+        int lst = ZSB_OK, st = ZSB_OK; uint32_t size = 0, ro[3] = {0, 0, 0}, ea = 0, eb = 0; bool has = false;
+        if (in) {
+            const ZsbBlockWork &w = work[bi];
+            lst = w.lit_status; st = w.status; size = w.out_size; ea = w.err_a; eb = w.err_b;
+            has = blocks[bi].type == ZSB_BT_COMPRESSED && w.nseq;
+            ro[0] = w.rep_out[0]; ro[1] = w.rep_out[1]; ro[2] = w.rep_out[2];
+        }
+        const uint32_t fm = __ballot_sync(FULL, in && (lst != ZSB_OK || st != ZSB_OK));
+        const uint32_t nrun = min(fm ? (uint32_t)__ffs(fm) - 1u : 32u, fr.n_blocks - k0);     // blocks of this group that are placed
+        uint32_t inc = lane < nrun ? size : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, d); if ((int)lane >= d) inc += t; }
+        uint32_t mine[3] = {rep[0], rep[1], rep[2]};
+        for (uint32_t i = 0; i < nrun; i++) {                            // the repeat offsets go through the group in order, the same in every lane
+            if (lane == i) { mine[0] = rep[0]; mine[1] = rep[1]; mine[2] = rep[2]; }
+            const bool h = __shfl_sync(FULL, (int)has, i) != 0;
+            const uint32_t o0 = __shfl_sync(FULL, ro[0], i), o1 = __shfl_sync(FULL, ro[1], i), o2 = __shfl_sync(FULL, ro[2], i);
+            if (h) { const uint32_t n0 = seq_real_offset(o0, rep), n1 = seq_real_offset(o1, rep), n2 = seq_real_offset(o2, rep); rep[0] = n0; rep[1] = n1; rep[2] = n2; }
+        }
+        if (lane < nrun) {
+            ZsbBlockWork &w = work[bi];
+            w.out_off = pos + (inc - size);
+            w.rep_in[0] = mine[0]; w.rep_in[1] = mine[1]; w.rep_in[2] = mine[2];
+        }
+        pos += __shfl_sync(FULL, inc, 31);
+        if (fm) {                                                        // Block::decode of the first block that failed: literals first (block.rs:83-85)
+            const int j = __ffs(fm) - 1;
+            const int jl = __shfl_sync(FULL, lst, j), js = __shfl_sync(FULL, st, j);
+            total = pos;
+            if (jl != ZSB_OK) return jl;
+            err_a = __shfl_sync(FULL, ea, j); err_b = __shfl_sync(FULL, eb, j);
+            return js;
+        }
+    }
+    total = pos;
+    return ZSB_OK;
+}
+
 // ======================================================================================= k_plan1
 // Several CTAs do the per-frame part side by side; the last one to finish (ticket) runs the scans, four blocks per thread.
 __global__ void __launch_bounds__(1024) k_plan1(const zsb_frame *__restrict__ frames, uint32_t nf, const zsb_block *__restrict__ blocks,
@@ -74,11 +172,20 @@ __global__ void __launch_bounds__(1024) k_plan1(const zsb_frame *__restrict__ fr
     __shared__ uint32_t s_last;
     const uint32_t tid = threadIdx.x;
     // (a) per-frame chaining of Huffman tables and table modes
-    for (uint32_t f = blockIdx.x * blockDim.x + tid; f < nf; f += gridDim.x * blockDim.x) {
+    for (uint32_t fb = blockIdx.x * blockDim.x + (tid & ~31u); fb < nf; fb += gridDim.x * blockDim.x) {
+        const uint32_t f = fb + (tid & 31u);
         ZsbFrameOut o; o.dst_off = 0; o.dst_len = 0; o.xxh64 = 0; o.err_a = 0; o.err_b = 0; o.pad = 0;
-        o.status = frames[f].status;
-        if (o.status == ZSB_OK && frames[f].kind == 0) o.status = chain_frame(frames[f], blocks, work, flags, o.err_a, o.err_b);
-        fout[f] = o;
+        o.status = f < nf ? frames[f].status : ZSB_OK;
+        const bool z = f < nf && o.status == ZSB_OK && frames[f].kind == 0;
+        const bool big = z && frames[f].n_blocks > PLAN_WARP_BLOCKS;
+        if (z && !big) o.status = chain_frame(frames[f], blocks, work, flags, o.err_a, o.err_b);
+        for (uint32_t m = __ballot_sync(FULL, big); m; m &= m - 1) {              // frames of many blocks: by the whole warp
+            const uint32_t j = __ffs(m) - 1;
+            uint32_t ea = 0, eb = 0;
+            const int rc = chain_frame_warp(frames[fb + j], blocks, work, flags, ea, eb, tid & 31u);
+            if ((tid & 31u) == j) { o.status = rc; o.err_a = ea; o.err_b = eb; }
+        }
+        if (f < nf) fout[f] = o;
     }
     __threadfence();
     __syncthreads();
@@ -889,20 +996,27 @@ __global__ void __launch_bounds__(1024) k_plan2(const zsb_frame *__restrict__ fr
     const uint32_t tid = threadIdx.x;
     if (cnt->overflow) return;
     // (a) per frame, all CTAs side by side: size and status
-    for (uint32_t f = blockIdx.x * blockDim.x + tid; f < nf; f += gridDim.x * blockDim.x) {
+    for (uint32_t fb = blockIdx.x * blockDim.x + (tid & ~31u); fb < nf; fb += gridDim.x * blockDim.x) {
+        const uint32_t f = fb + (tid & 31u);
         uint64_t len = 0;
-        int st = fout[f].status;
-        if (st == ZSB_OK) {
-            if (frames[f].kind == 1) len = (flags & ZSB_PRINT_SKIPPABLE) ? blocks[frames[f].first_block].size : 0;   // main.rs:45-49
-            else {
-                uint32_t ea = 0, eb = 0;
-                st = plan_frame(frames[f], blocks, work, len, ea, eb);
-                if (st != ZSB_OK) { fout[f].err_a = ea; fout[f].err_b = eb; }
-                if (st == ZSB_OK && frames[f].has_content_size && len != frames[f].content_size && !(flags & ZSB_REFERENCE_QUIRKS)) st = ZSB_E_CONTENT_SIZE;
-                if (st != ZSB_OK) len = 0;
-            }
+        int st = f < nf ? fout[f].status : ZSB_E_ARG;
+        const bool z = st == ZSB_OK && frames[f].kind == 0;
+        const bool big = z && frames[f].n_blocks > PLAN_WARP_BLOCKS;
+        uint32_t ea = 0, eb = 0;
+        if (st == ZSB_OK && frames[f].kind == 1) len = (flags & ZSB_PRINT_SKIPPABLE) ? blocks[frames[f].first_block].size : 0;   // main.rs:45-49
+        if (z && !big) st = plan_frame(frames[f], blocks, work, len, ea, eb);
+        for (uint32_t m = __ballot_sync(FULL, big); m; m &= m - 1) {              // frames of many blocks: by the whole warp
+            const uint32_t j = __ffs(m) - 1;
+            uint64_t l2 = 0; uint32_t a2 = 0, b2 = 0;
+            const int rc = plan_frame_warp(frames[fb + j], blocks, work, l2, a2, b2, tid & 31u);
+            if ((tid & 31u) == j) { st = rc; len = l2; ea = a2; eb = b2; }
         }
-        fout[f].dst_len = len; fout[f].status = st;
+        if (z) {
+            if (st != ZSB_OK) { fout[f].err_a = ea; fout[f].err_b = eb; }
+            if (st == ZSB_OK && frames[f].has_content_size && len != frames[f].content_size && !(flags & ZSB_REFERENCE_QUIRKS)) st = ZSB_E_CONTENT_SIZE;
+            if (st != ZSB_OK) len = 0;
+        }
+        if (f < nf) { fout[f].dst_len = len; fout[f].status = st; }
     }
     __threadfence();
     __syncthreads();
@@ -1040,6 +1154,30 @@ __global__ void __launch_bounds__(256) k_rawrle(const uint8_t *__restrict__ src,
 __device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
 __device__ __forceinline__ uint64_t xround(uint64_t acc, uint64_t in) { return rotl64(acc + in * XP2, 31) * XP1; }
 __device__ __forceinline__ uint64_t xmerge(uint64_t h, uint64_t v) { return (h ^ xround(0, v)) * XP1 + XP4; }
+// The accumulator chain is what bounds every XXH64 kernel here (round = rotl(acc + x * P2, 31) * P1, a dependent chain per accumulator), so it is
+// carried in the form that makes a round three levels deep instead of the seven nvcc makes of the expression above: the state is the ROTATED sum
+// r (acc = r * P1, P1 is odd: r0 = acc0 * P1^-1), and with a = x * P2 computed off the chain
+//      level 1   (sl, h0) = rl * P1.lo + a   (one IMAD.WIDE with a 64-bit addend: the carry into the high word is free)
+//                t = rl * P1.hi,  u = rh * P1.lo
+//      level 2   sh = h0 + t + u             (one IADD3)
+//      level 3   rl' = (sl:sh) >> 1,  rh' = (sh:sl) >> 1   (two funnel shifts: rotl 31 = swap halves, rotr 1)
+#define XP1_INV 0x887493432BADB37ull
+static_assert(XP1_INV * XP1 == 1ull, "P1^-1 mod 2^64");
+struct XAcc {
+    uint32_t rl, rh;
+    __device__ __forceinline__ void init(uint64_t acc) { const uint64_t r = acc * XP1_INV; rl = (uint32_t)r; rh = (uint32_t)(r >> 32); }
+    __device__ __forceinline__ void round_a(uint64_t a) {                       // a = x * P2
+        const uint64_t w = (uint64_t)rl * (uint32_t)XP1 + a;
+        const uint32_t sl = (uint32_t)w;
+        const uint32_t sh = (uint32_t)(w >> 32) + rl * (uint32_t)(XP1 >> 32) + rh * (uint32_t)XP1;
+        rl = __funnelshift_r(sh, sl, 1);
+        rh = __funnelshift_r(sl, sh, 1);
+    }
+    __device__ __forceinline__ void round(uint64_t x) { round_a(x * XP2); }
+    // z: zero at run time, unknown to ptxas, which otherwise moves a's own product into the chain (two dependent IMAD.WIDE per round)
+    __device__ __forceinline__ void round(uint64_t x, uint32_t z) { round_a((x * XP2) ^ z); }
+    __device__ __forceinline__ uint64_t acc() const { return ((uint64_t)rh << 32 | rl) * XP1; }
+};
 // 8 bytes at any alignment from two aligned words
 __device__ __forceinline__ uint64_t ld64_any(const uint8_t *p) {
     const uintptr_t a = (uintptr_t)p;
@@ -1060,9 +1198,11 @@ __device__ __forceinline__ uint64_t ld64_any(const uint8_t *p) {
 // accumulators and collect their words by shuffle.
 struct WaveCtx;
 __device__ void wave_advance(const WaveCtx &V);
+__device__ __forceinline__ uint64_t xxh_finish(const uint8_t *p, uint64_t len, uint64_t nstripes, uint64_t v1, uint64_t v2, uint64_t v3, uint64_t v4);
 __device__ __forceinline__ void xxh_trail(const uint8_t *p, uint64_t len, volatile unsigned long long *done, uint64_t *result, const WaveCtx *V = nullptr) {
     const uint32_t lane = threadIdx.x & 31, q = lane & 3;
-    uint64_t v = q == 0 ? XP1 + XP2 : q == 1 ? XP2 : q == 2 ? 0ull : 0ull - XP1;
+    XAcc va; va.init(q == 0 ? XP1 + XP2 : q == 1 ? XP2 : q == 2 ? 0ull : 0ull - XP1);
+    const uint32_t zero = blockIdx.y;                                  // (one-dimensional grids: see XAcc::round)
     const uint64_t nstripes = len >> 5;
     uint64_t cur = 0;
     constexpr int NR = 8;            // loads in flight per lane; 8 stripes each
@@ -1091,13 +1231,13 @@ __device__ __forceinline__ void xxh_trail(const uint8_t *p, uint64_t len, volati
 #pragma unroll
             for (int r = 0; r < NR; r++) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) { const uint64_t x = __shfl_sync(FULL, X[r], 4 * j + q); v = rotl64(v + x * XP2, 31) * XP1; }
+                for (int j = 0; j < 8; j++) va.round(__shfl_sync(FULL, X[r], 4 * j + q), zero);
             }
             cur += 8 * NR;
         }
         // the rest of the stretch (only at the end of the frame), stripe by stripe
         if (tgt == nstripes) {
-            for (; cur < tgt; cur++) { const uint64_t x = ld64_any(p + (cur << 5) + 8 * q); v = rotl64(v + x * XP2, 31) * XP1; }
+            for (; cur < tgt; cur++) va.round(ld64_any(p + (cur << 5) + 8 * q), zero);
         }
     }
     // everything is committed only once *done == len (the tail bytes)
@@ -1110,24 +1250,9 @@ __device__ __forceinline__ void xxh_trail(const uint8_t *p, uint64_t len, volati
         __syncwarp();
     }
     __threadfence();
+    const uint64_t v = va.acc();
     const uint64_t v1 = __shfl_sync(FULL, v, 0), v2 = __shfl_sync(FULL, v, 1), v3 = __shfl_sync(FULL, v, 2), v4 = __shfl_sync(FULL, v, 3);
-    if (lane == 0) {
-        uint64_t h;
-        if (len >= 32) {
-            h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
-            h = xmerge(h, v1); h = xmerge(h, v2); h = xmerge(h, v3); h = xmerge(h, v4);
-        } else h = XP5;
-        h += len;
-        const uint8_t *t = p + (nstripes << 5), *end = p + len;
-        while (t + 8 <= end) { h ^= xround(0, ld64_any(t)); h = rotl64(h, 27) * XP1 + XP4; t += 8; }
-        if (t + 4 <= end) {
-            uint32_t x = (uint32_t)__ldcg(t) | ((uint32_t)__ldcg(t + 1) << 8) | ((uint32_t)__ldcg(t + 2) << 16) | ((uint32_t)__ldcg(t + 3) << 24);
-            h ^= (uint64_t)x * XP1; h = rotl64(h, 23) * XP2 + XP3; t += 4;
-        }
-        while (t < end) { h ^= (uint64_t)__ldcg(t) * XP5; h = rotl64(h, 11) * XP1; t++; }
-        h ^= h >> 33; h *= XP2; h ^= h >> 29; h *= XP3; h ^= h >> 32;
-        *result = h;
-    }
+    if (lane == 0) *result = xxh_finish(p, len, nstripes, v1, v2, v3, v4);
 }
 
 // ======================================================================================= k_exec
@@ -2020,17 +2145,96 @@ __global__ void __launch_bounds__(LINK_THREADS) k_link_resolve(ZsbFrameOut *fout
     }
 }
 
-// XXH64 of the frames k_link_resolve wrote: a warp per frame (xxh_trail with everything committed), an SM to itself
+// XXH64 of the frames k_link_resolve wrote.  A frame is four dependent accumulator chains over all of its stripes (33.5 M rounds for 1 GiB)
+// whatever the number of threads, so the frame gets ONE warp with an SM to itself and everything else is kept off that chain: the bytes
+// come through a ring of XO_STAGES shared-memory tiles filled by bulk copies (cp.async.bulk + one mbarrier per tile, issued by lane 0 a ring
+// ahead: no load latency and no shuffle on the chain, the words of eight stripes are read one group ahead with LDS.64), lanes 0-3 own the
+// accumulators (the other lanes repeat them).  Tiles lie wholly inside the frame (16-byte aligned from the frame's aligned base, 16 bytes of
+// overhang for frames that start unaligned); the last < 2 tiles and the tail are read straight from HBM.
+#define XO_TILE 4096u
+#define XO_STAGES 8u
+#define XO_STRIDE (XO_TILE + 16u)
+__device__ __forceinline__ uint64_t xxh_finish(const uint8_t *p, uint64_t len, uint64_t nstripes, uint64_t v1, uint64_t v2, uint64_t v3, uint64_t v4) {
+    uint64_t h;
+    if (len >= 32) {
+        h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+        h = xmerge(h, v1); h = xmerge(h, v2); h = xmerge(h, v3); h = xmerge(h, v4);
+    } else h = XP5;
+    h += len;
+    const uint8_t *t = p + (nstripes << 5), *end = p + len;
+    while (t + 8 <= end) { h ^= xround(0, ld64_any(t)); h = rotl64(h, 27) * XP1 + XP4; t += 8; }
+    if (t + 4 <= end) {
+        uint32_t x = (uint32_t)__ldcg(t) | ((uint32_t)__ldcg(t + 1) << 8) | ((uint32_t)__ldcg(t + 2) << 16) | ((uint32_t)__ldcg(t + 3) << 24);
+        h ^= (uint64_t)x * XP1; h = rotl64(h, 23) * XP2 + XP3; t += 4;
+    }
+    while (t < end) { h ^= (uint64_t)__ldcg(t) * XP5; h = rotl64(h, 11) * XP1; t++; }
+    h ^= h >> 33; h *= XP2; h ^= h >> 29; h *= XP3; h ^= h >> 32;
+    return h;
+}
+template <bool ALIGNED8>
+__device__ __forceinline__ void xo_load(uint64_t (&X)[8], const uint8_t *tp, uint32_t sh) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const unsigned long long *a = reinterpret_cast<const unsigned long long *>(tp + 32 * j);
+        if (ALIGNED8) X[j] = a[0];
+        else X[j] = (a[0] >> sh) | (a[1] << (64 - sh));
+    }
+}
+template <bool ALIGNED8>
+__device__ __forceinline__ void xo_tile(XAcc &v, const uint8_t *tp, uint32_t sh, uint32_t z) {
+    uint64_t X[8], Y[8];
+    xo_load<ALIGNED8>(X, tp, sh);
+#pragma unroll 1
+    for (uint32_t g = 0; g < XO_TILE / 256; g += 2) {
+        xo_load<ALIGNED8>(Y, tp + 256 * (g + 1), sh);
+#pragma unroll
+        for (int j = 0; j < 8; j++) v.round(X[j], z);
+        if (g + 2 < XO_TILE / 256) xo_load<ALIGNED8>(X, tp + 256 * (g + 2), sh);
+#pragma unroll
+        for (int j = 0; j < 8; j++) v.round(Y[j], z);
+    }
+}
 __global__ void __launch_bounds__(32) k_xxh_one(const uint8_t *__restrict__ dst, ZsbFrameOut *fout, const zsb_frame *__restrict__ frames,
                                                 const ZsbLinkFrame *__restrict__ link_frames, const ZsbCounters *__restrict__ cnt) {
+    __shared__ __align__(128) uint8_t s_tile[XO_STAGES * XO_STRIDE];
+    __shared__ __align__(8) unsigned long long s_bar[XO_STAGES];
     if (cnt->overflow) return;
+    const uint32_t zero = blockIdx.y;                                    // (the grid is one-dimensional)
     const uint32_t f = link_frames[blockIdx.x].frame;
     if (!frames[f].has_checksum || fout[f].status != ZSB_OK) return;
-    __shared__ unsigned long long s_done;
     const uint64_t len = fout[f].dst_len;
-    if (threadIdx.x == 0) s_done = len;
+    const uint8_t *p = dst + fout[f].dst_off;
+    const uint32_t lane = threadIdx.x & 31, q = lane & 3;
+    XAcc va; va.init(q == 0 ? XP1 + XP2 : q == 1 ? XP2 : q == 2 ? 0ull : 0ull - XP1);
+    const uint64_t nstripes = len >> 5;
+    const uint32_t shift = (uint32_t)((uintptr_t)p & 15);
+    const uint8_t *base = p - shift;
+    const uint64_t ntiles = shift + len >= 16 + XO_TILE ? (shift + len - 16) / XO_TILE : 0;       // tile t reads base + t * XO_TILE .. + XO_TILE + 16
+    const uint32_t tile_sa = (uint32_t)__cvta_generic_to_shared(s_tile), bar_sa = (uint32_t)__cvta_generic_to_shared(s_bar);
+    if (lane == 0) {
+        for (uint32_t i = 0; i < XO_STAGES; i++) zsb_mbar_init(bar_sa + 8 * i, 1);
+        for (uint32_t i = 0; i < XO_STAGES && i < ntiles; i++) {
+            zsb_mbar_expect(bar_sa + 8 * i, XO_STRIDE);
+            zsb_bulk_g2s(tile_sa + i * XO_STRIDE, base + (uint64_t)i * XO_TILE, XO_STRIDE, bar_sa + 8 * i);
+        }
+    }
     __syncwarp();
-    xxh_trail(dst + fout[f].dst_off, len, &s_done, &fout[f].xxh64);
+    const uint32_t boff = shift + 8 * q, sh = (boff & 7) * 8;            // this lane's word of a stripe inside a tile: (boff & ~7) + 32 * stripe
+    for (uint64_t t = 0; t < ntiles; t++) {
+        const uint32_t st = (uint32_t)(t % XO_STAGES);
+        zsb_mbar_wait(bar_sa + 8 * st, (uint32_t)(t / XO_STAGES) & 1u);
+        const uint8_t *tp = s_tile + st * XO_STRIDE + (boff & ~7u);
+        if (sh == 0) xo_tile<true>(va, tp, 0, zero); else xo_tile<false>(va, tp, sh, zero);
+        __syncwarp();                                                     // every lane has read the tile: it may be filled again
+        if (lane == 0 && t + XO_STAGES < ntiles) {
+            zsb_mbar_expect(bar_sa + 8 * st, XO_STRIDE);
+            zsb_bulk_g2s(tile_sa + st * XO_STRIDE, base + (t + XO_STAGES) * XO_TILE, XO_STRIDE, bar_sa + 8 * st);
+        }
+    }
+    for (uint64_t cur = ntiles * (XO_TILE / 32); cur < nstripes; cur++) va.round(ld64_any(p + (cur << 5) + 8 * q));
+    const uint64_t v = va.acc();
+    const uint64_t v1 = __shfl_sync(FULL, v, 0), v2 = __shfl_sync(FULL, v, 1), v3 = __shfl_sync(FULL, v, 2), v4 = __shfl_sync(FULL, v, 3);
+    if (lane == 0) fout[f].xxh64 = xxh_finish(p, len, nstripes, v1, v2, v3, v4);
 }
 
 // ======================================================================================= k_xxh
@@ -2060,7 +2264,8 @@ __global__ void __launch_bounds__(32 * XXH_WARPS) k_xxh(const uint8_t *__restric
     const uint64_t nstripes = len >> 5;
     const uint32_t m = (uint32_t)(uintptr_t)p & 15u;
     // a frame longer than 4 GiB would overflow the 32-bit staging offsets: hash it in 2 GiB sections
-    uint64_t v = q == 0 ? XP1 + XP2 : q == 1 ? XP2 : q == 2 ? 0ull : 0ull - XP1;
+    XAcc va; va.init(q == 0 ? XP1 + XP2 : q == 1 ? XP2 : q == 2 ? 0ull : 0ull - XP1);
+    const uint32_t zero = blockIdx.y;                               // (the grid is one-dimensional: see XAcc::round)
     const uint64_t SECT = 1ull << 26;                               // stripes per section (2 GiB)
     // Frames that start 8-byte aligned (all of them when the sizes are multiples of 8) are read straight from HBM/L2: the four
     // lanes of a frame take the four words of a stripe (one full 32-byte sector per request), 32 stripes are requested while the
@@ -2088,10 +2293,10 @@ __global__ void __launch_bounds__(32 * XXH_WARPS) k_xxh(const uint8_t *__restric
         auto hash = [&](const uint64_t (&X)[NS], uint64_t st) {
             if (st + NS <= nstripes) {
 #pragma unroll
-                for (int s = 0; s < NS; s++) v = rotl64(v + X[s] * XP2, 31) * XP1;
+                for (int s = 0; s < NS; s++) va.round(X[s], zero);
             } else {
 #pragma unroll
-                for (int s = 0; s < NS; s++) if (st + s < nstripes) v = rotl64(v + X[s] * XP2, 31) * XP1;
+                for (int s = 0; s < NS; s++) if (st + s < nstripes) va.round(X[s], zero);
             }
         };
         fetch(A, 0); fetch(B, NS);
@@ -2143,41 +2348,25 @@ __global__ void __launch_bounds__(32 * XXH_WARPS) k_xxh(const uint8_t *__restric
                 uint64_t y[16];
                 if (sh == 0) {
 #pragma unroll
-                    for (int s = 0; s < 16; s++) y[s] = w[4 * s] * XP2;
+                    for (int s = 0; s < 16; s++) y[s] = (w[4 * s] * XP2) ^ zero;
                 } else {
 #pragma unroll
-                    for (int s = 0; s < 16; s++) y[s] = (zsb_shr64(w[4 * s], sh) | zsb_shl64(w[4 * s + 1], 64 - sh)) * XP2;
+                    for (int s = 0; s < 16; s++) y[s] = ((zsb_shr64(w[4 * s], sh) | zsb_shl64(w[4 * s + 1], 64 - sh)) * XP2) ^ zero;
                 }
 #pragma unroll
-                for (int s = 0; s < 16; s++) v = rotl64(v + y[s], 31) * XP1;
+                for (int s = 0; s < 16; s++) va.round_a(y[s]);
             } else {
                 for (uint32_t s = 0; s < 16 && s_lo + s < ns; s++) {
-                    const uint64_t x = zsb_shr64(w[4 * s], sh) | zsb_shl64(w[4 * s + 1], 64 - sh);
-                    v = xround(v, x);
+                    va.round(zsb_shr64(w[4 * s], sh) | zsb_shl64(w[4 * s + 1], 64 - sh));
                 }
             }
         }
     }
     __syncwarp();
     const uint32_t qb = lane & ~3u;
+    const uint64_t v = va.acc();
     const uint64_t v1 = __shfl_sync(FULL, v, qb), v2 = __shfl_sync(FULL, v, qb + 1), v3 = __shfl_sync(FULL, v, qb + 2), v4 = __shfl_sync(FULL, v, qb + 3);
-    if (ok && q == 0) {
-        uint64_t h;
-        if (len >= 32) {
-            h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
-            h = xmerge(h, v1); h = xmerge(h, v2); h = xmerge(h, v3); h = xmerge(h, v4);
-        } else h = XP5;
-        h += len;
-        const uint8_t *t = p + (nstripes << 5), *end = p + len;
-        while (t + 8 <= end) { h ^= xround(0, ld64_any(t)); h = rotl64(h, 27) * XP1 + XP4; t += 8; }
-        if (t + 4 <= end) {
-            uint32_t x = (uint32_t)__ldcg(t) | ((uint32_t)__ldcg(t + 1) << 8) | ((uint32_t)__ldcg(t + 2) << 16) | ((uint32_t)__ldcg(t + 3) << 24);
-            h ^= (uint64_t)x * XP1; h = rotl64(h, 23) * XP2 + XP3; t += 4;
-        }
-        while (t < end) { h ^= (uint64_t)__ldcg(t) * XP5; h = rotl64(h, 11) * XP1; t++; }
-        h ^= h >> 33; h *= XP2; h ^= h >> 29; h *= XP3; h ^= h >> 32;
-        fout[f].xxh64 = h;
-    }
+    if (ok && q == 0) fout[f].xxh64 = xxh_finish(p, len, nstripes, v1, v2, v3, v4);
 }
 
 // ======================================================================================= stage kernels (one lane)

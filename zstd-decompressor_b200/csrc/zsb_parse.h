@@ -147,11 +147,13 @@ ZSB_HDN void parse_block(const uint8_t *src, const zsb_block &blk, ZsbBlockWork 
 
 // Carries the Huffman table and the three table modes from block to block of one frame.
 // Returns the frame status (first failing block's status).
-ZSB_HDN int chain_frame(const zsb_frame &fr, const zsb_block *blocks, ZsbBlockWork *work, uint32_t flags, uint32_t &err_a, uint32_t &err_b) {
+// (chain_frame_from: the same walk from block k0 on with the state the blocks before it left -- the warp-cooperative form in k_plan1 hands a frame
+//  over to it at the first block that is not plain)
+ZSB_HDN int chain_frame_from(const zsb_frame &fr, const zsb_block *blocks, ZsbBlockWork *work, uint32_t flags, uint32_t &err_a, uint32_t &err_b,
+                             uint32_t k0, int64_t huf_src, int64_t t0, int64_t t1, int64_t t2) {
     const bool quirks = (flags & ZSB_REFERENCE_QUIRKS) != 0;
-    int64_t huf_src = -1;
-    int64_t tsrc[3] = {-1, -1, -1};
-    for (uint32_t k = 0; k < fr.n_blocks; k++) {
+    int64_t tsrc[3] = {t0, t1, t2};
+    for (uint32_t k = k0; k < fr.n_blocks; k++) {
         const uint32_t bi = fr.first_block + k;
         ZsbBlockWork &w = work[bi];
         if (blocks[bi].type != ZSB_BT_COMPRESSED) continue;
@@ -188,6 +190,10 @@ ZSB_HDN int chain_frame(const zsb_frame &fr, const zsb_block *blocks, ZsbBlockWo
         }
     }
     return ZSB_OK;
+}
+
+ZSB_HDN int chain_frame(const zsb_frame &fr, const zsb_block *blocks, ZsbBlockWork *work, uint32_t flags, uint32_t &err_a, uint32_t &err_b) {
+    return chain_frame_from(fr, blocks, work, flags, err_a, err_b, 0, -1, -1, -1, -1);
 }
 
 // Output placement and repeat-offset history of one frame, after the entropy stage.
