@@ -1159,8 +1159,10 @@ __device__ __forceinline__ uint64_t xmerge(uint64_t h, uint64_t v) { return (h ^
 // r (acc = r * P1, P1 is odd: r0 = acc0 * P1^-1), and with a = x * P2 computed off the chain
 //      level 1   (sl, h0) = rl * P1.lo + a   (one IMAD.WIDE with a 64-bit addend: the carry into the high word is free)
 //                t = rl * P1.hi,  u = rh * P1.lo
-//      level 2   sh = h0 + t + u             (one IADD3)
+//      level 2   sh = h0 + t + u             (ptxas makes two levels of it: u rides on t's IMAD, then one add; a forced three-input add -- vadd --
+//                                             comes with PRMTs on the chain and is no shorter)
 //      level 3   rl' = (sl:sh) >> 1,  rh' = (sh:sl) >> 1   (two funnel shifts: rotl 31 = swap halves, rotr 1)
+// Measured in k_xxh_one (one warp, an SM to itself): 50 -> 24.8 cycles per round.
 #define XP1_INV 0x887493432BADB37ull
 static_assert(XP1_INV * XP1 == 1ull, "P1^-1 mod 2^64");
 struct XAcc {
@@ -2146,14 +2148,14 @@ __global__ void __launch_bounds__(LINK_THREADS) k_link_resolve(ZsbFrameOut *fout
 }
 
 // XXH64 of the frames k_link_resolve wrote.  A frame is four dependent accumulator chains over all of its stripes (33.5 M rounds for 1 GiB)
-// whatever the number of threads, so the frame gets ONE warp with an SM to itself and everything else is kept off that chain: the bytes
-// come through a ring of XO_STAGES shared-memory tiles filled by bulk copies (cp.async.bulk + one mbarrier per tile, issued by lane 0 a ring
-// ahead: no load latency and no shuffle on the chain, the words of eight stripes are read one group ahead with LDS.64), lanes 0-3 own the
-// accumulators (the other lanes repeat them).  Tiles lie wholly inside the frame (16-byte aligned from the frame's aligned base, 16 bytes of
-// overhang for frames that start unaligned); the last < 2 tiles and the tail are read straight from HBM.
-#define XO_TILE 4096u
-#define XO_STAGES 8u
-#define XO_STRIDE (XO_TILE + 16u)
+// whatever the number of threads, so the frame gets ONE hashing warp with an SM to itself and everything else is kept off that warp: measured,
+// a single warp that also computes x * P2 is bound by its scheduler's multiplier pipe (nine IMAD-class instructions per round, 33 cycles per
+// round), not by the chain.  So the CTA is a three-stage pipeline of specialised warps:
+//   bulk copies (cp.async.bulk, one mbarrier per tile, issued by a helper thread a ring ahead) bring 4 KiB tiles of the frame into shared memory,
+//   warps 1-3 (other schedulers) turn every 8-byte word x into a = x * P2 -- at any alignment of the frame -- into a second ring,
+//   warp 0 reads a with LDS.64 one group of eight stripes ahead and runs nothing but the chain (XAcc::round_a); lanes 0-3 own the accumulators.
+// Hand-over by mbarriers both ways (tile filled / products ready / products consumed).  Tiles lie wholly inside the frame (16-byte aligned
+// from the frame's aligned base, 16 bytes of overhang for frames that start unaligned); the last < 2 tiles and the tail are read from HBM.
 __device__ __forceinline__ uint64_t xxh_finish(const uint8_t *p, uint64_t len, uint64_t nstripes, uint64_t v1, uint64_t v2, uint64_t v3, uint64_t v4) {
     uint64_t h;
     if (len >= 32) {
@@ -2171,65 +2173,86 @@ __device__ __forceinline__ uint64_t xxh_finish(const uint8_t *p, uint64_t len, u
     h ^= h >> 33; h *= XP2; h ^= h >> 29; h *= XP3; h ^= h >> 32;
     return h;
 }
-template <bool ALIGNED8>
-__device__ __forceinline__ void xo_load(uint64_t (&X)[8], const uint8_t *tp, uint32_t sh) {
+#define XO_TILE 4096u
+#define XO_STAGES 6u                 // raw tiles in flight
+#define XO_ASTAGES 4u                // tiles of products between the helpers and the hashing warp
+#define XO_STRIDE (XO_TILE + 16u)
+#define XO_HELPERS 96u
+__device__ __forceinline__ void zsb_mbar_arrive(uint32_t mbar_sa) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar_sa) : "memory"); }
+__device__ __forceinline__ void xo_load(uint64_t (&X)[8], const uint8_t *tp) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const unsigned long long *a = reinterpret_cast<const unsigned long long *>(tp + 32 * j);
-        if (ALIGNED8) X[j] = a[0];
-        else X[j] = (a[0] >> sh) | (a[1] << (64 - sh));
-    }
+    for (int j = 0; j < 8; j++) X[j] = *reinterpret_cast<const unsigned long long *>(tp + 32 * j);
 }
-template <bool ALIGNED8>
-__device__ __forceinline__ void xo_tile(XAcc &v, const uint8_t *tp, uint32_t sh, uint32_t z) {
-    uint64_t X[8], Y[8];
-    xo_load<ALIGNED8>(X, tp, sh);
-#pragma unroll 1
-    for (uint32_t g = 0; g < XO_TILE / 256; g += 2) {
-        xo_load<ALIGNED8>(Y, tp + 256 * (g + 1), sh);
-#pragma unroll
-        for (int j = 0; j < 8; j++) v.round(X[j], z);
-        if (g + 2 < XO_TILE / 256) xo_load<ALIGNED8>(X, tp + 256 * (g + 2), sh);
-#pragma unroll
-        for (int j = 0; j < 8; j++) v.round(Y[j], z);
-    }
-}
-__global__ void __launch_bounds__(32) k_xxh_one(const uint8_t *__restrict__ dst, ZsbFrameOut *fout, const zsb_frame *__restrict__ frames,
-                                                const ZsbLinkFrame *__restrict__ link_frames, const ZsbCounters *__restrict__ cnt) {
-    __shared__ __align__(128) uint8_t s_tile[XO_STAGES * XO_STRIDE];
-    __shared__ __align__(8) unsigned long long s_bar[XO_STAGES];
+__global__ void __launch_bounds__(32 + XO_HELPERS) k_xxh_one(const uint8_t *__restrict__ dst, ZsbFrameOut *fout, const zsb_frame *__restrict__ frames,
+                                                             const ZsbLinkFrame *__restrict__ link_frames, const ZsbCounters *__restrict__ cnt) {
+    __shared__ __align__(128) uint8_t s_raw[XO_STAGES * XO_STRIDE];
+    __shared__ __align__(128) uint8_t s_a[XO_ASTAGES * XO_TILE];
+    __shared__ __align__(8) unsigned long long s_bar[XO_STAGES + 2 * XO_ASTAGES];      // raw full | products full | products empty
     if (cnt->overflow) return;
-    const uint32_t zero = blockIdx.y;                                    // (the grid is one-dimensional)
     const uint32_t f = link_frames[blockIdx.x].frame;
     if (!frames[f].has_checksum || fout[f].status != ZSB_OK) return;
     const uint64_t len = fout[f].dst_len;
     const uint8_t *p = dst + fout[f].dst_off;
-    const uint32_t lane = threadIdx.x & 31, q = lane & 3;
-    XAcc va; va.init(q == 0 ? XP1 + XP2 : q == 1 ? XP2 : q == 2 ? 0ull : 0ull - XP1);
-    const uint64_t nstripes = len >> 5;
+    const uint32_t tid = threadIdx.x;
     const uint32_t shift = (uint32_t)((uintptr_t)p & 15);
     const uint8_t *base = p - shift;
     const uint64_t ntiles = shift + len >= 16 + XO_TILE ? (shift + len - 16) / XO_TILE : 0;       // tile t reads base + t * XO_TILE .. + XO_TILE + 16
-    const uint32_t tile_sa = (uint32_t)__cvta_generic_to_shared(s_tile), bar_sa = (uint32_t)__cvta_generic_to_shared(s_bar);
-    if (lane == 0) {
+    const uint32_t raw_sa = (uint32_t)__cvta_generic_to_shared(s_raw), bar_sa = (uint32_t)__cvta_generic_to_shared(s_bar);
+    const uint32_t afull_sa = bar_sa + 8 * XO_STAGES, aempty_sa = afull_sa + 8 * XO_ASTAGES;
+    if (tid == 0) {
         for (uint32_t i = 0; i < XO_STAGES; i++) zsb_mbar_init(bar_sa + 8 * i, 1);
-        for (uint32_t i = 0; i < XO_STAGES && i < ntiles; i++) {
-            zsb_mbar_expect(bar_sa + 8 * i, XO_STRIDE);
-            zsb_bulk_g2s(tile_sa + i * XO_STRIDE, base + (uint64_t)i * XO_TILE, XO_STRIDE, bar_sa + 8 * i);
-        }
+        for (uint32_t i = 0; i < XO_ASTAGES; i++) { zsb_mbar_init(afull_sa + 8 * i, XO_HELPERS); zsb_mbar_init(aempty_sa + 8 * i, 1); }
     }
-    __syncwarp();
-    const uint32_t boff = shift + 8 * q, sh = (boff & 7) * 8;            // this lane's word of a stripe inside a tile: (boff & ~7) + 32 * stripe
-    for (uint64_t t = 0; t < ntiles; t++) {
-        const uint32_t st = (uint32_t)(t % XO_STAGES);
-        zsb_mbar_wait(bar_sa + 8 * st, (uint32_t)(t / XO_STAGES) & 1u);
-        const uint8_t *tp = s_tile + st * XO_STRIDE + (boff & ~7u);
-        if (sh == 0) xo_tile<true>(va, tp, 0, zero); else xo_tile<false>(va, tp, sh, zero);
-        __syncwarp();                                                     // every lane has read the tile: it may be filled again
-        if (lane == 0 && t + XO_STAGES < ntiles) {
-            zsb_mbar_expect(bar_sa + 8 * st, XO_STRIDE);
-            zsb_bulk_g2s(tile_sa + st * XO_STRIDE, base + (t + XO_STAGES) * XO_TILE, XO_STRIDE, bar_sa + 8 * st);
+    __syncthreads();
+    if (tid >= 32) {
+        // ---- helpers: bulk copies and the products
+        const uint32_t hid = tid - 32;
+        if (hid == 0)
+            for (uint32_t i = 0; i < XO_STAGES && i < ntiles; i++) {
+                zsb_mbar_expect(bar_sa + 8 * i, XO_STRIDE);
+                zsb_bulk_g2s(raw_sa + i * XO_STRIDE, base + (uint64_t)i * XO_TILE, XO_STRIDE, bar_sa + 8 * i);
+            }
+        const uint32_t sh = (shift & 7) * 8;
+        for (uint64_t t = 0; t < ntiles; t++) {
+            const uint32_t st = (uint32_t)(t % XO_STAGES), sa = (uint32_t)(t % XO_ASTAGES);
+            zsb_mbar_wait(bar_sa + 8 * st, (uint32_t)(t / XO_STAGES) & 1u);                       // the tile has arrived
+            zsb_mbar_wait(aempty_sa + 8 * sa, ((uint32_t)(t / XO_ASTAGES) & 1u) ^ 1u);            // the products of tile t - XO_ASTAGES were consumed
+            const unsigned long long *rp = reinterpret_cast<const unsigned long long *>(s_raw + st * XO_STRIDE + (shift & 8u));
+            unsigned long long *ap = reinterpret_cast<unsigned long long *>(s_a + sa * XO_TILE);
+            for (uint32_t w = hid; w < XO_TILE / 8; w += XO_HELPERS) {
+                const uint64_t x = sh == 0 ? rp[w] : (rp[w] >> sh) | (rp[w + 1] << (64 - sh));
+                ap[w] = x * XP2;
+            }
+            zsb_mbar_arrive(afull_sa + 8 * sa);                                                    // (release: the products are visible to who waits)
+            asm volatile("bar.sync 1, %0;" ::"n"(XO_HELPERS) : "memory");                          // every helper has read the raw tile: it may be filled again
+            if (hid == 0 && t + XO_STAGES < ntiles) {
+                zsb_mbar_expect(bar_sa + 8 * st, XO_STRIDE);
+                zsb_bulk_g2s(raw_sa + st * XO_STRIDE, base + (t + XO_STAGES) * XO_TILE, XO_STRIDE, bar_sa + 8 * st);
+            }
         }
+        return;
+    }
+    // ---- warp 0: the chain
+    const uint32_t lane = tid, q = lane & 3;
+    XAcc va; va.init(q == 0 ? XP1 + XP2 : q == 1 ? XP2 : q == 2 ? 0ull : 0ull - XP1);
+    const uint64_t nstripes = len >> 5;
+    for (uint64_t t = 0; t < ntiles; t++) {
+        const uint32_t sa = (uint32_t)(t % XO_ASTAGES);
+        zsb_mbar_wait(afull_sa + 8 * sa, (uint32_t)(t / XO_ASTAGES) & 1u);
+        const uint8_t *tp = s_a + sa * XO_TILE + 8 * q;
+        uint64_t X[8], Y[8];
+        xo_load(X, tp);
+#pragma unroll 1
+        for (uint32_t g = 0; g < XO_TILE / 256; g += 2) {
+            xo_load(Y, tp + 256 * (g + 1));
+#pragma unroll
+            for (int j = 0; j < 8; j++) va.round_a(X[j]);
+            if (g + 2 < XO_TILE / 256) xo_load(X, tp + 256 * (g + 2));
+#pragma unroll
+            for (int j = 0; j < 8; j++) va.round_a(Y[j]);
+        }
+        __syncwarp();                                                     // every lane has read the products
+        if (lane == 0) zsb_mbar_arrive(aempty_sa + 8 * sa);
     }
     for (uint64_t cur = ntiles * (XO_TILE / 32); cur < nstripes; cur++) va.round(ld64_any(p + (cur << 5) + 8 * q));
     const uint64_t v = va.acc();
@@ -2516,7 +2539,7 @@ void zsbk_link(cudaStream_t st, uint32_t n_frames, uint32_t n_blocks, const uint
     k_link_resolve<<<(n_sm > 0 ? n_sm : 148) * 8, LINK_THREADS, 0, st>>>(fout, (const ZsbLinkFrame *)link_frames, n_frames, cnt, ent, tickets, dst);
 }
 void zsbk_xxh_one(cudaStream_t st, uint32_t n_frames, const uint8_t *dst, ZsbFrameOut *fout, const zsb_frame *frames, const void *link_frames, const ZsbCounters *cnt) {
-    if (n_frames) k_xxh_one<<<n_frames, 32, 0, st>>>(dst, fout, frames, (const ZsbLinkFrame *)link_frames, cnt);
+    if (n_frames) k_xxh_one<<<n_frames, 32 + XO_HELPERS, 0, st>>>(dst, fout, frames, (const ZsbLinkFrame *)link_frames, cnt);
 }
 void zsbk_xxh(cudaStream_t st, uint32_t n, const uint8_t *dst, ZsbFrameOut *fout, const uint32_t *list, const ZsbCounters *cnt) {
     if (n) k_xxh<<<(n + XXH_WARPS * XXH_FRAMES - 1) / (XXH_WARPS * XXH_FRAMES), 32 * XXH_WARPS, 0, st>>>(dst, fout, list, n, cnt);
