@@ -106,7 +106,8 @@ int emul_decode(const uint8_t *src_in, size_t n, uint32_t flags, uint8_t *out, s
     std::vector<std::vector<uint64_t>> recs(nb);
     for (size_t i = 0; i < nb; i++) {
         ZsbBlockWork &w = work[i];
-        if (blocks[i].type != ZSB_BT_COMPRESSED || w.status) continue;
+        if (blocks[i].type != ZSB_BT_COMPRESSED || (w.status && !ZSB_CHAIN_SEQ_ERROR(w.status))) continue;          // k_plan1 (b): the lists
+        const int chain_st = w.status;
         if (w.lit_type >= ZSB_LT_COMPRESSED) {                                                            // k_huf
             uint8_t weights[260]; uint32_t ftbl[512]; int16_t cnt[16]; uint32_t rank[16]; static uint16_t lut[2048];
             int nw = 0, mb = 0; uint32_t dl = 0;
@@ -143,7 +144,7 @@ int emul_decode(const uint8_t *src_in, size_t n, uint32_t flags, uint8_t *out, s
             }
             if (rc) { w.status = rc; continue; }
         }
-        if (w.nseq) {                                                                                     // k_seq (interleaved layout, lane 5 of 32)
+        if (w.nseq && !chain_st) {                                                                        // k_seq (interleaved layout, lane 5 of 32)
             const int TS = 32, LANE = 5;
             std::vector<uint32_t> tbl(3 * 512 * TS, 0xDEADBEEF); std::vector<int16_t> cnt(256 * TS, 0);
             uint32_t bases[89];

@@ -418,8 +418,11 @@ extern "C" int zsb_decode_launch(zsb_ctx *c) {
         const void *lfr = lm, *lbl = lm + 16 * (size_t)c->n_link;
         uint32_t *tickets = (uint32_t *)(lm + 16 * (size_t)c->n_link + 8 * (size_t)c->n_link_blocks);
         CK(c, cudaMemsetAsync(tickets, 0, 4 * (size_t)c->n_link, st));         // (a relaunch of the same prepared batch starts from zero again)
-        MARK(c, "k_link");   zsbk_link(st, c->n_link, c->n_link_blocks, src, blocks, work, fout, lbl, lfr, cnt, (const uint64_t *)c->seq_pool.p, (const uint8_t *)c->lit_pool.p,
-                                       (uint32_t *)c->link_ent.p, tickets, c->d_dst, c->n_sm); c->launches += 2;
+        for (int which = 1; which <= 2; which++) {
+            MARK(c, which == 1 ? "k_link_init" : "k_link_resolve");
+            zsbk_link(st, c->n_link, c->n_link_blocks, src, blocks, work, fout, lbl, lfr, cnt, (const uint64_t *)c->seq_pool.p, (const uint8_t *)c->lit_pool.p,
+                      (uint32_t *)c->link_ent.p, tickets, c->d_dst, c->n_sm, which); c->launches++;
+        }
     }
     // pipelined path: the shard's output may leave as soon as it is written -- the checksums are computed from HBM while the
     // download runs (both only read the output)

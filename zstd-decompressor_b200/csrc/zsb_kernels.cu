@@ -202,10 +202,11 @@ __global__ void __launch_bounds__(1024) k_plan1(const zsb_frame *__restrict__ fr
         for (int j = 0; j < 4; j++) {
             const uint32_t i = i0 + 4 * tid + j;
             lit_need[j] = 0; seq_need[j] = 0; hf[j] = 0; sf[j] = 0;
-            if (i < nb && blocks[i].type == ZSB_BT_COMPRESSED && __ldcg(&work[i].status) == ZSB_OK) {
+            const int bst = i < nb && blocks[i].type == ZSB_BT_COMPRESSED ? __ldcg(&work[i].status) : ZSB_E_ARG;
+            if (bst == ZSB_OK || ZSB_CHAIN_SEQ_ERROR(bst)) {
                 if (__ldcg(&work[i].lit_type) >= ZSB_LT_COMPRESSED) { lit_need[j] = ((uint64_t)__ldcg(&work[i].lit_regen) + 15) & ~15ull; hf[j] = 1; }
                 const uint32_t ns = __ldcg(&work[i].nseq);
-                if (ns) { seq_need[j] = ((uint64_t)ns + 1) & ~1ull; sf[j] = 1; }     // even: the records of a block start 16-byte aligned
+                if (ns && bst == ZSB_OK) { seq_need[j] = ((uint64_t)ns + 1) & ~1ull; sf[j] = 1; }     // even: the records of a block start 16-byte aligned
             }
             sl += lit_need[j]; ss += seq_need[j]; sh += hf[j]; sq += sf[j];
         }
@@ -2533,10 +2534,10 @@ void zsbk_exec2(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame
 }
 void zsbk_link(cudaStream_t st, uint32_t n_frames, uint32_t n_blocks, const uint8_t *src, const zsb_block *blocks, const ZsbBlockWork *work, ZsbFrameOut *fout,
                const void *link_blocks, const void *link_frames, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool,
-               uint32_t *ent, uint32_t *tickets, uint8_t *dst, int n_sm) {
+               uint32_t *ent, uint32_t *tickets, uint8_t *dst, int n_sm, int which) {
     if (!n_frames) return;
-    if (n_blocks) k_link_init<<<n_blocks, LINK_THREADS, 0, st>>>(src, blocks, work, fout, (const uint2 *)link_blocks, (const ZsbLinkFrame *)link_frames, cnt, seq_pool, lit_pool, ent);
-    k_link_resolve<<<(n_sm > 0 ? n_sm : 148) * 8, LINK_THREADS, 0, st>>>(fout, (const ZsbLinkFrame *)link_frames, n_frames, cnt, ent, tickets, dst);
+    if (n_blocks && (which & 1)) k_link_init<<<n_blocks, LINK_THREADS, 0, st>>>(src, blocks, work, fout, (const uint2 *)link_blocks, (const ZsbLinkFrame *)link_frames, cnt, seq_pool, lit_pool, ent);
+    if (which & 2) k_link_resolve<<<(n_sm > 0 ? n_sm : 148) * 8, LINK_THREADS, 0, st>>>(fout, (const ZsbLinkFrame *)link_frames, n_frames, cnt, ent, tickets, dst);
 }
 void zsbk_xxh_one(cudaStream_t st, uint32_t n_frames, const uint8_t *dst, ZsbFrameOut *fout, const zsb_frame *frames, const void *link_frames, const ZsbCounters *cnt) {
     if (n_frames) k_xxh_one<<<n_frames, 32 + XO_HELPERS, 0, st>>>(dst, fout, frames, (const ZsbLinkFrame *)link_frames, cnt);

@@ -44,7 +44,7 @@ void zsbk_exec2(cudaStream_t st, uint32_t n, const uint8_t *src, const zsb_frame
 // uint32 frame, uint32 0}; link_blocks: n_blocks x {uint32 block, uint32 index into link_frames}; tickets: n_frames zeroed words
 void zsbk_link(cudaStream_t st, uint32_t n_frames, uint32_t n_blocks, const uint8_t *src, const zsb_block *blocks, const ZsbBlockWork *work, ZsbFrameOut *fout,
                const void *link_blocks, const void *link_frames, const ZsbCounters *cnt, const uint64_t *seq_pool, const uint8_t *lit_pool,
-               uint32_t *ent, uint32_t *tickets, uint8_t *dst, int n_sm);
+               uint32_t *ent, uint32_t *tickets, uint8_t *dst, int n_sm, int which /* 1 k_link_init, 2 k_link_resolve, 3 both */);
 void zsbk_xxh_one(cudaStream_t st, uint32_t n_frames, const uint8_t *dst, ZsbFrameOut *fout, const zsb_frame *frames, const void *link_frames, const ZsbCounters *cnt);
 void zsbk_publish(cudaStream_t st, void *host_dev_ptr, const ZsbCounters *cnt, const ZsbFrameOut *fout, uint32_t nf);
 void zsbk_xxh(cudaStream_t st, uint32_t n, const uint8_t *dst, ZsbFrameOut *fout, const uint32_t *list, const ZsbCounters *cnt);

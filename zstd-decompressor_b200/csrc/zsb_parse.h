@@ -153,6 +153,20 @@ ZSB_HDN int chain_frame_from(const zsb_frame &fr, const zsb_block *blocks, ZsbBl
                              uint32_t k0, int64_t huf_src, int64_t t0, int64_t t1, int64_t t2) {
     const bool quirks = (flags & ZSB_REFERENCE_QUIRKS) != 0;
     int64_t tsrc[3] = {t0, t1, t2};
+    // Frame::parse reads the sections of every block before anything is decoded (frame.rs:210-223): the first block that failed to PARSE fails the
+    // frame, whatever the blocks before it would do when they are decoded
+    for (uint32_t k = k0; k < fr.n_blocks; k++) {
+        const uint32_t bi = fr.first_block + k;
+        if (blocks[bi].type != ZSB_BT_COMPRESSED || work[bi].status == ZSB_OK) continue;
+        err_a = work[bi].err_a; err_b = work[bi].err_b;
+        for (uint32_t j = k + 1; j < fr.n_blocks; j++)
+            if (work[fr.first_block + j].status == ZSB_OK) work[fr.first_block + j].status = ZSB_E_PREVIOUS_FRAME;
+        return work[bi].status;
+    }
+    // What follows are errors of Block::decode (the Huffman tree of literals.rs:59-66, the tables of sequences.rs:147-187), which runs block after block:
+    // they stay with their block (k_plan2 reports the first failing block in order, so an earlier block whose entropy decoding fails comes first),
+    // the blocks behind are never reached.  A block that fails in the sequence stage still has its literals decoded first (block.rs:83-85): k_plan1
+    // lists it for k_huf (ZSB_CHAIN_SEQ_ERROR).
     for (uint32_t k = k0; k < fr.n_blocks; k++) {
         const uint32_t bi = fr.first_block + k;
         ZsbBlockWork &w = work[bi];
@@ -183,14 +197,15 @@ ZSB_HDN int chain_frame_from(const zsb_frame &fr, const zsb_block *blocks, ZsbBl
             }
         }
         if (w.status != ZSB_OK) {
-            err_a = w.err_a; err_b = w.err_b;
-            for (uint32_t j = k + 1; j < fr.n_blocks; j++)                // not reached: the frame already failed
+            for (uint32_t j = k + 1; j < fr.n_blocks; j++)                // not reached: the frame fails here at the latest
                 if (work[fr.first_block + j].status == ZSB_OK) work[fr.first_block + j].status = ZSB_E_PREVIOUS_FRAME;
-            return w.status;
+            return ZSB_OK;
         }
     }
     return ZSB_OK;
 }
+// statuses chain_frame leaves on a block whose sequence stage cannot start: its literals are decoded all the same
+#define ZSB_CHAIN_SEQ_ERROR(st) ((st) == ZSB_E_NO_PREVIOUS_DECODER || (st) == ZSB_E_EMPTY_INPUT_DATA)
 
 ZSB_HDN int chain_frame(const zsb_frame &fr, const zsb_block *blocks, ZsbBlockWork *work, uint32_t flags, uint32_t &err_a, uint32_t &err_b) {
     return chain_frame_from(fr, blocks, work, flags, err_a, err_b, 0, -1, -1, -1, -1);
