@@ -204,3 +204,51 @@ def test_mutated_inputs_equal_the_oracle_exactly():
             if oc == 0:
                 assert out == want, name
     assert n == 540 and n_panic < 30
+
+
+def test_mutated_frames_of_many_blocks_equal_the_oracle():
+    """The same, on frames of 100-300 blocks (repeat-mode tables, treeless literals, raw and RLE blocks between compressed ones), where the ORDER
+    of the reference's stages matters: all blocks are parsed before any is decoded (frame.rs:210-223), then Block::decode runs block after
+    block, literals first (block.rs:83-85) -- a missing previous table in block k does not hide a corrupt bitstream in block k - 1.  Errors are
+    compared in stream order (main.rs:42-53: frame i is decoded before frame i + 1 is parsed).  Listed exception: status 101, a block that
+    regenerates more than 128 KiB (the reference has no limit; literal streams decoded to bit exhaustion can push a full block past it)."""
+    import gen_corpus as G
+    text = G.moby_text()
+    rnd = random.Random(7)
+    b = text[:150001] + bytes(rnd.getrandbits(8) for _ in range(20000)) + b"\0" * 30000 + text[300000:400003]
+    srcs = [G.compress(text[:1000001], level=9, window_log=12), G.compress(b, level=3, window_log=10),
+            G.compress(text[200000:1100007], level=9, window_log=13, content_size=False), corpora.fixture("moby-dick.txt.zst")]
+    r = random.Random(77)
+    n_same = n_big = 0
+    for src in srcs:
+        for _ in range(40):
+            m = corpora.mutate(r, src)
+            want, _, oerr = R.decode_frames(m, quirks=True)
+            oc = oerr.code if oerr is not None else 0
+            rc, out, frames, _ = E.decode(m, 4)
+            st = [f[0] for f in frames]
+            got = (next((s for s in st[:max(len(st) - 1, 0)] if s), 0) or rc) if rc else next((s for s in st if s), 0)
+            if oc == 99:
+                continue
+            if got == 101:
+                n_big += 1
+                continue
+            assert got == oc, (oc, got, len(m))
+            if oc == 0:
+                assert out == want
+            n_same += 1
+    assert n_same > 140 and n_big <= 4, (n_same, n_big)
+
+
+def test_round1_fuzz_findings_on_the_cpu_build():
+    """tests/golden/fuzz_fail_77_*.zst (see test_gpu_parity.py::test_round1_fuzz_findings_stay_fixed): the CPU build of the device code gives the
+    oracle's first error (in stream order) on both"""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name in ("fuzz_fail_77_2417.zst", "fuzz_fail_77_3976.zst"):
+        b = open(os.path.join(here, "golden", name), "rb").read()
+        _, _, oerr = R.decode_frames(b, quirks=True)
+        rc, out, frames, _ = E.decode(b, 4 | 1, cap=4 << 20)
+        st = [f[0] for f in frames]
+        got = (next((s for s in st[:max(len(st) - 1, 0)] if s), 0) or rc) if rc else next((s for s in st if s), 0)
+        assert got == (oerr.code if oerr is not None else 0), name

@@ -315,6 +315,27 @@ def test_gpu_matches_cpu_build_of_device_code(dec):
                     assert (res.dst_off[i], res.dst_len[i]) == (off, ln) and out[off:off + ln] == eout[off:off + ln], name
 
 
+def test_round1_fuzz_findings_stay_fixed(dec):
+    """tests/golden/fuzz_fail_77_*.zst: the two inputs on which tools/probes/fuzz_gpu.py (seed 77, iterations 2417 and 3976) once saw the GPU and
+    the g++ build of the device code disagree (a mutated welcome.zst followed by other frames; a 124-byte input whose RLE block repeats 1.4 MB).
+    Same statuses frame by frame, same bytes, with the probe's flags and capacity, and the oracle's first error."""
+    import os
+    import emul_lib as E
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name, flags in (("fuzz_fail_77_2417.zst", 5), ("fuzz_fail_77_3976.zst", 7)):
+        b = open(os.path.join(here, "golden", name), "rb").read()
+        sc0 = Z.Scan(b, flags)
+        cap = Z.capacity_bound(sc0, flags)
+        rc, eout, eframes, _ = E.decode(b, flags & ~2, cap=cap)
+        out, sc, res = dec.decode(b, flags, dst_cap=cap, scan=sc0)
+        assert sc.status == rc and [res.status[i] for i in range(sc.n_frames)] == [f[0] for f in eframes], name
+        for i, (st, off, ln) in enumerate(eframes):
+            if st == 0:
+                assert (res.dst_off[i], res.dst_len[i]) == (off, ln) and out[off:off + ln] == eout[off:off + ln], name
+        want, _, oerr = R.decode_frames(b, quirks=True)
+        assert stream_status(sc, res) == (oerr.code if oerr is not None else 0), name
+
+
 # ---------------------------------------------------------------- BASELINE full size (C2: 4096 x 128 KiB)
 def test_c2_full_size_round_trip(dec):
     import gen_corpus as G
