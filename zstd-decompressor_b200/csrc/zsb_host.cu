@@ -34,6 +34,7 @@ const int kMaxKernels = 16;
 const int kProfRing = 32;     // launches whose per-kernel events are kept
 const uint32_t kBigFrameBlocks = 64;   // frames with more blocks than this are executed by a whole CTA (k_exec), not a warp (k_exec2)
 const uint64_t kLitOverflow = 4u << 20; // ZSB_REFERENCE_QUIRKS: room behind the literal scratch for blocks whose (corrupted) streams regenerate more than announced
+const size_t kTinyBatchFrames = 64;    // ... and in batches of at most this many frames every frame: a warp on its own takes 1.2 ms for one 128 KiB block (k_exec2), k_link 0.2 ms
 const size_t kSmallBatchFrames = 296;  // batches of at most this many frames (two per SM) give every multi-block frame a CTA
 }  // namespace
 
@@ -238,7 +239,7 @@ extern "C" int zsb_decode_prepare(zsb_ctx *c, const uint8_t *src, size_t n, cons
         // ... and, in a batch too small to fill the GPU with warps (a single file of a few frames, like BASELINE config C1), every frame of
         // more than one block: a CTA takes 0.11 ms per block, a warp on its own 0.8 ms
         static const int big_env = getenv("ZSB_BIG_FRAME_BLOCKS") ? atoi(getenv("ZSB_BIG_FRAME_BLOCKS")) : -1;     // experiment knob
-        const uint32_t big = c->low_latency ? 0u : big_env >= 0 ? (uint32_t)big_env : nf <= kSmallBatchFrames ? 1u : kBigFrameBlocks;
+        const uint32_t big = c->low_latency ? 0u : big_env >= 0 ? (uint32_t)big_env : (nf <= kTinyBatchFrames && c->link_mode && !c->seqx) ? 0u : nf <= kSmallBatchFrames ? 1u : kBigFrameBlocks;
         const bool cta = has_c && frames[f].n_blocks > big;
         if (has_c) (cta ? execl : exec2l).push_back((uint32_t)f);
         // frames executed by k_exec<1024> are hashed by its trailing warp, all others by k_xxh

@@ -1983,6 +1983,8 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 7) k_exec2(const uint8_t *__re
 // HBM: 4 bytes of entry written and read back per output byte plus the chain hops, instead of 0.12 ms per 128 KiB block in order.
 #define LINK_RES 0x80000000u
 #define LINK_THREADS 256
+#define LINK_WIDE 4096u                       // k_link_init: a batch of 32 sequences that regenerates more bytes than this is shared by the CTA's warps
+#define LINK_WIDE_MAX 64
 #define LINK_CHUNK (LINK_THREADS * 16u)       // entries (output bytes) per ticket of k_link_resolve: every lane takes 16
 struct ZsbLinkFrame { uint64_t e_off; uint32_t frame, pad; };   // entries of listed frame li start at ent + e_off; entry j <-> dst byte (dst_off & ~15) + j
 
@@ -2032,7 +2034,14 @@ __global__ void __launch_bounds__(LINK_THREADS) k_link_init(const uint8_t *__res
     }
     const uint32_t r0 = W.rep_in[0], r1 = W.rep_in[1], r2 = W.rep_in[2];
     const uint32_t nbatch = (nseq + 31) / 32;
-    for (uint32_t bt = warp; bt < nbatch; bt += LINK_THREADS / 32) {
+    // A batch of 32 sequences is one warp's: lane = sequence for the records, then lane = output byte over the bytes the batch regenerates.  On text
+    // that is ~270 bytes per batch; on repetitive data a batch may regenerate the whole block with a handful of long matches (one warp, 4 096 rounds,
+    // 1.2 ms: the C4 corpus).  Batches of more than LINK_WIDE bytes are therefore put aside and taken by all warps together afterwards, every warp
+    // reading the batch's records again and walking every eighth 32-byte group.
+    __shared__ uint32_t s_wide[LINK_WIDE_MAX], s_nwide;
+    if (tid == 0) s_nwide = 0;
+    __syncthreads();
+    auto batch = [&](uint32_t bt, uint32_t first, uint32_t stride, bool may_defer) {
         // lane = sequence: where it starts and what it copies
         const uint32_t s = bt * 32 + lane;
         const bool valid = s < nseq;
@@ -2045,12 +2054,18 @@ __global__ void __launch_bounds__(LINK_THREADS) k_link_init(const uint8_t *__res
         const uint32_t rep[3] = {r0, r1, r2};
         uint32_t off = valid ? seq_real_offset((uint32_t)(rec >> (2 * ZSB_REC_POS_BITS)), rep) : 1u;
         const uint32_t dstm = out_start + ll;
-        if (valid && (off == 0 || (uint64_t)off > W.out_off + dstm)) { link_fail(fo, ZSB_E_IMPOSSIBLE_VALUE); off = 0; }   // decoding_context.rs:86-90
+        if (valid && (off == 0 || (uint64_t)off > W.out_off + dstm)) { if (first == 0) link_fail(fo, ZSB_E_IMPOSSIBLE_VALUE); off = 0; }   // decoding_context.rs:86-90
         // lane = output byte: the batch regenerates [lo, hi); a byte finds its sequence by bisection over the lanes' end positions
         const uint32_t lo = __shfl_sync(FULL, out_start, 0);
         const uint32_t nval = min(32u, nseq - bt * 32);
         const uint32_t hi = __shfl_sync(FULL, out_end, nval - 1);
-        for (uint32_t p0 = lo; p0 < hi; p0 += 32) {
+        if (may_defer && hi - lo > LINK_WIDE) {
+            uint32_t slot = LINK_WIDE_MAX;
+            if (lane == 0) slot = atomicAdd(&s_nwide, 1u);
+            slot = __shfl_sync(FULL, slot, 0);
+            if (slot < LINK_WIDE_MAX) { if (lane == 0) s_wide[slot] = bt; return; }          // (more than the list holds: this warp does it alone)
+        }
+        for (uint32_t p0 = lo + first; p0 < hi; p0 += stride) {
             const uint32_t p = p0 + lane;
             uint32_t o = 0;
 #pragma unroll
@@ -2066,7 +2081,11 @@ __global__ void __launch_bounds__(LINK_THREADS) k_link_init(const uint8_t *__res
                 E[p] = e;
             }
         }
-    }
+    };
+    for (uint32_t bt = warp; bt < nbatch; bt += LINK_THREADS / 32) batch(bt, 0, 32, true);
+    __syncthreads();
+    const uint32_t nwide = min(s_nwide, (uint32_t)LINK_WIDE_MAX);
+    for (uint32_t i = 0; i < nwide; i++) batch(s_wide[i], 32 * warp, 32 * (LINK_THREADS / 32), false);
 }
 
 // tickets: one zeroed word per listed frame.  Grid: a few CTAs per SM, every CTA goes through the frames in order.
