@@ -10,53 +10,10 @@
 #include "zsb_parse.h"
 #include "zsb_huf.h"
 #include "zsb_scan.h"
-
-#define MAGIC_ZSTD 0xFD2FB528u
-#define MAGIC_SKIP 0x184D2A50u
+#include "zsb_walk.h"
 
 // ======================================================================================= scan
-namespace {
-struct Cursor {   // == ForwardByteParser (parsing.rs:9,29-112)
-    const uint8_t *p; size_t n; size_t pos;
-    size_t left() const { return n - pos; }
-};
-struct ScanErr { int code; uint64_t a, b; };
-inline bool need(Cursor &c, size_t k, ScanErr &e) {
-    if (c.left() < k) { e.code = ZSB_E_NOT_ENOUGH_BYTES; e.a = k; e.b = c.left(); return false; }
-    return true;
-}
-inline uint64_t rd_le(const uint8_t *p, int n) { uint64_t v = 0; for (int i = 0; i < n; i++) v |= (uint64_t)p[i] << (8 * i); return v; }
-
-// Header::parse frame.rs:111-177
-bool parse_header(Cursor &c, zsb_frame &f, ScanErr &e) {
-    if (!need(c, 1, e)) return false;
-    const uint8_t b = c.p[c.pos++];
-    const unsigned dflag = b & 3, checksum = (b >> 2) & 1, reserved = (b >> 3) & 1, single = (b >> 5) & 1, csf = b >> 6;
-    if (reserved) { e.code = ZSB_E_FRAME_RESERVED; e.a = e.b = 0; return false; }
-    const int fcs = (csf == 0 && !single) ? 0 : (csf == 0 ? 1 : 1 << csf);
-    uint64_t window = 0;
-    if (!single) {                                                   // parse_window_descriptor frame.rs:179-187
-        if (!need(c, 1, e)) return false;
-        const uint8_t wd = c.p[c.pos++];
-        const uint64_t base = (uint64_t)1 << ((wd >> 3) + 10);
-        window = base + (base / 8) * (wd & 7);
-    }
-    f.has_dict_id = 0; f.dict_id = 0;
-    if (dflag) {
-        const size_t dl = (size_t)1 << (dflag - 1);
-        if (!need(c, dl, e)) return false;
-        f.dict_id = rd_le(c.p + c.pos, (int)dl); f.has_dict_id = 1; c.pos += dl;
-    }
-    f.has_content_size = 0; f.content_size = 0;
-    if (fcs) {
-        if (!need(c, (size_t)fcs, e)) return false;
-        f.content_size = rd_le(c.p + c.pos, fcs) + (fcs == 2 ? 256 : 0); f.has_content_size = 1; c.pos += (size_t)fcs;
-    }
-    f.has_checksum = (uint8_t)checksum; f.single_segment = (uint8_t)single;
-    f.window_size = single ? f.content_size : window;
-    return true;
-}
-}  // namespace
+// (the walk over one frame -- magic, header, block headers, checksum -- is zsb_walk.h, shared with the device scanner)
 
 // ZSB_REFERENCE_QUIRKS only.  The reference parses a block's sections -- literals header, Huffman tree, sequences header, FSE tables --
 // inside Block::parse, i.e. during the walk (ZStandard::parse is eager, frame.rs:210-223), while this library leaves them to the GPU.
@@ -174,59 +131,14 @@ extern "C" int zsb_block_sections(const uint8_t *src, size_t n, const zsb_block 
 // failed frame (no blocks, status = the error) and returns false; false with nothing appended when the input is exhausted.
 bool ZsbScanner::next() {
     if (done) return false;
-    Cursor c{src, n, pos};
-    if (c.left() == 0) { done = true; return false; }
+    if (n - pos == 0) { done = true; return false; }
     const bool quirks = (flags & ZSB_REFERENCE_QUIRKS) != 0;
-    ScanErr e{ZSB_OK, 0, 0};
+    ZsbWalkErr e{ZSB_OK, 0, 0};
     zsb_frame f; memset(&f, 0, sizeof f);
-    f.src_off = c.pos; f.first_block = (uint32_t)blocks.size();
-    bool ok = false;
-    do {
-        if (!need(c, 4, e)) break;                               // Frame::parse frame.rs:61-77
-        const uint32_t magic = (uint32_t)rd_le(c.p + c.pos, 4); c.pos += 4;
-        f.magic = magic;
-        if (magic == MAGIC_ZSTD) {
-            f.kind = 0;
-            if (!parse_header(c, f, e)) break;                   // ZStandard::parse frame.rs:198-230
-            if (f.window_size > max_window) { e.code = ZSB_E_WINDOW_TOO_BIG; e.a = max_window; e.b = f.window_size; break; }
-            if ((flags & ZSB_STRICT_DICT) && f.has_dict_id && f.dict_id != 0) { e.code = ZSB_E_DICTIONARY; e.a = f.dict_id; e.b = 0; break; }
-            bool bad = false;
-            for (;;) {                                           // Block::parse block.rs:43-72
-                if (c.left() < 3) { e.code = ZSB_E_NOT_ENOUGH_BYTES; e.a = 3; e.b = c.left(); bad = true; break; }
-                const uint32_t v = (uint32_t)rd_le(c.p + c.pos, 3); c.pos += 3;
-                zsb_block b; memset(&b, 0, sizeof b);
-                b.last = v & 1; b.type = (v >> 1) & 3; b.size = v >> 3; b.frame = (uint32_t)frames.size(); b.src_off = c.pos;
-                if (b.type == 3) { e.code = ZSB_E_RESERVED_BLOCK; e.a = e.b = 0; bad = true; break; }
-                if (b.type == ZSB_BT_RLE) {
-                    if (c.left() < 1) { e.code = ZSB_E_NOT_ENOUGH_BYTES; e.a = 1; e.b = 0; bad = true; break; }
-                    c.pos += 1;
-                } else {
-                    if (b.size == 0 && quirks) { e.code = ZSB_E_EMPTY_SLICE; e.a = e.b = 0; bad = true; break; }   // slice(0), SURVEY Q2
-                    if (c.left() < b.size) { e.code = ZSB_E_NOT_ENOUGH_BYTES; e.a = b.size; e.b = c.left(); bad = true; break; }
-                    c.pos += b.size;
-                }
-                blocks.push_back(b);
-                if (b.last) break;
-            }
-            if (bad) break;
-            if (f.has_checksum) {
-                if (c.left() < 4) { e.code = ZSB_E_MISSING_CHECKSUM; e.a = 4; e.b = c.left(); break; }
-                f.stored_checksum = (uint32_t)rd_le(c.p + c.pos, 4); c.pos += 4;
-            }
-            ok = true;
-        } else if ((magic ^ MAGIC_SKIP) <= 0x0F) {
-            f.kind = 1;
-            if (!need(c, 4, e)) break;
-            const uint32_t len = (uint32_t)rd_le(c.p + c.pos, 4); c.pos += 4;
-            if (len == 0 && quirks) { e.code = ZSB_E_EMPTY_SLICE; e.a = e.b = 0; break; }
-            if (!need(c, len, e)) break;
-            zsb_block b; memset(&b, 0, sizeof b);
-            b.type = ZSB_BT_SKIPPABLE; b.last = 1; b.size = len; b.frame = (uint32_t)frames.size(); b.src_off = c.pos;
-            blocks.push_back(b);
-            c.pos += len;
-            ok = true;
-        } else { e.code = ZSB_E_UNRECOGNIZED_MAGIC; e.a = magic; e.b = 0; }
-    } while (0);
+    f.first_block = (uint32_t)blocks.size();
+    uint64_t end = pos; uint32_t n_emitted = 0;
+    const bool ok = zsb_walk_frame(src, (uint64_t)n, (uint64_t)pos, flags, max_window, (uint32_t)frames.size(), f, end, e, n_emitted,
+                                   [&](const zsb_block &b) { blocks.push_back(b); });
     if (!ok) {
         if (quirks && f.kind == 0 && blocks.size() > f.first_block) {
             for (size_t i = f.first_block; i < blocks.size(); i++) {
@@ -241,9 +153,9 @@ bool ZsbScanner::next() {
         code = e.code; err_a = e.a; err_b = e.b; done = true;
         return false;
     }
-    f.n_blocks = (uint32_t)blocks.size() - f.first_block; f.src_len = c.pos - f.src_off; f.status = ZSB_OK;
+    f.n_blocks = (uint32_t)blocks.size() - f.first_block; f.src_len = end - f.src_off; f.status = ZSB_OK;
     frames.push_back(f);
-    pos = c.pos;
+    pos = (size_t)end;
     return true;
 }
 
