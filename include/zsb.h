@@ -187,6 +187,19 @@ int zsb_scan_decode(zsb_ctx *ctx, const uint8_t *src, size_t n, uint8_t *dst, si
                     zsb_frame **frames, size_t *n_frames, zsb_block **blocks, size_t *n_blocks,
                     zsb_result **results, uint64_t *dst_total, uint64_t *err_a, uint64_t *err_b);
 
+/* zsb_scan for compressed bytes that are resident in HBM (d_src: device pointer on the context's device, readable up to the next
+ * 128-byte boundary behind d_src + n): the walk itself runs on the GPU.  == ForwardByteParser::iter + Frame::parse like zsb_scan
+ * (parsing.rs:29-112, frame.rs:61-230, block.rs:43-72), but "each header says where the next one starts" is not followed as one
+ * dependent chain: every frame magic in the buffer is a candidate start, a lane per candidate walks its frame, pointer doubling over
+ * the successor lists orders the chain that begins at offset 0 (csrc/zsb_dscan.cu).  Same descriptor arrays (host memory, zsb_free),
+ * return value and error payload as zsb_scan on the same bytes.  Only the descriptors cross the host link; when the chain ends in a
+ * malformed frame under ZSB_REFERENCE_QUIRKS the bytes from that frame on are fetched for the reference's eager section parsing.
+ * zsb_scan_decode with ZSB_SRC_ON_DEVICE uses it, followed by one zsb_decode batch (dst on the host, or on the device with
+ * ZSB_DST_ON_DEVICE). */
+int zsb_scan_device(zsb_ctx *ctx, const uint8_t *d_src, size_t n, uint32_t flags, uint64_t max_window,
+                    zsb_frame **frames, size_t *n_frames, zsb_block **blocks, size_t *n_blocks,
+                    uint64_t *err_a, uint64_t *err_b);
+
 /* Page-locked host buffers for src/dst of zsb_decode: copies from and to pageable memory are staged by the driver and
  * block the calling thread, which serialises the shards of the pipelined path (a binding would back its input and
  * output Vec<u8> with these).  NULL on failure.  Not for zsb_free. */

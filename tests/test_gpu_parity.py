@@ -52,6 +52,84 @@ def decode_pinned(dec, blob, flags, cap=None):
         L.zsb_host_free(src); L.zsb_host_free(dst)
 
 
+# ---------------------------------------------------------------- the walk on the device (zsb_scan_device)
+def _same_scan(a, b, what):
+    import ctypes as C
+    assert (a.status, a.err_a, a.err_b, a.n_frames, a.n_blocks) == (b.status, b.err_a, b.err_b, b.n_frames, b.n_blocks), what
+    if a.n_frames:
+        assert C.string_at(a.frames, C.sizeof(Z.ZsbFrame) * a.n_frames) == C.string_at(b.frames, C.sizeof(Z.ZsbFrame) * b.n_frames), what
+    if a.n_blocks:
+        assert C.string_at(a.blocks, C.sizeof(Z.ZsbBlock) * a.n_blocks) == C.string_at(b.blocks, C.sizeof(Z.ZsbBlock) * b.n_blocks), what
+
+
+def _device_scan(dec, blob, flags, odd=0):
+    import torch
+    t = torch.zeros(len(blob) + odd + 256, dtype=torch.uint8, device="cuda:0")
+    if blob:
+        t[odd:odd + len(blob)] = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to("cuda:0")
+    torch.cuda.synchronize()
+    return Z.DeviceScan(dec.ctx, t.data_ptr() + odd, len(blob), flags), t
+
+
+def test_device_scan_equals_host_scan(dec):
+    """zsb_scan_device gives zsb_scan's descriptors, status and payload byte for byte: fixtures, every C4 mode, frames of many blocks,
+    concatenations with skippable frames, truncations at every kind of place, mutated inputs, buffers without a frame, odd addresses"""
+    import gen_corpus as G
+    cases = {n: corpora.fixture(n) for n in corpora.FIXTURE_NAMES}
+    cases["c4"] = corpora.c4()[0]
+    cases["c2"] = corpora.c2_small(64)[0]
+    cases["c3"] = corpora.c3_small(3 << 20)[0]
+    cases["empty"] = b""
+    cases["short"] = b"\x28\xb5\x2f"
+    cases["garbage"] = bytes(range(256)) * 5
+    cases["skip+garbage"] = b"\x50\x2a\x4d\x18\x03\x00\x00\x00abcXYZW"
+    cases["skip empty"] = b"\x5f\x2a\x4d\x18\x00\x00\x00\x00" + corpora.fixture("welcome.zst")
+    cases["magic in payload"] = b"\x50\x2a\x4d\x18\x0c\x00\x00\x00" + b"\x28\xb5\x2f\xfd" * 3 + corpora.fixture("welcome.zst") + b"\x28\xb5\x2f\xfd"
+    r = random.Random(5)
+    n_bad = 0
+    for name, d in list(cases.items()):
+        for flags in (0, Q):
+            for odd in (0, 3):
+                ds, keep = _device_scan(dec, d, flags, odd)
+                _same_scan(ds, Z.Scan(d, flags), (name, flags, odd))
+        if len(d) > 16:
+            for cut in sorted({1, 4, 5, 7, len(d) // 3, len(d) // 2, len(d) - 5, len(d) - 1} | {r.randrange(len(d)) for _ in range(6)}):
+                ds, keep = _device_scan(dec, d[:cut], Q)
+                hs = Z.Scan(d[:cut], Q)
+                _same_scan(ds, hs, (name, "cut", cut))
+                n_bad += hs.status != 0
+    for name, d in corpora.mutation_sources().items():
+        for k in range(40):
+            b = corpora.mutate(r, d)
+            for flags in (0, Q):
+                ds, keep = _device_scan(dec, b, flags)
+                hs = Z.Scan(b, flags)
+                _same_scan(ds, hs, (name, "mutation", k, flags))
+                n_bad += hs.status != 0
+    assert n_bad > 40
+    blob, exp = G.make_c2(4096, seed=2)                        # C2 at full size: 4 096 frames
+    ds, keep = _device_scan(dec, blob, Q)
+    _same_scan(ds, Z.Scan(blob, Q), "C2")
+    assert ds.n_frames == 4096 and ds.status == 0
+
+
+def test_scan_decode_of_a_device_resident_buffer(dec):
+    """zsb_scan_decode with ZSB_SRC_ON_DEVICE | ZSB_DST_ON_DEVICE: walk and decode without the compressed bytes or the output crossing the host link"""
+    import torch
+    import gen_corpus as G
+    blob, exp = G.make_c2(512, seed=7)
+    blob = blob + b"\x50\x2a\x4d\x18\x04\x00\x00\x00skip" + corpora.fixture("romeo.txt.zst")
+    exp = exp + R.decode_frames(corpora.fixture("romeo.txt.zst"), quirks=True)[0]
+    src = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to("cuda:0")
+    src = torch.cat([src, torch.zeros(256, dtype=torch.uint8, device="cuda:0")])
+    dst = torch.zeros(len(exp) + 4096, dtype=torch.uint8, device="cuda:0")
+    torch.cuda.synchronize()
+    sd = Z.ScanDecode(dec.ctx, (src.data_ptr(), len(blob)), (dst.data_ptr(), dst.numel()), Q | VER | Z.SRC_ON_DEVICE | Z.DST_ON_DEVICE)
+    assert sd.status == 0 and sd.first_error() is None and sd.n_frames == 514 and sd.total == len(exp)
+    assert all(sd.results[i].checksum_ok for i in range(512))
+    assert bytes(dst[:sd.total].cpu().numpy()) == exp
+
+
 # ---------------------------------------------------------------- stage level (mirrors the reference's tests)
 def test_fse_reference_vectors():                       # tests/decoders/fse.rs
     al, dist, table, consumed = Z.fse_table_parse([0x30, 0x6f, 0x9b, 0x03])

@@ -108,6 +108,8 @@ def lib():
     L.zsb_decode_finish.argtypes = [vp, u64p, u64p, i32p, u32p, u8p, u64p]
     L.zsb_scan_decode.argtypes = [vp, vp, sz, vp, sz, C.c_uint32, C.c_uint64, C.POINTER(C.POINTER(ZsbFrame)), C.POINTER(sz),
                                   C.POINTER(C.POINTER(ZsbBlock)), C.POINTER(sz), C.POINTER(C.POINTER(ZsbResult)), u64p, u64p, u64p]
+    L.zsb_scan_device.argtypes = [vp, vp, sz, C.c_uint32, C.c_uint64, C.POINTER(C.POINTER(ZsbFrame)), C.POINTER(sz),
+                                  C.POINTER(C.POINTER(ZsbBlock)), C.POINTER(sz), u64p, u64p]
     L.zsb_decompress.argtypes = [vp, vp, sz, C.c_uint32, C.POINTER(vp), C.POINTER(sz), u64p, u64p]
     L.zsb_fse_table_parse.argtypes = [vp, C.c_char_p, sz, C.c_int, u8p, C.POINTER(C.c_uint16), C.POINTER(sz), C.POINTER(C.c_int16), C.POINTER(sz)]
     L.zsb_fse_table_from_distribution.argtypes = [vp, C.c_uint8, C.POINTER(C.c_int16), sz, C.POINTER(C.c_uint16)]
@@ -165,6 +167,20 @@ class Scan:
             if getattr(self, "blocks", None): lib().zsb_free(self.blocks)
         except Exception:
             pass
+
+
+class DeviceScan(Scan):
+    """zsb_scan_device: the walk over a buffer resident in HBM, run on the GPU.  Same attributes as Scan; buf is the device pointer."""
+    def __init__(self, ctx, dev_ptr, n, flags=0, max_window=0):
+        self._keep = None
+        self.buf, self.n = C.c_void_p(dev_ptr), n
+        fp, bp = C.POINTER(ZsbFrame)(), C.POINTER(ZsbBlock)()
+        nf, nb, ea, eb = C.c_size_t(), C.c_size_t(), C.c_uint64(), C.c_uint64()
+        self.status = lib().zsb_scan_device(ctx.h, self.buf, n, flags, max_window, C.byref(fp), C.byref(nf), C.byref(bp), C.byref(nb), C.byref(ea), C.byref(eb))
+        self.frames, self.blocks, self.n_frames, self.n_blocks = fp, bp, nf.value, nb.value
+        self.err_a, self.err_b = ea.value, eb.value
+        if not fp and self.status:
+            raise ZsbError(self.status, what="zsb_scan_device" + (": " + ctx.cuda_error() if self.status == E_CUDA else ""))
 
 
 def _as_buffer(data):

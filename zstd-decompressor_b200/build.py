@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libzsb.so")
-SOURCES = ["zsb_kernels.cu", "zsb_host.cu", "zsb_multi.cu", "zsb_scan.cpp"]
+SOURCES = ["zsb_kernels.cu", "zsb_host.cu", "zsb_multi.cu", "zsb_dscan.cu", "zsb_scan.cpp"]
 HEADERS = ["zsb_common.h", "zsb_bits.h", "zsb_fse.h", "zsb_huf.h", "zsb_seq.h", "zsb_seqfast.h", "zsb_stream.h", "zsb_bulk.cuh", "zsb_parse.h", "zsb_kernels.h", "zsb_scan.h", "zsb_walk.h", "../../include/zsb.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]

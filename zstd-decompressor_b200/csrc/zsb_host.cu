@@ -14,6 +14,7 @@
 #include <vector>
 #include "zsb_kernels.h"
 #include "zsb_scan.h"
+#include "zsb_walk.h"
 
 // ======================================================================================= context
 namespace {
@@ -44,6 +45,7 @@ struct zsb_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_huf[kProfRing][2] = {};
     DevBuf src, frames, blocks, work, fout, huf_list, seq_list, rawrle_list, exec_list, exec2_list, xxh_list, lit_pool, seq_pool, slow_list, counters, dst, stage, pre_off, wave;
+    DevBuf dscan, dscan_blocks;                                    // zsb_scan_device: candidates, hash table, jump tables / block descriptors
     DevBuf link_ent, link_meta;                                    // k_link: one 32-bit entry per output byte of the listed frames; frame list, block list, tickets
     std::vector<uint64_t> h_link_meta;                             // host image of link_meta (frames: 2 words each, then blocks: 1 word each, then tickets)
     uint32_t n_link = 0, n_link_blocks = 0;                        // frames / blocks executed by k_link_init + k_link_resolve
@@ -129,7 +131,7 @@ extern "C" void zsb_ctx_destroy(zsb_ctx *c) {
     c->subs.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list, &c->exec2_list, &c->pre_off, &c->wave, &c->link_ent, &c->link_meta,
+    DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list, &c->exec2_list, &c->pre_off, &c->wave, &c->link_ent, &c->link_meta, &c->dscan, &c->dscan_blocks,
                      &c->xxh_list, &c->lit_pool, &c->seq_pool, &c->slow_list, &c->counters, &c->dst, &c->stage};
     for (DevBuf *b : all) b->release();
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) if (c->ev[r][i]) cudaEventDestroy(c->ev[r][i]);
@@ -715,6 +717,9 @@ extern "C" int zsb_decode(zsb_ctx *c, const uint8_t *src, size_t n, const zsb_fr
     return zsb_decode_finish(c, dst_off, dst_len, status, xxh32, checksum_ok, dst_total);
 }
 
+extern "C" int zsb_scan_device(zsb_ctx *c, const uint8_t *d_src, size_t n, uint32_t flags, uint64_t max_window,
+                               zsb_frame **frames_out, size_t *n_frames, zsb_block **blocks_out, size_t *n_blocks, uint64_t *err_a, uint64_t *err_b);
+
 // zsb_scan + zsb_decode in one call on host buffers, with the host walk overlapped: the walk stops at every shard boundary
 // (a fraction of the compressed bytes) and the frames found so far start uploading and decoding while the rest of the buffer
 // is still being walked.  Results are those of zsb_scan followed by zsb_decode.  Anything that keeps the pipelined path from
@@ -725,7 +730,27 @@ extern "C" int zsb_scan_decode(zsb_ctx *c, const uint8_t *src, size_t n, uint8_t
                                zsb_result **results_out, uint64_t *dst_total, uint64_t *err_a, uint64_t *err_b) {
     if (!c || c->is_sub || (!src && n) || !dst || !frames_out || !n_frames || !blocks_out || !n_blocks || !results_out) return ZSB_E_ARG;
     *frames_out = nullptr; *blocks_out = nullptr; *results_out = nullptr; *n_frames = 0; *n_blocks = 0;
-    flags &= ~(ZSB_SRC_ON_DEVICE | ZSB_DST_ON_DEVICE);
+    if (flags & ZSB_SRC_ON_DEVICE) {
+        // the compressed bytes are resident in HBM: the walk runs there too (zsb_scan_device), then one batch; dst is a host or (ZSB_DST_ON_DEVICE) a device buffer
+        uint64_t ea = 0, eb = 0, total = 0;
+        const int scan_rc = zsb_scan_device(c, src, n, flags, max_window, frames_out, n_frames, blocks_out, n_blocks, &ea, &eb);
+        if (!*frames_out) return scan_rc;
+        const size_t nf = *n_frames;
+        std::vector<uint64_t> off(nf + 1), len(nf + 1); std::vector<int32_t> st(nf + 1); std::vector<uint32_t> xh(nf + 1); std::vector<uint8_t> ck(nf + 1);
+        zsb_result *res = (zsb_result *)malloc(sizeof(zsb_result) * (nf + 1));
+        int rc = res ? zsb_decode(c, src, n, *frames_out, nf, *blocks_out, *n_blocks, dst, dst_cap, off.data(), len.data(), st.data(), xh.data(), ck.data(), &total, flags) : ZSB_E_NOMEM;
+        if (rc) { free(res); zsb_free(*frames_out); zsb_free(*blocks_out); *frames_out = nullptr; *blocks_out = nullptr; *n_frames = 0; *n_blocks = 0; return rc; }
+        for (size_t f = 0; f < nf; f++) {
+            res[f].dst_off = off[f]; res[f].dst_len = len[f]; res[f].status = st[f]; res[f].xxh32 = xh[f]; res[f].checksum_ok = ck[f]; memset(res[f].pad, 0, sizeof res[f].pad);
+            res[f].err_a = f < c->h_err_a.size() ? c->h_err_a[f] : 0; res[f].err_b = f < c->h_err_b.size() ? c->h_err_b[f] : 0;
+        }
+        *results_out = res;
+        if (dst_total) *dst_total = total;
+        if (err_a) *err_a = ea;
+        if (err_b) *err_b = eb;
+        return scan_rc;
+    }
+    flags &= ~ZSB_DST_ON_DEVICE;
     ZsbScanner sc(src, n, flags, max_window);
     Pipe P(c, src, dst, dst_cap, flags);
     bool streamed = n >= (16u << 20) && host_pinned(src) && host_pinned(dst);     // worth cutting up at all, and the copies asynchronous
@@ -779,6 +804,143 @@ extern "C" int zsb_scan_decode(zsb_ctx *c, const uint8_t *src, size_t n, uint8_t
     if (err_a) *err_a = sc.err_a;
     if (err_b) *err_b = sc.err_b;
     return sc.code;
+}
+
+// ======================================================================================= zsb_scan_device
+// zsb_scan for a buffer that is resident in HBM: the kernels of zsb_dscan.cu find the frames and blocks, the descriptors come back to the host.
+// Same arrays, status and payload as zsb_scan on the same bytes (tests/test_gpu_parity.py compares them byte for byte).
+extern "C" int zsb_scan_device(zsb_ctx *c, const uint8_t *d_src, size_t n, uint32_t flags, uint64_t max_window,
+                               zsb_frame **frames_out, size_t *n_frames, zsb_block **blocks_out, size_t *n_blocks, uint64_t *err_a, uint64_t *err_b) {
+    if (!c || !frames_out || !n_frames || !blocks_out || !n_blocks || (!d_src && n)) return ZSB_E_ARG;
+    *frames_out = nullptr; *blocks_out = nullptr; *n_frames = 0; *n_blocks = 0;
+    if (err_a) *err_a = 0;
+    if (err_b) *err_b = 0;
+    flags &= (ZSB_REFERENCE_QUIRKS | ZSB_STRICT_DICT);
+    if (!max_window) max_window = ZSB_MAX_WINDOW_DEFAULT;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const uint64_t kMaxCand = 1ull << 24;
+    std::vector<zsb_frame> frames; std::vector<zsb_block> blocks;
+    int code = ZSB_OK; uint64_t ea = 0, eb = 0;
+    uint64_t tail_off = 0;            // where the chain of well-formed frames ends
+    bool chain_failed = false;        // ... on a frame that fails (it is the last entry of `frames`)
+    uint64_t fail_emitted = 0;
+
+    auto host_walk = [&](uint64_t from) -> int {      // the host walker on a copy of src[from, n): frames from `from` on replace what follows
+        std::vector<uint8_t> h(n - from + 1);
+        CK(c, cudaMemcpyAsync(h.data(), d_src + from, n - from, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaStreamSynchronize(st));
+        ZsbScanner sc(h.data(), n - from, flags, max_window);
+        const size_t f0 = frames.size(), b0 = blocks.size();
+        while (sc.next()) {}
+        for (zsb_frame f : sc.frames) { f.src_off += from; f.first_block += (uint32_t)b0; frames.push_back(f); }
+        for (zsb_block b : sc.blocks) { b.src_off += from; b.frame += (uint32_t)f0; blocks.push_back(b); }
+        code = sc.code; ea = sc.err_a; eb = sc.err_b;
+        return ZSB_OK;
+    };
+
+    if (n >= 4) {
+        CK(c, c->dscan.ensure(256));
+        unsigned long long *d_count = (unsigned long long *)c->dscan.p;       // the arena's first 256 bytes
+        unsigned long long count = 0;
+        CK(c, cudaMemsetAsync(d_count, 0, 8, st));
+        zsbk_dscan_find(st, d_src, n, d_count, nullptr, 0, c->n_sm);
+        CK(c, cudaMemcpyAsync(&count, d_count, 8, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaStreamSynchronize(st));
+        if (count > kMaxCand) {                                               // a buffer that is mostly magic numbers: not worth the tables
+            const int rc = host_walk(0);
+            if (rc) return rc;
+            goto done;
+        }
+        if (count) {
+            const uint32_t ncand = (uint32_t)count, n1 = ncand + 1;
+            uint32_t levels = 1; while ((1ull << levels) < n1) levels++;
+            uint32_t mask = 1; while (mask < 2 * ncand + 2) mask <<= 1; mask -= 1;
+            size_t o = 256;
+            auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
+            const size_t o_pos = take(8ull * ncand), o_cand = take(sizeof(ZsbDscanCand) * (size_t)ncand), o_keys = take(8ull * (mask + 1ull)), o_vals = take(4ull * (mask + 1ull)),
+                         o_jump = take(4ull * (levels + 1ull) * n1), o_da = take(4ull * n1), o_db = take(4ull * n1), o_head = take(4), o_tail = take(8 * ZSB_DSCAN_TAIL_WORDS),
+                         o_order = take(4ull * ncand), o_fr = take(sizeof(zsb_frame) * (size_t)ncand), o_fb = take(4ull * ncand);
+            CK(c, c->dscan.ensure(o));
+            uint8_t *A = (uint8_t *)c->dscan.p;
+            d_count = (unsigned long long *)A;
+            uint64_t *d_pos = (uint64_t *)(A + o_pos); ZsbDscanCand *d_cand = (ZsbDscanCand *)(A + o_cand);
+            unsigned long long *d_keys = (unsigned long long *)(A + o_keys); uint32_t *d_vals = (uint32_t *)(A + o_vals), *d_jump = (uint32_t *)(A + o_jump);
+            uint32_t *d_da = (uint32_t *)(A + o_da), *d_db = (uint32_t *)(A + o_db), *d_head = (uint32_t *)(A + o_head), *d_order = (uint32_t *)(A + o_order), *d_fb = (uint32_t *)(A + o_fb);
+            uint64_t *d_tail = (uint64_t *)(A + o_tail); zsb_frame *d_fr = (zsb_frame *)(A + o_fr);
+            CK(c, cudaMemsetAsync(d_count, 0, 8, st));
+            CK(c, cudaMemsetAsync(d_keys, 0, 8ull * (mask + 1ull), st));
+            zsbk_dscan_find(st, d_src, n, d_count, d_pos, ncand, c->n_sm);
+            zsbk_dscan_parse(st, d_src, n, flags, max_window, d_pos, ncand, d_cand, d_keys, d_vals, mask);
+            zsbk_dscan_link(st, d_cand, ncand, n, d_keys, d_vals, mask, d_jump, levels, d_da, d_db, d_head);
+            uint32_t head = 0xFFFFFFFFu, nfr = 0;
+            CK(c, cudaMemcpyAsync(&head, d_head, 4, cudaMemcpyDeviceToHost, st));
+            CK(c, cudaStreamSynchronize(st));
+            if (head != 0xFFFFFFFFu) {
+                CK(c, cudaMemcpyAsync(&nfr, ((levels & 1) ? d_db : d_da) + head, 4, cudaMemcpyDeviceToHost, st));
+                CK(c, cudaStreamSynchronize(st));
+            }
+            if (nfr) {
+                uint64_t tail[ZSB_DSCAN_TAIL_WORDS] = {};
+                frames.resize(nfr);
+                zsbk_dscan_order(st, d_jump, levels, ncand, head, nfr, d_cand, d_order, d_fr, d_tail);
+                CK(c, cudaMemcpyAsync(frames.data(), d_fr, sizeof(zsb_frame) * (size_t)nfr, cudaMemcpyDeviceToHost, st));
+                CK(c, cudaMemcpyAsync(tail, d_tail, sizeof tail, cudaMemcpyDeviceToHost, st));
+                CK(c, cudaStreamSynchronize(st));
+                std::vector<uint32_t> fb(nfr);
+                uint64_t nb = 0;
+                for (uint32_t f = 0; f < nfr; f++) { fb[f] = (uint32_t)nb; frames[f].first_block = (uint32_t)nb; nb += frames[f].n_blocks; }
+                if (nb > 0xFFFFFFFFull) { c->last_err = "zsb_scan_device: more than 2^32 blocks"; return ZSB_E_ARG; }
+                blocks.resize(nb);
+                if (nb) {
+                    CK(c, c->dscan_blocks.ensure(sizeof(zsb_block) * (size_t)nb));
+                    CK(c, cudaMemcpyAsync(d_fb, fb.data(), 4ull * nfr, cudaMemcpyHostToDevice, st));
+                    zsbk_dscan_emit(st, d_src, n, flags, max_window, d_fr, d_fb, nfr, (zsb_block *)c->dscan_blocks.p);
+                    CK(c, cudaMemcpyAsync(blocks.data(), c->dscan_blocks.p, sizeof(zsb_block) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+                }
+                CK(c, cudaGetLastError());
+                CK(c, cudaStreamSynchronize(st));
+                if (tail[0]) tail_off = tail[1];
+                else { chain_failed = true; tail_off = frames[nfr - 1].src_off; code = frames[nfr - 1].status; ea = tail[3]; eb = tail[4]; fail_emitted = tail[5]; }
+            }
+        }
+    }
+    if (chain_failed) {
+        // ZSB_REFERENCE_QUIRKS: a section error of a block read before the point of failure comes first (eager_sections, zsb_scan.cpp): the host walker
+        // decides, on the bytes from the failing frame on
+        if ((flags & ZSB_REFERENCE_QUIRKS) && frames.back().kind == 0 && fail_emitted) {
+            frames.pop_back();
+            const int rc = host_walk(tail_off);
+            if (rc) return rc;
+        }
+    } else if (tail_off < n) {
+        // no frame starts here: fewer than four bytes, or four bytes that are no magic number (Frame::parse frame.rs:61-77)
+        zsb_frame f; memset(&f, 0, sizeof f);
+        f.src_off = tail_off; f.src_len = n - tail_off; f.first_block = (uint32_t)blocks.size();
+        if (n - tail_off < 4) { code = ZSB_E_NOT_ENOUGH_BYTES; ea = 4; eb = n - tail_off; }
+        else {
+            uint8_t m[4];
+            CK(c, cudaMemcpyAsync(m, d_src + tail_off, 4, cudaMemcpyDeviceToHost, st));
+            CK(c, cudaStreamSynchronize(st));
+            f.magic = (uint32_t)m[0] | (uint32_t)m[1] << 8 | (uint32_t)m[2] << 16 | (uint32_t)m[3] << 24;
+            if (zsb_is_frame_magic(f.magic)) { c->last_err = "zsb_scan_device: a frame start was not found as a candidate"; return ZSB_E_CUDA; }
+            code = ZSB_E_UNRECOGNIZED_MAGIC; ea = f.magic; eb = 0;
+        }
+        f.status = code;
+        frames.push_back(f);
+    }
+done:
+    {
+        zsb_frame *fo = (zsb_frame *)malloc(sizeof(zsb_frame) * (frames.size() + 1));
+        zsb_block *bo = (zsb_block *)malloc(sizeof(zsb_block) * (blocks.size() + 1));
+        if (!fo || !bo) { free(fo); free(bo); return ZSB_E_NOMEM; }
+        if (!frames.empty()) memcpy(fo, frames.data(), sizeof(zsb_frame) * frames.size());
+        if (!blocks.empty()) memcpy(bo, blocks.data(), sizeof(zsb_block) * blocks.size());
+        *frames_out = fo; *n_frames = frames.size(); *blocks_out = bo; *n_blocks = blocks.size();
+    }
+    if (err_a) *err_a = ea;
+    if (err_b) *err_b = eb;
+    return code;
 }
 
 // src/main.rs:42-58 : all-or-nothing whole-buffer decode

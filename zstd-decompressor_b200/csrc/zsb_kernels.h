@@ -52,3 +52,17 @@ void zsbk_stage_fse(cudaStream_t st, const uint8_t *desc, uint32_t n, int max_sy
                     int *res, uint32_t *cells, int16_t *dist_out);
 void zsbk_stage_huf(cudaStream_t st, const uint8_t *desc, uint32_t n, int *res, uint8_t *lens, uint16_t *lut);
 void zsbk_stage_records(cudaStream_t st, const uint32_t *tri, uint32_t nseq, uint32_t nlit, uint64_t *rec, ZsbBlockWork *w);
+
+// ---- zsb_dscan.cu: the frame / block walk on the device (zsb_scan_device)
+struct ZsbDscanCand { zsb_frame f; uint64_t end, ea, eb; uint32_t next, n_emitted; int32_t ok; uint32_t pad; };      // a failed walk: f.status, (ea, eb) = the error and its payload, n_emitted = blocks read before it
+void zsbk_dscan_find(cudaStream_t st, const uint8_t *src, uint64_t n, unsigned long long *count, uint64_t *pos_out, uint64_t cap, int n_sm);
+void zsbk_dscan_parse(cudaStream_t st, const uint8_t *src, uint64_t n, uint32_t flags, uint64_t max_window, const uint64_t *pos_list, uint32_t ncand,
+                      ZsbDscanCand *cand, unsigned long long *keys, uint32_t *vals, uint32_t mask);
+// jump: (levels + 1) x (ncand + 1) words; after the call the distances (frames from a node to the end of its chain) are in dist_a if `levels` is even, else dist_b
+void zsbk_dscan_link(cudaStream_t st, ZsbDscanCand *cand, uint32_t ncand, uint64_t n, const unsigned long long *keys, const uint32_t *vals, uint32_t mask,
+                     uint32_t *jump, uint32_t levels, uint32_t *dist_a, uint32_t *dist_b, uint32_t *head);
+void zsbk_dscan_order(cudaStream_t st, const uint32_t *jump, uint32_t levels, uint32_t ncand, uint32_t start, uint32_t nfr, const ZsbDscanCand *cand,
+                      uint32_t *order, zsb_frame *frames_out, uint64_t *tail);
+#define ZSB_DSCAN_TAIL_WORDS 6   // tail of the chain: {ok, end, node, ea, eb, n_emitted} of its last frame
+void zsbk_dscan_emit(cudaStream_t st, const uint8_t *src, uint64_t n, uint32_t flags, uint64_t max_window, const zsb_frame *frames, const uint32_t *first_block,
+                     uint32_t nfr, zsb_block *blocks_out);
