@@ -143,7 +143,7 @@ EXPORTED_SYMBOLS = [
     "zsb_decompress", "zsb_fse_table_parse", "zsb_fse_table_from_distribution", "zsb_huffman_parse", "zsb_execute_sequences",
     "zsb_xxh64", "zsb_strerror", "zsb_version", "zsb_shard_plan", "zsb_shard_extract", "zsb_host_alloc", "zsb_host_free", "zsb_scan_decode",
     "zsb_multi_create", "zsb_multi_destroy", "zsb_multi_device_count", "zsb_multi_ctx", "zsb_multi_calibrate", "zsb_multi_set_weights", "zsb_multi_get_weights",
-    "zsb_multi_last_error", "zsb_multi_scan_decode", "zsb_gather_peer", "zsb_decode_errors", "zsb_block_sections"]
+    "zsb_multi_last_error", "zsb_multi_scan_decode", "zsb_gather_peer", "zsb_decode_errors", "zsb_block_sections", "zsb_scan_device"]
 
 
 # ------------------------------------------------------------------------------------------ scan
