@@ -14,11 +14,11 @@ sc = Z.Scan(blob, 6)
 dec.prepare(src.data_ptr(), len(blob), sc, dst.data_ptr(), len(exp), 6 | 8 | 16)
 for _ in range(3):
     dec.launch(); r = dec.finish()
-buf = (C.c_longlong * (1024 * 4))()
+buf = (C.c_longlong * (1024 * 8))()
 assert Z.lib().zsb_debug_huf_timing(buf) == 0
-rows = [[buf[i * 4 + j] for j in range(4)] for i in range(1024)]
+rows = [r for r in ([buf[i * 8 + j] for j in range(8)] for i in range(1024)) if r[0]]      # (CTAs that ran)
 t0 = min(r[0] for r in rows)
 import statistics as S
-for name, f in (("start - first start", lambda r: r[0] - t0), ("tables", lambda r: r[1] - r[0]), ("  weights", lambda r: r[3] - r[0]), ("  lut", lambda r: r[1] - r[3]), ("streams", lambda r: r[2] - r[1]), ("end - first start", lambda r: r[2] - t0)):
+for name, f in (("start - first start", lambda r: r[0] - t0), ("tables", lambda r: r[1] - r[0]), ("  weights", lambda r: r[3] - r[0]), ("  lut", lambda r: r[1] - r[3]), ("    plan", lambda r: r[4] - r[3]), ("    cell starts", lambda r: r[5] - r[4]), ("    T1", lambda r: r[6] - r[5]), ("    pairs", lambda r: r[1] - r[6]), ("streams", lambda r: r[2] - r[1]), ("end - first start", lambda r: r[2] - t0)):
     c = [f(r) for r in rows]
     print(f"{name:24s} min {min(c):10d} median {S.median(c):12.1f} max {max(c):10d}")

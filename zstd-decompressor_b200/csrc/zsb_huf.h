@@ -212,13 +212,58 @@ ZSB_HDN int huf_decode_block_ref(const uint8_t *src, uint64_t src_end, uint64_t 
 
 
 // ---- fast stream decode ------------------------------------------------------------------------------
-// The same chain as huf_decode_stream with everything that is not on it removed: the window is reloaded once
-// per four symbols (4 x 11 bits fit), four symbols leave as one aligned 32-bit store, and the stream is decoded
-// for exactly `expect` symbols and must then be exactly empty.  Anything else (empty stream, missing end mark,
+// The chain of a stream is "cell -> bits consumed -> next cell"; everything else hangs off it.  The fast path therefore looks up TWO
+// symbols at a time where the next ten bits hold two whole codes: a table of 1 024 32-bit cells indexed by the next 10 bits of the stream,
+//     cell = s1 | s2 << 8 | l1 << 16 | long << 20 | count << 21 | ltot << 24
+//     count 2: two symbols s1 s2 in ltot = l1 + l2 <= 10 bits;  count 1: one symbol s1 in ltot = l1 bits (the next code does not fit; s2 = 0);
+//     long (count 1): the ten bits are the prefix of two 11-bit codes: the eleventh bit selects s1 (0) or s2 (1), ltot = l1 = 11
+// -- the same symbols as one-symbol lookups, cell by cell (a code is decoded from bits that determine it completely).  Only for
+// complete codes (every 10-bit prefix leads somewhere); everything else goes the careful way.  4 KiB like the one-symbol table of
+// 2 048 16-bit cells it replaces in k_huf's shared memory.
+// The table is built from T1, the first symbol under every 10-bit prefix (1 KiB; for a prefix of 11-bit codes the even child, the odd
+// one in `odd`), and the code lengths, which are the weights (len = maxbits + 1 - weight).
+#define ZSB_HUF_PAIR_BITS 10
+// T1 cells of one symbol: `at` = its first cell in the maxbits-bit table (huf_lut_plan's order), wt > 0 its weight
+ZSB_HD void huf_t1_put(uint8_t *t1, uint8_t *odd, int mb, uint32_t sym, uint32_t at, uint32_t wt) {
+    uint32_t a, len;
+    if (mb > ZSB_HUF_PAIR_BITS) {                                   // mb == 11: two cells of the big table per T1 cell
+        if (wt == 1) { if (at & 1u) odd[at >> 1] = (uint8_t)sym; else t1[at >> 1] = (uint8_t)sym; return; }
+        a = at >> 1; len = 1u << (wt - 2);
+    } else { a = at << (ZSB_HUF_PAIR_BITS - mb); len = (1u << (wt - 1)) << (ZSB_HUF_PAIR_BITS - mb); }
+#if defined(__CUDA_ARCH__)
+    if (len >= 16) {                                                // a is a multiple of len (a complete code): aligned
+        const uint32_t v = sym * 0x01010101u;
+        for (uint32_t k = 0; k < len; k += 16) *reinterpret_cast<uint4 *>(t1 + a + k) = make_uint4(v, v, v, v);
+    } else
+#endif
+    for (uint32_t k = 0; k < len; k++) t1[a + k] = (uint8_t)sym;
+}
+ZSB_HD uint32_t huf_pair_cell(uint32_t x, const uint8_t *t1, const uint8_t *odd, const uint8_t *weights, int ws, int mb) {
+    // (no branches: the four loads of a cell are dependent, the cells of one lane are meant to overlap)
+    const uint32_t s1 = t1[x], l1 = (uint32_t)mb + 1u - weights[s1 * ws];
+    const bool lng = l1 > ZSB_HUF_PAIR_BITS;
+    const uint32_t rest = (x << (lng ? 0u : l1)) & ((1u << ZSB_HUF_PAIR_BITS) - 1u);
+    const uint32_t s2 = t1[rest], l2 = (uint32_t)mb + 1u - weights[s2 * ws];
+    const uint32_t od = odd[x & 127u];
+    const bool two = !lng && l1 + l2 <= ZSB_HUF_PAIR_BITS;
+    const uint32_t b1 = lng ? od : two ? s2 : 0u, lt = two ? l1 + l2 : l1;
+    return s1 | b1 << 8 | l1 << 16 | (lng ? 1u : 0u) << 20 | (two ? 2u : 1u) << 21 | lt << 24;
+}
+// the same table from a finished one-symbol table (host builds: tests/emul); t1 / odd: 1 024 / 512 bytes of scratch
+ZSB_HDN void huf_pairs_from_lut(const uint16_t *lut, int mb, const uint8_t *weights, int ws, uint8_t *t1, uint8_t *odd, uint32_t *pair) {
+    for (uint32_t x = 0; x < (1u << ZSB_HUF_PAIR_BITS); x++) {
+        if (mb > ZSB_HUF_PAIR_BITS) { t1[x] = (uint8_t)lut[2 * x]; if (x < 512) odd[x] = (uint8_t)lut[2 * x + 1]; }
+        else t1[x] = (uint8_t)lut[x >> (ZSB_HUF_PAIR_BITS - mb)];
+    }
+    for (uint32_t x = 0; x < (1u << ZSB_HUF_PAIR_BITS); x++) pair[x] = huf_pair_cell(x, t1, odd, weights, ws, mb);
+}
+
+// The stream is decoded for exactly `expect` symbols and must then be exactly empty.  Anything else (empty stream, missing end mark,
 // over-read, bits left over, a stream too close to the buffer start) returns ZSB_NEEDS_SLOW and the caller runs
-// huf_decode_stream, which reports what the reference reports.  On the GPU the stream is staged through a
+// huf_decode_stream, which reports what the reference reports.  The window is reloaded once per five cells (5 x 11 bits fit), the
+// symbols collect in a register and leave as aligned 32-bit stores.  On the GPU the stream is staged through a
 // shared-memory ring (ring_sa, zsb_stream.h); the host build reads it in place.
-ZSB_HDN int huf_fast_stream(const uint8_t *src, uint64_t start, uint64_t end, const uint16_t *lut, int maxbits, uint8_t *out, uint32_t expect,
+ZSB_HDN int huf_fast_stream(const uint8_t *src, uint64_t start, uint64_t end, const uint32_t *pair, uint8_t *out, uint32_t expect,
                             uint32_t ring_sa) {
     if (end <= start || start < 16 || end - start > (1u << 24)) return ZSB_NEEDS_SLOW;
     const uint32_t lastb = src[end - 1];
@@ -242,47 +287,56 @@ ZSB_HDN int huf_fast_stream(const uint8_t *src, uint64_t start, uint64_t end, co
     const int32_t startbit = (int32_t)((start + mis - w0) * 8);
 #define HUF_LOAD(t_) fast_win_load(F, pw, t_)
 #endif
-    const uint32_t sh = 64u - (uint32_t)maxbits;
+    const uint32_t ish = 64u - ZSB_HUF_PAIR_BITS;
     uint32_t n = 0;
+    // one symbol: the first of a cell
+#define HUF_ONE() do { \
+        HUF_LOAD(top); \
+        const uint64_t W1 = fast_win_get(F); \
+        const uint32_t c = pair[(uint32_t)(W1 >> ish)]; \
+        uint32_t sy = c & 0xFFu; \
+        if (((c >> 20) & 1u) && ((W1 >> (ish - 1)) & 1u)) sy = (c >> 8) & 0xFFu; \
+        out[n++] = (uint8_t)sy; top -= (int32_t)((c >> 16) & 15u); } while (0)
+    // five cells from one window: 5 .. 10 symbols into `pend` (np8 bits pending, < 32 between windows), whole words out.
+    // The cells are looked up first -- that is the chain --, then the cursor moves and NEXT requests the words of the following window, and
+    // only then are the symbols of this window put away: that work (two thirds of the instructions) runs in the shadow of the next loads.
+    // lb: 8 when the cell is a prefix of two 11-bit codes and the eleventh bit of the window is set (the odd child, byte 1 of the cell)
+#define HUF_LOOKUP(c_, h_) const uint32_t h_ = (uint32_t)(W >> 32); const uint32_t c_ = pair[h_ >> (32u - ZSB_HUF_PAIR_BITS)]; W <<= (c_ >> 24)
+#define HUF_PUT(c_, h_) do { \
+        const uint32_t lg = (c_ >> 17) & 8u, lb = (h_ >> 18) & lg; \
+        const uint32_t sy = (c_ >> lb) & (0xFFFFu >> lg); \
+        pend |= (uint64_t)sy << np8; np8 += (c_ >> 18) & 0x18u; } while (0)
+#define HUF_FLUSH() do { if (np8 >= 32u) { *reinterpret_cast<uint32_t *>(out + n) = (uint32_t)pend; pend >>= 32; n += 4; np8 -= 32u; } } while (0)
+#define HUF_WINDOW(NEXT) do { \
+        uint64_t W = fast_win_get(F); \
+        HUF_LOOKUP(c0, h0); HUF_LOOKUP(c1, h1); HUF_LOOKUP(c2, h2); HUF_LOOKUP(c3, h3); HUF_LOOKUP(c4, h4); \
+        top -= (int32_t)((c0 >> 24) + (c1 >> 24) + (c2 >> 24) + (c3 >> 24) + (c4 >> 24)); \
+        NEXT; \
+        HUF_PUT(c0, h0); HUF_PUT(c1, h1); HUF_FLUSH(); HUF_PUT(c2, h2); HUF_PUT(c3, h3); HUF_FLUSH(); HUF_PUT(c4, h4); HUF_FLUSH(); } while (0)
     // single symbols until the output is 4-byte aligned
-    while (n < expect && (((uintptr_t)(out + n)) & 3)) {
-        HUF_LOAD(top);
-        const uint32_t cell = lut[(uint32_t)(fast_win_get(F) >> sh)];
-        out[n++] = (uint8_t)cell; top -= (int32_t)(cell >> 8);
-    }
+    while (n < expect && (((uintptr_t)(out + n)) & 3)) HUF_ONE();
+    uint64_t pend = 0; uint32_t np8 = 0;
 #if defined(__CUDA_ARCH__)
-    // eight steps of four symbols consume at most 352 bits, less than a 64-byte line: the ring is topped up once per eight
-    // steps, by all lanes of the warp in the same pass
-    for (; n + 32 <= expect; n += 32) {
+    // eight windows of five cells consume at most 440 bits, less than a 64-byte line: the ring is topped up once per eight
+    // windows, by all lanes of the warp in the same pass
+    while (n + (np8 >> 3) + 80 <= expect) {
         sr_check<6>(R, top);
-#pragma unroll 2
-        for (uint32_t k = 0; k < 32; k += 4) {
-            sr_load_nocheck<6>(R, F, top);
-            uint64_t W = fast_win_get(F);
-            const uint32_t c0 = lut[(uint32_t)(W >> sh)]; W <<= (c0 >> 8);
-            const uint32_t c1 = lut[(uint32_t)(W >> sh)]; W <<= (c1 >> 8);
-            const uint32_t c2 = lut[(uint32_t)(W >> sh)]; W <<= (c2 >> 8);
-            const uint32_t c3 = lut[(uint32_t)(W >> sh)];
-            top -= (int32_t)((c0 >> 8) + (c1 >> 8) + (c2 >> 8) + (c3 >> 8));
-            *reinterpret_cast<uint32_t *>(out + n + k) = (c0 & 0xFFu) | (c1 & 0xFFu) << 8 | (c2 & 0xFFu) << 16 | c3 << 24;
-        }
+        sr_load_nocheck<6>(R, F, top);
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) HUF_WINDOW(if (k < 7) sr_load_nocheck<6>(R, F, top));
     }
 #endif
-    for (; n + 4 <= expect; n += 4) {
+    while (n + (np8 >> 3) + 10 <= expect) {
         HUF_LOAD(top);
-        uint64_t W = fast_win_get(F);
-        const uint32_t c0 = lut[(uint32_t)(W >> sh)]; W <<= (c0 >> 8);
-        const uint32_t c1 = lut[(uint32_t)(W >> sh)]; W <<= (c1 >> 8);
-        const uint32_t c2 = lut[(uint32_t)(W >> sh)]; W <<= (c2 >> 8);
-        const uint32_t c3 = lut[(uint32_t)(W >> sh)];
-        top -= (int32_t)((c0 >> 8) + (c1 >> 8) + (c2 >> 8) + (c3 >> 8));
-        *reinterpret_cast<uint32_t *>(out + n) = (c0 & 0xFFu) | (c1 & 0xFFu) << 8 | (c2 & 0xFFu) << 16 | c3 << 24;
+        HUF_WINDOW((void)0);
     }
-    while (n < expect) {
-        HUF_LOAD(top);
-        const uint32_t cell = lut[(uint32_t)(fast_win_get(F) >> sh)];
-        out[n++] = (uint8_t)cell; top -= (int32_t)(cell >> 8);
-    }
+    while (np8) { out[n++] = (uint8_t)pend; pend >>= 8; np8 -= 8u; }
+    while (n < expect) HUF_ONE();
 #undef HUF_LOAD
+#undef HUF_ONE
+#undef HUF_LOOKUP
+#undef HUF_PUT
+#undef HUF_FLUSH
+#undef HUF_WINDOW
     return top == startbit ? ZSB_OK : ZSB_NEEDS_SLOW;
 }

@@ -234,17 +234,21 @@ __global__ void __launch_bounds__(1024) k_plan1(const zsb_frame *__restrict__ fr
 }
 
 // ======================================================================================= k_huf
-// Half a warp per CTA, 4 blocks per CTA: lane = 4 * slot + stream.  Per slot: LUT (4 KiB, aliased with the
-// weight FSE table while the weights are being decoded), weights, counts, ranks.  Per lane: a 256-byte ring
-// through which cp.async feeds its stream (zsb_stream.h).  The decode is one dependent chain per stream (LUT cell ->
-// code length -> next LUT index), so like k_seq the kernel is bound by the latency of that chain.
-#define HUF_SLOTS 4
+// Half a warp per CTA, 4 blocks per CTA: lane = 4 * slot + stream.  Per slot: the two-symbol table (4 KiB: 1 024 cells indexed by the next ten
+// bits of the stream, zsb_huf.h; aliased with the weight FSE table while the weights are being decoded), weights, counts, ranks.  Per lane: a
+// 256-byte ring through which cp.async feeds its stream (zsb_stream.h); before the streams start, the slot's four rings hold T1, the first
+// symbol under every 10-bit prefix, from which the four lanes build the table.  The decode is one dependent chain per stream (cell -> bits
+// consumed -> next cell), so like k_seq the kernel is bound by the latency of that chain: two symbols per cell where ten bits hold two codes
+// is what shortens it.  A stream the fast decode refuses and a block decoded the reference's way (quirks) need the one-symbol table of
+// 2 048 16-bit cells: it is laid out over the two-symbol table once the slot's fast streams are through.
+#define HUF_SLOTS 8
 #define HUF_THREADS (4 * HUF_SLOTS)
 #define HUF_MASK (HUF_THREADS == 32 ? 0xFFFFFFFFu : ((1u << HUF_THREADS) - 1u))
 #define HUF_LUT_BYTES (2u << ZSB_HUF_MAX_BITS)   // 4096
 struct __align__(16) HufSlot {
-    union { uint16_t lut[1 << ZSB_HUF_MAX_BITS]; uint32_t ftbl[512]; } u;
+    union { uint16_t lut[1 << ZSB_HUF_MAX_BITS]; uint32_t pair[1 << ZSB_HUF_PAIR_BITS]; uint32_t ftbl[512]; } u;
     uint8_t weights[260];
+    uint8_t odd[128];   // maxbits 11: the odd child under a 10-bit prefix of two 11-bit codes (huf_t1_put)
     uint16_t at[256];   // first LUT cell of every symbol (HUF_NO_ROOM: none); the four lanes of the slot fill the LUT from it
     int16_t cnt[ZSB_HUF_WEIGHT_SYMS];
     uint32_t rank[16];
@@ -252,8 +256,12 @@ struct __align__(16) HufSlot {
     int status;
     int n, loose;       // symbols with the implied one; the LUT starts out as ZSB_HUF_ABSENT (huf_lut_plan)
     int incomplete;     // ZSB_REFERENCE_QUIRKS: the reference's tree for these weights is not a complete code (huf_build_lut)
+    uint32_t stagger[4]; // the size is 16 mod 128: the same field of the eight slots of a CTA lies in eight different groups of four banks (the slots'
+                        // serial set-up loops run side by side in one warp and would otherwise collide on every access: measured 8-way)
 };
+static_assert(sizeof(HufSlot) % 128 == 16, "HufSlot: slots must be staggered over the shared-memory banks");
 #define HUF_NO_ROOM 0xFFFFu
+#define HUF_SMEM_BYTES (HUF_THREADS * 256 + HUF_SLOTS * sizeof(HufSlot))
 // `len` cells from lut[at] on: 16-byte stores where the alignment allows
 __device__ __forceinline__ void huf_fill(uint16_t *lut, uint32_t at, uint32_t len, uint32_t cell) {
     uint32_t a = at; const uint32_t e = at + len;
@@ -283,7 +291,7 @@ __device__ __noinline__ int huf_block_ref_device(const uint8_t *src, uint64_t sr
 }
 
 #ifdef ZSB_SEQ_TIMING
-__device__ long long g_huf_timing[1024][4];     // per CTA: start, tables built, streams decoded
+__device__ long long g_huf_timing[1024][8];     // per CTA: 0 start, 3 weights read, 4 planned, 5 cell starts known, 6 T1 filled, 1 tables built, 2 streams decoded
 extern "C" int zsb_debug_huf_timing(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_huf_timing, sizeof g_huf_timing); }
 #define HUF_T(i) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_huf_timing[blockIdx.x][i] = clock64(); } while (0)
 #else
@@ -292,8 +300,9 @@ extern "C" int zsb_debug_huf_timing(long long *out) { return (int)cudaMemcpyFrom
 __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__ src, uint64_t src_len, ZsbBlockWork *work,
                                             const uint32_t *__restrict__ huf_list, ZsbCounters *cnt,
                                             uint8_t *lit_pool, uint64_t lit_cap, uint64_t over_cap, uint32_t flags) {
-    __shared__ HufSlot slots[HUF_SLOTS];
-    __shared__ __align__(128) uint8_t rings[HUF_THREADS][256];
+    extern __shared__ __align__(128) uint8_t huf_smem[];                        // HUF_SMEM_BYTES: the rings, then the slots
+    uint8_t (*rings)[256] = reinterpret_cast<uint8_t (*)[256]>(huf_smem);
+    HufSlot *slots = reinterpret_cast<HufSlot *>(huf_smem + HUF_THREADS * 256);
     if (cnt->overflow) return;
     const bool quirks = (flags & ZSB_REFERENCE_QUIRKS) != 0;
     const uint32_t lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
@@ -314,6 +323,7 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__
         HufPlan P; P.mb = 0; P.n = 0; P.loose = false;
         bool inc = false;
         if (!rc) rc = huf_lut_plan(S.weights, 1, nw, S.rank, 1, P, quirks, &inc);
+        HUF_T(4);
         if (!rc) {
             for (int i = 0; i < P.n; i++) {                            // where every symbol's cells start: the classes fill up in symbol order
                 const uint32_t wt = S.weights[i];
@@ -329,7 +339,64 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__
         S.maxbits = P.mb; S.n = P.n; S.loose = P.loose ? 1 : 0; S.status = rc; S.incomplete = inc ? 1 : 0;
     }
     __syncwarp(HUF_MASK);
-    if (active && !S.status) {
+    HUF_T(5);
+    // the two-symbol table of a complete code: T1 in the slot's four rings (1 KiB, contiguous), then the cells
+    uint8_t *t1 = rings[4 * slot];
+    const bool pairs = active && !S.status && !S.incomplete;
+    if (pairs) {
+        for (int i = (int)stream; i < S.n; i += 4) {
+            const uint32_t wt = S.weights[i];
+            if (wt) huf_t1_put(t1, S.odd, S.maxbits, (uint32_t)i, S.at[i], wt);
+        }
+    }
+    __syncwarp(HUF_MASK);
+    HUF_T(6);
+    if (pairs) {
+        for (uint32_t x0 = stream + 4 * slot; x0 < (1u << ZSB_HUF_PAIR_BITS) + 4 * slot; x0 += 32) {      // four dependent loads per cell: eight cells side by side, stored
+            uint32_t cell[8];                                                                                 // together; the slots start at different words of T1 (bank-aligned)
+#pragma unroll
+            for (int k = 0; k < 8; k++) cell[k] = huf_pair_cell((x0 + 4 * k) & ((1u << ZSB_HUF_PAIR_BITS) - 1u), t1, S.odd, S.weights, 1, S.maxbits);
+#pragma unroll
+            for (int k = 0; k < 8; k++) S.u.pair[(x0 + 4 * k) & ((1u << ZSB_HUF_PAIR_BITS) - 1u)] = cell[k];
+        }
+    }
+    __syncwarp(HUF_MASK);
+    HUF_T(1);
+    int rc = 0;
+    bool inexact = false;                       // ZSB_REFERENCE_QUIRKS: this block's literals are decoded the reference's way
+    bool slow = false;                          // this stream goes through huf_decode_stream
+    uint32_t expect = 0, ooff = 0; uint64_t start = 0;
+    if (active) {
+        rc = S.status;
+        const ZsbBlockWork &w = work[bi];
+        if (!rc && quirks && (w.lit_inexact || S.incomplete)) inexact = true;
+        else if (!rc && stream < w.n_streams) {
+            const uint32_t regen = w.lit_regen;
+            start = w.lit_src;
+            if (w.n_streams == 1) { expect = regen; ooff = 0; }
+            else {
+                const uint32_t seg = (regen + 3) / 4; ooff = stream * seg; expect = stream < 3 ? seg : regen - 3 * seg;
+                for (uint32_t k = 0; k < stream; k++) start += w.stream_size[k];
+            }
+            rc = pairs ? huf_fast_stream(src, start, start + w.stream_size[stream], S.u.pair, lit_pool + w.lit_buf + ooff, expect,
+                                         (uint32_t)__cvta_generic_to_shared(rings[lane]))
+                       : ZSB_NEEDS_SLOW;
+            if (rc == ZSB_NEEDS_SLOW) {
+                rc = ZSB_OK;
+                if (quirks) inexact = true;      // not the shape Regenerated_Size promises: the reference does not care (literals.rs:55)
+                else slow = true;
+            }
+        }
+    }
+    __syncwarp(HUF_MASK);
+    HUF_T(2);
+    const uint32_t q0 = lane & ~3u;
+    const bool blk_inexact = __shfl_sync(HUF_MASK, (int)inexact, q0) || __shfl_sync(HUF_MASK, (int)inexact, q0 + 1) || __shfl_sync(HUF_MASK, (int)inexact, q0 + 2) ||
+                             __shfl_sync(HUF_MASK, (int)inexact, q0 + 3);
+    const bool blk_slow = __shfl_sync(HUF_MASK, (int)slow, q0) || __shfl_sync(HUF_MASK, (int)slow, q0 + 1) || __shfl_sync(HUF_MASK, (int)slow, q0 + 2) ||
+                          __shfl_sync(HUF_MASK, (int)slow, q0 + 3);
+    // (rare) the one-symbol table == huf_build_lut (zsb_huf.h), laid out by the four lanes of the slot over the two-symbol table
+    if ((blk_inexact || blk_slow) && active && !S.status) {
         const int mb = S.maxbits;
         if (S.loose) {
             for (uint32_t k = 8 * stream; k < (1u << mb); k += 32) {
@@ -339,7 +406,7 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__
         }
     }
     __syncwarp(HUF_MASK);
-    if (active && !S.status) {
+    if ((blk_inexact || blk_slow) && active && !S.status) {
         const int mb = S.maxbits;
         for (int i = (int)stream; i < S.n; i += 4) {
             const uint32_t at = S.at[i];
@@ -349,34 +416,7 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huf(const uint8_t *__restrict__
         }
     }
     __syncwarp(HUF_MASK);
-    HUF_T(1);
-    int rc = 0;
-    bool inexact = false;                       // ZSB_REFERENCE_QUIRKS: this block's literals are decoded the reference's way
-    if (active) {
-        rc = S.status;
-        const ZsbBlockWork &w = work[bi];
-        if (!rc && quirks && (w.lit_inexact || S.incomplete)) inexact = true;
-        else if (!rc && stream < w.n_streams) {
-            const uint32_t regen = w.lit_regen;
-            uint32_t seg, expect, ooff; uint64_t start = w.lit_src;
-            if (w.n_streams == 1) { expect = regen; ooff = 0; }
-            else {
-                seg = (regen + 3) / 4; ooff = stream * seg; expect = stream < 3 ? seg : regen - 3 * seg;
-                for (uint32_t k = 0; k < stream; k++) start += w.stream_size[k];
-            }
-            rc = huf_fast_stream(src, start, start + w.stream_size[stream], S.u.lut, S.maxbits, lit_pool + w.lit_buf + ooff, expect,
-                                 (uint32_t)__cvta_generic_to_shared(rings[lane]));
-            if (rc == ZSB_NEEDS_SLOW) {
-                if (quirks) { inexact = true; rc = ZSB_OK; }     // not the shape Regenerated_Size promises: the reference does not care (literals.rs:55)
-                else rc = huf_decode_stream(src, start, start + w.stream_size[stream], src_len, S.u.lut, S.maxbits, lit_pool + w.lit_buf + ooff, expect);
-            }
-        }
-    }
-    __syncwarp(HUF_MASK);
-    HUF_T(2);
-    const uint32_t q0 = lane & ~3u;
-    const bool blk_inexact = __shfl_sync(HUF_MASK, (int)inexact, q0) || __shfl_sync(HUF_MASK, (int)inexact, q0 + 1) || __shfl_sync(HUF_MASK, (int)inexact, q0 + 2) ||
-                             __shfl_sync(HUF_MASK, (int)inexact, q0 + 3);
+    if (slow) rc = huf_decode_stream(src, start, start + work[bi].stream_size[stream], src_len, S.u.lut, S.maxbits, lit_pool + work[bi].lit_buf + ooff, expect);
     if (blk_inexact && active && stream == 0 && !S.status) {
         rc = huf_block_ref_device(src, src_len, work[bi], S.u.lut, S.maxbits, cnt, lit_pool, lit_cap, over_cap);
     }
@@ -2477,6 +2517,8 @@ void zsbk_publish(cudaStream_t st, void *host_dev_ptr, const ZsbCounters *cnt, c
 cudaError_t zsbk_init() {
     cudaError_t e = set_smem((const void *)k_seq_slow, SEQ_SLOW_SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    e = set_smem((const void *)k_huf, HUF_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     e = set_smem((const void *)k_seq_t<SEQ_HELPERS, SEQ_WIN, 2, false>, SEQ_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     e = set_smem((const void *)k_seq_t<SEQX_WARPS, SEQX_WIN, SEQX_NBUF, true>, SEQX_SMEM_BYTES);
@@ -2494,7 +2536,7 @@ void zsbk_plan1(cudaStream_t st, const zsb_frame *frames, uint32_t nf, const zsb
 }
 void zsbk_huf(cudaStream_t st, uint32_t ncomp, const uint8_t *src, uint64_t src_len, ZsbBlockWork *work, const uint32_t *huf_list,
               ZsbCounters *cnt, uint8_t *lit_pool, uint64_t lit_cap, uint64_t over_cap, uint32_t flags) {
-    if (ncomp) k_huf<<<(ncomp + HUF_SLOTS - 1) / HUF_SLOTS, HUF_THREADS, 0, st>>>(src, src_len, work, huf_list, cnt, lit_pool, lit_cap, over_cap, flags);
+    if (ncomp) k_huf<<<(ncomp + HUF_SLOTS - 1) / HUF_SLOTS, HUF_THREADS, HUF_SMEM_BYTES, st>>>(src, src_len, work, huf_list, cnt, lit_pool, lit_cap, over_cap, flags);
 }
 void zsbk_seq(cudaStream_t st, uint32_t ncomp, const uint8_t *src, ZsbBlockWork *work, const uint32_t *seq_list, ZsbCounters *cnt,
               uint64_t *seq_pool, uint32_t *slow_list, bool shared_device, uint32_t chains_hint, const zsb_frame *frames, const zsb_block *blocks,
