@@ -26,7 +26,17 @@ def tour(dec, tag):
         for _ in range(6):
             d = corpora.mutate(rnd, src)
             dec.decode(d, Q | VER); n += 1
-    print(tag, n, "decodes")
+    # the walk on the device (zsb_scan_device) on the same inputs, truncations and mutations
+    import torch
+    for d in [corpora.fixture(x) for x in corpora.FIXTURE_NAMES] + [corpora.c4()[0], corpora.c2_small(64)[0][:300_000], b"", b"abc", bytes(range(256))] + \
+             [corpora.mutate(rnd, src) for src in list(corpora.mutation_sources().values())[:4] for _ in range(4)]:
+        for cut in (len(d), len(d) // 2, max(len(d) - 3, 0)):
+            t = torch.zeros(cut + 256, dtype=torch.uint8, device="cuda:0")
+            if cut: t[:cut] = torch.frombuffer(bytearray(d[:cut]), dtype=torch.uint8).to("cuda:0")
+            torch.cuda.synchronize()
+            ds = Z.DeviceScan(dec.ctx, t.data_ptr(), cut, Q); hs = Z.Scan(d[:cut], Q)
+            assert (ds.status, ds.n_frames, ds.n_blocks, ds.err_a, ds.err_b) == (hs.status, hs.n_frames, hs.n_blocks, hs.err_a, hs.err_b); n += 1
+    print(tag, n, "decodes and walks")
 
 
 tour(Z.Decoder(Z.Context(0)), "default")
