@@ -83,6 +83,35 @@ int emul_huf_parse(const uint8_t *desc, size_t n, uint8_t *lens, uint16_t *lut, 
     return rc;
 }
 
+// k_huf's two tables from one set of weights (nw weights, the last one implied): the one-symbol table (2^maxbits cells) and the two-symbol
+// table (1 024 cells) built the way the kernel builds it -- T1 and `odd` filled symbol by symbol from the cell starts (huf_t1_put), then
+// huf_pair_cell -- and, in pair_b, the same table derived from the finished one-symbol table (huf_pairs_from_lut).
+int emul_huf_pairs(const uint8_t *weights_in, int nw, uint16_t *lut, uint32_t *pair_a, uint32_t *pair_b, int *maxbits) {
+    uint8_t weights[260] = {0}; uint32_t rank[16]; uint16_t at[256];
+    memcpy(weights, weights_in, (size_t)nw);
+    HufPlan P; bool inc = false;
+    int rc = huf_lut_plan(weights, 1, nw, rank, 1, P, false, &inc);
+    if (rc) return rc;
+    if (inc) return ZSB_E_CORRUPT;
+    for (int i = 0; i < P.n; i++) {                                        // the cell starts, as in k_huf
+        const uint32_t wt = weights[i];
+        at[i] = 0xFFFF;
+        if (wt) { at[i] = (uint16_t)rank[wt]; rank[wt] += 1u << (wt - 1); }
+    }
+    static uint8_t t1[1 << ZSB_HUF_PAIR_BITS], odd[512];
+    memset(t1, 0xEE, sizeof t1); memset(odd, 0xEE, sizeof odd);
+    for (int i = 0; i < P.n; i++) if (weights[i]) huf_t1_put(t1, odd, P.mb, (uint32_t)i, at[i], weights[i]);
+    for (uint32_t x = 0; x < (1u << ZSB_HUF_PAIR_BITS); x++) pair_a[x] = huf_pair_cell(x, t1, odd, weights, 1, P.mb);
+    uint8_t w2[260] = {0}; memcpy(w2, weights_in, (size_t)nw);
+    int mb = 0;
+    rc = huf_build_lut(w2, 1, nw, lut, rank, 1, mb, nullptr);
+    if (rc) return rc;
+    static uint8_t t1b[1 << ZSB_HUF_PAIR_BITS], oddb[512];
+    huf_pairs_from_lut(lut, mb, w2, 1, t1b, oddb, pair_b);
+    *maxbits = mb;
+    return mb == P.mb ? ZSB_OK : ZSB_E_CORRUPT;
+}
+
 // Whole pipeline, serially: scan -> parse -> chain -> huffman -> sequences -> plan -> execute.
 // out/out_cap: output buffer; per-frame arrays sized n_frames as reported by zsb_scan.
 // Intermediates of the LAST compressed block that ran are exported for stage-level diffs when the

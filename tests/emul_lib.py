@@ -80,3 +80,14 @@ def huf_stats():
     v = [C.c_long() for _ in range(4)]
     lib().emul_huf_stats(*[C.byref(x) for x in v])
     return tuple(x.value for x in v)
+
+
+def huf_pairs(weights):
+    """-> (rc, maxbits, one-symbol table [(symbol, bits)] of 2^maxbits cells, two-symbol table built as k_huf builds it, the same derived from the
+    one-symbol table) for `weights` (the implied last weight not included)"""
+    L = lib()
+    w = (C.c_uint8 * len(weights))(*weights)
+    lut = (C.c_uint16 * 2048)(); pa = (C.c_uint32 * 1024)(); pb = (C.c_uint32 * 1024)(); mb = C.c_int()
+    L.emul_huf_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    rc = L.emul_huf_pairs(w, len(weights), lut, pa, pb, C.byref(mb))
+    return rc, mb.value, [(v & 0xFF, v >> 8) for v in lut[:1 << mb.value]] if rc == 0 else [], list(pa), list(pb)

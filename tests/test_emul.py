@@ -252,3 +252,53 @@ def test_round1_fuzz_findings_on_the_cpu_build():
         st = [f[0] for f in frames]
         got = (next((s for s in st[:max(len(st) - 1, 0)] if s), 0) or rc) if rc else next((s for s in st if s), 0)
         assert got == (oerr.code if oerr is not None else 0), name
+
+
+def test_two_symbol_huffman_table_equals_single_lookups():
+    """k_huf's table of two symbols per cell (zsb_huf.h): for random complete codes, every cell gives exactly what one-symbol lookups give --
+    the first code under the ten bits, the second one if it fits in what is left, both children where the ten bits are the prefix of two
+    11-bit codes -- and the table built from the cell starts (as the kernel does) equals the one derived from the finished one-symbol table"""
+    r = random.Random(11)
+    n_long = n_two = n_codes = 0
+    for trial in range(300):
+        mb = r.choice([4, 6, 8, 9, 10, 11, 11, 11])
+        # a random complete code: split leaves of a full binary tree until there are enough symbols
+        lens = [1, 1]
+        want = r.randrange(2, min(120, 1 << mb) + 1)
+        while len(lens) < want:
+            open_ = [i for i, l in enumerate(lens) if l < mb]
+            if not open_: break
+            l = lens.pop(r.choice(open_)); lens += [l + 1, l + 1]
+        if max(lens) != mb: continue
+        syms = r.sample(range(256), len(lens))
+        wts = [0] * (max(syms) + 1)
+        for s_, l in zip(syms, lens): wts[s_] = mb + 1 - l
+        # the last non-zero weight is implied (the description carries all but the last symbol)
+        last = max(syms)
+        rc, got_mb, lut, pa, pb = E.huf_pairs(wts[:last])
+        assert rc == 0 and got_mb == mb, (trial, rc, got_mb, mb)
+        assert pa == pb, trial
+        n_codes += 1
+
+        def one(bits, nbits):                    # one-symbol lookup on the top bits of a `nbits`-bit value, zero padded
+            idx = (bits << mb >> nbits) if nbits <= mb else bits >> (nbits - mb)
+            return lut[idx & ((1 << mb) - 1)]
+        for x in range(1024):
+            c = pa[x]
+            s1, s2, l1, lng, cnt, lt = c & 0xFF, (c >> 8) & 0xFF, (c >> 16) & 15, (c >> 20) & 1, (c >> 21) & 3, c >> 24
+            a_sym, a_len = one(x, 10)
+            if a_len > 10:                       # ten bits do not determine the code: both 11-bit children
+                assert mb == 11 and lng == 1 and cnt == 1 and l1 == 11 and lt == 11
+                assert (s1, 11) == lut[2 * x] and (s2, 11) == lut[2 * x + 1]
+                n_long += 1
+                continue
+            assert lng == 0 and s1 == a_sym and l1 == a_len
+            rest_bits = 10 - a_len
+            rest = x & ((1 << rest_bits) - 1)
+            b_sym, b_len = one(rest, rest_bits) if rest_bits else (0, 99)
+            if rest_bits and b_len <= rest_bits:
+                assert cnt == 2 and s2 == b_sym and lt == a_len + b_len
+                n_two += 1
+            else:
+                assert cnt == 1 and s2 == 0 and lt == a_len
+    assert n_codes > 100 and n_long > 200 and n_two > 10000
