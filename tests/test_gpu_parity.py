@@ -136,6 +136,22 @@ def test_scan_decode_of_a_device_resident_buffer(dec):
     assert sd.status == 0 and sd.first_error() is None and sd.n_frames == 514 and sd.total == len(exp)
     assert all(sd.results[i].checksum_ok for i in range(512))
     assert bytes(dst[:sd.total].cpu().numpy()) == exp
+    # the same buffer with a host destination, and malformed variants (a frame that fails to decode in the middle, a truncated tail, trailing
+    # garbage): statuses, payloads, placement and bytes equal those of the host path (zsb_scan + zsb_decode on host buffers)
+    import ctypes as C
+    bad = bytearray(blob); bad[len(blob) // 2] ^= 0x5A
+    for name, b in (("intact", blob), ("flipped byte", bytes(bad)), ("truncated", blob[:len(blob) - 7]), ("garbage behind", blob + b"\x01\x02\x03\x04\x05")):
+        fl = Q | VER
+        want_out, hsc, hres = dec.decode(b, fl)
+        d = torch.cat([torch.frombuffer(bytearray(b), dtype=torch.uint8).to("cuda:0"), torch.zeros(256, dtype=torch.uint8, device="cuda:0")])
+        cap = max(Z.capacity_bound(hsc, fl), 1)
+        out = C.create_string_buffer(cap)
+        torch.cuda.synchronize()
+        sd = Z.ScanDecode(dec.ctx, (d.data_ptr(), len(b)), (C.addressof(out), cap), fl | Z.SRC_ON_DEVICE)
+        assert (sd.status, sd.err_a, sd.err_b, sd.n_frames, sd.n_blocks) == (hsc.status, hsc.err_a, hsc.err_b, hsc.n_frames, hsc.n_blocks), name
+        assert [sd.results[i].status for i in range(sd.n_frames)] == [hres.status[i] for i in range(hsc.n_frames)], name
+        assert [(sd.results[i].dst_off, sd.results[i].dst_len) for i in range(sd.n_frames)] == [(hres.dst_off[i], hres.dst_len[i]) for i in range(hsc.n_frames)], name
+        assert sd.total == hres.total.value and out.raw[:sd.total] == want_out, name
 
 
 # ---------------------------------------------------------------- stage level (mirrors the reference's tests)
