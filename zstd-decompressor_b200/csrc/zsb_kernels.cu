@@ -1851,9 +1851,12 @@ __device__ __forceinline__ void ex2_batch(Ex2State &X, const Ex2Lit &L, uint64_t
                     }
                     __syncwarp();
                 }
-                // ---- whole 16-byte units of the batch go to HBM
+                // ---- whole 16-byte units go to HBM -- not after every batch: a batch of text regenerates ~270 bytes, 17 units for 32 lanes, and the
+                // bookkeeping costs the same for 17 as for 128.  Bytes may stay in the ring as long as the next batch still fits behind them
+                // (it regenerates at most GIANT bytes, and everything below ring_lo = B1 - RING must be in HBM): the ring is flushed when more than
+                // RING - GIANT bytes are pending, and at the end of a block.
                 const int32_t hi = (int32_t)B1 - (int32_t)((X.g0 + B1) & 15u);
-                if (hi > X.flushed) {
+                if (hi > X.flushed && (!has_next || (int32_t)B1 - X.flushed > (int32_t)(RING - GIANT))) {
                     if (((X.g0 + (uint32_t)X.flushed) & 15u) == 0) {           // the usual case: whole 16-byte units only, at most a few per lane
                         for (int32_t p = X.flushed + 16 * (int32_t)lane; p < hi; p += 512)
                             *reinterpret_cast<uint4 *>(X.gblk + p) = *reinterpret_cast<const uint4 *>(X.ring + ((X.g0 + (uint32_t)p) & (RING - 1u)));
