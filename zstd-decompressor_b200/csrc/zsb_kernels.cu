@@ -1745,7 +1745,9 @@ __device__ __forceinline__ void ex2_batch(Ex2State &X, const Ex2Lit &L, uint64_t
                 const uint32_t ll = lit_end - p_lit;
                 uint32_t ml = out_end - p_out - ll;
                                 const uint32_t dstm = p_out + ll;
-                if (is_seq && (off == 0 || (uint64_t)off > P0 + dstm)) { X.err = ZSB_E_IMPOSSIBLE_VALUE; ml = 0; }    // decoding_context.rs:86-90
+                // decoding_context.rs:86-90; in 32 bits: the frames this executor takes are far below 2 GiB, beyond that every 31-bit offset has its source
+                const uint32_t P0s = P0 > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)P0;
+                if (is_seq && (off == 0 || off > P0s + dstm)) { X.err = ZSB_E_IMPOSSIBLE_VALUE; ml = 0; }
                 const int32_t srcp = (int32_t)dstm - (int32_t)off;
                 const uint32_t B0 = __shfl_sync(FULL, p_out, 0), B1 = X.c_out;
                 if (B1 - B0 > GIANT) {
@@ -1986,11 +1988,12 @@ __global__ void __launch_bounds__(32 * EX2_WARPS, 7) k_exec2(const uint8_t *__re
             X.c_out = 0; X.c_lit = 0; X.lr_has = false;
             // records are requested two batches ahead: the batch after this one is looked at early (its literals are prefetched)
             uint64_t rec_next = lane < nseq ? __ldg(seqs + lane) : 0ull, rec_next2 = lane + 32 < nseq ? __ldg(seqs + lane + 32) : 0ull;
-            for (uint32_t b0 = 0; b0 < items; b0 += 32) {
+            const uint64_t *rec_ahead = seqs + lane + 64;
+            for (uint32_t b0 = 0; b0 < items; b0 += 32, rec_ahead += 32) {
                 const uint32_t i = b0 + lane;
                 const uint64_t rec = rec_next;
                 rec_next = rec_next2;
-                if (i + 64 < nseq) rec_next2 = __ldg(seqs + i + 64);
+                if (i + 64 < nseq) rec_next2 = __ldg(rec_ahead);
                 const bool is_seq = i < nseq;
                 const uint32_t out_end = is_seq ? (uint32_t)rec & ZSB_REC_POS_MASK : out_size;
                 const uint32_t lit_end = is_seq ? (uint32_t)(rec >> ZSB_REC_POS_BITS) & ZSB_REC_POS_MASK : regen;
