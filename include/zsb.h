@@ -187,8 +187,8 @@ int zsb_scan_decode(zsb_ctx *ctx, const uint8_t *src, size_t n, uint8_t *dst, si
                     zsb_frame **frames, size_t *n_frames, zsb_block **blocks, size_t *n_blocks,
                     zsb_result **results, uint64_t *dst_total, uint64_t *err_a, uint64_t *err_b);
 
-/* zsb_scan for compressed bytes that are resident in HBM (d_src: device pointer on the context's device, readable up to the next
- * 128-byte boundary behind d_src + n): the walk itself runs on the GPU.  == ForwardByteParser::iter + Frame::parse like zsb_scan
+/* zsb_scan for compressed bytes that are resident in HBM (d_src: device pointer on the context's device, readable from the 16-byte
+ * boundary at or below d_src up to the next 128-byte boundary behind d_src + n -- any cudaMalloc'd buffer or sub-range of one is): the walk itself runs on the GPU.  == ForwardByteParser::iter + Frame::parse like zsb_scan
  * (parsing.rs:29-112, frame.rs:61-230, block.rs:43-72), but "each header says where the next one starts" is not followed as one
  * dependent chain: every frame magic in the buffer is a candidate start, a lane per candidate walks its frame, pointer doubling over
  * the successor lists orders the chain that begins at offset 0 (csrc/zsb_dscan.cu).  Same descriptor arrays (host memory, zsb_free),

@@ -45,7 +45,7 @@ struct zsb_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_huf[kProfRing][2] = {};
     DevBuf src, frames, blocks, work, fout, huf_list, seq_list, rawrle_list, exec_list, exec2_list, xxh_list, lit_pool, seq_pool, slow_list, counters, dst, stage, pre_off, wave;
-    DevBuf dscan, dscan_blocks;                                    // zsb_scan_device: candidates, hash table, jump tables / block descriptors
+    DevBuf dscan, dscan_blocks, dscan_pos;                                  // zsb_scan_device: candidates, hash table, jump tables / block descriptors
     DevBuf link_ent, link_meta;                                    // k_link: one 32-bit entry per output byte of the listed frames; frame list, block list, tickets
     std::vector<uint64_t> h_link_meta;                             // host image of link_meta (frames: 2 words each, then blocks: 1 word each, then tickets)
     uint32_t n_link = 0, n_link_blocks = 0;                        // frames / blocks executed by k_link_init + k_link_resolve
@@ -131,7 +131,7 @@ extern "C" void zsb_ctx_destroy(zsb_ctx *c) {
     c->subs.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list, &c->exec2_list, &c->pre_off, &c->wave, &c->link_ent, &c->link_meta, &c->dscan, &c->dscan_blocks,
+    DevBuf *all[] = {&c->src, &c->frames, &c->blocks, &c->work, &c->fout, &c->huf_list, &c->seq_list, &c->rawrle_list, &c->exec_list, &c->exec2_list, &c->pre_off, &c->wave, &c->link_ent, &c->link_meta, &c->dscan, &c->dscan_blocks, &c->dscan_pos,
                      &c->xxh_list, &c->lit_pool, &c->seq_pool, &c->slow_list, &c->counters, &c->dst, &c->stage};
     for (DevBuf *b : all) b->release();
     for (int r = 0; r < kProfRing; r++) for (int i = 0; i <= kMaxKernels; i++) if (c->ev[r][i]) cudaEventDestroy(c->ev[r][i]);
@@ -840,13 +840,24 @@ extern "C" int zsb_scan_device(zsb_ctx *c, const uint8_t *d_src, size_t n, uint3
     };
 
     if (n >= 4) {
-        CK(c, c->dscan.ensure(256));
-        unsigned long long *d_count = (unsigned long long *)c->dscan.p;       // the arena's first 256 bytes
+        // one pass finds the candidates when there are no more than a guess allows (one per 2 KiB of input, at least 65 536); a buffer with more
+        // of them is searched again with room for all
+        uint64_t pos_cap = n / 2048 > 65536 ? n / 2048 : 65536;
+        CK(c, c->dscan_pos.ensure(256 + 8 * pos_cap));
+        unsigned long long *d_count = (unsigned long long *)c->dscan_pos.p;   // the first 256 bytes of the position list
+        uint64_t *d_pos = (uint64_t *)((uint8_t *)c->dscan_pos.p + 256);
         unsigned long long count = 0;
         CK(c, cudaMemsetAsync(d_count, 0, 8, st));
-        zsbk_dscan_find(st, d_src, n, d_count, nullptr, 0, c->n_sm);
+        zsbk_dscan_find(st, d_src, n, d_count, d_pos, pos_cap, c->n_sm);
         CK(c, cudaMemcpyAsync(&count, d_count, 8, cudaMemcpyDeviceToHost, st));
         CK(c, cudaStreamSynchronize(st));
+        if (count > pos_cap && count <= kMaxCand) {
+            pos_cap = count;
+            CK(c, c->dscan_pos.ensure(256 + 8 * pos_cap));
+            d_count = (unsigned long long *)c->dscan_pos.p; d_pos = (uint64_t *)((uint8_t *)c->dscan_pos.p + 256);
+            CK(c, cudaMemsetAsync(d_count, 0, 8, st));
+            zsbk_dscan_find(st, d_src, n, d_count, d_pos, pos_cap, c->n_sm);
+        }
         if (count > kMaxCand) {                                               // a buffer that is mostly magic numbers: not worth the tables
             const int rc = host_walk(0);
             if (rc) return rc;
@@ -856,21 +867,18 @@ extern "C" int zsb_scan_device(zsb_ctx *c, const uint8_t *d_src, size_t n, uint3
             const uint32_t ncand = (uint32_t)count, n1 = ncand + 1;
             uint32_t levels = 1; while ((1ull << levels) < n1) levels++;
             uint32_t mask = 1; while (mask < 2 * ncand + 2) mask <<= 1; mask -= 1;
-            size_t o = 256;
+            size_t o = 0;
             auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
-            const size_t o_pos = take(8ull * ncand), o_cand = take(sizeof(ZsbDscanCand) * (size_t)ncand), o_keys = take(8ull * (mask + 1ull)), o_vals = take(4ull * (mask + 1ull)),
+            const size_t o_cand = take(sizeof(ZsbDscanCand) * (size_t)ncand), o_keys = take(8ull * (mask + 1ull)), o_vals = take(4ull * (mask + 1ull)),
                          o_jump = take(4ull * (levels + 1ull) * n1), o_da = take(4ull * n1), o_db = take(4ull * n1), o_head = take(4), o_tail = take(8 * ZSB_DSCAN_TAIL_WORDS),
                          o_order = take(4ull * ncand), o_fr = take(sizeof(zsb_frame) * (size_t)ncand), o_fb = take(4ull * ncand);
             CK(c, c->dscan.ensure(o));
             uint8_t *A = (uint8_t *)c->dscan.p;
-            d_count = (unsigned long long *)A;
-            uint64_t *d_pos = (uint64_t *)(A + o_pos); ZsbDscanCand *d_cand = (ZsbDscanCand *)(A + o_cand);
+            ZsbDscanCand *d_cand = (ZsbDscanCand *)(A + o_cand);
             unsigned long long *d_keys = (unsigned long long *)(A + o_keys); uint32_t *d_vals = (uint32_t *)(A + o_vals), *d_jump = (uint32_t *)(A + o_jump);
             uint32_t *d_da = (uint32_t *)(A + o_da), *d_db = (uint32_t *)(A + o_db), *d_head = (uint32_t *)(A + o_head), *d_order = (uint32_t *)(A + o_order), *d_fb = (uint32_t *)(A + o_fb);
             uint64_t *d_tail = (uint64_t *)(A + o_tail); zsb_frame *d_fr = (zsb_frame *)(A + o_fr);
-            CK(c, cudaMemsetAsync(d_count, 0, 8, st));
             CK(c, cudaMemsetAsync(d_keys, 0, 8ull * (mask + 1ull), st));
-            zsbk_dscan_find(st, d_src, n, d_count, d_pos, ncand, c->n_sm);
             zsbk_dscan_parse(st, d_src, n, flags, max_window, d_pos, ncand, d_cand, d_keys, d_vals, mask);
             zsbk_dscan_link(st, d_cand, ncand, n, d_keys, d_vals, mask, d_jump, levels, d_da, d_db, d_head);
             uint32_t head = 0xFFFFFFFFu, nfr = 0;
