@@ -491,7 +491,9 @@ def run_ours(args):
         elif tj.get("workload") != w or (w in ("C2", "C5") and tj.get("frames") != frames_n):
             traffic_note = f"profiles/traffic.json was captured on {tj.get('workload')} / {tj.get('frames')} frames"
         else:
-            traffic = tj.get("kernels", {}).get(dom[0], {}).get("total")
+            ks = tj.get("kernels", {})                      # (ncu names the template instance: "void k_seq_t<16, 128, 2, 0>" is k_seq)
+            ent = ks.get(dom[0]) or next((v for k, v in ks.items() if (dom[0] + "_t<") in k), {})
+            traffic = ent.get("total")
             traffic_note = f"ncu --set full capture {tj.get('captured')}, dram__bytes_read.sum + dram__bytes_write.sum of {dom[0]}"
     except Exception:
         pass
