@@ -85,6 +85,9 @@ def test_device_scan_equals_host_scan(dec):
     cases["skip+garbage"] = b"\x50\x2a\x4d\x18\x03\x00\x00\x00abcXYZW"
     cases["skip empty"] = b"\x5f\x2a\x4d\x18\x00\x00\x00\x00" + corpora.fixture("welcome.zst")
     cases["magic in payload"] = b"\x50\x2a\x4d\x18\x0c\x00\x00\x00" + b"\x28\xb5\x2f\xfd" * 3 + corpora.fixture("welcome.zst") + b"\x28\xb5\x2f\xfd"
+    w = corpora.fixture("welcome.zst")
+    cases["frames inside a skippable payload"] = b"\x50\x2a\x4d\x18" + len(w + w).to_bytes(4, "little") + w + w + corpora.fixture("romeo.txt.zst") + w   # candidates that parse and chain, never reached from offset 0
+    cases["a frame cut inside a skippable payload"] = b"\x51\x2a\x4d\x18" + (len(w) - 9).to_bytes(4, "little") + w[:len(w) - 9] + corpora.fixture("romeo.txt.zst")
     r = random.Random(5)
     n_bad = 0
     for name, d in list(cases.items()):
